@@ -1,0 +1,192 @@
+/*
+ * nnab.h — C ABI of the nnaudio-b200 hot path (libnnab.so).
+ *
+ * The reference (KinWaiCheuk/nnAudio v0.3.3) is pure Python/PyTorch and has no
+ * FFI of its own; its hot path is the body of each module's forward():
+ * reflect/constant centre padding, conv1d(x, basis, stride=hop) framing +
+ * contraction, and the element-wise / filterbank / dB / DCT tail.  Each entry
+ * point below replaces exactly one such forward body (file:line cited per
+ * function, paths relative to Installation/nnAudio/) and is what a ctypes /
+ * cffi binding inside the reference would call.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; every data pointer is a DEVICE pointer owned by the
+ *     caller unless the name starts with h_ (host memory);
+ *   - inputs are the reference's own fp32 buffers, in the reference's own
+ *     layouts (row-major, last dim contiguous); outputs are freshly written
+ *     contiguous fp32 tensors in the reference's output layout;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); the call
+ *     never synchronises, never allocates device memory and never throws;
+ *   - return 0 on success or a negative nnab_status; nnab_strerror() names it;
+ *   - `workspace` is caller-provided scratch of at least the number of bytes
+ *     the matching nnab_*_workspace_bytes() query returns (may be NULL iff
+ *     that query returns 0);
+ *   - `path` selects the kernel family: NNAB_PATH_AUTO picks the tcgen05/TMA
+ *     kernel when shape/alignment allow and the packed basis is supplied,
+ *     otherwise the generic SIMT kernel.  Both are sm_100a CUDA; there is no
+ *     CPU fallback.
+ */
+#ifndef NNAB_H_
+#define NNAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* every entry point below is exported; everything else in the library is hidden */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define NNAB_ABI_VERSION 1
+
+typedef enum nnab_status {
+  NNAB_OK = 0,
+  NNAB_EINVAL = -1,     /* bad argument / shape mismatch                      */
+  NNAB_EALIGN = -2,     /* forced tcgen05 path but alignment rules not met    */
+  NNAB_EARCH = -3,      /* device is not sm_100                               */
+  NNAB_ECUDA = -4,      /* a CUDA runtime / driver call failed                */
+  NNAB_EWORKSPACE = -5, /* workspace NULL or too small                        */
+  NNAB_EUNSUPPORTED = -6
+} nnab_status;
+
+/* centre padding mode (stft.py:278-289, cqt.py:740-746) */
+#define NNAB_PAD_REFLECT 0
+#define NNAB_PAD_CONSTANT 1
+
+/* output formats */
+#define NNAB_FMT_MAGNITUDE 0   /* (B, F, T)     sqrt(re^2 + im^2 [+ eps])            */
+#define NNAB_FMT_COMPLEX 1     /* (B, F, T, 2)  (re, im)                             */
+#define NNAB_FMT_PHASE_ANGLE 2 /* (B, F, T)     atan2(im + 0.0, re)   STFT 'Phase'   */
+#define NNAB_FMT_PHASE_UNIT 3  /* (B, F, T, 2)  (cos, sin)(atan2(im, re)) CQT 'Phase'*/
+
+/* kernel family */
+#define NNAB_PATH_AUTO 0
+#define NNAB_PATH_SIMT 1
+#define NNAB_PATH_TCGEN05 2
+
+int nnab_abi_version(void);
+const char* nnab_strerror(int status);
+/* Last CUDA error string recorded by a call that returned NNAB_ECUDA (thread local). */
+const char* nnab_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * Basis packing for the tcgen05 path.
+ *
+ * Splits the fp32 basis pair (re rows, im rows), each (F, K) row-major, into
+ * bf16 hi/lo planes (x = hi + lo to ~2^-17) laid out for TMA/UMMA:
+ *   packed[plane][tile*BN + part*BN/2 + j][k]   plane 0 = hi, 1 = lo
+ *   part 0 = re rows, part 1 = NEGATED im rows, j < BN/2 bins per tile
+ * with K padded to a multiple of 64 and bins zero-padded to a multiple of BN/2
+ * (BN = nnab_pack_tile_n()).  Negation folds the reference's minus signs
+ * (stft.py:308-311 `-spec_imag`, cqt.py:750 `-conv1d(...)`) into the basis.
+ * ------------------------------------------------------------------------- */
+int nnab_pack_tile_n(void);
+size_t nnab_packed_basis_bytes(int F, int K);
+int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K,
+                    void* packed, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * STFT.forward — features/stft.py:256-316.
+ *   x        (B, L) rows with pitch x_pitch floats
+ *   wcos/wsin (F, n_fft) = the module's `wcos` / `wsin` buffers (window applied)
+ *   out      Magnitude/Phase: (B, F, T); Complex: (B, F, T, 2) = (real, -imag)
+ *   T must equal (L + 2*pad - n_fft)/hop + 1, pad = center ? n_fft/2 : 0
+ *   sqrt_eps = 1e-8 iff the module is trainable (stft.py:301-304), else 0
+ * ------------------------------------------------------------------------- */
+size_t nnab_stft_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop,
+                                 int center, int path);
+int nnab_stft_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
+                      const float* wcos, const float* wsin, const void* packed,
+                      int n_fft, int F, int hop, int center, int pad_mode,
+                      int out_format, float sqrt_eps, float* out, int64_t T,
+                      void* workspace, size_t ws_bytes, int path, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * MelSpectrogram.forward / Gammatonegram.forward — features/mel.py:171-189,
+ * features/gammatone.py:171-189:  out = fb @ (|STFT(x)| ** power).
+ *   fb (n_fb, F) = `mel_basis` or `gammatone_basis`;  out (B, n_fb, T)
+ * ------------------------------------------------------------------------- */
+size_t nnab_filterbank_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop,
+                                       int center, int n_fb, int path);
+int nnab_stft_filterbank_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
+                                 const float* wcos, const float* wsin, const void* packed,
+                                 int n_fft, int F, int hop, int center, int pad_mode,
+                                 float sqrt_eps, float power, const float* fb, int n_fb,
+                                 float* out, int64_t T, void* workspace, size_t ws_bytes,
+                                 int path, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * MFCC.forward — features/mel.py:309-326 (= mel -> _power_to_db :263-279 ->
+ * _dct(norm='ortho') :281-307 -> [:, :n_mfcc]).
+ *   top_db < 0 means None;  dct (n_mfcc, n_mels) fp32 orthonormal DCT-II rows;
+ *   out (B, n_mfcc, T)
+ * ------------------------------------------------------------------------- */
+size_t nnab_mfcc_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop,
+                                 int center, int n_mels, int path);
+int nnab_mfcc_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
+                      const float* wcos, const float* wsin, const void* packed,
+                      int n_fft, int F, int hop, int center, int pad_mode,
+                      float sqrt_eps, float power, const float* mel_basis, int n_mels,
+                      float amin, float ref, float top_db, const float* dct, int n_mfcc,
+                      float* out, int64_t T, void* workspace, size_t ws_bytes,
+                      int path, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * CQT1992v2.forward — features/cqt.py:712-780.
+ *   k_real/k_imag (n_bins, width) = `cqt_kernels_real/imag` buffers
+ *   h_k_begin/h_k_end: HOST int32[n_bins], the non-zero tap support
+ *     [begin, end) of every bin (NULL = treat the bank as dense)
+ *   scale: DEVICE fp32[n_bins] per-bin factor (sqrt(lenghts) for 'librosa') or
+ *     NULL; scale_all: scalar factor (2 for 'wrap', else 1)
+ *   out_format: MAGNITUDE, COMPLEX (real, imag) or PHASE_UNIT (cos, sin)
+ * ------------------------------------------------------------------------- */
+size_t nnab_cqt1992v2_workspace_bytes(int64_t B, int64_t L, int width, int n_bins, int hop,
+                                      int center, int path);
+int nnab_cqt1992v2_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
+                           const float* k_real, const float* k_imag, const void* packed,
+                           const int32_t* h_k_begin, const int32_t* h_k_end,
+                           int n_bins, int width, int hop, int center, int pad_mode,
+                           const float* scale, float scale_all, int out_format,
+                           float sqrt_eps, float* out, int64_t T,
+                           void* workspace, size_t ws_bytes, int path, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * CQT2010v2.forward / VQT.forward — features/cqt.py:1070-1139,
+ * features/vqt.py:143-215 (+ utils.py:73-124 downsampling, :498-521
+ * get_cqt_complex with its reflect -> zero-padding fallback).
+ *   h_k_real/h_k_imag: HOST arrays of n_octaves DEVICE pointers, octave 0 = top;
+ *     bank i is (n_filters, h_widths[i]) fp32 (CQT2010v2 passes the same bank
+ *     n_octaves times)
+ *   lowpass (256) = `lowpass_filter`; early_filter (256) or NULL with
+ *     early_factor (1 = inactive) = `early_downsample_filter`
+ *   hop = the module's hop_length AFTER early downsampling
+ *   scale: DEVICE fp32[n_bins] = downsample_factor * sqrt(lenghts) etc.
+ *   out (B, n_bins, T[, 2]);  T = floor(L_early / hop) + 1 for every octave,
+ *     otherwise NNAB_EINVAL (the reference's torch.cat would fail)
+ * ------------------------------------------------------------------------- */
+size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor);
+int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
+                             int n_octaves, const float* const* h_k_real,
+                             const float* const* h_k_imag, const int32_t* h_widths,
+                             int n_filters, const float* lowpass, const float* early_filter,
+                             int early_factor, int hop, int pad_mode, int n_bins,
+                             const float* scale, float scale_all, int out_format,
+                             float sqrt_eps, float* out, int64_t T,
+                             void* workspace, size_t ws_bytes, int path, void* stream);
+
+/* Kernel launches issued by this library since load (process wide; used by
+ * bench.py for its `gpu_launches` claim). */
+uint64_t nnab_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNAB_H_ */

@@ -1,0 +1,294 @@
+"""ctypes binding of ``libnnab.so`` (C ABI in ``include/nnab.h``).
+
+PyTorch is used only for device memory and the current CUDA stream; every
+compute call goes through the C ABI with raw device pointers.  There is no
+CPU / eager fallback: if the library is missing, or a tensor is not a CUDA
+fp32 tensor, the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnnab.so")
+
+PAD_REFLECT, PAD_CONSTANT = 0, 1
+FMT_MAGNITUDE, FMT_COMPLEX, FMT_PHASE_ANGLE, FMT_PHASE_UNIT = 0, 1, 2, 3
+PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+
+_PATH_NAMES = {"auto": PATH_AUTO, "simt": PATH_SIMT, "tcgen05": PATH_TCGEN05}
+
+# every symbol include/nnab.h declares: (restype, argtypes)
+_P = c_void_p
+SIGNATURES = {
+    "nnab_abi_version": (c_int, []),
+    "nnab_strerror": (c_char_p, [c_int]),
+    "nnab_last_cuda_error": (c_char_p, []),
+    "nnab_launch_count": (c_uint64, []),
+    "nnab_pack_tile_n": (c_int, []),
+    "nnab_packed_basis_bytes": (c_size_t, [c_int, c_int]),
+    "nnab_pack_basis": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "nnab_stft_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "nnab_stft_forward": (
+        c_int,
+        [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+         c_float, _P, c_int64, _P, c_size_t, c_int, _P],
+    ),
+    "nnab_filterbank_workspace_bytes": (
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "nnab_stft_filterbank_forward": (
+        c_int,
+        [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
+         c_float, _P, c_int, _P, c_int64, _P, c_size_t, c_int, _P],
+    ),
+    "nnab_mfcc_workspace_bytes": (
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "nnab_mfcc_forward": (
+        c_int,
+        [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
+         c_float, _P, c_int, c_float, c_float, c_float, _P, c_int, _P, c_int64, _P, c_size_t,
+         c_int, _P],
+    ),
+    "nnab_cqt1992v2_workspace_bytes": (
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "nnab_cqt1992v2_forward": (
+        c_int,
+        [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+         _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
+    ),
+    "nnab_cqt_pyramid_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "nnab_cqt_pyramid_forward": (
+        c_int,
+        [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int,
+         c_int, _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
+    ),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load ``libnnab.so`` once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA extension must be built first "
+                "(python -c 'import __graft_entry__ as g; g.build()' or "
+                "nnaudio_b200/csrc/build.sh). nnaudio_b200 has no CPU fallback."
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if a declared symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        if handle.nnab_abi_version() != 1:
+            raise ImportError("libnnab.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def default_path() -> int:
+    """Kernel family selector; ``NNAUDIO_B200_PATH=auto|simt|tcgen05``."""
+    return _PATH_NAMES[os.environ.get("NNAUDIO_B200_PATH", "auto").lower()]
+
+
+def resolve_path(path) -> int:
+    if path is None:
+        return default_path()
+    if isinstance(path, str):
+        return _PATH_NAMES[path.lower()]
+    return int(path)
+
+
+def launch_count() -> int:
+    return int(lib().nnab_launch_count())
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        L = lib()
+        msg = L.nnab_strerror(rc).decode()
+        if rc == -4:
+            msg += ": " + L.nnab_last_cuda_error().decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {rc})")
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: nnaudio_b200 runs only on CUDA (sm_100a) tensors; "
+            "there is no CPU fallback"
+        )
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _workspace(nbytes: int, device):
+    if nbytes <= 0:
+        return None, 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return ws, nbytes
+
+
+def _rows(x: torch.Tensor):
+    """(B, L) view with unit inner stride -> (tensor, B, L, pitch)."""
+    x = _dev_f32(x, "x")
+    if x.dim() != 2:
+        raise ValueError("internal: expected (B, L)")
+    if x.stride(-1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+        x = x.contiguous()
+    pitch = x.stride(0) if x.shape[0] > 1 else x.shape[1]
+    return x, x.shape[0], x.shape[1], pitch
+
+
+# --------------------------------------------------------------------------- #
+# basis packing (tcgen05 path)
+# --------------------------------------------------------------------------- #
+def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor):
+    """bf16 hi/lo split of an (F, K) fp32 basis pair in the TMA/UMMA layout, or
+    ``None`` when the library has no tcgen05 kernel for it."""
+    L = lib()
+    F, K = w_re.shape
+    nbytes = L.nnab_packed_basis_bytes(F, K)
+    if nbytes == 0:
+        return None
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w_re.device)
+    with torch.cuda.device(w_re.device):
+        _check(L.nnab_pack_basis(_ptr(w_re), _ptr(w_im), F, K, _ptr(packed), _stream(w_re.device)),
+               "nnab_pack_basis")
+    return packed
+
+
+# --------------------------------------------------------------------------- #
+# forward calls
+# --------------------------------------------------------------------------- #
+def stft_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, out_format, sqrt_eps,
+                 path=None):
+    L = lib()
+    x, B, Ln, pitch = _rows(x)
+    F = wcos.shape[0]
+    pad = n_fft // 2 if center else 0
+    T = (Ln + 2 * pad - n_fft) // hop + 1
+    shape = (B, F, T, 2) if out_format == FMT_COMPLEX else (B, F, T)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    path = resolve_path(path)
+    with torch.cuda.device(x.device):
+        ws, wsb = _workspace(L.nnab_stft_workspace_bytes(B, Ln, n_fft, F, hop, int(center), path),
+                             x.device)
+        rc = L.nnab_stft_forward(_ptr(x), B, Ln, pitch, _ptr(wcos), _ptr(wsin), _ptr(packed),
+                                 n_fft, F, hop, int(center), pad_mode, out_format, sqrt_eps,
+                                 _ptr(out), T, _ptr(ws), wsb, path, _stream(x.device))
+    _check(rc, "nnab_stft_forward")
+    return out
+
+
+def stft_filterbank_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, power,
+                            fb, path=None):
+    L = lib()
+    x, B, Ln, pitch = _rows(x)
+    F = wcos.shape[0]
+    n_fb = fb.shape[0]
+    pad = n_fft // 2 if center else 0
+    T = (Ln + 2 * pad - n_fft) // hop + 1
+    out = torch.empty((B, n_fb, T), dtype=torch.float32, device=x.device)
+    path = resolve_path(path)
+    with torch.cuda.device(x.device):
+        ws, wsb = _workspace(
+            L.nnab_filterbank_workspace_bytes(B, Ln, n_fft, F, hop, int(center), n_fb, path),
+            x.device)
+        rc = L.nnab_stft_filterbank_forward(
+            _ptr(x), B, Ln, pitch, _ptr(wcos), _ptr(wsin), _ptr(packed), n_fft, F, hop,
+            int(center), pad_mode, sqrt_eps, power, _ptr(fb), n_fb, _ptr(out), T, _ptr(ws), wsb,
+            path, _stream(x.device))
+    _check(rc, "nnab_stft_filterbank_forward")
+    return out
+
+
+def mfcc_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, power, mel_basis,
+                 amin, ref, top_db, dct, path=None):
+    L = lib()
+    x, B, Ln, pitch = _rows(x)
+    F = wcos.shape[0]
+    n_mels = mel_basis.shape[0]
+    n_mfcc = dct.shape[0]
+    pad = n_fft // 2 if center else 0
+    T = (Ln + 2 * pad - n_fft) // hop + 1
+    out = torch.empty((B, n_mfcc, T), dtype=torch.float32, device=x.device)
+    path = resolve_path(path)
+    with torch.cuda.device(x.device):
+        ws, wsb = _workspace(
+            L.nnab_mfcc_workspace_bytes(B, Ln, n_fft, F, hop, int(center), n_mels, path), x.device)
+        rc = L.nnab_mfcc_forward(
+            _ptr(x), B, Ln, pitch, _ptr(wcos), _ptr(wsin), _ptr(packed), n_fft, F, hop,
+            int(center), pad_mode, sqrt_eps, power, _ptr(mel_basis), n_mels, amin, ref,
+            -1.0 if top_db is None else float(top_db), _ptr(dct), n_mfcc, _ptr(out), T, _ptr(ws),
+            wsb, path, _stream(x.device))
+    _check(rc, "nnab_mfcc_forward")
+    return out
+
+
+def cqt1992v2_forward(x, k_real, k_imag, packed, k_begin, k_end, hop, center, pad_mode, scale,
+                      scale_all, out_format, sqrt_eps, path=None):
+    """k_begin / k_end: host int32 numpy arrays (per-bin support) or None."""
+    L = lib()
+    x, B, Ln, pitch = _rows(x)
+    n_bins, width = k_real.shape
+    pad = width // 2 if center else 0
+    T = (Ln + 2 * pad - width) // hop + 1
+    shape = (B, n_bins, T) if out_format == FMT_MAGNITUDE else (B, n_bins, T, 2)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    path = resolve_path(path)
+    kb = k_begin.ctypes.data_as(c_void_p) if k_begin is not None else None
+    ke = k_end.ctypes.data_as(c_void_p) if k_end is not None else None
+    with torch.cuda.device(x.device):
+        ws, wsb = _workspace(
+            L.nnab_cqt1992v2_workspace_bytes(B, Ln, width, n_bins, hop, int(center), path),
+            x.device)
+        rc = L.nnab_cqt1992v2_forward(
+            _ptr(x), B, Ln, pitch, _ptr(k_real), _ptr(k_imag), _ptr(packed), kb, ke, n_bins,
+            width, hop, int(center), pad_mode, _ptr(scale), scale_all, out_format, sqrt_eps,
+            _ptr(out), T, _ptr(ws), wsb, path, _stream(x.device))
+    _check(rc, "nnab_cqt1992v2_forward")
+    return out
+
+
+def cqt_pyramid_forward(x, banks_real, banks_imag, lowpass, early_filter, early_factor, hop,
+                        pad_mode, n_bins, scale, scale_all, out_format, sqrt_eps, T, path=None):
+    """banks_*: lists (octave 0 = top) of (n_filters, width_i) fp32 CUDA tensors."""
+    L = lib()
+    x, B, Ln, pitch = _rows(x)
+    n_oct = len(banks_real)
+    n_filters = banks_real[0].shape[0]
+    re_arr = (c_void_p * n_oct)(*[t.data_ptr() for t in banks_real])
+    im_arr = (c_void_p * n_oct)(*[t.data_ptr() for t in banks_imag])
+    widths = (c_int32 * n_oct)(*[int(t.shape[1]) for t in banks_real])
+    shape = (B, n_bins, T) if out_format == FMT_MAGNITUDE else (B, n_bins, T, 2)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    path = resolve_path(path)
+    if path == PATH_TCGEN05:
+        path = PATH_AUTO
+    with torch.cuda.device(x.device):
+        ws, wsb = _workspace(L.nnab_cqt_pyramid_workspace_bytes(B, Ln, n_oct, early_factor),
+                             x.device)
+        rc = L.nnab_cqt_pyramid_forward(
+            _ptr(x), B, Ln, pitch, n_oct, re_arr, im_arr, widths, n_filters, _ptr(lowpass),
+            _ptr(early_filter), early_factor, hop, pad_mode, n_bins, _ptr(scale), scale_all,
+            out_format, sqrt_eps, _ptr(out), T, _ptr(ws), wsb, path, _stream(x.device))
+    _check(rc, "nnab_cqt_pyramid_forward")
+    return out

@@ -1,0 +1,66 @@
+// Output-format epilogue shared by the SIMT and tcgen05 framed kernels.
+// Mirrors the element-wise tails of the reference forward() bodies:
+//   STFT   stft.py:299-316     CQT1992v2  cqt.py:752-780
+//   CQT2010v2 cqt.py:1112-1139 Mel/Gammatone power  mel.py:186
+#pragma once
+
+#include "common.cuh"
+
+namespace nnab {
+
+struct EpiParams {
+  const float* scale;  // per-bin factor or nullptr
+  float scale_all;
+  int fmt;
+  float eps;
+  float power;
+  float* out;
+  int64_t T;
+  int out_bins;
+  int bin_offset;
+  int F;
+};
+
+// re/im are the final-signed contraction results for (clip b, bin f, frame t).
+__device__ __forceinline__ void epi_store(const EpiParams& e, int64_t b, int f, int64_t t,
+                                          float re, float im) {
+  const int row = f + e.bin_offset;
+  if (row < 0 || row >= e.out_bins) return;
+  float s = e.scale_all;
+  if (e.scale != nullptr) s *= __ldg(e.scale + f);
+  re *= s;
+  im *= s;
+  const int64_t idx = ((int64_t)b * e.out_bins + row) * e.T + t;
+  switch (e.fmt) {
+    case NNAB_FMT_MAGNITUDE: {
+      // pow(2) + pow(2) (+ eps) then sqrt, each step rounded like the reference
+      float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+      if (e.eps != 0.f) p = __fadd_rn(p, e.eps);
+      e.out[idx] = sqrtf(p);
+    } break;
+    case NNAB_FMT_COMPLEX: {
+      reinterpret_cast<float2*>(e.out)[idx] = make_float2(re, im);
+    } break;
+    case NNAB_FMT_PHASE_ANGLE: {
+      e.out[idx] = atan2f(im + 0.0f, re);
+    } break;
+    case NNAB_FMT_PHASE_UNIT: {
+      const float ang = atan2f(im, re);
+      float sn, cs;
+      sincosf(ang, &sn, &cs);
+      reinterpret_cast<float2*>(e.out)[idx] = make_float2(cs, sn);
+    } break;
+    default: {  // FMT_POWER
+      float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+      if (e.eps != 0.f) p = __fadd_rn(p, e.eps);
+      const float m = sqrtf(p);
+      float v;
+      if (e.power == 2.0f) v = __fmul_rn(m, m);
+      else if (e.power == 1.0f) v = m;
+      else v = powf(m, e.power);
+      e.out[idx] = v;
+    } break;
+  }
+}
+
+}  // namespace nnab

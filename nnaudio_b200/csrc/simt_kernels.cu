@@ -1,0 +1,425 @@
+// Generic fp32 CUDA-core kernels of libnnab.so (sm_100a):
+//   * framed complex contraction (any hop / K / F, sparse-support aware)
+//   * filterbank GEMM  out = fb @ P      (mel.py:188, gammatone.py:188)
+//   * MFCC tail        dB -> top_db clamp -> DCT   (mel.py:263-307, 325)
+//   * FIR decimation   conv1d(x, fir, stride=n, padding=127)  (utils.py:73-124)
+// They are the first-correct path and the fallback for shapes the tcgen05/TMA
+// kernel does not take (hop % 8 != 0, tiny banks, ...).  No CPU fallback exists.
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace nnab {
+
+// --------------------------------------------------------------------------
+// sample fetch with the centre padding folded into the index
+// (nn.ReflectionPad1d / nn.ConstantPad1d semantics, stft.py:278-289)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ float fetch_padded(const float* __restrict__ xb, int64_t L, int64_t j,
+                                              int pad_mode) {
+  if (j < 0) {
+    if (pad_mode == NNAB_PAD_CONSTANT) return 0.f;
+    j = -j;
+  } else if (j >= L) {
+    if (pad_mode == NNAB_PAD_CONSTANT) return 0.f;
+    j = 2 * (L - 1) - j;
+  }
+  return (j >= 0 && j < L) ? __ldg(xb + j) : 0.f;
+}
+
+// --------------------------------------------------------------------------
+// framed complex contraction, SIMT
+//   CTA tile: 128 frames x (16*TN) bins, 256 threads, thread tile 8 x TN x {re,im}
+// --------------------------------------------------------------------------
+constexpr int SIMT_MAX_BIN_TILES = 128;
+
+struct SimtParams {
+  const float* x;
+  int64_t L, x_pitch;
+  const float* w_re;
+  const float* w_im;
+  int F, K, hop, pad, pad_mode;
+  int n_ranges;  // 0 => dense [0, K) for every bin tile
+  int kb[SIMT_MAX_BIN_TILES];
+  int ke[SIMT_MAX_BIN_TILES];
+  EpiParams epi;
+};
+
+template <int TN>
+__global__ void __launch_bounds__(256) framed_cplx_simt_kernel(const SimtParams p) {
+  constexpr int TM = 8, BM = 128, BNB = 16 * TN, BK = 16;
+  __shared__ float As[BM][BK + 1];
+  __shared__ __align__(16) float Wr[BK][BNB + 4];
+  __shared__ __align__(16) float Wi[BK][BNB + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;  // frame lane
+  const int ty = tid >> 4;  // bin group
+  const int64_t b = blockIdx.z;
+  const int64_t t0 = (int64_t)blockIdx.x * BM;
+  const int f0 = blockIdx.y * BNB;
+  const float* __restrict__ xb = p.x + b * p.x_pitch;
+
+  int kbeg = 0, kend = p.K;
+  if (p.n_ranges > 0) {
+    kbeg = p.kb[blockIdx.y];
+    kend = p.ke[blockIdx.y];
+  }
+
+  float acc_re[TM][TN], acc_im[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc_re[i][j] = acc_im[i][j] = 0.f;
+
+  const int lk = tid & 15;
+  const int lr = tid >> 4;
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    const int k = k0 + lk;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = lr + 16 * i;
+      const int64_t t = t0 + m;
+      float v = 0.f;
+      if (t < p.epi.T && k < kend)
+        v = fetch_padded(xb, p.L, t * (int64_t)p.hop + k - p.pad, p.pad_mode);
+      As[m][lk] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < TN; ++i) {
+      const int j = lr + 16 * i;
+      const int f = f0 + j;
+      float vr = 0.f, vi = 0.f;
+      if (f < p.F && k < kend) {
+        vr = __ldg(p.w_re + (int64_t)f * p.K + k);
+        vi = __ldg(p.w_im + (int64_t)f * p.K + k);
+      }
+      Wr[lk][j] = vr;
+      Wi[lk][j] = vi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], wr[TN], wi[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[tx + 16 * i][kk];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        wr[j] = Wr[kk][ty * TN + j];
+        wi[j] = Wi[kk][ty * TN + j];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          acc_re[i][j] = fmaf(a[i], wr[j], acc_re[i][j]);
+          acc_im[i][j] = fmaf(a[i], wi[j], acc_im[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int f = f0 + ty * TN + j;
+    if (f >= p.F) continue;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int64_t t = t0 + tx + 16 * i;
+      if (t < p.epi.T) epi_store(p.epi, b, f, t, acc_re[i][j], -acc_im[i][j]);
+    }
+  }
+}
+
+int launch_framed_simt(const FramedProblem& q, cudaStream_t stream) {
+  if (q.B <= 0 || q.T <= 0 || q.F <= 0) return NNAB_OK;
+  if (q.B > 65535) return NNAB_EUNSUPPORTED;
+  SimtParams p;
+  p.x = q.x; p.L = q.L; p.x_pitch = q.x_pitch;
+  p.w_re = q.w_re; p.w_im = q.w_im;
+  p.F = q.F; p.K = q.K; p.hop = q.hop; p.pad = q.pad; p.pad_mode = q.pad_mode;
+  p.epi.scale = q.scale; p.epi.scale_all = q.scale_all; p.epi.fmt = q.fmt;
+  p.epi.eps = q.eps; p.epi.power = q.power; p.epi.out = q.out; p.epi.T = q.T;
+  p.epi.out_bins = q.out_bins; p.epi.bin_offset = q.bin_offset; p.epi.F = q.F;
+
+  const int TN = (q.F > 32) ? 4 : 2;
+  const int BNB = 16 * TN;
+  const int n_tiles = (q.F + BNB - 1) / BNB;
+  p.n_ranges = 0;
+  if (q.h_k_begin != nullptr && q.h_k_end != nullptr && n_tiles <= SIMT_MAX_BIN_TILES) {
+    p.n_ranges = n_tiles;
+    for (int tl = 0; tl < n_tiles; ++tl) {
+      int lo = q.K, hi = 0;
+      for (int f = tl * BNB; f < q.F && f < (tl + 1) * BNB; ++f) {
+        if (q.h_k_end[f] > q.h_k_begin[f]) {
+          lo = q.h_k_begin[f] < lo ? q.h_k_begin[f] : lo;
+          hi = q.h_k_end[f] > hi ? q.h_k_end[f] : hi;
+        }
+      }
+      if (hi < lo) { lo = 0; hi = 0; }
+      if (lo < 0) lo = 0;
+      if (hi > q.K) hi = q.K;
+      p.kb[tl] = lo;
+      p.ke[tl] = hi;
+    }
+  }
+  dim3 grid((unsigned)ceil_div64(q.T, 128), (unsigned)n_tiles, (unsigned)q.B);
+  if (TN == 4)
+    framed_cplx_simt_kernel<4><<<grid, 256, 0, stream>>>(p);
+  else
+    framed_cplx_simt_kernel<2><<<grid, 256, 0, stream>>>(p);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// --------------------------------------------------------------------------
+// filterbank GEMM: out[b, j, t] = sum_f fb[j, f] * P[b, f, t]
+//   CTA tile 64 filters x 128 frames, BK = 16 bins; all-zero fb blocks (the
+//   mel matrix is ~98.5 % zeros) skip their P tile entirely.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) filterbank_kernel(const float* __restrict__ P,
+                                                         const float* __restrict__ fb, int F,
+                                                         int64_t T, int n_fb,
+                                                         float* __restrict__ out) {
+  constexpr int BJ = 64, BT = 128, BK = 16;
+  __shared__ float Ps[BK][BT];
+  __shared__ __align__(16) float Fs[BK][BJ + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  const int64_t b = blockIdx.z;
+  const int64_t t0 = (int64_t)blockIdx.x * BT;
+  const int j0 = blockIdx.y * BJ;
+  const float* __restrict__ Pb = P + b * (int64_t)F * T;
+
+  float acc[8][4];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[jj][i] = 0.f;
+
+  const int lk = tid & 15, lr = tid >> 4;
+  for (int fk = 0; fk < F; fk += BK) {
+    int nz = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = lr + 16 * i;
+      float v = 0.f;
+      if (j0 + j < n_fb && fk + lk < F) v = __ldg(fb + (int64_t)(j0 + j) * F + fk + lk);
+      Fs[lk][j] = v;
+      nz |= (v != 0.f);
+    }
+    nz = __syncthreads_or(nz);
+    if (!nz) continue;  // uniform: nothing of this filter tile lives in these bins
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + 256 * i;
+      const int r = idx >> 7, c = idx & 127;
+      float v = 0.f;
+      if (fk + r < F && t0 + c < T) v = __ldg(Pb + (int64_t)(fk + r) * T + t0 + c);
+      Ps[r][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float pv[4], w[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = Ps[kk][tx + 32 * i];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) w[jj] = Fs[kk][ty * 8 + jj];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[jj][i] = fmaf(w[jj], pv[i], acc[jj][i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = j0 + ty * 8 + jj;
+    if (j >= n_fb) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t t = t0 + tx + 32 * i;
+      if (t < T) out[((int64_t)b * n_fb + j) * T + t] = acc[jj][i];
+    }
+  }
+}
+
+int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t T, int n_fb,
+                      float* out, cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || n_fb <= 0) return NNAB_OK;
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  dim3 grid((unsigned)ceil_div64(T, 128), (unsigned)((n_fb + 63) / 64), (unsigned)B);
+  filterbank_kernel<<<grid, 256, 0, stream>>>(P, fb, F, T, n_fb, out);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// --------------------------------------------------------------------------
+// MFCC tail
+//   pass 1: per-clip max of max(S, amin)  (float bits are monotone for > 0)
+//   pass 2: dB, clamp to (clip max dB - top_db), orthonormal DCT-II rows
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clip_max_kernel(const float* __restrict__ S,
+                                                       int64_t per_clip, float amin,
+                                                       unsigned int* __restrict__ clip_max) {
+  const int64_t b = blockIdx.y;
+  const float* __restrict__ Sb = S + b * per_clip;
+  float m = amin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_clip;
+       i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, __ldg(Sb + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+    atomicMax(clip_max + b, __float_as_uint(m));  // m >= amin > 0
+  }
+}
+
+constexpr int MFCC_CHUNK = 32;
+
+__global__ void __launch_bounds__(128) mfcc_tail_kernel(const float* __restrict__ S, int n_mels,
+                                                        int64_t T, float amin, float ref_db,
+                                                        float top_db,
+                                                        const unsigned int* __restrict__ clip_max,
+                                                        const float* __restrict__ dct, int n_mfcc,
+                                                        float* __restrict__ out) {
+  extern __shared__ float dsm[];  // [MFCC_CHUNK][n_mels]
+  const int64_t b = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float* __restrict__ Sb = S + b * (int64_t)n_mels * T;
+  float floor_db = -INFINITY;
+  if (top_db >= 0.f) {
+    const float peak = 10.0f * log10f(__uint_as_float(clip_max[b])) - ref_db;
+    floor_db = peak - top_db;
+  }
+  for (int c0 = 0; c0 < n_mfcc; c0 += MFCC_CHUNK) {
+    const int nc = min(MFCC_CHUNK, n_mfcc - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc * n_mels; i += blockDim.x)
+      dsm[i] = __ldg(dct + (int64_t)c0 * n_mels + i);
+    __syncthreads();
+    if (t < T) {
+      float acc[MFCC_CHUNK];
+#pragma unroll
+      for (int c = 0; c < MFCC_CHUNK; ++c) acc[c] = 0.f;
+      for (int m = 0; m < n_mels; ++m) {
+        float v = 10.0f * log10f(fmaxf(__ldg(Sb + (int64_t)m * T + t), amin)) - ref_db;
+        v = fmaxf(v, floor_db);
+#pragma unroll
+        for (int c = 0; c < MFCC_CHUNK; ++c)
+          if (c < nc) acc[c] = fmaf(dsm[c * n_mels + m], v, acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < MFCC_CHUNK; ++c)
+        if (c < nc) out[((int64_t)b * n_mfcc + c0 + c) * T + t] = acc[c];
+    }
+  }
+}
+
+// `scratch` holds B uint32 (per-clip max bits), provided by the caller's workspace.
+int launch_mfcc_tail(const float* mel, int64_t B, int n_mels, int64_t T, float amin,
+                          float ref, float top_db, const float* dct, int n_mfcc, float* out,
+                          unsigned int* scratch, cudaStream_t stream) {
+  if (B <= 0 || T <= 0) return NNAB_OK;
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  const size_t smem = (size_t)MFCC_CHUNK * n_mels * sizeof(float);
+  if (smem > 200 * 1024) return NNAB_EUNSUPPORTED;
+  const float ref_db = 10.0f * log10f(fmaxf(amin, fabsf(ref)));
+  if (top_db >= 0.f) {
+    NNAB_CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)B * sizeof(unsigned int), stream));
+    const int64_t per_clip = (int64_t)n_mels * T;
+    int gx = (int)ceil_div64(per_clip, 256 * 8);
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    clip_max_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(mel, per_clip, amin, scratch);
+    NNAB_LAUNCH_CHECK();
+  }
+  if (smem > 48 * 1024)
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(mfcc_tail_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div64(T, 128), (unsigned)B);
+  mfcc_tail_kernel<<<grid, 128, smem, stream>>>(mel, n_mels, T, amin, ref_db, top_db, scratch,
+                                                dct, n_mfcc, out);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// --------------------------------------------------------------------------
+// FIR decimation: y[n] = sum_j fir[j] * x[n*factor + j - (taps-1)/2], zero outside
+//   Polyphase in shared memory so a thread's 4 consecutive outputs slide over
+//   unit-stride data: 2 LDS.128 per 16 FMAs.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fir_decimate_kernel(
+    const float* __restrict__ x, int64_t L, int64_t x_pitch, const float* __restrict__ fir,
+    int taps, int factor, int qtaps, int ph_len, float* __restrict__ y, int64_t Ly,
+    int64_t y_pitch) {
+  extern __shared__ __align__(16) float fsm[];
+  float* xs = fsm;                    // [factor][ph_len]
+  float* fs = fsm + factor * ph_len;  // [factor][qtaps]
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.y;
+  const int64_t n0 = (int64_t)blockIdx.x * 1024;
+  const int64_t base = n0 * factor - (taps - 1) / 2;
+  const float* __restrict__ xb = x + b * x_pitch;
+
+  for (int idx = tid; idx < ph_len * factor; idx += 256) {
+    const int64_t g = base + idx;
+    const float v = (g >= 0 && g < L) ? __ldg(xb + g) : 0.f;
+    xs[(idx % factor) * ph_len + idx / factor] = v;
+  }
+  for (int j = tid; j < qtaps * factor; j += 256)
+    fs[(j % factor) * qtaps + j / factor] = (j < taps) ? __ldg(fir + j) : 0.f;
+  __syncthreads();
+
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ph = 0; ph < factor; ++ph) {
+    const float* xp = xs + ph * ph_len + 4 * tid;
+    const float* fp = fs + ph * qtaps;
+    float4 v0 = *reinterpret_cast<const float4*>(xp);
+    for (int qb = 0; qb < qtaps; qb += 4) {
+      const float4 v1 = *reinterpret_cast<const float4*>(xp + qb + 4);
+      const float4 f = *reinterpret_cast<const float4*>(fp + qb);
+      const float w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        acc[o] = fmaf(f.x, w[o], acc[o]);
+        acc[o] = fmaf(f.y, w[o + 1], acc[o]);
+        acc[o] = fmaf(f.z, w[o + 2], acc[o]);
+        acc[o] = fmaf(f.w, w[o + 3], acc[o]);
+      }
+      v0 = v1;
+    }
+  }
+  float* __restrict__ yb = y + b * y_pitch;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int64_t n = n0 + 4 * tid + o;
+    if (n < Ly) yb[n] = acc[o];
+  }
+}
+
+int launch_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* fir,
+                        int taps, int factor, float* y, int64_t Ly, int64_t y_pitch,
+                        cudaStream_t stream) {
+  if (B <= 0 || Ly <= 0) return NNAB_OK;
+  if (B > 65535 || factor < 1 || taps < 1) return NNAB_EUNSUPPORTED;
+  int qtaps = (taps + factor - 1) / factor;
+  qtaps = (qtaps + 3) & ~3;
+  const int ph_len = 1024 + qtaps + 4;  // +4: the rolling float4 window reads one vector ahead
+  const size_t smem = (size_t)factor * (ph_len + qtaps) * sizeof(float);
+  if (smem > 200 * 1024) return NNAB_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(fir_decimate_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div64(Ly, 1024), (unsigned)B);
+  fir_decimate_kernel<<<grid, 256, smem, stream>>>(x, L, x_pitch, fir, taps, factor, qtaps,
+                                                   ph_len, y, Ly, y_pitch);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+}  // namespace nnab

@@ -1,0 +1,83 @@
+"""Host-side helpers shared by the feature modules (argument checks that raise
+the reference's exception types *before* the C call, and the cache of
+device-side packed bases)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _C
+
+PAD_MODES = {"reflect": _C.PAD_REFLECT, "constant": _C.PAD_CONSTANT}
+
+
+def broadcast_dim(x: torch.Tensor) -> torch.Tensor:
+    """utils.py:206-222 — accept (L), (B, L) or (B, 1, L); returns a (B, L) view
+    (the reference inserts the singleton conv channel instead)."""
+    if x.dim() == 2:
+        return x
+    if x.dim() == 1:
+        return x[None, :]
+    if x.dim() == 3:
+        if x.shape[1] != 1:
+            raise RuntimeError(
+                f"expected input with 1 channel, got {x.shape[1]} channels (shape {tuple(x.shape)})"
+            )
+        return x[:, 0, :]
+    raise ValueError("Only support input with shape = (batch, len) or shape = (len)")
+
+
+def pad_mode_id(pad_mode: str) -> int:
+    try:
+        return PAD_MODES[pad_mode]
+    except KeyError:
+        raise ValueError(f"unsupported pad_mode {pad_mode!r}; use 'reflect' or 'constant'")
+
+
+def forward_only_guard(module: torch.nn.Module, x: torch.Tensor):
+    """The fused kernels are forward-only in this round:
+    refuse loudly rather than return a silently non-differentiable result."""
+    if not torch.is_grad_enabled():
+        return
+    if x.requires_grad or any(p.requires_grad for p in module.parameters()):
+        raise NotImplementedError(
+            "nnaudio_b200 kernels are forward-only: run under torch.no_grad() "
+            "(autograd through the fused kernels is not implemented yet)"
+        )
+
+
+class PackedBasis:
+    """Cache of the (F, K) fp32 views and the bf16 hi/lo packed copy of a basis
+    pair, invalidated when the source tensors change (load_state_dict, .to(),
+    optimiser steps)."""
+
+    def __init__(self):
+        self._key = None
+        self._packed = None
+
+    def get(self, w_re: torch.Tensor, w_im: torch.Tensor):
+        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, str(w_re.device))
+        if key != self._key:
+            self._packed = _C.pack_basis(w_re, w_im)
+            self._key = key
+        return self._packed
+
+
+def as_matrix(buf: torch.Tensor) -> torch.Tensor:
+    """(F, 1, K) conv-style buffer -> contiguous (F, K) fp32 CUDA view."""
+    t = buf.detach()
+    _C._dev_f32(t, "basis")
+    t = t.reshape(t.shape[0], t.shape[-1])
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def tap_support(bank_2d: np.ndarray):
+    """Per-row [begin, end) of the non-zero taps of a (n_bins, width) bank
+    (real and imaginary parts combined by the caller)."""
+    nz = bank_2d != 0
+    any_nz = nz.any(axis=1)
+    first = nz.argmax(axis=1)
+    last = bank_2d.shape[1] - nz[:, ::-1].argmax(axis=1)
+    begin = np.where(any_nz, first, 0).astype(np.int32)
+    end = np.where(any_nz, last, 0).astype(np.int32)
+    return np.ascontiguousarray(begin), np.ascontiguousarray(end)

@@ -1,0 +1,352 @@
+"""``CQT1992v2``, ``CQT2010v2`` and the ``CQT`` alias — drop-ins for
+``nnAudio.features.cqt`` (cqt.py:561-803, :805-1139, :1142-1145).
+
+Buffer names follow the reference, including its spelling ``lenghts``.
+"""
+from __future__ import annotations
+
+import warnings
+from time import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _C, design
+from ._common import (PackedBasis, as_matrix, broadcast_dim, forward_only_guard, pad_mode_id,
+                      tap_support)
+
+_FORMATS = {
+    "Magnitude": _C.FMT_MAGNITUDE,
+    "Complex": _C.FMT_COMPLEX,
+    "Phase": _C.FMT_PHASE_UNIT,
+}
+_NORMALIZATIONS = ("librosa", "convolutional", "wrap")
+
+
+def _check_format_and_norm(output_format, normalization_type):
+    if normalization_type not in _NORMALIZATIONS:
+        raise ValueError(
+            "The normalization_type %r is not part of our current options." % normalization_type
+        )
+    if output_format not in _FORMATS:
+        raise ValueError(
+            f"output_format must be 'Magnitude', 'Complex' or 'Phase', got {output_format!r}"
+        )
+
+
+class _ScaleCache:
+    """sqrt(lenghts) * factor on the device, recomputed when ``lenghts`` changes."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, lenghts: torch.Tensor, factor: float):
+        key = (lenghts.data_ptr(), lenghts._version, float(factor), str(lenghts.device))
+        if key != self._key:
+            s = torch.sqrt(lenghts.detach().float())
+            if factor != 1:
+                s = s * factor
+            self._val = s.contiguous()
+            self._key = key
+        return self._val
+
+
+class CQT1992v2(nn.Module):
+    """Time-domain constant-Q transform with one wavelet bank spanning all bins
+    (cqt.py:655-780).  ``forward(x, output_format=None,
+    normalization_type='librosa')`` returns ``(B, n_bins, T)`` (Magnitude) or
+    ``(B, n_bins, T, 2)`` (Complex = (real, imag); Phase = (cos, sin))."""
+
+    def __init__(
+        self,
+        sr=22050,
+        hop_length=512,
+        fmin=32.70,
+        fmax=None,
+        n_bins=84,
+        bins_per_octave=12,
+        filter_scale=1,
+        norm=1,
+        window="hann",
+        center=True,
+        pad_mode="reflect",
+        trainable=False,
+        output_format="Magnitude",
+        verbose=True,
+    ):
+        super().__init__()
+        self.trainable = trainable
+        self.hop_length = hop_length
+        self.center = center
+        self.pad_mode = pad_mode
+        self.output_format = output_format
+
+        Q = float(filter_scale) / (2 ** (1 / bins_per_octave) - 1)
+        if verbose:
+            print("Creating CQT kernels ...", end="\r")
+        start = time()
+        bank, self.kernel_width, lengths, freqs = design.cqt_bank(
+            Q, sr, fmin, n_bins, bins_per_octave, norm, window, fmax
+        )
+        self.register_buffer("lenghts", torch.tensor(lengths).float())
+        self.frequencies = freqs
+
+        k_real = torch.tensor(bank.real).unsqueeze(1)
+        k_imag = torch.tensor(bank.imag).unsqueeze(1)
+        if trainable:
+            self.register_parameter("cqt_kernels_real", nn.Parameter(k_real, requires_grad=True))
+            self.register_parameter("cqt_kernels_imag", nn.Parameter(k_imag, requires_grad=True))
+        else:
+            self.register_buffer("cqt_kernels_real", k_real)
+            self.register_buffer("cqt_kernels_imag", k_imag)
+
+        self._packed = PackedBasis()
+        self._scale = _ScaleCache()
+        self._support_key = None
+        self._support = (None, None)
+        if verbose:
+            print("CQT kernels created, time used = {:.4f} seconds".format(time() - start))
+
+    def _tap_support(self):
+        """Host int32 [begin, end) of each wavelet's non-zero taps, from the
+        *current* buffer contents (dense when the bank is trainable)."""
+        if self.trainable:
+            return None, None
+        kr, ki = self.cqt_kernels_real, self.cqt_kernels_imag
+        key = (kr.data_ptr(), kr._version, ki.data_ptr(), ki._version)
+        if key != self._support_key:
+            both = (kr.detach()[:, 0, :] != 0) | (ki.detach()[:, 0, :] != 0)
+            self._support = tap_support(both.cpu().numpy())
+            self._support_key = key
+        return self._support
+
+    def forward(self, x, output_format=None, normalization_type="librosa"):
+        output_format = output_format or self.output_format
+        _check_format_and_norm(output_format, normalization_type)
+        x = broadcast_dim(x)
+        pad = self.kernel_width // 2 if self.center else 0
+        if self.center and self.pad_mode == "reflect" and x.shape[-1] <= pad:
+            raise RuntimeError(
+                "Padding size should be less than the corresponding input dimension, but got: "
+                f"padding ({pad}, {pad}) at dimension 2 of input {tuple(x[:, None, :].shape)}"
+            )
+        if x.shape[-1] + 2 * pad < self.kernel_width:
+            raise RuntimeError("Kernel size can't be greater than actual input size")
+        forward_only_guard(self, x)
+
+        k_real, k_imag = as_matrix(self.cqt_kernels_real), as_matrix(self.cqt_kernels_imag)
+        packed = self._packed.get(k_real, k_imag)
+        k_begin, k_end = self._tap_support()
+        scale, scale_all = None, 1.0
+        if normalization_type == "librosa":
+            scale = self._scale.get(self.lenghts, 1.0)
+        elif normalization_type == "wrap":
+            scale_all = 2.0
+        eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
+        return _C.cqt1992v2_forward(
+            x, k_real, k_imag, packed, k_begin, k_end, self.hop_length, self.center,
+            pad_mode_id(self.pad_mode), scale, scale_all, _FORMATS[output_format], eps,
+        )
+
+
+class CQT(CQT1992v2):
+    """Alias of :class:`CQT1992v2` (cqt.py:1142-1145)."""
+
+    pass
+
+
+def _octave_plan(L, hop, widths, pad_mode):
+    """Per-octave signal lengths of the ÷2 pyramid and whether the reference's
+    reflect padding would fall back to zero padding (utils.py:505-517).
+    Returns (T, fallback_flags) or raises like torch.cat would."""
+    lens, hops, flags = [], [], []
+    cur, h = L, hop
+    for i, w in enumerate(widths):
+        if i > 0:
+            cur = (cur - 2) // 2 + 1 if cur >= 2 else 0
+            h = h // 2
+        lens.append(cur)
+        hops.append(h)
+        flags.append(pad_mode == "reflect" and w // 2 >= cur)
+    if min(hops) <= 0 or min(lens) <= 0:
+        raise RuntimeError(
+            "CQT pyramid: hop_length or signal too small for the number of octaves "
+            f"(lengths {lens}, hops {hops})"
+        )
+    Ts = [l // h + 1 for l, h in zip(lens, hops)]
+    if len(set(Ts)) != 1:
+        raise RuntimeError(
+            f"Sizes of tensors must match except in dimension 1 (octave frame counts {Ts})"
+        )
+    return Ts[0], flags
+
+
+class CQT2010v2(nn.Module):
+    """Constant-Q transform by the resampling method: one top-octave bank reused
+    over a ÷2 anti-aliased pyramid (cqt.py:901-1139).  Like the reference, the
+    ``window`` and ``norm`` constructor arguments do not influence the bank
+    (cqt.py:1023-1031 never forwards them)."""
+
+    def __init__(
+        self,
+        sr=22050,
+        hop_length=512,
+        fmin=32.70,
+        fmax=None,
+        n_bins=84,
+        filter_scale=1,
+        bins_per_octave=12,
+        norm=True,
+        basis_norm=1,
+        window="hann",
+        pad_mode="reflect",
+        earlydownsample=True,
+        trainable=False,
+        output_format="Magnitude",
+        verbose=True,
+    ):
+        super().__init__()
+        self.norm = norm
+        self.hop_length = hop_length
+        self.pad_mode = pad_mode
+        self.n_bins = n_bins
+        self.earlydownsample = earlydownsample
+        self.trainable = trainable
+        self.output_format = output_format
+
+        Q = float(filter_scale) / (2 ** (1 / bins_per_octave) - 1)
+
+        if verbose:
+            print("Creating low pass filter ...", end="\r")
+        start = time()
+        lowpass = torch.tensor(design.lowpass_fir(0.50, 256, 0.001))
+        self.register_buffer("lowpass_filter", lowpass[None, None, :])
+        if verbose:
+            print("Low pass filter created, time used = {:.4f} seconds".format(time() - start))
+
+        n_filters = min(bins_per_octave, n_bins)
+        self.n_octaves = int(np.ceil(float(n_bins) / bins_per_octave))
+        if verbose:
+            print("num_octave = ", self.n_octaves)
+
+        # lowest bin of the top-octave bank (cqt.py:970-983)
+        self.fmin_t = fmin * 2 ** (self.n_octaves - 1)
+        remainder = n_bins % bins_per_octave
+        if remainder == 0:
+            fmax_t = self.fmin_t * 2 ** ((bins_per_octave - 1) / bins_per_octave)
+        else:
+            fmax_t = self.fmin_t * 2 ** ((remainder - 1) / bins_per_octave)
+        self.fmin_t = fmax_t / 2 ** (1 - 1 / bins_per_octave)
+        if fmax_t > sr / 2:
+            raise ValueError(
+                "The top bin {}Hz has exceeded the Nyquist frequency, \
+                            please reduce the n_bins".format(
+                    fmax_t
+                )
+            )
+
+        if self.earlydownsample:
+            if verbose:
+                print("Creating early downsampling filter ...", end="\r")
+            start = time()
+            sr, self.hop_length, self.downsample_factor, early_fir = design.early_downsample_plan(
+                sr, hop_length, fmax_t, Q, self.n_octaves
+            )
+            self.earlydownsample = early_fir is not None
+            if verbose:
+                if self.earlydownsample:
+                    print("Can do early downsample, factor = ", self.downsample_factor)
+                else:
+                    print("No early downsampling is required, downsample_factor = ",
+                          self.downsample_factor)
+            self.register_buffer(
+                "early_downsample_filter",
+                torch.tensor(early_fir)[None, None, :] if early_fir is not None else None,
+            )
+            if verbose:
+                print("Early downsampling filter created, \
+                        time used = {:.4f} seconds".format(time() - start))
+        else:
+            self.downsample_factor = 1.0
+
+        if verbose:
+            print("Creating CQT kernels ...", end="\r")
+        start = time()
+        basis, self.n_fft, _, _ = design.cqt_bank(
+            Q, sr, self.fmin_t, n_filters, bins_per_octave, norm=basis_norm, topbin_check=False
+        )
+        freqs = fmin * 2.0 ** (np.r_[0:n_bins] / np.double(bins_per_octave))
+        self.frequencies = freqs
+        lenghts = np.ceil(Q * sr / freqs)
+        self.register_buffer("lenghts", torch.tensor(lenghts).float())
+
+        self.basis = basis
+        k_real = torch.tensor(basis.real).unsqueeze(1)
+        k_imag = torch.tensor(basis.imag).unsqueeze(1)
+        if trainable:
+            self.register_parameter("cqt_kernels_real", nn.Parameter(k_real, requires_grad=True))
+            self.register_parameter("cqt_kernels_imag", nn.Parameter(k_imag, requires_grad=True))
+        else:
+            self.register_buffer("cqt_kernels_real", k_real)
+            self.register_buffer("cqt_kernels_imag", k_imag)
+        if verbose:
+            print("CQT kernels created, time used = {:.4f} seconds".format(time() - start))
+
+        # kept for attribute parity (cqt.py:1065-1068); the kernels pad in-flight
+        if self.pad_mode == "constant":
+            self.padding = nn.ConstantPad1d(self.n_fft // 2, 0)
+        elif self.pad_mode == "reflect":
+            self.padding = nn.ReflectionPad1d(self.n_fft // 2)
+        self._scale = _ScaleCache()
+
+    def _banks(self):
+        k_real, k_imag = as_matrix(self.cqt_kernels_real), as_matrix(self.cqt_kernels_imag)
+        return [k_real] * self.n_octaves, [k_imag] * self.n_octaves
+
+    def forward(self, x, output_format=None, normalization_type="librosa"):
+        output_format = output_format or self.output_format
+        _check_format_and_norm(output_format, normalization_type)
+        x = broadcast_dim(x)
+        forward_only_guard(self, x)
+        return _pyramid_forward(self, x, output_format, normalization_type)
+
+
+def _pyramid_forward(mod, x, output_format, normalization_type):
+    """Shared by CQT2010v2 and VQT: plan the octave lengths on the host (for the
+    reference's warnings / errors), then one C call."""
+    banks_real, banks_imag = mod._banks()
+    early = mod.early_downsample_filter if mod.earlydownsample else None
+    factor = int(mod.downsample_factor) if mod.earlydownsample else 1
+    L = x.shape[-1]
+    L0 = (L - 2) // factor + 1 if factor > 1 else L
+    if factor > 1 and L < 2:
+        raise RuntimeError("Kernel size can't be greater than actual input size")
+    widths = [int(b.shape[1]) for b in banks_real]
+    T, fallbacks = _octave_plan(L0, mod.hop_length, widths, mod.pad_mode)
+    for i, fb in enumerate(fallbacks):
+        if fb:
+            warnings.warn(
+                f"\ninput size = {(x.shape[0], 1, L0)}\tkernel size = {widths[i]}\n"
+                "padding with reflection mode might not be the best choice, try using constant padding",
+                UserWarning,
+            )
+    scale, scale_all = None, 1.0
+    dsf = float(mod.downsample_factor)
+    if normalization_type == "librosa":
+        scale = mod._scale.get(mod.lenghts, dsf)
+    elif normalization_type == "wrap":
+        scale_all = 2.0 * dsf
+    else:
+        scale_all = dsf
+    eps = 1e-8 if (mod.trainable and output_format == "Magnitude") else 0.0
+    lowpass = mod.lowpass_filter.detach().reshape(-1)
+    early_flat = early.detach().reshape(-1) if early is not None else None
+    for t in (lowpass, early_flat):
+        if t is not None:
+            _C._dev_f32(t, "filter")
+    return _C.cqt_pyramid_forward(
+        x, banks_real, banks_imag, lowpass, early_flat, factor, mod.hop_length,
+        pad_mode_id(mod.pad_mode), mod.n_bins, scale, scale_all, _FORMATS[output_format], eps, T,
+    )

@@ -1,0 +1,162 @@
+"""``STFT`` — drop-in for ``nnAudio.features.stft.STFT`` (stft.py:68-361).
+
+Same constructor / forward signature, attribute and buffer names
+(``wsin``, ``wcos`` ``(F,1,n_fft)``, ``window_mask`` ``(1,n_fft,1)``,
+optional ``kernel_sin_inv`` / ``kernel_cos_inv``), but ``forward`` is one call
+into ``libnnab.so`` instead of ReflectionPad1d + 2x conv1d + element-wise ops.
+"""
+from __future__ import annotations
+
+from time import time
+
+import torch
+import torch.nn as nn
+
+from .. import _C, design
+from ._common import PackedBasis, as_matrix, broadcast_dim, forward_only_guard, pad_mode_id
+
+_FORMATS = {
+    "Magnitude": _C.FMT_MAGNITUDE,
+    "Complex": _C.FMT_COMPLEX,
+    "Phase": _C.FMT_PHASE_ANGLE,
+}
+
+
+class STFT(nn.Module):
+    """Short-time Fourier transform of ``(L)``, ``(B, L)`` or ``(B, 1, L)``
+    waveforms.  Arguments follow the reference (stft.py:153-170).
+
+    Returns ``(B, F, T)`` for ``'Magnitude'`` and ``'Phase'`` and
+    ``(B, F, T, 2)`` for ``'Complex'`` (real, imag), ``T = L // hop + 1`` when
+    ``center=True``.
+    """
+
+    def __init__(
+        self,
+        n_fft=2048,
+        win_length=None,
+        freq_bins=None,
+        hop_length=None,
+        window="hann",
+        freq_scale="no",
+        center=True,
+        pad_mode="reflect",
+        iSTFT=False,
+        fmin=50,
+        fmax=6000,
+        sr=22050,
+        trainable=False,
+        output_format="Complex",
+        verbose=True,
+    ):
+        super().__init__()
+        if win_length is None:
+            win_length = n_fft
+        if hop_length is None:
+            hop_length = int(win_length // 4)
+
+        self.output_format = output_format
+        self.trainable = trainable
+        self.stride = hop_length
+        self.center = center
+        self.pad_mode = pad_mode
+        self.n_fft = n_fft
+        self.freq_bins = freq_bins
+        self.pad_amount = self.n_fft // 2
+        self.window = window
+        self.win_length = win_length
+        self.iSTFT = iSTFT
+        start = time()
+
+        kernel_sin, kernel_cos, self.bins2freq, self.bin_list, window_mask = design.fourier_basis(
+            n_fft,
+            win_length=win_length,
+            freq_bins=freq_bins,
+            window=window,
+            freq_scale=freq_scale,
+            fmin=fmin,
+            fmax=fmax,
+            sr=sr,
+            verbose=verbose,
+        )
+        kernel_sin = torch.tensor(kernel_sin, dtype=torch.float)
+        kernel_cos = torch.tensor(kernel_cos, dtype=torch.float)
+
+        if iSTFT:
+            # state_dict compatibility only; the inverse transform is not on the
+            # accelerated path.
+            sin_inv = torch.cat((kernel_sin, -kernel_sin[1:-1].flip(0)), 0)
+            cos_inv = torch.cat((kernel_cos, kernel_cos[1:-1].flip(0)), 0)
+            self.register_buffer("kernel_sin_inv", sin_inv.unsqueeze(-1))
+            self.register_buffer("kernel_cos_inv", cos_inv.unsqueeze(-1))
+
+        # window applied in fp32, like stft.py:230-232
+        window_mask = torch.tensor(window_mask)
+        wsin = kernel_sin * window_mask
+        wcos = kernel_cos * window_mask
+        if self.trainable:
+            self.register_parameter("wsin", nn.Parameter(wsin, requires_grad=True))
+            self.register_parameter("wcos", nn.Parameter(wcos, requires_grad=True))
+        else:
+            self.register_buffer("wsin", wsin)
+            self.register_buffer("wcos", wcos)
+        self.register_buffer("window_mask", window_mask.unsqueeze(0).unsqueeze(-1))
+
+        self._packed = PackedBasis()
+        if verbose:
+            print("STFT kernels created, time used = {:.4f} seconds".format(time() - start))
+
+    # ------------------------------------------------------------------ #
+    def _checked_input(self, x):
+        """Shape / length checks with the reference's exception types
+        (utils.py:219-221, stft.py:283-286)."""
+        self.num_samples = x.shape[-1]
+        x = broadcast_dim(x)
+        if self.center and self.pad_mode == "reflect":
+            if self.num_samples < self.pad_amount:
+                raise AssertionError(
+                    "Signal length shorter than reflect padding length (n_fft // 2)."
+                )
+            if self.num_samples == self.pad_amount:
+                raise RuntimeError(
+                    "Padding size should be less than the corresponding input dimension"
+                )
+        pad = self.pad_amount if self.center else 0
+        if self.num_samples + 2 * pad < self.n_fft:
+            raise RuntimeError("Kernel size can't be greater than actual input size")
+        return x
+
+    def _bases(self):
+        wcos, wsin = as_matrix(self.wcos), as_matrix(self.wsin)
+        if self.freq_bins is not None and self.freq_bins < wcos.shape[0]:
+            wcos, wsin = wcos[: self.freq_bins], wsin[: self.freq_bins]
+        return wcos, wsin, self._packed.get(wcos, wsin)
+
+    def forward(self, x, output_format=None):
+        output_format = output_format or self.output_format
+        if output_format not in _FORMATS:
+            raise ValueError(
+                f"output_format must be 'Magnitude', 'Complex' or 'Phase', got {output_format!r}"
+            )
+        x = self._checked_input(x)
+        forward_only_guard(self, x)
+        wcos, wsin, packed = self._bases()
+        eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
+        return _C.stft_forward(
+            x, wcos, wsin, packed, self.n_fft, self.stride, self.center,
+            pad_mode_id(self.pad_mode), _FORMATS[output_format], eps,
+        )
+
+    def inverse(self, X, onesided=True, length=None, refresh_win=True):
+        if not (hasattr(self, "kernel_sin_inv") and hasattr(self, "kernel_cos_inv")):
+            raise NameError(
+                "Please activate the iSTFT module by setting `iSTFT=True` if you want to use `inverse`"
+            )
+        raise NotImplementedError(
+            "STFT.inverse is outside the accelerated hot path of nnaudio_b200 (SURVEY.md §8f #2)"
+        )
+
+    def extra_repr(self) -> str:
+        return "n_fft={}, Fourier Kernel size={}, iSTFT={}, trainable={}".format(
+            self.n_fft, (*self.wsin.shape,), self.iSTFT, self.trainable
+        )

@@ -1,0 +1,326 @@
+"""CPU ORACLE — test infrastructure only.  NOT part of the product path.
+
+A plain NumPy restatement of the reference nnAudio *forward* algorithms
+(KinWaiCheuk/nnAudio v0.3.3, ``Installation/nnAudio``) for the hot path of
+SURVEY.md §8(a).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
+module, and only as the checker / the CPU arm — never from ``nnaudio_b200``.
+
+Parity pin: every function below is checked in ``tests/test_oracle_golden.py``
+against (i) the reference's own golden vectors
+(``Installation/tests/ground-truths/*cqt*.npy``, replayed from
+``tests/golden/ref_ground_truths.npz``) and (ii) outputs of the unmodified
+reference imported in the build container (``tests/golden/make_golden.py`` ->
+``tests/golden/ref_outputs.npz``).
+
+All functions take the module's *buffers* (float32 arrays, exactly what
+``state_dict()`` holds) plus scalar configuration, and compute in ``dtype``
+(float64 for checking, float32 when timed as the CPU baseline).  The framing +
+basis contraction the reference performs with ``conv1d(x, basis, stride=hop)``
+is done here as strided frames times the basis matrix (BLAS), which is the same
+arithmetic.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+__all__ = [
+    "broadcast_dim",
+    "pad_signal",
+    "framed_contraction",
+    "stft",
+    "melspectrogram",
+    "power_to_db",
+    "dct_ortho_fft_route",
+    "mfcc",
+    "cqt1992v2",
+    "downsample_by_n",
+    "cqt_octave_complex",
+    "cqt2010v2",
+    "vqt",
+]
+
+
+# --------------------------------------------------------------------------- #
+# shared helpers
+# --------------------------------------------------------------------------- #
+def broadcast_dim(x: np.ndarray) -> np.ndarray:
+    """utils.py:206-222 — (L)->(1,L), (B,L) pass, (B,1,L)->(B,L) (channel dim
+    is squeezed here because every consumer has exactly one input channel)."""
+    if x.ndim == 1:
+        return x[None, :]
+    if x.ndim == 2:
+        return x
+    if x.ndim == 3:
+        return x[:, 0, :]
+    raise ValueError("Only support input with shape = (batch, len) or shape = (len)")
+
+
+def pad_signal(x: np.ndarray, pad: int, mode: str) -> np.ndarray:
+    """nn.ReflectionPad1d(pad) / nn.ConstantPad1d(pad, 0) on the last axis
+    (stft.py:278-289, cqt.py:740-746).  Reflect requires pad < L like torch."""
+    if pad == 0:
+        return x
+    if mode == "reflect":
+        if pad >= x.shape[-1]:
+            raise RuntimeError("reflect padding must be smaller than the input length")
+        return np.pad(x, ((0, 0), (pad, pad)), mode="reflect")
+    if mode == "constant":
+        return np.pad(x, ((0, 0), (pad, pad)), mode="constant")
+    raise ValueError("unknown pad_mode %r" % (mode,))
+
+
+def framed_contraction(xp: np.ndarray, basis: np.ndarray, hop: int, chunk: int = 2048):
+    """``conv1d(xp[:,None,:], basis[:,None,:], stride=hop)`` as frames x basis^T.
+
+    xp (B, Lp), basis (N, K)  ->  (B, N, T) with T = (Lp-K)//hop + 1.
+    """
+    B, Lp = xp.shape
+    N, K = basis.shape
+    if Lp < K:
+        raise RuntimeError("input shorter than the kernel")
+    T = (Lp - K) // hop + 1
+    out = np.empty((B, N, T), dtype=xp.dtype)
+    bt = np.ascontiguousarray(basis.T)
+    st = xp.strides[-1]
+    for b in range(B):
+        frames = np.lib.stride_tricks.as_strided(
+            xp[b], shape=(T, K), strides=(hop * st, st), writeable=False
+        )
+        for t0 in range(0, T, chunk):
+            t1 = min(T, t0 + chunk)
+            out[b, :, t0:t1] = (np.ascontiguousarray(frames[t0:t1]) @ bt).T
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# STFT family
+# --------------------------------------------------------------------------- #
+def stft(
+    x,
+    wsin,
+    wcos,
+    hop,
+    center=True,
+    pad_mode="reflect",
+    output_format="Complex",
+    trainable=False,
+    freq_bins=None,
+    dtype=np.float64,
+):
+    """STFT.forward (stft.py:256-316).
+
+    wsin/wcos: (F, 1, n_fft) windowed bases.  Magnitude -> (B,F,T);
+    Complex -> (B,F,T,2) = (real, -imag); Phase -> (B,F,T) =
+    atan2(-imag + 0.0, real).
+    """
+    x = broadcast_dim(np.asarray(x)).astype(dtype)
+    ws = np.asarray(wsin)[:, 0, :].astype(dtype)
+    wc = np.asarray(wcos)[:, 0, :].astype(dtype)
+    n_fft = ws.shape[-1]
+    if center:
+        if pad_mode == "reflect" and x.shape[-1] < n_fft // 2:
+            raise AssertionError("Signal length shorter than reflect padding length (n_fft // 2).")
+        x = pad_signal(x, n_fft // 2, pad_mode)
+    imag = framed_contraction(x, ws, hop)
+    real = framed_contraction(x, wc, hop)
+    if freq_bins is not None:
+        real, imag = real[:, :freq_bins], imag[:, :freq_bins]
+    if output_format == "Magnitude":
+        spec = real ** 2 + imag ** 2
+        return np.sqrt(spec + dtype(1e-8)) if trainable else np.sqrt(spec)
+    if output_format == "Complex":
+        return np.stack((real, -imag), -1)
+    if output_format == "Phase":
+        return np.arctan2(-imag + 0.0, real)
+    raise ValueError("unknown output_format %r" % (output_format,))
+
+
+def melspectrogram(x, wsin, wcos, fbank, hop, power=2.0, center=True, pad_mode="reflect",
+                   trainable_stft=False, dtype=np.float64):
+    """MelSpectrogram.forward / Gammatonegram.forward (mel.py:171-189,
+    gammatone.py:171-189): ``fbank @ (|STFT| ** power)``; note the reference
+    takes sqrt first and then raises to ``power``."""
+    mag = stft(x, wsin, wcos, hop, center, pad_mode, "Magnitude", trainable_stft, None, dtype)
+    spec = mag ** dtype(power)
+    return np.matmul(np.asarray(fbank).astype(dtype), spec)
+
+
+def power_to_db(S, amin=1e-10, ref=1.0, top_db=80.0):
+    """MFCC._power_to_db (mel.py:263-279); the top_db floor is relative to the
+    per-clip maximum over (mel, time)."""
+    dt = S.dtype.type
+    log_spec = dt(10.0) * np.log10(np.maximum(S, dt(amin)))
+    log_spec = log_spec - dt(10.0) * np.log10(np.maximum(dt(amin), dt(abs(ref))))
+    if top_db is not None:
+        if top_db < 0:
+            raise ValueError("top_db must be non-negative")
+        peak = log_spec.reshape(log_spec.shape[0], -1).max(1)[:, None, None]
+        log_spec = np.maximum(log_spec, peak - dt(top_db))
+    return log_spec
+
+
+def dct_ortho_fft_route(x):
+    """MFCC._dct(norm='ortho') (mel.py:281-307): DCT-II along axis 1 of
+    (B, N, T) via the even/odd re-ordering + FFT + twiddle route."""
+    v_in = np.transpose(x, (0, 2, 1))
+    N = v_in.shape[-1]
+    v = np.concatenate([v_in[:, :, ::2], v_in[:, :, 1::2][:, :, ::-1]], axis=2)
+    Vc = np.fft.fft(v, axis=-1)
+    k = -np.arange(N, dtype=x.dtype)[None, :] * np.pi / (2 * N)
+    V = Vc.real * np.cos(k) - Vc.imag * np.sin(k)
+    V[:, :, 0] /= np.sqrt(N) * 2
+    V[:, :, 1:] /= np.sqrt(N / 2) * 2
+    V = 2 * V
+    return np.transpose(V, (0, 2, 1)).astype(x.dtype)
+
+
+def mfcc(x, wsin, wcos, mel_basis, hop, n_mfcc=20, power=2.0, amin=1e-10, ref=1.0,
+         top_db=80.0, center=True, pad_mode="reflect", dtype=np.float64):
+    """MFCC.forward (mel.py:309-326)."""
+    S = melspectrogram(x, wsin, wcos, mel_basis, hop, power, center, pad_mode, False, dtype)
+    db = power_to_db(S, amin, ref, top_db)
+    return dct_ortho_fft_route(db)[:, :n_mfcc, :]
+
+
+# --------------------------------------------------------------------------- #
+# CQT family
+# --------------------------------------------------------------------------- #
+def _cqt_normalise(real, imag, lenghts, normalization_type, dtype):
+    if normalization_type == "librosa":
+        s = np.sqrt(np.asarray(lenghts).astype(np.float32)).astype(dtype).reshape(-1, 1)
+        return real * s, imag * s
+    if normalization_type == "convolutional":
+        return real, imag
+    if normalization_type == "wrap":
+        return real * 2, imag * 2
+    raise ValueError(
+        "The normalization_type %r is not part of our current options." % normalization_type
+    )
+
+
+def _cqt_format(real, imag, output_format, trainable, dtype):
+    if output_format == "Magnitude":
+        p = real ** 2 + imag ** 2
+        return np.sqrt(p + dtype(1e-8)) if trainable else np.sqrt(p)
+    if output_format == "Complex":
+        return np.stack((real, imag), -1)
+    if output_format == "Phase":
+        ang = np.arctan2(imag, real)
+        return np.stack((np.cos(ang), np.sin(ang)), -1)
+    raise ValueError("unknown output_format %r" % (output_format,))
+
+
+def cqt1992v2(x, kernels_real, kernels_imag, lenghts, hop, center=True, pad_mode="reflect",
+              output_format="Magnitude", normalization_type="librosa", trainable=False,
+              dtype=np.float64):
+    """CQT1992v2.forward (cqt.py:712-780): real = conv(x, Kr), imag = -conv(x, Ki),
+    scale, then Magnitude / Complex (re, im) / Phase (cos, sin)."""
+    x = broadcast_dim(np.asarray(x)).astype(dtype)
+    kr = np.asarray(kernels_real)[:, 0, :].astype(dtype)
+    ki = np.asarray(kernels_imag)[:, 0, :].astype(dtype)
+    if center:
+        x = pad_signal(x, kr.shape[-1] // 2, pad_mode)
+    real = framed_contraction(x, kr, hop, chunk=256)
+    imag = -framed_contraction(x, ki, hop, chunk=256)
+    real, imag = _cqt_normalise(real, imag, lenghts, normalization_type, dtype)
+    return _cqt_format(real, imag, output_format, trainable, dtype)
+
+
+def downsample_by_n(x, fir, n):
+    """utils.py:73-100: conv1d(x, fir, stride=n, padding=(len(fir)-1)//2), i.e.
+    zero padding of 127 on both sides for the 256-tap filters."""
+    fir = np.asarray(fir).reshape(1, -1).astype(x.dtype)
+    p = (fir.shape[-1] - 1) // 2
+    xp = np.pad(x, ((0, 0), (p, p)), mode="constant")
+    return framed_contraction(xp, fir, n)[:, 0, :]
+
+
+def cqt_octave_complex(x, kr, ki, hop, pad, pad_mode):
+    """utils.py:498-521 get_cqt_complex: try the module's padding, on failure
+    (reflect pad >= length) warn and zero-pad by kernel_width//2."""
+    try:
+        xp = pad_signal(x, pad, pad_mode)
+    except RuntimeError:
+        warnings.warn(
+            "padding with reflection mode might not be the best choice, try using constant padding",
+            UserWarning,
+        )
+        xp = np.pad(x, ((0, 0), (kr.shape[-1] // 2,) * 2), mode="constant")
+    real = framed_contraction(xp, kr, hop)
+    imag = -framed_contraction(xp, ki, hop)
+    return real, imag
+
+
+def _pyramid(x, banks, hop, n_bins, lowpass, pads, pad_mode, early_fir, early_factor, dtype):
+    """Shared octave pyramid of CQT2010v2 (one bank reused) and VQT (one bank
+    per octave): top octave on x, then repeatedly halve with the 256-tap FIR
+    and halve the hop; octaves are stacked low -> high and the lowest surplus
+    bins are dropped (cqt.py:1086-1105, vqt.py:158-189)."""
+    x = broadcast_dim(np.asarray(x)).astype(dtype)
+    if early_fir is not None:
+        x = downsample_by_n(x, early_fir, int(early_factor))
+    reals, imags = [], []
+    x_down = x
+    for i, (kr, ki) in enumerate(banks):
+        if i > 0:
+            x_down = downsample_by_n(x_down, lowpass, 2)
+            hop = hop // 2
+        kr2 = np.asarray(kr)[:, 0, :].astype(dtype)
+        ki2 = np.asarray(ki)[:, 0, :].astype(dtype)
+        r, im = cqt_octave_complex(x_down, kr2, ki2, hop, pads[i], pad_mode)
+        reals.insert(0, r)
+        imags.insert(0, im)
+    real = np.concatenate(reals, axis=1)[:, -n_bins:, :]
+    imag = np.concatenate(imags, axis=1)[:, -n_bins:, :]
+    return real, imag
+
+
+def cqt2010v2(x, kernels_real, kernels_imag, lowpass_filter, lenghts, hop, n_bins, n_octaves,
+              pad_mode="reflect", early_downsample_filter=None, downsample_factor=1,
+              output_format="Magnitude", normalization_type="librosa", trainable=False,
+              dtype=np.float64):
+    """CQT2010v2.forward (cqt.py:1070-1139).  ``hop`` is the module's
+    post-early-downsample hop_length."""
+    width = np.asarray(kernels_real).shape[-1]
+    banks = [(kernels_real, kernels_imag)] * n_octaves
+    real, imag = _pyramid(x, banks, hop, n_bins, lowpass_filter, [width // 2] * n_octaves,
+                          pad_mode, early_downsample_filter, downsample_factor, dtype)
+    real, imag = real * downsample_factor, imag * downsample_factor
+    if normalization_type == "librosa":
+        s = np.sqrt(np.asarray(lenghts).astype(np.float32)).astype(dtype).reshape(-1, 1)
+        real, imag = real * s, imag * s
+    elif normalization_type == "convolutional":
+        pass
+    elif normalization_type == "wrap":
+        real, imag = real * 2, imag * 2
+    else:
+        raise ValueError(
+            "The normalization_type %r is not part of our current options." % normalization_type
+        )
+    return _cqt_format(real, imag, output_format, trainable, dtype)
+
+
+def vqt(x, banks, lowpass_filter, lenghts, hop, n_bins, pad_mode="reflect",
+        early_downsample_filter=None, downsample_factor=1, output_format="Magnitude",
+        normalization_type="librosa", trainable=False, dtype=np.float64):
+    """VQT.forward (vqt.py:143-215): ``banks`` = [(real_i, imag_i)] for octave
+    i = 0 (top) .. n_octaves-1; each octave pads by its own bank width // 2."""
+    pads = [np.asarray(kr).shape[-1] // 2 for kr, _ in banks]
+    real, imag = _pyramid(x, banks, hop, n_bins, lowpass_filter, pads, pad_mode,
+                          early_downsample_filter, downsample_factor, dtype)
+    real, imag = real * downsample_factor, imag * downsample_factor
+    if normalization_type == "librosa":
+        s = np.sqrt(np.asarray(lenghts).astype(np.float32)).astype(dtype).reshape(-1, 1)
+        real, imag = real * s, imag * s
+    elif normalization_type == "convolutional":
+        pass
+    elif normalization_type == "wrap":
+        real, imag = real * 2, imag * 2
+    else:
+        raise ValueError(
+            "The normalization_type %r is not part of our current options." % normalization_type
+        )
+    return _cqt_format(real, imag, output_format, trainable, dtype)

@@ -1,0 +1,121 @@
+"""Parity cases shared by ``make_golden.py`` (runs the unmodified reference in the
+build container) and the test-suite (runs the oracle and the CUDA path).
+
+Inputs are regenerated from the spec (NumPy ``RandomState`` / ``scipy.signal.chirp``
+are platform-stable), so only the reference OUTPUTS are stored in
+``ref_outputs.npz``.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.signal import chirp
+
+
+def make_input(spec) -> np.ndarray:
+    kind = spec[0]
+    if kind == "randn":
+        _, seed, shape = spec
+        return np.random.RandomState(seed).standard_normal(shape).astype(np.float32)
+    if kind == "randn_decay":
+        # clips with very different levels: exercises MFCC's per-clip top_db floor
+        _, seed, shape = spec
+        x = np.random.RandomState(seed).standard_normal(shape).astype(np.float32)
+        gains = (10.0 ** (-np.arange(shape[0]))).astype(np.float32)[:, None]
+        t = np.linspace(0, 1, shape[1], dtype=np.float32)[None, :]
+        return (x * gains * np.exp(-6.0 * t)).astype(np.float32)
+    if kind == "chirp":
+        # the reference's own golden-vector input (tests/test_cqt.py:94-103)
+        _, method = spec
+        fs, t, f0, f1 = 44100, 1, 55, 22050
+        s = np.linspace(0, t, fs * t)
+        return chirp(s, f0, 1, f1, method=method).astype(np.float32)[None, :]
+    raise ValueError(kind)
+
+
+# id, class name, ctor kwargs, input spec, list of forward kwargs
+CASES = [
+    # ---- STFT (cfg1 of BASELINE.json first) --------------------------------
+    ("stft_cfg1", "STFT", dict(n_fft=512, hop_length=256, sr=16000), ("randn", 0, (1, 16000)),
+     [dict(output_format="Complex"), dict(output_format="Magnitude"), dict(output_format="Phase")]),
+    ("stft_winlen_hamming", "STFT", dict(n_fft=512, win_length=400, hop_length=128, window="hamming"),
+     ("randn", 1, (2, 4000)), [dict(output_format="Complex")]),
+    ("stft_linear_bins", "STFT",
+     dict(n_fft=256, freq_bins=80, freq_scale="linear", fmin=50, fmax=6000, sr=22050, hop_length=64),
+     ("randn", 2, (2, 2000)), [dict(output_format="Complex")]),
+    ("stft_log_nocenter_oddhop", "STFT",
+     dict(n_fft=256, freq_bins=60, freq_scale="log", fmin=50, fmax=6000, sr=22050, hop_length=100,
+          center=False),
+     ("randn", 3, (1, 3000)), [dict(output_format="Magnitude")]),
+    ("stft_constant_pad", "STFT", dict(n_fft=512, hop_length=128, pad_mode="constant"),
+     ("randn", 4, (2, 3000)), [dict(output_format="Magnitude"), dict(output_format="Phase")]),
+    ("stft_trainable_eps", "STFT", dict(n_fft=512, hop_length=128, trainable=True),
+     ("randn", 5, (1, 3000)), [dict(output_format="Magnitude")]),
+    ("stft_2048", "STFT", dict(n_fft=2048, hop_length=512), ("randn", 6, (1, 22050)),
+     [dict(output_format="Magnitude")]),
+    ("stft_default_hop_1d_input", "STFT", dict(n_fft=256, window="hann"), ("randn", 7, (1, 4000)),
+     [dict(output_format="Complex")]),
+    # ---- MelSpectrogram -----------------------------------------------------
+    ("mel_small", "MelSpectrogram", dict(sr=16000, n_fft=512, hop_length=128, n_mels=40),
+     ("randn", 10, (2, 8000)), [dict()]),
+    ("mel_cfg2_shape", "MelSpectrogram", dict(sr=22050, n_fft=2048, hop_length=512, n_mels=128),
+     ("randn", 11, (2, 22050)), [dict()]),
+    ("mel_htk_power1_winlen", "MelSpectrogram",
+     dict(sr=16000, n_fft=1024, win_length=1000, hop_length=256, n_mels=64, power=1.0, htk=True,
+          fmin=20, fmax=7600),
+     ("randn", 12, (1, 8000)), [dict()]),
+    # ---- MFCC ---------------------------------------------------------------
+    ("mfcc_cfg5_shape", "MFCC", dict(sr=16000), ("randn_decay", 20, (3, 16000)), [dict()]),
+    ("mfcc_small_no_topdb", "MFCC",
+     dict(sr=22050, n_mfcc=13, n_fft=512, hop_length=160, n_mels=40, top_db=None),
+     ("randn", 21, (2, 6000)), [dict()]),
+    # ---- Gammatonegram ------------------------------------------------------
+    ("gammatone_small", "Gammatonegram", dict(sr=22050, n_fft=1024, n_bins=32, hop_length=256),
+     ("randn", 30, (2, 8000)), [dict()]),
+    ("gammatone_default", "Gammatonegram", dict(sr=22050), ("randn", 31, (1, 22050)), [dict()]),
+    # ---- CQT1992v2 ----------------------------------------------------------
+    ("cqt1992v2_random", "CQT1992v2",
+     dict(sr=22050, fmin=220, n_bins=48, bins_per_octave=12, hop_length=256),
+     ("randn", 40, (2, 16000)),
+     [dict(output_format="Complex"),
+      dict(output_format="Magnitude", normalization_type="wrap"),
+      dict(output_format="Phase", normalization_type="convolutional")]),
+    ("cqt1992v2_nocenter", "CQT1992v2",
+     dict(sr=22050, fmin=440, n_bins=24, hop_length=128, center=False, pad_mode="constant"),
+     ("randn", 41, (1, 8000)), [dict(output_format="Magnitude")]),
+    # ---- CQT2010v2 ----------------------------------------------------------
+    ("cqt2010v2_random", "CQT2010v2", dict(sr=22050, n_bins=84), ("randn", 50, (2, 32768)),
+     [dict(output_format="Magnitude"), dict(output_format="Complex")]),
+    ("cqt2010v2_early_downsample", "CQT2010v2", dict(sr=44100, n_bins=72, fmin=32.7),
+     ("randn", 51, (1, 40000)), [dict(output_format="Complex")]),
+    ("cqt2010v2_reflect_fallback", "CQT2010v2", dict(sr=22050, n_bins=84),
+     ("randn", 52, (1, 6000)), [dict(output_format="Complex")]),
+    ("cqt2010v2_cfg4_bins88", "CQT2010v2", dict(sr=22050, n_bins=88), ("randn", 53, (1, 16384)),
+     [dict(output_format="Magnitude"), dict(output_format="Phase", normalization_type="wrap")]),
+    # ---- VQT ----------------------------------------------------------------
+    ("vqt_gamma0", "VQT", dict(sr=22050, gamma=0), ("randn", 50, (2, 32768)),
+     [dict(output_format="Magnitude")]),
+    ("vqt_gamma5", "VQT", dict(sr=22050, gamma=5, n_bins=60), ("randn", 61, (1, 32768)),
+     [dict(output_format="Complex")]),
+]
+
+# The reference's own golden vectors (Installation/tests/ground-truths/*.npy) and
+# the test that loads each one (tests/test_cqt.py:94-262).
+#   key in ref_ground_truths.npz -> (class, chirp method, forward kwargs, transform)
+REF_GROUND_TRUTHS = {
+    "log-sweep-cqt-1992-mag": ("CQT1992v2", "logarithmic", dict(output_format="Magnitude"), "log1e-5"),
+    "log-sweep-cqt-1992-complex": ("CQT1992v2", "logarithmic", dict(output_format="Complex"), None),
+    "log-sweep-cqt-1992-phase": ("CQT1992v2", "logarithmic", dict(output_format="Phase"), None),
+    "linear-sweep-cqt-1992-mag": ("CQT1992v2", "linear", dict(output_format="Magnitude"), "log1e-5"),
+    "linear-sweep-cqt-1992-complex": ("CQT1992v2", "linear", dict(output_format="Complex"), None),
+    "linear-sweep-cqt-1992-phase": ("CQT1992v2", "linear", dict(output_format="Phase"), None),
+    "log-sweep-cqt-2010-mag": ("CQT2010v2", "logarithmic", dict(output_format="Magnitude"), "log1e-2"),
+    "log-sweep-cqt-2010-complex": ("CQT2010v2", "logarithmic", dict(output_format="Complex"), None),
+    "linear-sweep-cqt-2010-mag": ("CQT2010v2", "linear", dict(output_format="Magnitude"), "log1e-2"),
+    "linear-sweep-cqt-2010-complex": ("CQT2010v2", "linear", dict(output_format="Complex"), None),
+}
+SWEEP_CTOR = dict(sr=44100, fmin=55, n_bins=207, bins_per_octave=24)
+
+
+def out_key(case_id: str, fwd_kwargs: dict) -> str:
+    tag = "_".join(f"{k[:3]}-{v}" for k, v in sorted(fwd_kwargs.items()))
+    return f"{case_id}|{tag}" if tag else case_id

@@ -1,0 +1,86 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference (nnAudio
+v0.3.3, imported read-only from ``$NNAUDIO_REF`` = /root/reference/Installation)
+on CPU in the build container.  The GPU box has no /root/reference, so the
+outputs are committed:
+
+  ref_outputs.npz        reference forward() outputs for tests/golden/cases.py
+  ref_buffers.json       sha256 of every state_dict buffer of the case modules
+  ref_ground_truths.npz  the reference's own golden vectors, re-encoded from
+                         Installation/tests/ground-truths/*.npy (test fixtures,
+                         not source code) — pinned by tests/test_cqt.py:94-262
+
+Run:  PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("NNAUDIO_REF", "/root/reference/Installation")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
+
+from cases import CASES, REF_GROUND_TRUTHS, SWEEP_CTOR, make_input, out_key  # noqa: E402
+
+from nnAudio import features as ref_features  # noqa: E402
+
+
+def sha(t: torch.Tensor) -> str:
+    a = np.ascontiguousarray(t.detach().cpu().numpy())
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def main():
+    torch.manual_seed(0)
+    outputs, buffers = {}, {}
+    for cid, cls, ctor, inp, fwds in CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = getattr(ref_features, cls)(verbose=False, **ctor)
+        buffers[cid] = {k: [list(v.shape), sha(v)] for k, v in mod.state_dict().items()
+                        if v is not None}
+        x = torch.from_numpy(make_input(inp))
+        if cid == "stft_default_hop_1d_input":
+            x = x[0]
+        for kw in fwds:
+            with torch.no_grad(), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                y = mod(x, **kw)
+            outputs[out_key(cid, kw)] = y.numpy().astype(np.float32)
+            print(f"{out_key(cid, kw):60s} {tuple(y.shape)}")
+    np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **outputs)
+    with open(os.path.join(HERE, "ref_buffers.json"), "w") as f:
+        json.dump(buffers, f, indent=1, sort_keys=True)
+
+    # the reference's own golden vectors + a self-check that the reference still
+    # reproduces them at its own tolerance (tests/test_cqt.py: rtol=atol=1e-3)
+    gt_dir = os.path.join(REF, "tests", "ground-truths")
+    gts = {}
+    for key, (cls, method, kw, transform) in REF_GROUND_TRUTHS.items():
+        gt = np.load(os.path.join(gt_dir, key + "-ground-truth.npy"))
+        gts[key] = gt.astype(np.float32)
+        mod = getattr(ref_features, cls)(verbose=False, **SWEEP_CTOR)
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            y = mod(torch.from_numpy(make_input(("chirp", method))), **kw)
+        if transform == "log1e-5":
+            y = torch.log(y + 1e-5)
+        elif transform == "log1e-2":
+            y = torch.log(y + 1e-2)
+        ok = np.allclose(y.numpy(), gt, rtol=1e-3, atol=1e-3)
+        print(f"{key:40s} gt{gt.shape} ref reproduces: {ok}  maxabs {np.abs(y.numpy()-gt).max():.3e}")
+        assert ok, key
+    np.savez_compressed(os.path.join(HERE, "ref_ground_truths.npz"), **gts)
+    print("wrote fixtures to", HERE)
+
+
+if __name__ == "__main__":
+    main()
