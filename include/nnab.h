@@ -182,6 +182,14 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
  * bench.py for its `gpu_launches` claim). */
 uint64_t nnab_launch_count(void);
 
+/* Live timing of the dominant kernel (the framed contraction) for bench.py's
+ * roofline: while enabled, every framed-contraction launch is bracketed by a
+ * cudaEvent pair recorded on the launching stream.  nnab_profile_read()
+ * synchronises those events, returns the summed duration in ms and the number
+ * of launches timed since the last read, and resets the accumulator. */
+void nnab_profile_enable(int on);
+int nnab_profile_read(double* framed_ms, uint64_t* framed_launches);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

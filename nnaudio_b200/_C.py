@@ -29,6 +29,8 @@ SIGNATURES = {
     "nnab_strerror": (c_char_p, [c_int]),
     "nnab_last_cuda_error": (c_char_p, []),
     "nnab_launch_count": (c_uint64, []),
+    "nnab_profile_enable": (None, [c_int]),
+    "nnab_profile_read": (c_int, [_P, _P]),
     "nnab_pack_tile_n": (c_int, []),
     "nnab_packed_basis_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_basis": (c_int, [_P, _P, c_int, c_int, _P, _P]),
@@ -107,6 +109,18 @@ def resolve_path(path) -> int:
 
 def launch_count() -> int:
     return int(lib().nnab_launch_count())
+
+
+def profile_enable(on: bool):
+    lib().nnab_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """(summed ms, launches) of the framed-contraction kernel since the last read."""
+    ms = ctypes.c_double(0.0)
+    n = c_uint64(0)
+    _check(lib().nnab_profile_read(ctypes.byref(ms), ctypes.byref(n)), "nnab_profile_read")
+    return ms.value, int(n.value)
 
 
 def _check(rc: int, what: str):

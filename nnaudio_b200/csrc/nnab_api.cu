@@ -1,7 +1,10 @@
 // extern "C" entry points of libnnab.so — see include/nnab.h for the contract
 // and the reference file:line each call replaces.
 #include <atomic>
+#include <mutex>
 #include <string.h>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -43,8 +46,45 @@ static int check_arch() {
   return major == 10 ? NNAB_OK : NNAB_EARCH;
 }
 
+// ---- optional in-stream timing of the framed contraction (bench.py) --------
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pairs;  // recorded, unread
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
+
+static bool prof_begin(cudaStream_t s, std::pair<cudaEvent_t, cudaEvent_t>* pr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return false;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_free.empty()) {
+    *pr = g_prof_free.back();
+    g_prof_free.pop_back();
+  } else {
+    if (cudaEventCreate(&pr->first) != cudaSuccess) return false;
+    if (cudaEventCreate(&pr->second) != cudaSuccess) return false;
+  }
+  cudaEventRecord(pr->first, s);
+  return true;
+}
+static void prof_end(cudaStream_t s, const std::pair<cudaEvent_t, cudaEvent_t>& pr) {
+  cudaEventRecord(pr.second, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_pairs.push_back(pr);
+}
+
+static int run_framed_inner(const FramedProblem& p, const void* packed, void* ws, size_t ws_bytes,
+                            int path, cudaStream_t stream);
+
 // Run one framed contraction on the requested kernel family.
 static int run_framed(const FramedProblem& p, const void* packed, void* ws, size_t ws_bytes,
+                      int path, cudaStream_t stream) {
+  std::pair<cudaEvent_t, cudaEvent_t> pr;
+  const bool timed = prof_begin(stream, &pr);
+  const int rc = run_framed_inner(p, packed, ws, ws_bytes, path, stream);
+  if (timed) prof_end(stream, pr);
+  return rc;
+}
+
+static int run_framed_inner(const FramedProblem& p, const void* packed, void* ws, size_t ws_bytes,
                       int path, cudaStream_t stream) {
   bool use_tc = false;
   if (path == NNAB_PATH_TCGEN05) {
@@ -90,6 +130,26 @@ const char* nnab_strerror(int status) {
 const char* nnab_last_cuda_error(void) { return g_err; }
 
 uint64_t nnab_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void nnab_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+int nnab_profile_read(double* framed_ms, uint64_t* framed_launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double total = 0.0;
+  uint64_t n = 0;
+  for (auto& pr : g_prof_pairs) {
+    NNAB_CUDA_TRY(cudaEventSynchronize(pr.second));
+    float ms = 0.f;
+    NNAB_CUDA_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    total += ms;
+    ++n;
+    g_prof_free.push_back(pr);
+  }
+  g_prof_pairs.clear();
+  if (framed_ms) *framed_ms = total;
+  if (framed_launches) *framed_launches = n;
+  return NNAB_OK;
+}
 
 int nnab_pack_tile_n(void) { return tc_tile_n(); }
 size_t nnab_packed_basis_bytes(int F, int K) { return tc_packed_bytes(F, K); }
@@ -337,7 +397,7 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
     p.bin_offset = n_bins - n_filters * (i + 1);
     // per-bin scale is indexed by OUTPUT row: shift the pointer by the same offset
     p.scale = scale ? scale + p.bin_offset : nullptr;
-    if ((rc = launch_framed_simt(p, s))) return rc;
+    if ((rc = run_framed(p, nullptr, nullptr, 0, NNAB_PATH_SIMT, s))) return rc;
   }
   return NNAB_OK;
 }

@@ -1,10 +1,643 @@
-// tcgen05 / TMA framed contraction (placeholder until the kernel lands).
+// tcgen05 / TMA framed contraction for sm_100a.
+//
+//   D[g, n] = sum_k A[g, k] * W[n, k]        g = virtual frame, n = basis row
+//
+// * A is never materialised: the padded waveform is written once as bf16 hi/lo
+//   planes (pad_split_kernel) with a per-clip pitch that is a multiple of hop, so
+//   the frames of the WHOLE batch form one Toeplitz matrix whose row g starts at
+//   element g*hop.  TMA reads 128-frame x BK tiles of it straight into
+//   128B/64B-swizzled shared memory (either as a plain (rows x hop) matrix when
+//   BK | hop, or through an overlapping-stride tensor map otherwise).
+// * W (basis) is pre-split into bf16 hi/lo planes, re rows and NEGATED im rows
+//   grouped per N tile (pack_basis_kernel).
+// * fp32 parity on bf16 tensor cores: x*w ~= xhi*whi + xlo*whi + xhi*wlo
+//   (3 tcgen05.mma passes into one fp32 TMEM accumulator; error ~2^-16).
+// * Warp roles (256 threads, 1 CTA/SM, persistent over output tiles):
+//     warp 0  TMA producer      warp 1  MMA issuer      warp 2  TMEM alloc
+//     warps 4-7  epilogue: tcgen05.ld -> magnitude/complex/phase/power ->
+//                coalesced stores in the reference's (B, F, T[,2]) layout
+//   smem full/empty mbarrier ring + double-buffered TMEM accumulators.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "epilogue.cuh"
+
 namespace nnab {
-bool tc_supported(const FramedProblem&) { return false; }
-size_t tc_workspace_bytes(int64_t, int64_t, int, int, int) { return 0; }
-int launch_framed_tc(const FramedProblem&, const void*, void*, size_t, cudaStream_t) { return NNAB_EUNSUPPORTED; }
-size_t tc_packed_bytes(int, int) { return 0; }
-int tc_pack_basis(const float*, const float*, int, int, void*, cudaStream_t) { return NNAB_EUNSUPPORTED; }
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+constexpr int TC_MAX_N_TILES = 128;
+constexpr int TC_ACC_STRIDE = 256;  // TMEM columns per accumulator buffer
+
+static inline int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
+
+// N tile (columns = re + im rows of bn/2 bins): minimise padded columns.
+static int choose_bn(int F) {
+  const int cols = 2 * F;
+  if (cols <= 256) return round_up_i(cols, 16) < 32 ? 32 : round_up_i(cols, 16);
+  int best = 256, best_total = round_up_i(cols, 256);
+  for (int bn = 240; bn >= 128; bn -= 16) {
+    const int total = (cols + bn - 1) / bn * bn;
+    if (total < best_total) { best_total = total; best = bn; }
+  }
+  return best;
+}
+
 int tc_tile_n() { return 256; }
+
+size_t tc_packed_bytes(int F, int K) {
+  const int bn = choose_bn(F);
+  const int n_tiles = (2 * F + bn - 1) / bn;
+  const size_t rows = (size_t)n_tiles * bn;
+  const size_t kpad = (size_t)round_up_i(K, 64);
+  return 2 * rows * kpad * sizeof(__nv_bfloat16);
+}
+
+// ---------------------------------------------------------------------------
+// geometry of the split / padded signal workspace
+// ---------------------------------------------------------------------------
+struct SplitGeom {
+  int64_t t_slots;       // virtual frames per clip
+  int64_t nv;            // virtual frames in the batch
+  int64_t rows;          // rows of the (rows x hop) view incl. K overhang
+  int64_t plane_stride;  // elements per plane
+};
+
+static SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad) {
+  SplitGeom g;
+  g.t_slots = (L + 2 * (int64_t)pad + hop - 1) / hop;
+  g.nv = B * g.t_slots;
+  const int kpad = round_up_i(K, 64);
+  g.rows = g.nv + (kpad + hop - 1) / hop + 1;
+  g.plane_stride = (g.rows * hop + 63) / 64 * 64;
+  return g;
+}
+
+size_t tc_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
+  const SplitGeom g = split_geom(B, L, K, hop, pad);
+  return (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+}
+
+bool tc_supported(const FramedProblem& p) {
+  if (p.hop <= 0 || (p.hop % 8) != 0) return false;  // TMA: 16-byte row stride in bf16
+  if (p.K < 16) return false;
+  if (p.L + 2 * (int64_t)p.pad < p.K) return false;
+  const SplitGeom g = split_geom(p.B > 0 ? p.B : 1, p.L, p.K, p.hop, p.pad);
+  if (g.rows >= (1ll << 31) || g.plane_stride >= (1ll << 38)) return false;
+  const int bn = choose_bn(p.F);
+  if ((2 * p.F + bn - 1) / bn > TC_MAX_N_TILES) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// pre-pass kernels
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// One thread = 8 consecutive samples of one clip's slot region (16-byte stores).
+__global__ void __launch_bounds__(256) pad_split_kernel(
+    const float* __restrict__ x, int64_t L, int64_t x_pitch, int pad, int pad_mode,
+    int64_t clip_pitch, int64_t plane_stride, __nv_bfloat16* __restrict__ planes) {
+  const int64_t b = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= clip_pitch) return;
+  const float* __restrict__ xb = x + b * x_pitch;
+  const int64_t padded_len = L + 2 * (int64_t)pad;
+  __align__(16) __nv_bfloat16 hi[8];
+  __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int64_t i = i0 + e;
+    float v = 0.f;
+    if (i < padded_len) {
+      int64_t j = i - pad;
+      if (j < 0) j = (pad_mode == NNAB_PAD_REFLECT) ? -j : -1;
+      else if (j >= L) j = (pad_mode == NNAB_PAD_REFLECT) ? 2 * (L - 1) - j : -1;
+      if (j >= 0 && j < L) v = __ldg(xb + j);
+    }
+    split_bf16(v, hi[e], lo[e]);
+  }
+  const int64_t o = b * clip_pitch + i0;
+  *reinterpret_cast<uint4*>(planes + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(planes + plane_stride + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// packed[plane][tile*bn + part*bn/2 + j][k]; part 1 rows are NEGATED im rows.
+__global__ void __launch_bounds__(256) pack_basis_kernel(
+    const float* __restrict__ w_re, const float* __restrict__ w_im, int F, int K, int bn,
+    int rows, int kpad, __nv_bfloat16* __restrict__ packed) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k8 = kpad / 8;
+  if (idx >= (int64_t)rows * k8) return;
+  const int r = (int)(idx / k8);
+  const int k0 = (int)(idx % k8) * 8;
+  const int half = bn / 2;
+  const int tile = r / bn, within = r % bn;
+  const int part = within / half, j = within % half;
+  const int f = tile * half + j;
+  __align__(16) __nv_bfloat16 hi[8];
+  __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    float v = 0.f;
+    if (f < F && k < K)
+      v = part == 0 ? __ldg(w_re + (int64_t)f * K + k) : -__ldg(w_im + (int64_t)f * K + k);
+    split_bf16(v, hi[e], lo[e]);
+  }
+  const int64_t o = (int64_t)r * kpad + k0;
+  *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(packed + (int64_t)rows * kpad + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
+                  cudaStream_t stream) {
+  const int bn = choose_bn(F);
+  const int n_tiles = (2 * F + bn - 1) / bn;
+  const int rows = n_tiles * bn;
+  const int kpad = round_up_i(K, 64);
+  const int64_t threads = (int64_t)rows * (kpad / 8);
+  pack_basis_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+      w_re, w_im, F, K, bn, rows, kpad, (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a descriptor / barrier bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {  // 4 s
+        printf("nnab: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n",
+               (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major swizzled smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused when swizzled) | [32,46) SBO>>4 |
+//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t SBO = (8u * BK * 2u) >> 4;  // 8 rows of one swizzle atom
+  constexpr uint64_t LAYOUT = (BK == 64) ? 2 : 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (SBO << 32) | (1ull << 46) |
+         (LAYOUT << 61);
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+struct TcParams {
+  int num_m_tiles, num_n_tiles, bn;
+  int rows_mode;   // 1: A viewed as (rows x hop) matrix (BK | hop); 0: overlapping-stride map
+  int hop;
+  int64_t nv, t_slots, T;
+  int kb_begin[TC_MAX_N_TILES];
+  int kb_end[TC_MAX_N_TILES];
+  EpiParams epi;
+};
+
+template <int BK, int STAGES>
+struct TcSmem {
+  static constexpr uint32_t A_BYTES = TC_BM * BK * 2;
+  static constexpr uint32_t B_BYTES = 256 * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
+};
+
+template <int BK, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const TcParams p) {
+  using S = TcSmem<BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const uint32_t b_tile_bytes = (uint32_t)p.bn * BK * 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * TC_BM;
+        const int n0 = n_tile * p.bn;
+        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), 2 * S::A_BYTES + 2 * b_tile_bytes);
+          const int k0 = kb * BK;
+          int c0 = k0, c1 = m0;
+          if (p.rows_mode) {
+            c1 = m0 + k0 / p.hop;
+            c0 = k0 - (k0 / p.hop) * p.hop;
+          }
+          tma_load_3d(sb, &tm_a, full_bar(stage), c0, c1, 0);
+          tma_load_3d(sb + S::A_BYTES, &tm_a, full_bar(stage), c0, c1, 1);
+          tma_load_3d(sb + 2 * S::A_BYTES, &tm_b, full_bar(stage), k0, n0, 0);
+          tma_load_3d(sb + 2 * S::A_BYTES + S::B_BYTES, &tm_b, full_bar(stage), k0, n0, 1);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
+        uint32_t accumulate = 0;
+        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t koff = (uint32_t)k * 32u;  // 16 bf16 along K inside the swizzle atom
+            const uint64_t a_hi = make_smem_desc<BK>(sb + koff);
+            const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
+            const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
+            const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+            umma_bf16(d_tmem, a_lo, b_hi, idesc, accumulate);
+            umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+            accumulate = 1u;
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7 <-> TMEM lane quarters) =====================
+    const int quarter = warp & 3;
+    const int half = p.bn >> 1;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * TC_BM + quarter * 32 + lane;
+      const int64_t b = g / p.t_slots;
+      const int64_t t = g - b * p.t_slots;
+      const bool valid = (g < p.nv) && (t < p.T);
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)acc * TC_ACC_STRIDE;
+      for (int c0 = 0; c0 < half; c0 += 32) {
+        uint32_t re[32], im[32];
+        tmem_ld32(trow + (uint32_t)c0, re);
+        tmem_ld32(trow + (uint32_t)(half + c0), im);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int f = n_tile * half + c0 + j;
+            if (c0 + j < half && f < p.epi.F)
+              epi_store(p.epi, b, f, t, __uint_as_float(re[j]), __uint_as_float(im[j]));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int encode_3d(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
+                     int bk) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error_text("cuTensorMapEncodeTiled entry point not available");
+    return NNAB_ECUDA;
+  }
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstr[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[200];
+    snprintf(msg, sizeof(msg),
+             "cuTensorMapEncodeTiled failed (%d): dims {%llu,%llu,%llu} strides {%llu,%llu} box {%u,%u}",
+             (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, box0, box1);
+    set_error_text(msg);
+    return NNAB_ECUDA;
+  }
+  return NNAB_OK;
+}
+
+template <int BK, int STAGES>
+static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                            int grid, cudaStream_t stream) {
+  using S = TcSmem<BK, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc_kernel<BK, STAGES>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    configured = true;
+  }
+  framed_tc_kernel<BK, STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, prm);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace, size_t ws_bytes,
+                     cudaStream_t stream) {
+  if (q.B <= 0 || q.T <= 0 || q.F <= 0) return NNAB_OK;
+  if (packed == nullptr) return NNAB_EINVAL;
+  const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (q.B > 65535) return NNAB_EUNSUPPORTED;
+
+  int bk = 64;
+  if (const char* e = getenv("NNAB_TC_BK")) bk = atoi(e) == 32 ? 32 : 64;
+
+  const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+  const int kpad = round_up_i(q.K, 64);
+  const int bn = choose_bn(q.F);
+  const int n_tiles = (2 * q.F + bn - 1) / bn;
+  const int rows_w = n_tiles * bn;
+  __nv_bfloat16* planes =
+      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+
+  // ---- 1. padded + split signal -------------------------------------------------
+  const int64_t clip_pitch = g.t_slots * q.hop;
+  const int64_t tail = g.plane_stride - g.nv * q.hop;  // K overhang rows: must be finite zeros
+  for (int pl = 0; pl < 2; ++pl)
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * q.hop, 0,
+                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
+  {
+    dim3 grid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
+    pad_split_kernel<<<grid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode, clip_pitch,
+                                               g.plane_stride, planes);
+    NNAB_LAUNCH_CHECK();
+  }
+
+  // ---- 2. tensor maps ---------------------------------------------------------------
+  CUtensorMap ma, mb;
+  const int rows_mode = (q.hop % bk == 0) ? 1 : 0;
+  int rc;
+  if (rows_mode) {
+    rc = encode_3d(&ma, planes, (uint64_t)q.hop, (uint64_t)g.rows, 2, (uint64_t)q.hop * 2,
+                   (uint64_t)g.plane_stride * 2, bk, TC_BM, bk);
+  } else {
+    // overlapping rows: row g starts at element g*hop and is kpad long
+    rc = encode_3d(&ma, planes, (uint64_t)kpad, (uint64_t)g.nv, 2, (uint64_t)q.hop * 2,
+                   (uint64_t)g.plane_stride * 2, bk, TC_BM, bk);
+  }
+  if (rc) return rc;
+  rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
+                 (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, bk, bn, bk);
+  if (rc) return rc;
+
+  // ---- 3. parameters ---------------------------------------------------------------
+  TcParams prm;
+  prm.num_m_tiles = (int)ceil_div64(g.nv, TC_BM);
+  prm.num_n_tiles = n_tiles;
+  prm.bn = bn;
+  prm.rows_mode = rows_mode;
+  prm.hop = q.hop;
+  prm.nv = g.nv;
+  prm.t_slots = g.t_slots;
+  prm.T = q.T;
+  const int nkb = kpad / bk;
+  const int half = bn / 2;
+  for (int tl = 0; tl < n_tiles; ++tl) {
+    int lo = 0, hi = (q.K + bk - 1) / bk;
+    if (q.h_k_begin != nullptr && q.h_k_end != nullptr) {
+      int klo = q.K, khi = 0;
+      for (int f = tl * half; f < q.F && f < (tl + 1) * half; ++f)
+        if (q.h_k_end[f] > q.h_k_begin[f]) {
+          klo = q.h_k_begin[f] < klo ? q.h_k_begin[f] : klo;
+          khi = q.h_k_end[f] > khi ? q.h_k_end[f] : khi;
+        }
+      if (khi > klo) {
+        lo = klo / bk;
+        hi = (khi + bk - 1) / bk;
+      } else {
+        lo = 0;
+        hi = 1;
+      }
+    }
+    if (hi > nkb) hi = nkb;
+    if (lo >= hi) lo = hi - 1;
+    prm.kb_begin[tl] = lo;
+    prm.kb_end[tl] = hi;
+  }
+  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
+  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
+  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t tiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  if (bk == 64) return launch_tc_kernel<64, 2>(ma, mb, prm, grid, stream);
+  return launch_tc_kernel<32, 4>(ma, mb, prm, grid, stream);
+}
+
 }  // namespace nnab

@@ -1,0 +1,96 @@
+"""Host-side behaviour of the nn.Module boundary that needs no GPU: the
+reference's exception types (SURVEY.md §8 b1 'Conventions'), buffer names,
+attribute surface, octave planning, and the loud no-CPU-fallback failure."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import nnaudio_b200 as nb
+from nnaudio_b200.features.cqt import _octave_plan
+from nnaudio_b200.features._common import broadcast_dim, tap_support
+
+
+def test_broadcast_dim_rules():
+    assert broadcast_dim(torch.zeros(7)).shape == (1, 7)
+    assert broadcast_dim(torch.zeros(2, 7)).shape == (2, 7)
+    assert broadcast_dim(torch.zeros(2, 1, 7)).shape == (2, 7)
+    with pytest.raises(ValueError, match="Only support input with shape"):
+        broadcast_dim(torch.zeros(1, 1, 2, 7))
+
+
+def test_cpu_tensor_fails_loudly_no_fallback():
+    m = nb.STFT(n_fft=256, verbose=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 4000))
+
+
+def test_reference_exceptions_raised_before_the_c_call():
+    m = nb.STFT(n_fft=512, verbose=False)
+    with pytest.raises(AssertionError, match="shorter than reflect padding"):
+        m(torch.randn(1, 100))
+    with pytest.raises(ValueError):
+        m(torch.randn(1, 4000), output_format="nope")
+    q = nb.CQT1992v2(sr=22050, fmin=220, n_bins=12, verbose=False)
+    with pytest.raises(ValueError, match="normalization_type"):
+        q(torch.randn(1, 4000), normalization_type="bogus")
+    with pytest.raises(RuntimeError, match="Padding size"):
+        q(torch.randn(1, 100))
+    with pytest.raises(ValueError, match="Nyquist"):
+        nb.CQT1992v2(sr=8000, fmin=220, n_bins=84, verbose=False)
+    with pytest.raises(ValueError, match="Nyquist"):
+        nb.CQT2010v2(sr=8000, n_bins=96, verbose=False)
+
+
+def test_forward_only_guard():
+    m = nb.STFT(n_fft=256, trainable=True, verbose=False)
+    assert isinstance(m.wsin, torch.nn.Parameter) and m.wsin.requires_grad
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        m(torch.randn(1, 4000))
+
+
+def test_attribute_surface_matches_reference():
+    s = nb.STFT(n_fft=512, hop_length=128, verbose=False)
+    for a in ("stride", "n_fft", "pad_amount", "freq_bins", "bins2freq", "bin_list", "win_length",
+              "center", "pad_mode", "trainable", "output_format"):
+        assert hasattr(s, a), a
+    assert "n_fft=512" in s.extra_repr()
+    mel = nb.MelSpectrogram(verbose=False)
+    assert isinstance(mel.stft, nb.STFT) and mel.power == 2.0 and mel.stride == 512
+    mf = nb.MFCC(sr=16000, verbose=False)
+    assert mf.n_mfcc == 20 and mf.m_mfcc == 20 and mf.top_db == 80.0
+    assert "_dct_rows" not in mf.state_dict()
+    c = nb.CQT2010v2(n_bins=88, verbose=False)
+    assert c.n_octaves == 8 and c.n_fft == 256 and c.earlydownsample is False
+    assert issubclass(nb.CQT, nb.CQT1992v2)
+    v = nb.VQT(gamma=3, verbose=False)
+    assert v.n_filters == 12 and v.gamma == 3
+
+
+def test_octave_plan_lengths_and_fallback():
+    # cfg4 level lengths of SURVEY.md §8 row a14
+    T, flags = _octave_plan(661500, 512, [256] * 8, "reflect")
+    assert T == 1292 and not any(flags)
+    T, flags = _octave_plan(6000, 512, [256] * 7, "reflect")
+    assert T == 12 and flags == [False] * 6 + [True]
+    with pytest.raises(RuntimeError):
+        _octave_plan(6001, 500, [256] * 7, "reflect")  # octave frame counts diverge
+
+
+def test_tap_support_of_cqt_bank():
+    q = nb.CQT1992v2(sr=22050, fmin=220, n_bins=24, verbose=False)
+    kb, ke = q._tap_support()
+    lens = q.lenghts.numpy().astype(int)
+    assert ((ke - kb) <= lens).all() and ((ke - kb) >= lens - 2).all()
+    b, e = tap_support(np.array([[0, 0, 1, 2, 0], [0, 0, 0, 0, 0]]))
+    assert (b.tolist(), e.tolist()) == ([2, 0], [4, 0])
+
+
+def test_legacy_spectrogram_alias_warns():
+    import importlib, sys
+    sys.modules.pop("nnaudio_b200.Spectrogram", None)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        mod = importlib.import_module("nnaudio_b200.Spectrogram")
+    assert mod.STFT is nb.STFT and any("deprecated" in str(x.message) for x in w)
