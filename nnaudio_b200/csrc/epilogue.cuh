@@ -63,4 +63,43 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int64_t b, int f, 
   }
 }
 
+// Compile-time-format variant for the tcgen05 kernel: keeps the 32x unrolled
+// TMEM read-out loop small enough to stay in the instruction cache.
+//   FMT: 0..3 = NNAB_FMT_*, 4 = FMT_POWER.  `dst` already points at element
+//   (b, bin_offset, t) of the output (float2 elements for the 2-channel formats).
+template <int FMT>
+__device__ __forceinline__ void epi_store_fmt(const EpiParams& e, float* dst, int f, float re,
+                                              float im) {
+  const int row = f + e.bin_offset;
+  if (row < 0 || row >= e.out_bins) return;
+  float s = e.scale_all;
+  if (e.scale != nullptr) s *= __ldg(e.scale + f);
+  re *= s;
+  im *= s;
+  const int64_t off = (int64_t)f * e.T;
+  if constexpr (FMT == NNAB_FMT_MAGNITUDE) {
+    float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+    if (e.eps != 0.f) p = __fadd_rn(p, e.eps);
+    dst[off] = sqrtf(p);
+  } else if constexpr (FMT == NNAB_FMT_COMPLEX) {
+    reinterpret_cast<float2*>(dst)[off] = make_float2(re, im);
+  } else if constexpr (FMT == NNAB_FMT_PHASE_ANGLE) {
+    dst[off] = atan2f(im + 0.0f, re);
+  } else if constexpr (FMT == NNAB_FMT_PHASE_UNIT) {
+    const float ang = atan2f(im, re);
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    reinterpret_cast<float2*>(dst)[off] = make_float2(cs, sn);
+  } else {
+    float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+    if (e.eps != 0.f) p = __fadd_rn(p, e.eps);
+    const float m = sqrtf(p);
+    float v;
+    if (e.power == 2.0f) v = __fmul_rn(m, m);
+    else if (e.power == 1.0f) v = m;
+    else v = powf(m, e.power);
+    dst[off] = v;
+  }
+}
+
 }  // namespace nnab

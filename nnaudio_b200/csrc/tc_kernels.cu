@@ -321,7 +321,7 @@ struct TcSmem {
   static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
 };
 
-template <int BK, int STAGES>
+template <int BK, int STAGES, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const TcParams p) {
@@ -451,17 +451,27 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const bool valid = (g < p.nv) && (t < p.T);
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
+      constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
+      float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+      const int f_base = n_tile * half;
       for (int c0 = 0; c0 < half; c0 += 32) {
         uint32_t re[32], im[32];
         tmem_ld32(trow + (uint32_t)c0, re);
         tmem_ld32(trow + (uint32_t)(half + c0), im);
         tmem_ld_wait();
         if (valid) {
+          const int jmax = min(32, min(half - c0, p.epi.F - f_base - c0));
+          if (jmax == 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int f = n_tile * half + c0 + j;
-            if (c0 + j < half && f < p.epi.F)
-              epi_store(p.epi, b, f, t, __uint_as_float(re[j]), __uint_as_float(im[j]));
+            for (int j = 0; j < 32; ++j)
+              epi_store_fmt<FMT>(p.epi, dst, f_base + c0 + j, __uint_as_float(re[j]),
+                                 __uint_as_float(im[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < jmax)
+                epi_store_fmt<FMT>(p.epi, dst, f_base + c0 + j, __uint_as_float(re[j]),
+                                   __uint_as_float(im[j]));
           }
         }
       }
@@ -529,19 +539,32 @@ static int encode_3d(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1, uin
   return NNAB_OK;
 }
 
-template <int BK, int STAGES>
-static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
-                            int grid, cudaStream_t stream) {
+template <int BK, int STAGES, int FMT>
+static int launch_tc_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                                int grid, cudaStream_t stream) {
   using S = TcSmem<BK, STAGES>;
   static bool configured = false;
   if (!configured) {
-    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc_kernel<BK, STAGES>,
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc_kernel<BK, STAGES, FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
     configured = true;
   }
-  framed_tc_kernel<BK, STAGES><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, prm);
+  framed_tc_kernel<BK, STAGES, FMT><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, prm);
   NNAB_LAUNCH_CHECK();
   return NNAB_OK;
+}
+
+template <int BK, int STAGES>
+static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                            int grid, cudaStream_t stream) {
+  switch (prm.epi.fmt) {
+    case NNAB_FMT_MAGNITUDE: return launch_tc_kernel_fmt<BK, STAGES, 0>(ma, mb, prm, grid, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc_kernel_fmt<BK, STAGES, 1>(ma, mb, prm, grid, stream);
+    case NNAB_FMT_PHASE_ANGLE: return launch_tc_kernel_fmt<BK, STAGES, 2>(ma, mb, prm, grid, stream);
+    case NNAB_FMT_PHASE_UNIT: return launch_tc_kernel_fmt<BK, STAGES, 3>(ma, mb, prm, grid, stream);
+    case FMT_POWER: return launch_tc_kernel_fmt<BK, STAGES, 4>(ma, mb, prm, grid, stream);
+    default: return NNAB_EINVAL;
+  }
 }
 
 int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace, size_t ws_bytes,

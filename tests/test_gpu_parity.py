@@ -18,6 +18,8 @@ from helpers import (CASES, REF_GROUND_TRUTHS, SWEEP_CTOR, build, case_input, is
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 PATHS = ["simt", "auto"]
+# smallest |X| / max|X| at which phases are compared (fp32 SIMT vs split-bf16 tensor path)
+PHASE_FLOOR = {"simt": 1e-3, "auto": 0.05}
 
 
 def _run(mod, x, kw, path):
@@ -45,8 +47,11 @@ def test_cuda_matches_reference_and_oracle(case, path):
         assert np.isfinite(got).all()
         orc = run_oracle(cls, mod, x, kw)
         if is_phase(kw):
+            # a phase is only as accurate as |X| allows: with |dX| <= 1e-4 max|X| the angle
+            # error is <= 1e-4 max|X| / |X|; compare where that bound is below the 2e-3 used
             mag = run_oracle(cls, mod, x, dict(kw, output_format="Magnitude"))
-            keep = mag > 1e-3 * mag.max()
+            keep = mag > PHASE_FLOOR[path] * mag.max()
+            assert keep.sum() > 20
             for ref in (want, orc):
                 d = np.abs(phase_to_unit(cls, got)[keep] - phase_to_unit(cls, ref)[keep]).max()
                 assert d < 2e-3, (cid, kw, path, d)
@@ -72,13 +77,21 @@ def test_cuda_matches_reference_ground_truths(key, path):
     if transform is not None:
         eps = 1e-5 if transform == "log1e-5" else 1e-2
         lin_gt = np.exp(gt.astype(np.float64)) - eps
+        # the 1e-4 bar on the linear magnitude, everywhere
         assert np.abs(y - lin_gt).max() < 1e-4 * np.abs(lin_gt).max()
-        keep = y > 1e-2 * eps + 1e-5 * y.max()
+        # log(X + eps) at the reference's own rtol/atol where the log is conditioned well
+        # enough for a 1e-4 (max-relative) implementation: d(log) = dX / (X + eps).  The fp32
+        # SIMT path holds it nearly everywhere, the split-bf16 tensor-core path (|dX| up to
+        # ~5e-5 max|X| at K = 32768) from 10 % of the peak upwards.
+        floor = 1e-5 if path == "simt" else 0.1
+        keep = y > 1e-2 * eps + floor * y.max()
+        assert keep.sum() > 50
         assert np.allclose(np.log(y[keep] + eps), gt[keep], rtol=1e-3, atol=1e-3)
         return
     if is_phase(kw):
         mag = run_oracle(cls, build(cls, SWEEP_CTOR), x, dict(kw, output_format="Magnitude"))
-        keep = mag > 1e-3 * mag.max()
+        keep = mag > PHASE_FLOOR[path] * mag.max()
+        assert keep.sum() > 20
         assert np.allclose(y[keep], gt[keep], rtol=1e-3, atol=2e-3)
         return
     assert np.allclose(y, gt, rtol=1e-3, atol=1e-3)
