@@ -106,18 +106,32 @@ int nnab_stft_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                       void* workspace, size_t ws_bytes, int path, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Banded filterbank table (tcgen05 path): for every FFT bin the (at most two)
+ * non-zero weights of the (n_fb, F) filterbank.  Mel banks are banded like that;
+ * for denser banks (gammatone) *h_max_nnz > 2 and the forward calls must be
+ * given fb_table = NULL (they then run the un-fused filterbank GEMM).
+ * Init-time helper: this call synchronises `stream` to return *h_max_nnz.
+ * ------------------------------------------------------------------------- */
+size_t nnab_filterbank_table_bytes(int F);
+int nnab_build_filterbank_table(const float* fb, int n_fb, int F, void* table,
+                                int* h_max_nnz, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * MelSpectrogram.forward / Gammatonegram.forward — features/mel.py:171-189,
  * features/gammatone.py:171-189:  out = fb @ (|STFT(x)| ** power).
  *   fb (n_fb, F) = `mel_basis` or `gammatone_basis`;  out (B, n_fb, T)
+ *   fb_table: table from nnab_build_filterbank_table (max_nnz <= 2) or NULL.
+ *     With a table and the tcgen05 path the filterbank is applied in the
+ *     contraction kernel's epilogue (no (B,F,T) intermediate in HBM).
  * ------------------------------------------------------------------------- */
 size_t nnab_filterbank_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop,
-                                       int center, int n_fb, int path);
+                                       int center, int n_fb, int path, int has_table);
 int nnab_stft_filterbank_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                                  const float* wcos, const float* wsin, const void* packed,
                                  int n_fft, int F, int hop, int center, int pad_mode,
                                  float sqrt_eps, float power, const float* fb, int n_fb,
-                                 float* out, int64_t T, void* workspace, size_t ws_bytes,
-                                 int path, void* stream);
+                                 const void* fb_table, float* out, int64_t T,
+                                 void* workspace, size_t ws_bytes, int path, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * MFCC.forward — features/mel.py:309-326 (= mel -> _power_to_db :263-279 ->
@@ -126,14 +140,14 @@ int nnab_stft_filterbank_forward(const float* x, int64_t B, int64_t L, int64_t x
  *   out (B, n_mfcc, T)
  * ------------------------------------------------------------------------- */
 size_t nnab_mfcc_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop,
-                                 int center, int n_mels, int path);
+                                 int center, int n_mels, int path, int has_table);
 int nnab_mfcc_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                       const float* wcos, const float* wsin, const void* packed,
                       int n_fft, int F, int hop, int center, int pad_mode,
                       float sqrt_eps, float power, const float* mel_basis, int n_mels,
-                      float amin, float ref, float top_db, const float* dct, int n_mfcc,
-                      float* out, int64_t T, void* workspace, size_t ws_bytes,
-                      int path, void* stream);
+                      const void* fb_table, float amin, float ref, float top_db,
+                      const float* dct, int n_mfcc, float* out, int64_t T,
+                      void* workspace, size_t ws_bytes, int path, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * CQT1992v2.forward — features/cqt.py:712-780.

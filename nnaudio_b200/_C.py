@@ -40,19 +40,21 @@ SIGNATURES = {
         [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
          c_float, _P, c_int64, _P, c_size_t, c_int, _P],
     ),
+    "nnab_filterbank_table_bytes": (c_size_t, [c_int]),
+    "nnab_build_filterbank_table": (c_int, [_P, c_int, c_int, _P, _P, _P]),
     "nnab_filterbank_workspace_bytes": (
-        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int]),
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "nnab_stft_filterbank_forward": (
         c_int,
         [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
-         c_float, _P, c_int, _P, c_int64, _P, c_size_t, c_int, _P],
+         c_float, _P, c_int, _P, _P, c_int64, _P, c_size_t, c_int, _P],
     ),
     "nnab_mfcc_workspace_bytes": (
-        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int]),
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "nnab_mfcc_forward": (
         c_int,
         [_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
-         c_float, _P, c_int, c_float, c_float, c_float, _P, c_int, _P, c_int64, _P, c_size_t,
+         c_float, _P, c_int, _P, c_float, c_float, c_float, _P, c_int, _P, c_int64, _P, c_size_t,
          c_int, _P],
     ),
     "nnab_cqt1992v2_workspace_bytes": (
@@ -189,6 +191,20 @@ def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor):
     return packed
 
 
+def build_filterbank_table(fb: torch.Tensor):
+    """Banded (<= 2 non-zeros per FFT bin) table of an (n_fb, F) filterbank for the
+    fused tcgen05 epilogue, or ``None`` when the bank is denser (e.g. gammatone).
+    Init-time: synchronises the current stream once."""
+    L = lib()
+    n_fb, F = fb.shape
+    table = torch.empty(L.nnab_filterbank_table_bytes(F), dtype=torch.uint8, device=fb.device)
+    max_nnz = ctypes.c_int(0)
+    with torch.cuda.device(fb.device):
+        _check(L.nnab_build_filterbank_table(_ptr(fb), n_fb, F, _ptr(table), ctypes.byref(max_nnz),
+                                             _stream(fb.device)), "nnab_build_filterbank_table")
+    return table if max_nnz.value <= 2 else None
+
+
 # --------------------------------------------------------------------------- #
 # forward calls
 # --------------------------------------------------------------------------- #
@@ -213,7 +229,7 @@ def stft_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, out_format
 
 
 def stft_filterbank_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, power,
-                            fb, path=None):
+                            fb, fb_table=None, path=None):
     L = lib()
     x, B, Ln, pitch = _rows(x)
     F = wcos.shape[0]
@@ -224,18 +240,19 @@ def stft_filterbank_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode,
     path = resolve_path(path)
     with torch.cuda.device(x.device):
         ws, wsb = _workspace(
-            L.nnab_filterbank_workspace_bytes(B, Ln, n_fft, F, hop, int(center), n_fb, path),
+            L.nnab_filterbank_workspace_bytes(B, Ln, n_fft, F, hop, int(center), n_fb, path,
+                                              int(fb_table is not None)),
             x.device)
         rc = L.nnab_stft_filterbank_forward(
             _ptr(x), B, Ln, pitch, _ptr(wcos), _ptr(wsin), _ptr(packed), n_fft, F, hop,
-            int(center), pad_mode, sqrt_eps, power, _ptr(fb), n_fb, _ptr(out), T, _ptr(ws), wsb,
-            path, _stream(x.device))
+            int(center), pad_mode, sqrt_eps, power, _ptr(fb), n_fb, _ptr(fb_table), _ptr(out), T,
+            _ptr(ws), wsb, path, _stream(x.device))
     _check(rc, "nnab_stft_filterbank_forward")
     return out
 
 
 def mfcc_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, power, mel_basis,
-                 amin, ref, top_db, dct, path=None):
+                 amin, ref, top_db, dct, fb_table=None, path=None):
     L = lib()
     x, B, Ln, pitch = _rows(x)
     F = wcos.shape[0]
@@ -247,10 +264,11 @@ def mfcc_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, 
     path = resolve_path(path)
     with torch.cuda.device(x.device):
         ws, wsb = _workspace(
-            L.nnab_mfcc_workspace_bytes(B, Ln, n_fft, F, hop, int(center), n_mels, path), x.device)
+            L.nnab_mfcc_workspace_bytes(B, Ln, n_fft, F, hop, int(center), n_mels, path,
+                                        int(fb_table is not None)), x.device)
         rc = L.nnab_mfcc_forward(
             _ptr(x), B, Ln, pitch, _ptr(wcos), _ptr(wsin), _ptr(packed), n_fft, F, hop,
-            int(center), pad_mode, sqrt_eps, power, _ptr(mel_basis), n_mels, amin, ref,
+            int(center), pad_mode, sqrt_eps, power, _ptr(mel_basis), n_mels, _ptr(fb_table), amin, ref,
             -1.0 if top_db is None else float(top_db), _ptr(dct), n_mfcc, _ptr(out), T, _ptr(ws),
             wsb, path, _stream(x.device))
     _check(rc, "nnab_mfcc_forward")

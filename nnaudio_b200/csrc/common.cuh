@@ -40,6 +40,13 @@ void count_launch();
 // followed by a per-bin scale and one of the output formats of nnab.h (or the
 // internal POWER format used by the filterbank ops).
 constexpr int FMT_POWER = 100;  // internal: (sqrt(re^2+im^2+eps)) ** power -> (B,F,T)
+constexpr int FMT_FBANK = 101;  // internal (tcgen05 only): power -> banded filterbank -> (B,n_fb,T)
+
+// Banded filterbank table: the (at most two) non-zero weights of every FFT bin.
+struct FbEntry {
+  int j0, j1;    // filter rows (-1 = none)
+  float w0, w1;
+};
 
 struct FramedProblem {
   const float* x;      // (B, L) rows, pitch x_pitch
@@ -60,6 +67,8 @@ struct FramedProblem {
   int bin_offset;      // output row of bin 0 (may be negative: rows < 0 dropped)
   const int32_t* h_k_begin;  // host, per-bin support or nullptr
   const int32_t* h_k_end;
+  const FbEntry* fb_table;   // FMT_FBANK: device table [F]; out is (B, n_fb, T), pre-zeroed
+  int n_fb;
 };
 
 int launch_framed_simt(const FramedProblem& p, cudaStream_t stream);
@@ -73,6 +82,8 @@ size_t tc_packed_bytes(int F, int K);
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream);
 int tc_tile_n();
+int launch_fb_table(const float* fb, int n_fb, int F, FbEntry* table, int* d_max_nnz,
+                    cudaStream_t stream);
 
 // filterbank / MFCC tail / FIR decimation (simt_kernels.cu)
 int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t T, int n_fb,

@@ -19,7 +19,19 @@ struct EpiParams {
   int out_bins;
   int bin_offset;
   int F;
+  const FbEntry* fb_table;  // FMT_FBANK
+  int n_fb;
 };
+
+__device__ __forceinline__ float epi_power(const EpiParams& e, float re, float im) {
+  // |X| first, then ** power, like `stft(x, "Magnitude") ** self.power` (mel.py:186)
+  float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+  if (e.eps != 0.f) p = __fadd_rn(p, e.eps);
+  const float m = sqrtf(p);
+  if (e.power == 2.0f) return __fmul_rn(m, m);
+  if (e.power == 1.0f) return m;
+  return powf(m, e.power);
+}
 
 // re/im are the final-signed contraction results for (clip b, bin f, frame t).
 __device__ __forceinline__ void epi_store(const EpiParams& e, int64_t b, int f, int64_t t,

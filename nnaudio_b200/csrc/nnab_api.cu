@@ -195,13 +195,35 @@ static size_t power_bytes(int64_t B, int F, int64_t T) {
   return align_up((size_t)B * F * T * sizeof(float), 256);
 }
 
+size_t nnab_filterbank_table_bytes(int F) { return (size_t)F * sizeof(FbEntry) + 64; }
+
+int nnab_build_filterbank_table(const float* fb, int n_fb, int F, void* table, int* h_max_nnz,
+                                void* stream) {
+  if (fb == nullptr || table == nullptr || h_max_nnz == nullptr || n_fb <= 0 || F <= 0)
+    return NNAB_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  int* d_max = reinterpret_cast<int*>(reinterpret_cast<char*>(table) + (size_t)F * sizeof(FbEntry));
+  int rc = launch_fb_table(fb, n_fb, F, reinterpret_cast<FbEntry*>(table), d_max, s);
+  if (rc) return rc;
+  NNAB_CUDA_TRY(cudaMemcpyAsync(h_max_nnz, d_max, sizeof(int), cudaMemcpyDeviceToHost, s));
+  NNAB_CUDA_TRY(cudaStreamSynchronize(s));
+  return NNAB_OK;
+}
+
+static bool fused_fbank(int path, const void* packed, const void* fb_table, int n_fft, int hop) {
+  return fb_table != nullptr && packed != nullptr && path != NNAB_PATH_SIMT &&
+         wants_tc(path, n_fft, hop);
+}
+
 size_t nnab_filterbank_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop,
-                                       int center, int n_fb, int path) {
+                                       int center, int n_fb, int path, int has_table) {
   (void)n_fb;
   const int pad = center ? n_fft / 2 : 0;
   const int64_t T = frames_of(L, n_fft, hop, pad);
-  size_t n = power_bytes(B, F, T);
-  if (wants_tc(path, n_fft, hop)) n += tc_workspace_bytes(B, L, n_fft, hop, pad);
+  const bool tc = wants_tc(path, n_fft, hop);
+  size_t n = 0;
+  if (!(has_table && tc)) n += power_bytes(B, F, T);  // un-fused: (B,F,T) power spectrogram
+  if (tc) n += tc_workspace_bytes(B, L, n_fft, hop, pad);
   return n;
 }
 
@@ -223,40 +245,63 @@ int nnab_stft_filterbank_forward(const float* x, int64_t B, int64_t L, int64_t x
                                  const float* wcos, const float* wsin, const void* packed,
                                  int n_fft, int F, int hop, int center, int pad_mode,
                                  float sqrt_eps, float power, const float* fb, int n_fb,
-                                 float* out, int64_t T, void* workspace, size_t ws_bytes,
-                                 int path, void* stream) {
+                                 const void* fb_table, float* out, int64_t T, void* workspace,
+                                 size_t ws_bytes, int path, void* stream) {
   const int pad = center ? n_fft / 2 : 0;
   int rc = check_common(x, B, L, x_pitch, n_fft, F, hop, pad, pad_mode, T);
   if (rc) return rc;
   if (wcos == nullptr || wsin == nullptr || fb == nullptr || out == nullptr || n_fb <= 0)
     return NNAB_EINVAL;
   if ((rc = check_arch())) return rc;
-  const size_t need = nnab_filterbank_workspace_bytes(B, L, n_fft, F, hop, center, n_fb, path);
+  cudaStream_t s = (cudaStream_t)stream;
+  bool fused = fused_fbank(path, packed, fb_table, n_fft, hop);
+  if (fused) {
+    FramedProblem p{};
+    p.x = x; p.B = B; p.L = L; p.x_pitch = x_pitch;
+    p.w_re = wcos; p.w_im = wsin; p.F = F; p.K = n_fft; p.hop = hop;
+    p.pad = pad; p.pad_mode = pad_mode; p.scale = nullptr; p.scale_all = 1.f;
+    p.fmt = FMT_FBANK; p.eps = sqrt_eps; p.power = power; p.out = out; p.T = T;
+    p.out_bins = n_fb; p.bin_offset = 0;
+    p.fb_table = reinterpret_cast<const FbEntry*>(fb_table); p.n_fb = n_fb;
+    if (tc_supported(p)) {
+      const size_t need = tc_workspace_bytes(B, L, n_fft, hop, pad);
+      if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+      // the epilogue accumulates filter sums with fp32 atomics: start from zero
+      NNAB_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * n_fb * T * sizeof(float), s));
+      return run_framed(p, packed, workspace, ws_bytes, NNAB_PATH_TCGEN05, s);
+    }
+    fused = false;
+  }
+  const size_t need = nnab_filterbank_workspace_bytes(B, L, n_fft, F, hop, center, n_fb, path, 0);
   if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
   float* P = (float*)workspace;
   const size_t pb = power_bytes(B, F, T);
-  cudaStream_t s = (cudaStream_t)stream;
   rc = power_spectrogram(x, B, L, x_pitch, wcos, wsin, packed, n_fft, F, hop, pad, pad_mode,
                          sqrt_eps, power, P, T, (char*)workspace + pb, ws_bytes - pb, path, s);
   if (rc) return rc;
   return launch_filterbank(P, fb, B, F, T, n_fb, out, s);
 }
 
+static size_t mel_bytes(int64_t B, int n_mels, int64_t T) {
+  return align_up((size_t)B * n_mels * T * sizeof(float), 256);
+}
+
 size_t nnab_mfcc_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop, int center,
-                                 int n_mels, int path) {
+                                 int n_mels, int path, int has_table) {
   const int pad = center ? n_fft / 2 : 0;
   const int64_t T = frames_of(L, n_fft, hop, pad);
-  return nnab_filterbank_workspace_bytes(B, L, n_fft, F, hop, center, n_mels, path) +
-         align_up((size_t)B * n_mels * T * sizeof(float), 256) +
-         align_up((size_t)B * sizeof(unsigned int), 256);
+  // the un-fused size is the upper bound (a huge batch can still fall back to it)
+  const size_t fbw = nnab_filterbank_workspace_bytes(B, L, n_fft, F, hop, center, n_mels, path, 0);
+  (void)has_table;
+  return align_up(fbw, 256) + mel_bytes(B, n_mels, T) + align_up((size_t)B * sizeof(unsigned int), 256);
 }
 
 int nnab_mfcc_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* wcos,
                       const float* wsin, const void* packed, int n_fft, int F, int hop,
                       int center, int pad_mode, float sqrt_eps, float power,
-                      const float* mel_basis, int n_mels, float amin, float ref, float top_db,
-                      const float* dct, int n_mfcc, float* out, int64_t T, void* workspace,
-                      size_t ws_bytes, int path, void* stream) {
+                      const float* mel_basis, int n_mels, const void* fb_table, float amin,
+                      float ref, float top_db, const float* dct, int n_mfcc, float* out,
+                      int64_t T, void* workspace, size_t ws_bytes, int path, void* stream) {
   const int pad = center ? n_fft / 2 : 0;
   int rc = check_common(x, B, L, x_pitch, n_fft, F, hop, pad, pad_mode, T);
   if (rc) return rc;
@@ -264,15 +309,15 @@ int nnab_mfcc_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch, con
       out == nullptr || n_mels <= 0 || n_mfcc <= 0 || !(amin > 0.f))
     return NNAB_EINVAL;
   if ((rc = check_arch())) return rc;
-  const size_t need = nnab_mfcc_workspace_bytes(B, L, n_fft, F, hop, center, n_mels, path);
+  const size_t need = nnab_mfcc_workspace_bytes(B, L, n_fft, F, hop, center, n_mels, path, 0);
   if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
-  const size_t fbw = nnab_filterbank_workspace_bytes(B, L, n_fft, F, hop, center, n_mels, path);
-  const size_t melb = align_up((size_t)B * n_mels * T * sizeof(float), 256);
+  const size_t fbw =
+      align_up(nnab_filterbank_workspace_bytes(B, L, n_fft, F, hop, center, n_mels, path, 0), 256);
   float* mel = (float*)((char*)workspace + fbw);
-  unsigned int* scratch = (unsigned int*)((char*)workspace + fbw + melb);
+  unsigned int* scratch = (unsigned int*)((char*)workspace + fbw + mel_bytes(B, n_mels, T));
   rc = nnab_stft_filterbank_forward(x, B, L, x_pitch, wcos, wsin, packed, n_fft, F, hop, center,
-                                    pad_mode, sqrt_eps, power, mel_basis, n_mels, mel, T,
-                                    workspace, fbw, path, stream);
+                                    pad_mode, sqrt_eps, power, mel_basis, n_mels, fb_table, mel,
+                                    T, workspace, fbw, path, stream);
   if (rc) return rc;
   return launch_mfcc_tail(mel, B, n_mels, T, amin, ref, top_db, dct, n_mfcc, out, scratch,
                           (cudaStream_t)stream);

@@ -140,6 +140,8 @@ int launch_framed_simt(const FramedProblem& q, cudaStream_t stream) {
   p.epi.scale = q.scale; p.epi.scale_all = q.scale_all; p.epi.fmt = q.fmt;
   p.epi.eps = q.eps; p.epi.power = q.power; p.epi.out = q.out; p.epi.T = q.T;
   p.epi.out_bins = q.out_bins; p.epi.bin_offset = q.bin_offset; p.epi.F = q.F;
+  p.epi.fb_table = nullptr; p.epi.n_fb = 0;
+  if (q.fmt == FMT_FBANK) return NNAB_EINVAL;  // fused filterbank exists on the tcgen05 path only
 
   const int TN = (q.F > 32) ? 4 : 2;
   const int BNB = 16 * TN;
@@ -242,6 +244,35 @@ __global__ void __launch_bounds__(256) filterbank_kernel(const float* __restrict
       if (t < T) out[((int64_t)b * n_fb + j) * T + t] = acc[jj][i];
     }
   }
+}
+
+// One thread per FFT bin: record its (<= 2) non-zero filter weights and the
+// largest per-bin count (a dense bank such as the gammatone one reports > 2 and
+// is then served by the un-fused filterbank GEMM).
+__global__ void fb_table_kernel(const float* __restrict__ fb, int n_fb, int F,
+                                FbEntry* __restrict__ table, int* __restrict__ max_nnz) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  FbEntry e{-1, -1, 0.f, 0.f};
+  int nnz = 0;
+  for (int j = 0; j < n_fb; ++j) {
+    const float w = __ldg(fb + (int64_t)j * F + f);
+    if (w != 0.f) {
+      if (nnz == 0) { e.j0 = j; e.w0 = w; }
+      else if (nnz == 1) { e.j1 = j; e.w1 = w; }
+      ++nnz;
+    }
+  }
+  table[f] = e;
+  atomicMax(max_nnz, nnz);
+}
+
+int launch_fb_table(const float* fb, int n_fb, int F, FbEntry* table, int* d_max_nnz,
+                    cudaStream_t stream) {
+  NNAB_CUDA_TRY(cudaMemsetAsync(d_max_nnz, 0, sizeof(int), stream));
+  fb_table_kernel<<<(F + 127) / 128, 128, 0, stream>>>(fb, n_fb, F, table, d_max_nnz);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
 }
 
 int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t T, int n_fb,

@@ -451,9 +451,46 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const bool valid = (g < p.nv) && (t < p.T);
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
+      const int f_base = n_tile * half;
+      if constexpr (FMT == 5) {
+        // ---- fused banded filterbank: two running filter sums per frame ----
+        float* mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
+        int cj0 = -1, cj1 = -1;
+        float a0 = 0.f, a1 = 0.f;
+        for (int c0 = 0; c0 < half; c0 += 32) {
+          uint32_t re[32], im[32];
+          tmem_ld32(trow + (uint32_t)c0, re);
+          tmem_ld32(trow + (uint32_t)(half + c0), im);
+          tmem_ld_wait();
+          const int jmax = min(32, min(half - c0, p.epi.F - f_base - c0));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < jmax) {  // warp-uniform
+              const int4 raw = __ldg(reinterpret_cast<const int4*>(p.epi.fb_table) + f_base + c0 + j);
+              const float pw = epi_power(p.epi, __uint_as_float(re[j]), __uint_as_float(im[j]));
+              if (raw.x != cj0) {
+                if (raw.x == cj1) {
+                  const int tj = cj0; cj0 = cj1; cj1 = tj;
+                  const float ta = a0; a0 = a1; a1 = ta;
+                } else {
+                  if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * p.epi.T, a0);
+                  cj0 = raw.x; a0 = 0.f;
+                }
+              }
+              if (raw.y != cj1) {
+                if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * p.epi.T, a1);
+                cj1 = raw.y; a1 = 0.f;
+              }
+              a0 = fmaf(__int_as_float(raw.z), pw, a0);
+              a1 = fmaf(__int_as_float(raw.w), pw, a1);
+            }
+          }
+        }
+        if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * p.epi.T, a0);
+        if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * p.epi.T, a1);
+      } else {
       constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
       float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
-      const int f_base = n_tile * half;
       for (int c0 = 0; c0 < half; c0 += 32) {
         uint32_t re[32], im[32];
         tmem_ld32(trow + (uint32_t)c0, re);
@@ -474,6 +511,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                    __uint_as_float(im[j]));
           }
         }
+      }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -563,6 +601,7 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
     case NNAB_FMT_PHASE_ANGLE: return launch_tc_kernel_fmt<BK, STAGES, 2>(ma, mb, prm, grid, stream);
     case NNAB_FMT_PHASE_UNIT: return launch_tc_kernel_fmt<BK, STAGES, 3>(ma, mb, prm, grid, stream);
     case FMT_POWER: return launch_tc_kernel_fmt<BK, STAGES, 4>(ma, mb, prm, grid, stream);
+    case FMT_FBANK: return launch_tc_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, grid, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -653,6 +692,8 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
   prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
   prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+  prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
+  if (q.fmt == FMT_FBANK && (q.fb_table == nullptr || q.n_fb <= 0)) return NNAB_EINVAL;
 
   int dev = 0, sms = 148;
   NNAB_CUDA_TRY(cudaGetDevice(&dev));

@@ -81,3 +81,19 @@ def tap_support(bank_2d: np.ndarray):
     begin = np.where(any_nz, first, 0).astype(np.int32)
     end = np.where(any_nz, last, 0).astype(np.int32)
     return np.ascontiguousarray(begin), np.ascontiguousarray(end)
+
+
+class FilterbankTable:
+    """Cache of the banded-filterbank table used by the fused tcgen05 epilogue
+    (rebuilt when the filterbank tensor changes; ``None`` for dense banks)."""
+
+    def __init__(self):
+        self._key = None
+        self._table = None
+
+    def get(self, fb: torch.Tensor):
+        key = (fb.data_ptr(), fb._version, str(fb.device))
+        if key != self._key:
+            self._table = _C.build_filterbank_table(fb)
+            self._key = key
+        return self._table

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import forward_only_guard, pad_mode_id
+from ._common import FilterbankTable, forward_only_guard, pad_mode_id
 from .stft import STFT
 
 
@@ -71,6 +71,7 @@ class Gammatonegram(nn.Module):
             self.register_parameter("gammatone_basis", nn.Parameter(basis, requires_grad=True))
         else:
             self.register_buffer("gammatone_basis", basis)
+        self._fb_table = FilterbankTable()
 
     def forward(self, x):
         x = self.stft._checked_input(x)
@@ -82,7 +83,7 @@ class Gammatonegram(nn.Module):
         eps = 1e-8 if self.stft.trainable else 0.0
         return _C.stft_filterbank_forward(
             x, wcos, wsin, packed, self.n_fft, self.stride, self.center,
-            pad_mode_id(self.pad_mode), eps, float(self.power), fb,
+            pad_mode_id(self.pad_mode), eps, float(self.power), fb, self._fb_table.get(fb),
         )
 
     def extra_repr(self) -> str:

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import as_matrix, forward_only_guard, pad_mode_id
+from ._common import FilterbankTable, as_matrix, forward_only_guard, pad_mode_id
 from .stft import STFT
 
 
@@ -73,6 +73,7 @@ class MelSpectrogram(nn.Module):
             self.register_parameter("mel_basis", nn.Parameter(mel_basis, requires_grad=True))
         else:
             self.register_buffer("mel_basis", mel_basis)
+        self._fb_table = FilterbankTable()
 
     def _filterbank(self):
         return self.mel_basis
@@ -87,7 +88,7 @@ class MelSpectrogram(nn.Module):
         eps = 1e-8 if self.stft.trainable else 0.0
         return _C.stft_filterbank_forward(
             x, wcos, wsin, packed, self.n_fft, self.stride, self.center,
-            pad_mode_id(self.pad_mode), eps, float(self.power), fb,
+            pad_mode_id(self.pad_mode), eps, float(self.power), fb, self._fb_table.get(fb),
         )
 
     def extra_repr(self) -> str:
@@ -140,7 +141,7 @@ class MFCC(nn.Module):
         return _C.mfcc_forward(
             x, wcos, wsin, packed, mel.n_fft, mel.stride, mel.center, pad_mode_id(mel.pad_mode),
             eps, float(mel.power), fb, self._amin_host, self._ref_host, self.top_db,
-            self._dct_rows,
+            self._dct_rows, mel._fb_table.get(fb),
         )
 
     def extra_repr(self) -> str:
