@@ -1,0 +1,86 @@
+"""Batch-sharded multi-GPU execution.
+
+Clips are independent, so the transform itself needs no collective: rank ``r``
+(one process per GPU, ``torch.distributed``/NCCL) owns a contiguous slice of the
+batch.  The only exchange is the optional gather of the output spectrograms,
+one ``all_gather_into_tensor`` over NVLink/NVSwitch (the batch is the outermost
+output dimension, so shards are contiguous blocks of the gathered tensor).
+
+The reference's counterpart is ``torch.nn.DataParallel`` (single process,
+scatter → replicate the module every forward → gather; tests/test_stft.py:122-141).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous balanced partition of ``total`` clips over ``world`` ranks
+    (the first ``total % world`` ranks hold one extra clip)."""
+    base, extra = divmod(total, world)
+    bounds, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        bounds.append((start, start + n))
+        start += n
+    return bounds
+
+
+class BatchShardedTransform:
+    """Wrap a spectrogram module (or any ``x -> y`` callable whose leading
+    dimension is the clip axis) for one-process-per-GPU execution.
+
+    ``forward(x_local)`` transforms this rank's shard and, when ``gather`` is
+    true, returns the spectrograms of the WHOLE batch on every rank.
+    """
+
+    def __init__(self, transform: Callable[[torch.Tensor], torch.Tensor],
+                 group: Optional[dist.ProcessGroup] = None, gather: bool = True):
+        self.transform = transform
+        self.group = group
+        self.gather = gather
+        self._buf = None
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    @property
+    def rank(self) -> int:
+        return dist.get_rank(self.group) if dist.is_initialized() else 0
+
+    def local_slice(self, x_global: torch.Tensor) -> torch.Tensor:
+        """This rank's shard of a batch that every rank holds (or can index)."""
+        lo, hi = shard_bounds(x_global.shape[0], self.world)[self.rank]
+        return x_global[lo:hi]
+
+    def __call__(self, x_local: torch.Tensor, total: Optional[int] = None) -> torch.Tensor:
+        return self.forward(x_local, total)
+
+    def forward(self, x_local: torch.Tensor, total: Optional[int] = None) -> torch.Tensor:
+        y = self.transform(x_local)
+        world = self.world
+        if not self.gather or world == 1:
+            return y
+        n_local = y.shape[0]
+        if total is None:
+            total = n_local * world  # equal shards
+        bounds = shard_bounds(total, world)
+        n_max = max(hi - lo for lo, hi in bounds)
+        if (n_local, ) != (bounds[self.rank][1] - bounds[self.rank][0], ):
+            raise ValueError(f"rank {self.rank}: local batch {n_local} does not match its shard {bounds[self.rank]}")
+        y = y.contiguous()
+        if n_local < n_max:  # ragged tail: pad to the common shard size for the collective
+            pad = torch.zeros((n_max - n_local,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
+            y = torch.cat((y, pad), 0)
+        shape = (world * n_max,) + tuple(y.shape[1:])
+        if self._buf is None or self._buf.shape != shape or self._buf.device != y.device:
+            self._buf = torch.empty(shape, dtype=y.dtype, device=y.device)
+        dist.all_gather_into_tensor(self._buf, y, group=self.group)
+        if n_max * world == total:
+            return self._buf
+        parts = [self._buf[r * n_max: r * n_max + (hi - lo)] for r, (lo, hi) in enumerate(bounds)]
+        return torch.cat(parts, 0)
