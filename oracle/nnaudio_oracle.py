@@ -72,10 +72,12 @@ def pad_signal(x: np.ndarray, pad: int, mode: str) -> np.ndarray:
     raise ValueError("unknown pad_mode %r" % (mode,))
 
 
-def framed_contraction(xp: np.ndarray, basis: np.ndarray, hop: int, chunk: int = 2048):
+def framed_contraction(xp: np.ndarray, basis: np.ndarray, hop: int, max_rows: int = 8192):
     """``conv1d(xp[:,None,:], basis[:,None,:], stride=hop)`` as frames x basis^T.
 
-    xp (B, Lp), basis (N, K)  ->  (B, N, T) with T = (Lp-K)//hop + 1.
+    xp (B, Lp), basis (N, K)  ->  (B, N, T) with T = (Lp-K)//hop + 1.  Frames of
+    several clips are stacked into one GEMM of up to ``max_rows`` rows (what an
+    im2col-style conv1d does), so BLAS can use every host core.
     """
     B, Lp = xp.shape
     N, K = basis.shape
@@ -85,13 +87,23 @@ def framed_contraction(xp: np.ndarray, basis: np.ndarray, hop: int, chunk: int =
     out = np.empty((B, N, T), dtype=xp.dtype)
     bt = np.ascontiguousarray(basis.T)
     st = xp.strides[-1]
-    for b in range(B):
-        frames = np.lib.stride_tricks.as_strided(
-            xp[b], shape=(T, K), strides=(hop * st, st), writeable=False
-        )
-        for t0 in range(0, T, chunk):
-            t1 = min(T, t0 + chunk)
-            out[b, :, t0:t1] = (np.ascontiguousarray(frames[t0:t1]) @ bt).T
+    if T > max_rows:  # long clips: chunk along time
+        for b in range(B):
+            frames = np.lib.stride_tricks.as_strided(
+                xp[b], shape=(T, K), strides=(hop * st, st), writeable=False)
+            for t0 in range(0, T, max_rows):
+                t1 = min(T, t0 + max_rows)
+                out[b, :, t0:t1] = (np.ascontiguousarray(frames[t0:t1]) @ bt).T
+        return out
+    nb = max(1, max_rows // T)
+    block = np.empty((nb * T, K), dtype=xp.dtype)
+    for b0 in range(0, B, nb):
+        b1 = min(B, b0 + nb)
+        for i, b in enumerate(range(b0, b1)):
+            block[i * T:(i + 1) * T] = np.lib.stride_tricks.as_strided(
+                xp[b], shape=(T, K), strides=(hop * st, st), writeable=False)
+        res = block[: (b1 - b0) * T] @ bt
+        out[b0:b1] = res.reshape(b1 - b0, T, N).transpose(0, 2, 1)
     return out
 
 
@@ -124,8 +136,8 @@ def stft(
         if pad_mode == "reflect" and x.shape[-1] < n_fft // 2:
             raise AssertionError("Signal length shorter than reflect padding length (n_fft // 2).")
         x = pad_signal(x, n_fft // 2, pad_mode)
-    imag = framed_contraction(x, ws, hop)
-    real = framed_contraction(x, wc, hop)
+    both = framed_contraction(x, np.concatenate((wc, ws), 0), hop)  # one pass over the frames
+    real, imag = both[:, : wc.shape[0]], both[:, wc.shape[0]:]
     if freq_bins is not None:
         real, imag = real[:, :freq_bins], imag[:, :freq_bins]
     if output_format == "Magnitude":
@@ -223,8 +235,8 @@ def cqt1992v2(x, kernels_real, kernels_imag, lenghts, hop, center=True, pad_mode
     ki = np.asarray(kernels_imag)[:, 0, :].astype(dtype)
     if center:
         x = pad_signal(x, kr.shape[-1] // 2, pad_mode)
-    real = framed_contraction(x, kr, hop, chunk=256)
-    imag = -framed_contraction(x, ki, hop, chunk=256)
+    both = framed_contraction(x, np.concatenate((kr, ki), 0), hop, max_rows=512)
+    real, imag = both[:, : kr.shape[0]], -both[:, kr.shape[0]:]
     real, imag = _cqt_normalise(real, imag, lenghts, normalization_type, dtype)
     return _cqt_format(real, imag, output_format, trainable, dtype)
 
@@ -249,9 +261,8 @@ def cqt_octave_complex(x, kr, ki, hop, pad, pad_mode):
             UserWarning,
         )
         xp = np.pad(x, ((0, 0), (kr.shape[-1] // 2,) * 2), mode="constant")
-    real = framed_contraction(xp, kr, hop)
-    imag = -framed_contraction(xp, ki, hop)
-    return real, imag
+    both = framed_contraction(xp, np.concatenate((kr, ki), 0), hop)
+    return both[:, : kr.shape[0]], -both[:, kr.shape[0]:]
 
 
 def _pyramid(x, banks, hop, n_bins, lowpass, pads, pad_mode, early_fir, early_factor, dtype):
