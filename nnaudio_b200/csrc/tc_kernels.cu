@@ -275,6 +275,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -311,6 +319,101 @@ struct TcParams {
   int kb_end[TC_MAX_N_TILES];
   EpiParams epi;
 };
+
+// Read one 128-frame x bn accumulator tile out of TMEM (this warp's 32 lanes =
+// 32 consecutive frames) and emit it in the requested output format.
+template <int FMT>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, int64_t g,
+                                              int n_tile, int half) {
+      const int64_t b = g / p.t_slots;
+      const int64_t t = g - b * p.t_slots;
+      const bool valid = (g < p.nv) && (t < p.T);
+      const int f_base = n_tile * half;
+      if constexpr (FMT == 5) {
+        // ---- fused banded filterbank: two running filter sums per frame ----
+        float* mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
+        int cj0 = -1, cj1 = -1;
+        float a0 = 0.f, a1 = 0.f;
+        // rolled loop over 8-column TMEM loads: the body must stay I-cache resident
+        // (a 32x unrolled version was ~80 KB of code per tile and fetch-stalled)
+#pragma unroll 1
+        for (int c0 = 0; c0 < half; c0 += 8) {
+          uint32_t re[8], im[8];
+          tmem_ld8(trow + (uint32_t)c0, re);
+          tmem_ld8(trow + (uint32_t)(half + c0), im);
+          tmem_ld_wait();
+          const int jmax = min(8, min(half - c0, p.epi.F - f_base - c0));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < jmax) {  // warp-uniform
+              const int4 raw = __ldg(reinterpret_cast<const int4*>(p.epi.fb_table) + f_base + c0 + j);
+              const float pw = epi_power(p.epi, __uint_as_float(re[j]), __uint_as_float(im[j]));
+              if (raw.x != cj0) {
+                if (raw.x == cj1) {
+                  const int tj = cj0; cj0 = cj1; cj1 = tj;
+                  const float ta = a0; a0 = a1; a1 = ta;
+                } else {
+                  if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * p.epi.T, a0);
+                  cj0 = raw.x; a0 = 0.f;
+                }
+              }
+              if (raw.y != cj1) {
+                if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * p.epi.T, a1);
+                cj1 = raw.y; a1 = 0.f;
+              }
+              a0 = fmaf(__int_as_float(raw.z), pw, a0);
+              a1 = fmaf(__int_as_float(raw.w), pw, a1);
+            }
+          }
+        }
+        if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * p.epi.T, a0);
+        if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * p.epi.T, a1);
+      } else {
+      constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
+      float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+      if constexpr (FMT == NNAB_FMT_MAGNITUDE || FMT == NNAB_FMT_COMPLEX) {
+        // light per-bin code: 32 columns per TMEM load, fully unrolled
+        for (int c0 = 0; c0 < half; c0 += 32) {
+          uint32_t re[32], im[32];
+          tmem_ld32(trow + (uint32_t)c0, re);
+          tmem_ld32(trow + (uint32_t)(half + c0), im);
+          tmem_ld_wait();
+          if (valid) {
+            const int jmax = min(32, min(half - c0, p.epi.F - f_base - c0));
+            if (jmax == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                epi_store_fmt<FMT>(p.epi, dst, f_base + c0 + j, __uint_as_float(re[j]),
+                                   __uint_as_float(im[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < jmax)
+                  epi_store_fmt<FMT>(p.epi, dst, f_base + c0 + j, __uint_as_float(re[j]),
+                                     __uint_as_float(im[j]));
+            }
+          }
+        }
+      } else {
+        // atan2f / sincosf / powf bodies: rolled loop over 8 columns keeps the code I-cache sized
+#pragma unroll 1
+        for (int c0 = 0; c0 < half; c0 += 8) {
+          uint32_t re[8], im[8];
+          tmem_ld8(trow + (uint32_t)c0, re);
+          tmem_ld8(trow + (uint32_t)(half + c0), im);
+          tmem_ld_wait();
+          if (valid) {
+            const int jmax = min(8, min(half - c0, p.epi.F - f_base - c0));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < jmax)
+                epi_store_fmt<FMT>(p.epi, dst, f_base + c0 + j, __uint_as_float(re[j]),
+                                   __uint_as_float(im[j]));
+          }
+        }
+      }
+      }
+}
 
 template <int BK, int STAGES>
 struct TcSmem {
@@ -446,73 +549,9 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const int64_t g = (int64_t)m_tile * TC_BM + quarter * 32 + lane;
-      const int64_t b = g / p.t_slots;
-      const int64_t t = g - b * p.t_slots;
-      const bool valid = (g < p.nv) && (t < p.T);
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
-      const int f_base = n_tile * half;
-      if constexpr (FMT == 5) {
-        // ---- fused banded filterbank: two running filter sums per frame ----
-        float* mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
-        int cj0 = -1, cj1 = -1;
-        float a0 = 0.f, a1 = 0.f;
-        for (int c0 = 0; c0 < half; c0 += 32) {
-          uint32_t re[32], im[32];
-          tmem_ld32(trow + (uint32_t)c0, re);
-          tmem_ld32(trow + (uint32_t)(half + c0), im);
-          tmem_ld_wait();
-          const int jmax = min(32, min(half - c0, p.epi.F - f_base - c0));
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < jmax) {  // warp-uniform
-              const int4 raw = __ldg(reinterpret_cast<const int4*>(p.epi.fb_table) + f_base + c0 + j);
-              const float pw = epi_power(p.epi, __uint_as_float(re[j]), __uint_as_float(im[j]));
-              if (raw.x != cj0) {
-                if (raw.x == cj1) {
-                  const int tj = cj0; cj0 = cj1; cj1 = tj;
-                  const float ta = a0; a0 = a1; a1 = ta;
-                } else {
-                  if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * p.epi.T, a0);
-                  cj0 = raw.x; a0 = 0.f;
-                }
-              }
-              if (raw.y != cj1) {
-                if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * p.epi.T, a1);
-                cj1 = raw.y; a1 = 0.f;
-              }
-              a0 = fmaf(__int_as_float(raw.z), pw, a0);
-              a1 = fmaf(__int_as_float(raw.w), pw, a1);
-            }
-          }
-        }
-        if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * p.epi.T, a0);
-        if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * p.epi.T, a1);
-      } else {
-      constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
-      float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
-      for (int c0 = 0; c0 < half; c0 += 32) {
-        uint32_t re[32], im[32];
-        tmem_ld32(trow + (uint32_t)c0, re);
-        tmem_ld32(trow + (uint32_t)(half + c0), im);
-        tmem_ld_wait();
-        if (valid) {
-          const int jmax = min(32, min(half - c0, p.epi.F - f_base - c0));
-          if (jmax == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              epi_store_fmt<FMT>(p.epi, dst, f_base + c0 + j, __uint_as_float(re[j]),
-                                 __uint_as_float(im[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < jmax)
-                epi_store_fmt<FMT>(p.epi, dst, f_base + c0 + j, __uint_as_float(re[j]),
-                                   __uint_as_float(im[j]));
-          }
-        }
-      }
-      }
+      epilogue_tile<FMT>(p, trow, g, n_tile, half);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -525,6 +564,237 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes a
+// 256-frame x bn tile.  Each CTA stages its own 128 A rows and HALF of the B
+// tile (CTA 0: the re rows, CTA 1: the negated im rows), the leader issues
+// M=256 MMAs that read B from both SMs, and every CTA keeps its 128 x bn
+// accumulators in its own TMEM.  Per SM this halves the B operand reads and TMA
+// fills — the shared-memory bandwidth that bounds the 1-CTA kernel at ~76 %.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (optionally with expect_tx) on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t bar, uint32_t cta, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+      ::"r"(bar), "r"(cta), "r"(bytes)
+      : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int BK, int STAGES>
+struct Tc2Smem {
+  static constexpr uint32_t A_BYTES = TC_BM * BK * 2;
+  static constexpr uint32_t B_BYTES = 128 * BK * 2;  // half of a bn <= 256 tile
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BK, int STAGES, int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const TcParams p) {
+  using S = Tc2Smem<BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };            // used in the leader
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };  // per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };       // per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };  // leader
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);   // one arrive.expect_tx per CTA's producer
+      mbar_init(empty_bar(s), 1);  // multicast commit from the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA credit
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-frame pairs here
+  const int halfn = p.bn >> 1;
+  const uint32_t b_half_bytes = (uint32_t)halfn * BK * 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        const int n0 = n_tile * p.bn + (int)cta * halfn;
+        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+          mbar_expect_tx_remote(full_bar(stage), 0, 2 * S::A_BYTES + 2 * b_half_bytes);
+          const int k0 = kb * BK;
+          int c0 = k0, c1 = m0;
+          if (p.rows_mode) {
+            c1 = m0 + k0 / p.hop;
+            c0 = k0 - (k0 / p.hop) * p.hop;
+          }
+          tma_load_3d_2sm(sb, &tm_a, full_bar(stage), c0, c1, 0);
+          tma_load_3d_2sm(sb + S::A_BYTES, &tm_a, full_bar(stage), c0, c1, 1);
+          tma_load_3d_2sm(sb + 2 * S::A_BYTES, &tm_b, full_bar(stage), k0, n0, 0);
+          tma_load_3d_2sm(sb + 2 * S::A_BYTES + S::B_BYTES, &tm_b, full_bar(stage), k0, n0, 1);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
+                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n_tile = tile % p.num_n_tiles;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
+        uint32_t accumulate = 0;
+        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t koff = (uint32_t)k * 32u;
+            const uint64_t a_hi = make_smem_desc<BK>(sb + koff);
+            const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
+            const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
+            const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+            umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+            umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+            accumulate = 1u;
+          }
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)acc * TC_ACC_STRIDE;
+      epilogue_tile<FMT>(p, trow, g, n_tile, halfn);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still touch it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -592,6 +862,47 @@ static int launch_tc_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, co
   return NNAB_OK;
 }
 
+template <int BK, int STAGES, int FMT>
+static int launch_tc2_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                                 int n_pairs, cudaStream_t stream) {
+  using S = Tc2Smem<BK, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2_kernel<BK, STAGES, FMT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2_kernel<BK, STAGES, FMT>, ma, mb, prm));
+  count_launch();
+  return NNAB_OK;
+}
+
+template <int BK, int STAGES>
+static int launch_tc2_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                             int n_pairs, cudaStream_t stream) {
+  switch (prm.epi.fmt) {
+    case NNAB_FMT_MAGNITUDE: return launch_tc2_kernel_fmt<BK, STAGES, 0>(ma, mb, prm, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc2_kernel_fmt<BK, STAGES, 1>(ma, mb, prm, n_pairs, stream);
+    case NNAB_FMT_PHASE_ANGLE: return launch_tc2_kernel_fmt<BK, STAGES, 2>(ma, mb, prm, n_pairs, stream);
+    case NNAB_FMT_PHASE_UNIT: return launch_tc2_kernel_fmt<BK, STAGES, 3>(ma, mb, prm, n_pairs, stream);
+    case FMT_POWER: return launch_tc2_kernel_fmt<BK, STAGES, 4>(ma, mb, prm, n_pairs, stream);
+    case FMT_FBANK: return launch_tc2_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, n_pairs, stream);
+    default: return NNAB_EINVAL;
+  }
+}
+
 template <int BK, int STAGES>
 static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                             int grid, cudaStream_t stream) {
@@ -639,6 +950,14 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   }
 
   // ---- 2. tensor maps ---------------------------------------------------------------
+  // CTA pairs (cta_group::2) by default when there are enough 256-frame tiles to fill the
+  // 74 SM pairs; NNAB_TC_CTA=1|2 overrides (debugging / A-B measurements).
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int cta_group = (ceil_div64(g.nv, 2 * TC_BM) * n_tiles >= sms / 2) ? 2 : 1;
+  if (const char* e = getenv("NNAB_TC_CTA")) cta_group = atoi(e) == 2 ? 2 : 1;
+  if (cta_group == 2) bk = 64;
   CUtensorMap ma, mb;
   const int rows_mode = (q.hop % bk == 0) ? 1 : 0;
   int rc;
@@ -652,7 +971,8 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   }
   if (rc) return rc;
   rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
-                 (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, bk, bn, bk);
+                 (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, bk,
+                 cta_group == 2 ? bn / 2 : bn, bk);
   if (rc) return rc;
 
   // ---- 3. parameters ---------------------------------------------------------------
@@ -695,9 +1015,12 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
   if (q.fmt == FMT_FBANK && (q.fb_table == nullptr || q.n_fb <= 0)) return NNAB_EINVAL;
 
-  int dev = 0, sms = 148;
-  NNAB_CUDA_TRY(cudaGetDevice(&dev));
-  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (cta_group == 2) {
+    prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);  // 256-frame pair tiles
+    const int64_t ptiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
+    const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+    return launch_tc2_kernel<64, 3>(ma, mb, prm, n_pairs, stream);
+  }
   const int64_t tiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
   if (bk == 64) return launch_tc_kernel<64, 2>(ma, mb, prm, grid, stream);

@@ -43,6 +43,7 @@ class BatchShardedTransform:
         self.group = group
         self.gather = gather
         self._buf = None
+        self._slots = {}
 
     @property
     def world(self) -> int:
@@ -84,3 +85,22 @@ class BatchShardedTransform:
             return self._buf
         parts = [self._buf[r * n_max: r * n_max + (hi - lo)] for r, (lo, hi) in enumerate(bounds)]
         return torch.cat(parts, 0)
+
+    # ------------------------------------------------------------------ #
+    def forward_async(self, x_local: torch.Tensor, slot: int = 0):
+        """Pipelined variant for back-to-back batches with equal shards: transform
+        the shard, enqueue the output all-gather on NCCL's stream and return
+        ``(work, gathered)`` immediately.  ``work.wait()`` makes the CURRENT stream
+        wait for the gather; until then the next batch's transform overlaps it.
+        ``slot`` selects one of the caller's rotating gather buffers."""
+        y = self.transform(x_local).contiguous()
+        world = self.world
+        if not self.gather or world == 1:
+            return None, y
+        shape = (world * y.shape[0],) + tuple(y.shape[1:])
+        buf = self._slots.get(slot)
+        if buf is None or buf.shape != shape or buf.device != y.device:
+            buf = torch.empty(shape, dtype=y.dtype, device=y.device)
+            self._slots[slot] = buf
+        work = dist.all_gather_into_tensor(buf, y, group=self.group, async_op=True)
+        return work, buf
