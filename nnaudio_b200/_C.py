@@ -64,10 +64,11 @@ SIGNATURES = {
         [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
          _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
     ),
-    "nnab_cqt_pyramid_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "nnab_cqt_pyramid_workspace_bytes": (
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int]),
     "nnab_cqt_pyramid_forward": (
         c_int,
-        [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int,
+        [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int,
          c_int, _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
     ),
 }
@@ -300,27 +301,30 @@ def cqt1992v2_forward(x, k_real, k_imag, packed, k_begin, k_end, hop, center, pa
     return out
 
 
-def cqt_pyramid_forward(x, banks_real, banks_imag, lowpass, early_filter, early_factor, hop,
-                        pad_mode, n_bins, scale, scale_all, out_format, sqrt_eps, T, path=None):
-    """banks_*: lists (octave 0 = top) of (n_filters, width_i) fp32 CUDA tensors."""
+def cqt_pyramid_forward(x, banks_real, banks_imag, packed, lowpass, early_filter, early_factor,
+                        hop, pad_mode, n_bins, scale, scale_all, out_format, sqrt_eps, T,
+                        path=None):
+    """banks_*: lists (octave 0 = top) of (n_filters, width_i) fp32 CUDA tensors;
+    packed: list of packed-basis tensors (or None entries) per octave."""
     L = lib()
     x, B, Ln, pitch = _rows(x)
     n_oct = len(banks_real)
     n_filters = banks_real[0].shape[0]
     re_arr = (c_void_p * n_oct)(*[t.data_ptr() for t in banks_real])
     im_arr = (c_void_p * n_oct)(*[t.data_ptr() for t in banks_imag])
+    pk_arr = (c_void_p * n_oct)(*[(t.data_ptr() if t is not None else None) for t in packed])
     widths = (c_int32 * n_oct)(*[int(t.shape[1]) for t in banks_real])
+    max_width = max(int(t.shape[1]) for t in banks_real)
     shape = (B, n_bins, T) if out_format == FMT_MAGNITUDE else (B, n_bins, T, 2)
     out = torch.empty(shape, dtype=torch.float32, device=x.device)
     path = resolve_path(path)
-    if path == PATH_TCGEN05:
-        path = PATH_AUTO
     with torch.cuda.device(x.device):
-        ws, wsb = _workspace(L.nnab_cqt_pyramid_workspace_bytes(B, Ln, n_oct, early_factor),
-                             x.device)
+        ws, wsb = _workspace(
+            L.nnab_cqt_pyramid_workspace_bytes(B, Ln, n_oct, early_factor, max_width, hop, path),
+            x.device)
         rc = L.nnab_cqt_pyramid_forward(
-            _ptr(x), B, Ln, pitch, n_oct, re_arr, im_arr, widths, n_filters, _ptr(lowpass),
-            _ptr(early_filter), early_factor, hop, pad_mode, n_bins, _ptr(scale), scale_all,
-            out_format, sqrt_eps, _ptr(out), T, _ptr(ws), wsb, path, _stream(x.device))
+            _ptr(x), B, Ln, pitch, n_oct, re_arr, im_arr, pk_arr, widths, n_filters,
+            _ptr(lowpass), _ptr(early_filter), early_factor, hop, pad_mode, n_bins, _ptr(scale),
+            scale_all, out_format, sqrt_eps, _ptr(out), T, _ptr(ws), wsb, path, _stream(x.device))
     _check(rc, "nnab_cqt_pyramid_forward")
     return out

@@ -362,9 +362,8 @@ static inline int64_t decimated_len(int64_t len, int factor) {
   return len < 2 ? 0 : (len - 2) / factor + 1;
 }
 
-size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor) {
+static size_t pyramid_level_bytes(int64_t B, int64_t L, int early_factor) {
   // [early (B, L0)] + ping/pong level buffers (B, <= L0/2 + 1)
-  (void)n_octaves;
   const int64_t L0 = early_factor > 1 ? decimated_len(L, early_factor) : L;
   size_t n = 0;
   if (early_factor > 1) n += align_up((size_t)B * align_up((size_t)L0, 4) * sizeof(float), 256);
@@ -373,9 +372,22 @@ size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int
   return n;
 }
 
+size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor,
+                                        int max_width, int hop, int path) {
+  (void)n_octaves;
+  size_t n = pyramid_level_bytes(B, L, early_factor);
+  if (path != NNAB_PATH_SIMT) {
+    // split-signal scratch of the largest level (level 0), reused by every octave
+    const int64_t L0 = early_factor > 1 ? decimated_len(L, early_factor) : L;
+    n += tc_workspace_bytes(B, L0, max_width, hop, max_width / 2);
+  }
+  return n;
+}
+
 int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch, int n_octaves,
                              const float* const* h_k_real, const float* const* h_k_imag,
-                             const int32_t* h_widths, int n_filters, const float* lowpass,
+                             const void* const* h_packed, const int32_t* h_widths, int n_filters,
+                             const float* lowpass,
                              const float* early_filter, int early_factor, int hop, int pad_mode,
                              int n_bins, const float* scale, float scale_all, int out_format,
                              float sqrt_eps, float* out, int64_t T, void* workspace,
@@ -389,13 +401,18 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
       out_format != NNAB_FMT_PHASE_UNIT)
     return NNAB_EINVAL;
   if (pad_mode != NNAB_PAD_REFLECT && pad_mode != NNAB_PAD_CONSTANT) return NNAB_EINVAL;
-  if (path == NNAB_PATH_TCGEN05) return NNAB_EALIGN;  // no tcgen05 pyramid yet
   int rc = check_arch();
   if (rc) return rc;
-  const size_t need = nnab_cqt_pyramid_workspace_bytes(B, L, n_octaves, early_factor);
+  int max_width = 0;
+  for (int i = 0; i < n_octaves; ++i) max_width = h_widths[i] > max_width ? h_widths[i] : max_width;
+  const size_t need =
+      nnab_cqt_pyramid_workspace_bytes(B, L, n_octaves, early_factor, max_width, hop, path);
   if (need > 0 && (workspace == nullptr || ws_bytes < need)) return NNAB_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
 
+  const size_t level_bytes = pyramid_level_bytes(B, L, early_factor);
+  char* tc_ws = (char*)workspace + level_bytes;
+  const size_t tc_ws_bytes = ws_bytes - level_bytes;
   char* wsp = (char*)workspace;
   const float* cur = x;
   int64_t cur_len = L, cur_pitch = x_pitch;
@@ -442,7 +459,14 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
     p.bin_offset = n_bins - n_filters * (i + 1);
     // per-bin scale is indexed by OUTPUT row: shift the pointer by the same offset
     p.scale = scale ? scale + p.bin_offset : nullptr;
-    if ((rc = run_framed(p, nullptr, nullptr, 0, NNAB_PATH_SIMT, s))) return rc;
+    const void* pk = (h_packed != nullptr) ? h_packed[i] : nullptr;
+    if (pk != nullptr && path != NNAB_PATH_SIMT && tc_supported(p) &&
+        tc_ws_bytes >= tc_workspace_bytes(B, cur_len, width, cur_hop, pad)) {
+      if ((rc = run_framed(p, pk, tc_ws, tc_ws_bytes, NNAB_PATH_TCGEN05, s))) return rc;
+    } else {
+      if (path == NNAB_PATH_TCGEN05) return NNAB_EALIGN;
+      if ((rc = run_framed(p, nullptr, nullptr, 0, NNAB_PATH_SIMT, s))) return rc;
+    }
   }
   return NNAB_OK;
 }

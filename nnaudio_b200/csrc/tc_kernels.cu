@@ -65,13 +65,21 @@ struct SplitGeom {
   int64_t plane_stride;  // elements per plane
 };
 
+// Frames t = p, p + np, p + 2 np, ... (phase p of np = 8 / gcd(hop, 8)) start at
+// multiples of hop * np, which is always a multiple of 8 samples = 16 bytes in
+// bf16: every hop is served by TMA, one pass per phase over a signal shifted by
+// p * hop samples.
+static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
+static int num_phases(int hop) { return 8 / gcd_i(hop, 8); }
+
 static SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad) {
+  const int hop_eff = hop * num_phases(hop);
   SplitGeom g;
-  g.t_slots = (L + 2 * (int64_t)pad + hop - 1) / hop;
+  g.t_slots = (L + 2 * (int64_t)pad + hop_eff - 1) / hop_eff;
   g.nv = B * g.t_slots;
   const int kpad = round_up_i(K, 64);
-  g.rows = g.nv + (kpad + hop - 1) / hop + 1;
-  g.plane_stride = (g.rows * hop + 63) / 64 * 64;
+  g.rows = g.nv + (kpad + hop_eff - 1) / hop_eff + 1;
+  g.plane_stride = (g.rows * hop_eff + 63) / 64 * 64;
   return g;
 }
 
@@ -81,8 +89,7 @@ size_t tc_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
 }
 
 bool tc_supported(const FramedProblem& p) {
-  if (p.hop <= 0 || (p.hop % 8) != 0) return false;  // TMA: 16-byte row stride in bf16
-  if (p.K < 16) return false;
+  if (p.hop <= 0 || p.K < 16) return false;
   if (p.L + 2 * (int64_t)p.pad < p.K) return false;
   const SplitGeom g = split_geom(p.B > 0 ? p.B : 1, p.L, p.K, p.hop, p.pad);
   if (g.rows >= (1ll << 31) || g.plane_stride >= (1ll << 38)) return false;
@@ -101,7 +108,7 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 
 // One thread = 8 consecutive samples of one clip's slot region (16-byte stores).
 __global__ void __launch_bounds__(256) pad_split_kernel(
-    const float* __restrict__ x, int64_t L, int64_t x_pitch, int pad, int pad_mode,
+    const float* __restrict__ x, int64_t L, int64_t x_pitch, int pad, int pad_mode, int shift,
     int64_t clip_pitch, int64_t plane_stride, __nv_bfloat16* __restrict__ planes) {
   const int64_t b = blockIdx.y;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(256) pad_split_kernel(
   __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int64_t i = i0 + e;
+    const int64_t i = i0 + e + shift;  // index into the centre-padded clip
     float v = 0.f;
     if (i < padded_len) {
       int64_t j = i - pad;
@@ -313,8 +320,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 struct TcParams {
   int num_m_tiles, num_n_tiles, bn;
   int rows_mode;   // 1: A viewed as (rows x hop) matrix (BK | hop); 0: overlapping-stride map
-  int hop;
-  int64_t nv, t_slots, T;
+  int hop;          // effective hop (hop * phases)
+  int t_mul, t_add;  // output frame index = t * t_mul + t_add (frame phases)
+  int64_t nv, t_slots, T;  // T = valid frames of this phase
   int kb_begin[TC_MAX_N_TILES];
   int kb_end[TC_MAX_N_TILES];
   EpiParams epi;
@@ -326,8 +334,9 @@ template <int FMT>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, int64_t g,
                                               int n_tile, int half) {
       const int64_t b = g / p.t_slots;
-      const int64_t t = g - b * p.t_slots;
-      const bool valid = (g < p.nv) && (t < p.T);
+      const int64_t tl = g - b * p.t_slots;
+      const bool valid = (g < p.nv) && (tl < p.T);
+      const int64_t t = tl * p.t_mul + p.t_add;  // frame index in the output
       const int f_base = n_tile * half;
       if constexpr (FMT == 5) {
         // ---- fused banded filterbank: two running filter sums per frame ----
@@ -928,6 +937,8 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   int bk = 64;
   if (const char* e = getenv("NNAB_TC_BK")) bk = atoi(e) == 32 ? 32 : 64;
 
+  const int n_ph = num_phases(q.hop);
+  const int hop_eff = q.hop * n_ph;
   const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
   const int kpad = round_up_i(q.K, 64);
   const int bn = choose_bn(q.F);
@@ -936,20 +947,14 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   __nv_bfloat16* planes =
       reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 
-  // ---- 1. padded + split signal -------------------------------------------------
-  const int64_t clip_pitch = g.t_slots * q.hop;
-  const int64_t tail = g.plane_stride - g.nv * q.hop;  // K overhang rows: must be finite zeros
+  // K overhang rows past the last clip must be finite zeros (the basis is zero-padded there)
+  const int64_t clip_pitch = g.t_slots * hop_eff;
+  const int64_t tail = g.plane_stride - g.nv * hop_eff;
   for (int pl = 0; pl < 2; ++pl)
-    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * q.hop, 0,
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hop_eff, 0,
                                   (size_t)tail * sizeof(__nv_bfloat16), stream));
-  {
-    dim3 grid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
-    pad_split_kernel<<<grid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode, clip_pitch,
-                                               g.plane_stride, planes);
-    NNAB_LAUNCH_CHECK();
-  }
 
-  // ---- 2. tensor maps ---------------------------------------------------------------
+  // ---- tensor maps (shared by all phases) -------------------------------------------
   // CTA pairs (cta_group::2) by default when there are enough 256-frame tiles to fill the
   // 74 SM pairs; NNAB_TC_CTA=1|2 overrides (debugging / A-B measurements).
   int dev = 0, sms = 148;
@@ -959,14 +964,14 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   if (const char* e = getenv("NNAB_TC_CTA")) cta_group = atoi(e) == 2 ? 2 : 1;
   if (cta_group == 2) bk = 64;
   CUtensorMap ma, mb;
-  const int rows_mode = (q.hop % bk == 0) ? 1 : 0;
+  const int rows_mode = (hop_eff % bk == 0) ? 1 : 0;
   int rc;
   if (rows_mode) {
-    rc = encode_3d(&ma, planes, (uint64_t)q.hop, (uint64_t)g.rows, 2, (uint64_t)q.hop * 2,
+    rc = encode_3d(&ma, planes, (uint64_t)hop_eff, (uint64_t)g.rows, 2, (uint64_t)hop_eff * 2,
                    (uint64_t)g.plane_stride * 2, bk, TC_BM, bk);
   } else {
-    // overlapping rows: row g starts at element g*hop and is kpad long
-    rc = encode_3d(&ma, planes, (uint64_t)kpad, (uint64_t)g.nv, 2, (uint64_t)q.hop * 2,
+    // overlapping rows: row g starts at element g*hop_eff and is kpad long
+    rc = encode_3d(&ma, planes, (uint64_t)kpad, (uint64_t)g.nv, 2, (uint64_t)hop_eff * 2,
                    (uint64_t)g.plane_stride * 2, bk, TC_BM, bk);
   }
   if (rc) return rc;
@@ -975,16 +980,15 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
                  cta_group == 2 ? bn / 2 : bn, bk);
   if (rc) return rc;
 
-  // ---- 3. parameters ---------------------------------------------------------------
+  // ---- parameters -------------------------------------------------------------------
   TcParams prm;
-  prm.num_m_tiles = (int)ceil_div64(g.nv, TC_BM);
   prm.num_n_tiles = n_tiles;
   prm.bn = bn;
   prm.rows_mode = rows_mode;
-  prm.hop = q.hop;
+  prm.hop = hop_eff;
   prm.nv = g.nv;
   prm.t_slots = g.t_slots;
-  prm.T = q.T;
+  prm.t_mul = n_ph;
   const int nkb = kpad / bk;
   const int half = bn / 2;
   for (int tl = 0; tl < n_tiles; ++tl) {
@@ -1015,16 +1019,32 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
   if (q.fmt == FMT_FBANK && (q.fb_table == nullptr || q.n_fb <= 0)) return NNAB_EINVAL;
 
-  if (cta_group == 2) {
-    prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);  // 256-frame pair tiles
-    const int64_t ptiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
-    const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
-    return launch_tc2_kernel<64, 3>(ma, mb, prm, n_pairs, stream);
+  // ---- one pad/split + GEMM pass per frame phase ----------------------------------------
+  for (int ph = 0; ph < n_ph; ++ph) {
+    if (ph >= q.T) break;
+    prm.t_add = ph;
+    prm.T = (q.T - ph + n_ph - 1) / n_ph;  // frames t = ph, ph + n_ph, ... < T
+    {
+      dim3 grid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
+      pad_split_kernel<<<grid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
+                                                 ph * q.hop, clip_pitch, g.plane_stride, planes);
+      NNAB_LAUNCH_CHECK();
+    }
+    if (cta_group == 2) {
+      prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);  // 256-frame pair tiles
+      const int64_t ptiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
+      const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+      rc = launch_tc2_kernel<64, 3>(ma, mb, prm, n_pairs, stream);
+    } else {
+      prm.num_m_tiles = (int)ceil_div64(g.nv, TC_BM);
+      const int64_t tiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
+      const int grid = (int)(tiles < sms ? tiles : sms);
+      rc = (bk == 64) ? launch_tc_kernel<64, 2>(ma, mb, prm, grid, stream)
+                      : launch_tc_kernel<32, 4>(ma, mb, prm, grid, stream);
+    }
+    if (rc) return rc;
   }
-  const int64_t tiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  if (bk == 64) return launch_tc_kernel<64, 2>(ma, mb, prm, grid, stream);
-  return launch_tc_kernel<32, 4>(ma, mb, prm, grid, stream);
+  return NNAB_OK;
 }
 
 }  // namespace nnab

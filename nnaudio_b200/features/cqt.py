@@ -300,10 +300,12 @@ class CQT2010v2(nn.Module):
         elif self.pad_mode == "reflect":
             self.padding = nn.ReflectionPad1d(self.n_fft // 2)
         self._scale = _ScaleCache()
+        self._packed = PackedBasis()
 
     def _banks(self):
         k_real, k_imag = as_matrix(self.cqt_kernels_real), as_matrix(self.cqt_kernels_imag)
-        return [k_real] * self.n_octaves, [k_imag] * self.n_octaves
+        packed = self._packed.get(k_real, k_imag)  # one bank shared by every octave
+        return [k_real] * self.n_octaves, [k_imag] * self.n_octaves, [packed] * self.n_octaves
 
     def forward(self, x, output_format=None, normalization_type="librosa"):
         output_format = output_format or self.output_format
@@ -316,7 +318,7 @@ class CQT2010v2(nn.Module):
 def _pyramid_forward(mod, x, output_format, normalization_type):
     """Shared by CQT2010v2 and VQT: plan the octave lengths on the host (for the
     reference's warnings / errors), then one C call."""
-    banks_real, banks_imag = mod._banks()
+    banks_real, banks_imag, packed = mod._banks()
     early = mod.early_downsample_filter if mod.earlydownsample else None
     factor = int(mod.downsample_factor) if mod.earlydownsample else 1
     L = x.shape[-1]
@@ -347,6 +349,6 @@ def _pyramid_forward(mod, x, output_format, normalization_type):
         if t is not None:
             _C._dev_f32(t, "filter")
     return _C.cqt_pyramid_forward(
-        x, banks_real, banks_imag, lowpass, early_flat, factor, mod.hop_length,
+        x, banks_real, banks_imag, packed, lowpass, early_flat, factor, mod.hop_length,
         pad_mode_id(mod.pad_mode), mod.n_bins, scale, scale_all, _FORMATS[output_format], eps, T,
     )

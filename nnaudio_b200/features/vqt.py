@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import design
-from ._common import as_matrix, broadcast_dim, forward_only_guard
+from ._common import PackedBasis, as_matrix, broadcast_dim, forward_only_guard
 from .cqt import _ScaleCache, _check_format_and_norm, _pyramid_forward
 
 
@@ -132,11 +132,13 @@ class VQT(nn.Module):
                 torch.tensor(basis.imag.astype(np.float32)).unsqueeze(1),
             )
         self._scale = _ScaleCache()
+        self._packed = [PackedBasis() for _ in range(self.n_octaves)]
 
     def _banks(self):
         re = [as_matrix(getattr(self, f"cqt_kernels_real_{i}")) for i in range(self.n_octaves)]
         im = [as_matrix(getattr(self, f"cqt_kernels_imag_{i}")) for i in range(self.n_octaves)]
-        return re, im
+        packed = [self._packed[i].get(re[i], im[i]) for i in range(self.n_octaves)]
+        return re, im, packed
 
     def forward(self, x, output_format=None, normalization_type="librosa"):
         output_format = output_format or self.output_format

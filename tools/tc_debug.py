@@ -40,6 +40,10 @@ def main():
         ("stft1024/160 (overlap map)", nb.STFT(n_fft=1024, hop_length=160, verbose=False), (2, 16000), dict(output_format="Magnitude")),
         ("mel cfg2 x4", nb.MelSpectrogram(sr=22050, n_fft=2048, hop_length=512, n_mels=128, verbose=False), (4, 220500), {}),
         ("cqt1992v2 84", nb.CQT1992v2(sr=44100, n_bins=84, fmin=32.7, verbose=False), (2, 100000), dict(output_format="Complex")),
+        ("stft512/100 (2 phases)", nb.STFT(n_fft=512, hop_length=100, verbose=False), (2, 16000), dict(output_format="Complex")),
+        ("stft256/37 (8 phases)", nb.STFT(n_fft=256, hop_length=37, verbose=False), (2, 9000), dict(output_format="Magnitude")),
+        ("cqt2010v2 pyramid", nb.CQT2010v2(sr=22050, n_bins=88, verbose=False), (3, 65536), dict(output_format="Complex")),
+        ("vqt pyramid", nb.VQT(sr=22050, gamma=3, verbose=False), (2, 65536), dict(output_format="Magnitude")),
     ]
     only = [a for a in sys.argv[1:] if not a.startswith('--')] or None
     for name, mod, shape, kw in cases:
