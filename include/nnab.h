@@ -182,16 +182,26 @@ int nnab_cqt1992v2_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch
  *   out (B, n_bins, T[, 2]);  T = floor(L_early / hop) + 1 for every octave,
  *     otherwise NNAB_EINVAL (the reference's torch.cat would fail)
  * ------------------------------------------------------------------------- */
+/* Packed (bf16 hi/lo, banded-Toeplitz) form of a 256-tap decimation FIR for the
+ * tensor-core pyramid: lowpass_filter with dec = 2, early_downsample_filter with
+ * dec = early_factor.  Init-time, cached by the caller. */
+size_t nnab_packed_fir_bytes(int taps, int dec);
+int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* stream);
+
 size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor,
                                         int max_width, int hop, int path);
 /*   h_packed: HOST array of n_octaves DEVICE pointers to the nnab_pack_basis() copy of
  *     each bank (octave i's real/imag pair), or NULL / NULL entries = CUDA-core kernel
- *     for that octave.  The anti-alias FIR stages run on CUDA cores in either case. */
+ *     for that octave.
+ *   lowpass_packed / early_packed: nnab_pack_fir() copies or NULL.  With all packed
+ *     inputs present the whole pyramid runs on the tensor cores: every anti-alias stage
+ *     is a framed contraction whose epilogue writes the next level's padded bf16 planes. */
 int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                              int n_octaves, const float* const* h_k_real,
                              const float* const* h_k_imag, const void* const* h_packed,
                              const int32_t* h_widths,
-                             int n_filters, const float* lowpass, const float* early_filter,
+                             int n_filters, const float* lowpass, const void* lowpass_packed,
+                             const float* early_filter, const void* early_packed,
                              int early_factor, int hop, int pad_mode, int n_bins,
                              const float* scale, float scale_all, int out_format,
                              float sqrt_eps, float* out, int64_t T,

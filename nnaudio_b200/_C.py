@@ -64,12 +64,14 @@ SIGNATURES = {
         [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
          _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
     ),
+    "nnab_packed_fir_bytes": (c_size_t, [c_int, c_int]),
+    "nnab_pack_fir": (c_int, [_P, c_int, c_int, _P, _P]),
     "nnab_cqt_pyramid_workspace_bytes": (
         c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int]),
     "nnab_cqt_pyramid_forward": (
         c_int,
-        [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int,
-         c_int, _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
+        [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int, c_int,
+         c_int, c_int, _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
     ),
 }
 
@@ -192,6 +194,17 @@ def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor):
     return packed
 
 
+def pack_fir(fir: torch.Tensor, dec: int):
+    """Banded-Toeplitz bf16 hi/lo packing of a decimation FIR (tensor-core pyramid)."""
+    L = lib()
+    taps = fir.numel()
+    packed = torch.empty(L.nnab_packed_fir_bytes(taps, dec), dtype=torch.uint8, device=fir.device)
+    with torch.cuda.device(fir.device):
+        _check(L.nnab_pack_fir(_ptr(fir), taps, dec, _ptr(packed), _stream(fir.device)),
+               "nnab_pack_fir")
+    return packed
+
+
 def build_filterbank_table(fb: torch.Tensor):
     """Banded (<= 2 non-zeros per FFT bin) table of an (n_fb, F) filterbank for the
     fused tcgen05 epilogue, or ``None`` when the bank is denser (e.g. gammatone).
@@ -301,9 +314,9 @@ def cqt1992v2_forward(x, k_real, k_imag, packed, k_begin, k_end, hop, center, pa
     return out
 
 
-def cqt_pyramid_forward(x, banks_real, banks_imag, packed, lowpass, early_filter, early_factor,
-                        hop, pad_mode, n_bins, scale, scale_all, out_format, sqrt_eps, T,
-                        path=None):
+def cqt_pyramid_forward(x, banks_real, banks_imag, packed, lowpass, lowpass_packed, early_filter,
+                        early_packed, early_factor, hop, pad_mode, n_bins, scale, scale_all,
+                        out_format, sqrt_eps, T, path=None):
     """banks_*: lists (octave 0 = top) of (n_filters, width_i) fp32 CUDA tensors;
     packed: list of packed-basis tensors (or None entries) per octave."""
     L = lib()
@@ -324,7 +337,8 @@ def cqt_pyramid_forward(x, banks_real, banks_imag, packed, lowpass, early_filter
             x.device)
         rc = L.nnab_cqt_pyramid_forward(
             _ptr(x), B, Ln, pitch, n_oct, re_arr, im_arr, pk_arr, widths, n_filters,
-            _ptr(lowpass), _ptr(early_filter), early_factor, hop, pad_mode, n_bins, _ptr(scale),
+            _ptr(lowpass), _ptr(lowpass_packed), _ptr(early_filter), _ptr(early_packed),
+            early_factor, hop, pad_mode, n_bins, _ptr(scale),
             scale_all, out_format, sqrt_eps, _ptr(out), T, _ptr(ws), wsb, path, _stream(x.device))
     _check(rc, "nnab_cqt_pyramid_forward")
     return out

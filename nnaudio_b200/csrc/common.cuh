@@ -41,6 +41,19 @@ void count_launch();
 // internal POWER format used by the filterbank ops).
 constexpr int FMT_POWER = 100;  // internal: (sqrt(re^2+im^2+eps)) ** power -> (B,F,T)
 constexpr int FMT_FBANK = 101;  // internal (tcgen05 only): power -> banded filterbank -> (B,n_fb,T)
+constexpr int FMT_DECIM = 102;  // internal (tcgen05 only): FIR decimator stage of the CQT pyramid
+
+// FMT_DECIM epilogue target: the NEXT pyramid level, written as bf16 hi/lo planes in
+// the layout the tensor-core kernels read (sample m of clip b at b*pitch + off + m).
+//   pc: input of the level's octave CQT — reflect (or zero) margins of `pc_off` samples
+//   pf: input of the level's own FIR stage — zero margins, samples at offset 128
+//   y32: optional fp32 copy (levels whose hop needs several frame phases)
+struct DecimParams {
+  void* pc; int64_t pc_plane, pc_pitch; int pc_off, pc_reflect;
+  void* pf; int64_t pf_plane, pf_pitch;
+  float* y32; int64_t y32_pitch;
+  int64_t len_out;  // valid samples per clip of the next level
+};
 
 // Banded filterbank table: the (at most two) non-zero weights of every FFT bin.
 struct FbEntry {
@@ -69,6 +82,8 @@ struct FramedProblem {
   const int32_t* h_k_end;
   const FbEntry* fb_table;   // FMT_FBANK: device table [F]; out is (B, n_fb, T), pre-zeroed
   int n_fb;
+  const void* presplit;      // tcgen05: already padded + split signal planes (skip pad_split)
+  DecimParams dec;           // FMT_DECIM
 };
 
 int launch_framed_simt(const FramedProblem& p, cudaStream_t stream);
@@ -82,6 +97,19 @@ size_t tc_packed_bytes(int F, int K);
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream);
 int tc_tile_n();
+// split-signal geometry / helpers for callers that manage the planes themselves (pyramid)
+void tc_split_geometry(int64_t B, int64_t L, int K, int hop, int pad, int64_t* t_slots,
+                       int64_t* plane_stride, int* hop_eff);
+int tc_pad_split(const float* x, int64_t B, int64_t L, int64_t x_pitch, int K, int hop, int pad,
+                 int pad_mode, void* planes, cudaStream_t stream);
+int tc_pad_split2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
+                  int K_a, int hop_a, int pad_a, int mode_a, void* planes_a,
+                  int K_b, int hop_b, int pad_b, int mode_b, void* planes_b, cudaStream_t stream);
+int tc_zero_margins(void* planes, int64_t B, int64_t L, int K, int hop, int pad, int64_t keep_lo,
+                    int64_t keep_hi, cudaStream_t stream);
+size_t tc_packed_fir_bytes(int taps, int dec);
+int tc_fir_k(int taps, int dec);
+int tc_pack_fir(const float* fir, int taps, int dec, void* packed, cudaStream_t stream);
 int launch_fb_table(const float* fb, int n_fb, int F, FbEntry* table, int* d_max_nnz,
                     cudaStream_t stream);
 

@@ -21,6 +21,7 @@ struct EpiParams {
   int F;
   const FbEntry* fb_table;  // FMT_FBANK
   int n_fb;
+  DecimParams dec;          // FMT_DECIM
 };
 
 __device__ __forceinline__ float epi_power(const EpiParams& e, float re, float im) {

@@ -2,6 +2,7 @@
 // and the reference file:line each call replaces.
 #include <atomic>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <utility>
 #include <vector>
@@ -372,26 +373,232 @@ static size_t pyramid_level_bytes(int64_t B, int64_t L, int early_factor) {
   return n;
 }
 
+// ---- plan of the all-tensor-core pyramid -----------------------------------------
+constexpr int FIR_TAPS = 256;
+constexpr int FIR_OFF = 128;  // sample m of a level sits at plane offset 128 + m in FIR inputs
+
+struct PyrLevel {
+  int64_t len;
+  int hop, width, pad, mode;
+  bool presplit;          // octave reads pre-split planes (single frame phase)
+  size_t pc, pf, y32;     // workspace offsets (SIZE_MAX = not needed)
+  int64_t pc_pitch, pc_plane, pf_pitch, pf_plane, y32_pitch;
+};
+
+static size_t planes_bytes(int64_t B, int64_t L, int K, int hop, int pad, int64_t* pitch,
+                           int64_t* plane) {
+  int64_t t_slots = 0, ps = 0;
+  int he = 0;
+  tc_split_geometry(B, L, K, hop, pad, &t_slots, &ps, &he);
+  if (pitch) *pitch = t_slots * he;
+  if (plane) *plane = ps;
+  return align_up((size_t)(2 * ps) * 2, 256);
+}
+
+// Fills lv[0..n_octaves) and returns the workspace size; `pf_early` receives the offset of
+// the raw-signal FIR input when early downsampling is active.
+static size_t plan_pyramid(int64_t B, int64_t L, int n_octaves, int early_factor, int hop,
+                           const int32_t* widths, int fixed_width, int pad_mode, PyrLevel* lv,
+                           size_t* pf_early) {
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += n; return o; };
+  int64_t len = L;
+  if (early_factor > 1) {
+    const size_t o = take(planes_bytes(B, L, tc_fir_k(FIR_TAPS, early_factor), 128 * early_factor,
+                                       FIR_OFF, nullptr, nullptr));
+    if (pf_early) *pf_early = o;
+    len = decimated_len(L, early_factor);
+  }
+  int cur_hop = hop;
+  for (int i = 0; i < n_octaves; ++i) {
+    if (i > 0) { len = decimated_len(len, 2); cur_hop /= 2; }
+    PyrLevel& l = lv[i];
+    l.len = len; l.hop = cur_hop;
+    l.width = widths ? widths[i] : fixed_width;
+    l.pad = l.width / 2;
+    l.mode = (pad_mode == NNAB_PAD_REFLECT && l.pad >= len) ? NNAB_PAD_CONSTANT : pad_mode;
+    l.presplit = cur_hop > 0 && (cur_hop % 8) == 0;
+    l.pc = l.pf = l.y32 = SIZE_MAX;
+    l.pc_pitch = l.pc_plane = l.pf_pitch = l.pf_plane = l.y32_pitch = 0;
+    if (len <= 0 || cur_hop <= 0) continue;
+    const bool from_x = (i == 0 && early_factor <= 1);  // level 0 is the caller's fp32 input
+    if (l.presplit)
+      l.pc = take(planes_bytes(B, len, l.width, cur_hop, l.pad, &l.pc_pitch, &l.pc_plane));
+    else if (!from_x) {
+      l.y32_pitch = (int64_t)align_up((size_t)len, 8);
+      l.y32 = take(align_up((size_t)B * l.y32_pitch * sizeof(float), 256));
+    }
+    if (i < n_octaves - 1)
+      l.pf = take(planes_bytes(B, len, tc_fir_k(FIR_TAPS, 2), 256, FIR_OFF, &l.pf_pitch,
+                               &l.pf_plane));
+  }
+  // scratch for octaves that run from fp32 (several frame phases): sized for the first such level
+  for (int i = 0; i < n_octaves; ++i)
+    if (!lv[i].presplit && lv[i].len > 0 && lv[i].hop > 0) {
+      off += tc_workspace_bytes(B, lv[i].len, lv[i].width, lv[i].hop, lv[i].pad);
+      break;
+    }
+  return off;
+}
+
+size_t nnab_packed_fir_bytes(int taps, int dec) { return tc_packed_fir_bytes(taps, dec); }
+int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* stream) {
+  if (fir == nullptr || packed == nullptr || taps <= 0 || dec < 1) return NNAB_EINVAL;
+  return tc_pack_fir(fir, taps, dec, packed, (cudaStream_t)stream);
+}
+
 size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor,
                                         int max_width, int hop, int path) {
-  (void)n_octaves;
   size_t n = pyramid_level_bytes(B, L, early_factor);
   if (path != NNAB_PATH_SIMT) {
-    // split-signal scratch of the largest level (level 0), reused by every octave
+    // (a) per-octave tensor-core path: split-signal scratch of the largest level
     const int64_t L0 = early_factor > 1 ? decimated_len(L, early_factor) : L;
     n += tc_workspace_bytes(B, L0, max_width, hop, max_width / 2);
+    // (b) all-tensor-core pyramid: every level's planes (upper bound with max_width)
+    if (n_octaves <= 32) {
+      PyrLevel lv[32];
+      const size_t full = plan_pyramid(B, L, n_octaves, early_factor, hop, nullptr, max_width,
+                                       NNAB_PAD_REFLECT, lv, nullptr) + 1024;
+      if (full > n) n = full;
+    }
   }
   return n;
+}
+
+// All-tensor-core pyramid; returns NNAB_EUNSUPPORTED when the plan cannot be used (the caller
+// then takes the per-octave path).
+static int pyramid_fused(const float* x, int64_t B, int64_t L, int64_t x_pitch, int n_octaves,
+                         const float* const* h_k_real, const float* const* h_k_imag,
+                         const void* const* h_packed, const int32_t* h_widths, int n_filters,
+                         const void* lowpass_packed, const void* early_packed, int early_factor,
+                         int hop, int pad_mode, int n_bins, const float* scale, float scale_all,
+                         int out_format, float sqrt_eps, float* out, int64_t T, void* workspace,
+                         size_t ws_bytes, cudaStream_t s) {
+  if (n_octaves > 32 || B > 65535) return NNAB_EUNSUPPORTED;
+  PyrLevel lv[32];
+  size_t pf_early = SIZE_MAX;
+  const size_t need = plan_pyramid(B, L, n_octaves, early_factor, hop, h_widths, 0, pad_mode, lv,
+                                   &pf_early);
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  if (need + 256 > ws_bytes) return NNAB_EUNSUPPORTED;
+  for (int i = 0; i < n_octaves; ++i) {
+    if (lv[i].len <= 0 || lv[i].hop <= 0) return NNAB_EINVAL;
+    if (frames_of(lv[i].len, lv[i].width, lv[i].hop, lv[i].pad) != T) return NNAB_EINVAL;
+  }
+  // scratch region for fp32-driven octaves lives after the planned buffers
+  size_t planned = 0;
+  {
+    PyrLevel tmp[32];
+    planned = plan_pyramid(B, L, n_octaves, early_factor, hop, h_widths, 0, pad_mode, tmp, nullptr);
+    for (int i = 0; i < n_octaves; ++i)
+      if (!tmp[i].presplit) {
+        planned -= tc_workspace_bytes(B, tmp[i].len, tmp[i].width, tmp[i].hop, tmp[i].pad);
+        break;
+      }
+  }
+  char* scratch = ws + planned;
+  const size_t scratch_bytes = ws_bytes - 256 - planned;
+  int rc;
+
+  // One FIR stage: planes `src` (level signal, zero margins) -> level `dst`
+  auto fir_stage = [&](const void* src, int64_t src_len, int dec, const void* fir_packed,
+                       PyrLevel& dst) -> int {
+    const int kf = tc_fir_k(FIR_TAPS, dec);
+    // parts of the destination buffers the epilogue never writes
+    if (dst.pc != SIZE_MAX) {
+      const bool refl = dst.mode == NNAB_PAD_REFLECT;
+      rc = tc_zero_margins(ws + dst.pc, B, dst.len, dst.width, dst.hop, dst.pad,
+                           refl ? 0 : dst.pad, refl ? dst.len + 2 * dst.pad : dst.pad + dst.len, s);
+      if (rc) return rc;
+    }
+    if (dst.pf != SIZE_MAX) {
+      rc = tc_zero_margins(ws + dst.pf, B, dst.len, tc_fir_k(FIR_TAPS, 2), 256, FIR_OFF, FIR_OFF,
+                           FIR_OFF + dst.len, s);
+      if (rc) return rc;
+    }
+    FramedProblem p{};
+    p.x = nullptr; p.B = B; p.L = src_len; p.x_pitch = 0;
+    p.w_re = nullptr; p.w_im = nullptr; p.F = 64; p.K = kf; p.hop = 128 * dec;
+    p.pad = FIR_OFF; p.pad_mode = NNAB_PAD_CONSTANT; p.scale = nullptr; p.scale_all = 1.f;
+    p.fmt = FMT_DECIM; p.eps = 0.f; p.power = 1.f; p.out = nullptr;
+    p.T = (dst.len + 127) / 128;
+    p.out_bins = 64; p.bin_offset = 0;
+    p.presplit = src;
+    p.dec.pc = dst.pc != SIZE_MAX ? ws + dst.pc : nullptr;
+    p.dec.pc_plane = dst.pc_plane; p.dec.pc_pitch = dst.pc_pitch; p.dec.pc_off = dst.pad;
+    p.dec.pc_reflect = dst.mode == NNAB_PAD_REFLECT ? 1 : 0;
+    p.dec.pf = dst.pf != SIZE_MAX ? ws + dst.pf : nullptr;
+    p.dec.pf_plane = dst.pf_plane; p.dec.pf_pitch = dst.pf_pitch;
+    p.dec.y32 = dst.y32 != SIZE_MAX ? (float*)(ws + dst.y32) : nullptr;
+    p.dec.y32_pitch = dst.y32_pitch;
+    p.dec.len_out = dst.len;
+    return run_framed(p, fir_packed, nullptr, 0, NNAB_PATH_TCGEN05, s);
+  };
+
+  // ---- level 0 ------------------------------------------------------------------------
+  const float* x0 = x;         // fp32 level-0 signal when available
+  int64_t x0_pitch = x_pitch;
+  if (early_factor > 1) {
+    rc = tc_pad_split(x, B, L, x_pitch, tc_fir_k(FIR_TAPS, early_factor), 128 * early_factor,
+                      FIR_OFF, NNAB_PAD_CONSTANT, ws + pf_early, s);
+    if (rc) return rc;
+    if ((rc = fir_stage(ws + pf_early, L, early_factor, early_packed, lv[0]))) return rc;
+    x0 = lv[0].y32 != SIZE_MAX ? (const float*)(ws + lv[0].y32) : nullptr;
+    x0_pitch = lv[0].y32_pitch;
+  } else {
+    if (lv[0].pc != SIZE_MAX && lv[0].pf != SIZE_MAX) {
+      // one pass over x: reflect-padded copy for the octave CQT + zero-margin copy for the FIR
+      rc = tc_pad_split2(x, B, L, x_pitch, lv[0].width, lv[0].hop, lv[0].pad, lv[0].mode,
+                         ws + lv[0].pc, tc_fir_k(FIR_TAPS, 2), 256, FIR_OFF, NNAB_PAD_CONSTANT,
+                         ws + lv[0].pf, s);
+      if (rc) return rc;
+    } else if (lv[0].pc != SIZE_MAX) {
+      rc = tc_pad_split(x, B, L, x_pitch, lv[0].width, lv[0].hop, lv[0].pad, lv[0].mode,
+                        ws + lv[0].pc, s);
+      if (rc) return rc;
+    } else if (lv[0].pf != SIZE_MAX) {
+      rc = tc_pad_split(x, B, L, x_pitch, tc_fir_k(FIR_TAPS, 2), 256, FIR_OFF, NNAB_PAD_CONSTANT,
+                        ws + lv[0].pf, s);
+      if (rc) return rc;
+    }
+  }
+
+  // ---- octaves --------------------------------------------------------------------------
+  for (int i = 0; i < n_octaves; ++i) {
+    PyrLevel& l = lv[i];
+    FramedProblem p{};
+    p.B = B; p.L = l.len;
+    p.w_re = h_k_real[i]; p.w_im = h_k_imag[i]; p.F = n_filters; p.K = l.width; p.hop = l.hop;
+    p.pad = l.pad; p.pad_mode = l.mode; p.scale_all = scale_all;
+    p.fmt = out_format; p.eps = sqrt_eps; p.power = 1.f; p.out = out; p.T = T;
+    p.out_bins = n_bins;
+    p.bin_offset = n_bins - n_filters * (i + 1);
+    p.scale = scale ? scale + p.bin_offset : nullptr;
+    if (l.presplit) {
+      p.x = nullptr; p.x_pitch = 0; p.presplit = ws + l.pc;
+      if ((rc = run_framed(p, h_packed[i], nullptr, 0, NNAB_PATH_TCGEN05, s))) return rc;
+    } else {
+      const float* src = (i == 0) ? x0 : (const float*)(ws + l.y32);
+      const int64_t pitch = (i == 0) ? x0_pitch : l.y32_pitch;
+      if (src == nullptr) return NNAB_EINVAL;
+      p.x = src; p.x_pitch = pitch; p.presplit = nullptr;
+      if ((rc = run_framed(p, h_packed[i], scratch, scratch_bytes, NNAB_PATH_TCGEN05, s))) return rc;
+    }
+    if (i < n_octaves - 1)
+      if ((rc = fir_stage(ws + l.pf, l.len, 2, lowpass_packed, lv[i + 1]))) return rc;
+  }
+  return NNAB_OK;
 }
 
 int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch, int n_octaves,
                              const float* const* h_k_real, const float* const* h_k_imag,
                              const void* const* h_packed, const int32_t* h_widths, int n_filters,
-                             const float* lowpass,
-                             const float* early_filter, int early_factor, int hop, int pad_mode,
-                             int n_bins, const float* scale, float scale_all, int out_format,
-                             float sqrt_eps, float* out, int64_t T, void* workspace,
-                             size_t ws_bytes, int path, void* stream) {
+                             const float* lowpass, const void* lowpass_packed,
+                             const float* early_filter, const void* early_packed,
+                             int early_factor, int hop, int pad_mode, int n_bins,
+                             const float* scale, float scale_all, int out_format, float sqrt_eps,
+                             float* out, int64_t T, void* workspace, size_t ws_bytes, int path,
+                             void* stream) {
   if (x == nullptr || out == nullptr || h_k_real == nullptr || h_k_imag == nullptr ||
       h_widths == nullptr || lowpass == nullptr || B < 0 || L <= 0 || x_pitch < L ||
       n_octaves <= 0 || n_filters <= 0 || hop <= 0 || n_bins <= 0 || early_factor < 1)
@@ -410,6 +617,18 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
   if (need > 0 && (workspace == nullptr || ws_bytes < need)) return NNAB_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
 
+  // ---- all-tensor-core pyramid when every packed operand is available -------------------
+  bool all_packed = (path != NNAB_PATH_SIMT) && h_packed != nullptr && lowpass_packed != nullptr &&
+                    (early_factor <= 1 || early_packed != nullptr);
+  for (int i = 0; all_packed && i < n_octaves; ++i) all_packed = h_packed[i] != nullptr;
+  if (all_packed && getenv("NNAB_PYRAMID_UNFUSED") == nullptr) {
+    rc = pyramid_fused(x, B, L, x_pitch, n_octaves, h_k_real, h_k_imag, h_packed, h_widths,
+                       n_filters, lowpass_packed, early_packed, early_factor, hop, pad_mode, n_bins,
+                       scale, scale_all, out_format, sqrt_eps, out, T, workspace, ws_bytes, s);
+    if (rc != NNAB_EUNSUPPORTED) return rc;
+  }
+
+  // ---- per-octave path: CUDA-core FIR stages, octaves on either kernel family -----------
   const size_t level_bytes = pyramid_level_bytes(B, L, early_factor);
   char* tc_ws = (char*)workspace + level_bytes;
   const size_t tc_ws_bytes = ws_bytes - level_bytes;

@@ -90,7 +90,8 @@ size_t tc_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
 
 bool tc_supported(const FramedProblem& p) {
   if (p.hop <= 0 || p.K < 16) return false;
-  if (p.L + 2 * (int64_t)p.pad < p.K) return false;
+  // (pre-split planes are laid out by the caller, which guarantees >= 1 valid frame)
+  if (p.presplit == nullptr && p.L + 2 * (int64_t)p.pad < p.K) return false;
   const SplitGeom g = split_geom(p.B > 0 ? p.B : 1, p.L, p.K, p.hop, p.pad);
   if (g.rows >= (1ll << 31) || g.plane_stride >= (1ll << 38)) return false;
   const int bn = choose_bn(p.F);
@@ -134,6 +135,44 @@ __global__ void __launch_bounds__(256) pad_split_kernel(
   *reinterpret_cast<uint4*>(planes + plane_stride + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// Two differently padded split copies of the same batch in one pass over x (level 0 of
+// the CQT pyramid: reflect-padded copy for the octave CQT + zero-margin copy for the FIR).
+__global__ void __launch_bounds__(256) pad_split2_kernel(
+    const float* __restrict__ x, int64_t L, int64_t x_pitch,
+    int pad_a, int mode_a, int64_t pitch_a, int64_t plane_a, __nv_bfloat16* __restrict__ pa,
+    int pad_b, int mode_b, int64_t pitch_b, int64_t plane_b, __nv_bfloat16* __restrict__ pb) {
+  const int64_t b = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const float* __restrict__ xb = x + b * x_pitch;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const int pad = which ? pad_b : pad_a;
+    const int mode = which ? mode_b : mode_a;
+    const int64_t pitch = which ? pitch_b : pitch_a;
+    const int64_t plane = which ? plane_b : plane_a;
+    __nv_bfloat16* __restrict__ dst = which ? pb : pa;
+    if (i0 >= pitch) continue;
+    const int64_t padded_len = L + 2 * (int64_t)pad;
+    __align__(16) __nv_bfloat16 hi[8];
+    __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int64_t i = i0 + e;
+      float v = 0.f;
+      if (i < padded_len) {
+        int64_t j = i - pad;
+        if (j < 0) j = (mode == NNAB_PAD_REFLECT) ? -j : -1;
+        else if (j >= L) j = (mode == NNAB_PAD_REFLECT) ? 2 * (L - 1) - j : -1;
+        if (j >= 0 && j < L) v = __ldg(xb + j);
+      }
+      split_bf16(v, hi[e], lo[e]);
+    }
+    const int64_t o = b * pitch + i0;
+    *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + plane + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 // packed[plane][tile*bn + part*bn/2 + j][k]; part 1 rows are NEGATED im rows.
 __global__ void __launch_bounds__(256) pack_basis_kernel(
     const float* __restrict__ w_re, const float* __restrict__ w_im, int F, int K, int bn,
@@ -171,6 +210,131 @@ int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* pack
   const int64_t threads = (int64_t)rows * (kpad / 8);
   pack_basis_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
       w_re, w_im, F, K, bn, rows, kpad, (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// Decimating FIR as a framed contraction: frame t of the zero-padded level signal
+// (sample m at plane offset 128 + m, hop 128*dec) against the banded Toeplitz rows
+//   H[j][k] = fir[k - 1 - dec*j]        j = 0..127 outputs per frame
+// gives y[128 t + j] = sum_m fir[m] x[dec*(128 t + j) + m - 127]
+// (utils.py:73-100: conv1d(stride=dec, padding=127)).  Rows 0..63 sit in the "re" half
+// of the single N tile and rows 64..127 in the "im" half (not negated).
+int tc_fir_k(int taps, int dec) { return round_up_i(dec * 127 + taps + 1, 64); }
+size_t tc_packed_fir_bytes(int taps, int dec) {
+  return (size_t)2 * 128 * tc_fir_k(taps, dec) * sizeof(__nv_bfloat16);
+}
+
+__global__ void __launch_bounds__(256) pack_fir_kernel(const float* __restrict__ fir, int taps,
+                                                       int dec, int kpad,
+                                                       __nv_bfloat16* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * kpad) return;
+  const int r = idx / kpad, k = idx % kpad;
+  const int m = k - 1 - dec * r;
+  const float v = (m >= 0 && m < taps) ? __ldg(fir + m) : 0.f;
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  packed[idx] = hi;
+  packed[(int64_t)128 * kpad + idx] = lo;
+}
+
+int tc_pack_fir(const float* fir, int taps, int dec, void* packed, cudaStream_t stream) {
+  const int kpad = tc_fir_k(taps, dec);
+  pack_fir_kernel<<<(128 * kpad + 255) / 256, 256, 0, stream>>>(fir, taps, dec, kpad,
+                                                               (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+void tc_split_geometry(int64_t B, int64_t L, int K, int hop, int pad, int64_t* t_slots,
+                       int64_t* plane_stride, int* hop_eff) {
+  const SplitGeom g = split_geom(B, L, K, hop, pad);
+  if (t_slots) *t_slots = g.t_slots;
+  if (plane_stride) *plane_stride = g.plane_stride;
+  if (hop_eff) *hop_eff = hop * num_phases(hop);
+}
+
+static int zero_tail(__nv_bfloat16* planes, const SplitGeom& g, int hop_eff, cudaStream_t stream) {
+  const int64_t tail = g.plane_stride - g.nv * hop_eff;
+  for (int pl = 0; pl < 2; ++pl)
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hop_eff, 0,
+                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
+  return NNAB_OK;
+}
+
+// phase-0 pad + split of an fp32 batch into caller-managed planes
+int tc_pad_split(const float* x, int64_t B, int64_t L, int64_t x_pitch, int K, int hop, int pad,
+                 int pad_mode, void* planes_v, cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  const SplitGeom g = split_geom(B, L, K, hop, pad);
+  const int hop_eff = hop * num_phases(hop);
+  __nv_bfloat16* planes = (__nv_bfloat16*)planes_v;
+  int rc = zero_tail(planes, g, hop_eff, stream);
+  if (rc) return rc;
+  const int64_t clip_pitch = g.t_slots * hop_eff;
+  dim3 grid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)B);
+  pad_split_kernel<<<grid, 256, 0, stream>>>(x, L, x_pitch, pad, pad_mode, 0, clip_pitch,
+                                             g.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+int tc_pad_split2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
+                  int K_a, int hop_a, int pad_a, int mode_a, void* planes_a,
+                  int K_b, int hop_b, int pad_b, int mode_b, void* planes_b, cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  const SplitGeom ga = split_geom(B, L, K_a, hop_a, pad_a);
+  const SplitGeom gb = split_geom(B, L, K_b, hop_b, pad_b);
+  const int he_a = hop_a * num_phases(hop_a), he_b = hop_b * num_phases(hop_b);
+  int rc = zero_tail((__nv_bfloat16*)planes_a, ga, he_a, stream);
+  if (rc) return rc;
+  if ((rc = zero_tail((__nv_bfloat16*)planes_b, gb, he_b, stream))) return rc;
+  const int64_t pitch_a = ga.t_slots * he_a, pitch_b = gb.t_slots * he_b;
+  const int64_t pmax = pitch_a > pitch_b ? pitch_a : pitch_b;
+  dim3 grid((unsigned)ceil_div64(pmax, 256 * 8), (unsigned)B);
+  pad_split2_kernel<<<grid, 256, 0, stream>>>(x, L, x_pitch, pad_a, mode_a, pitch_a,
+                                              ga.plane_stride, (__nv_bfloat16*)planes_a, pad_b,
+                                              mode_b, pitch_b, gb.plane_stride,
+                                              (__nv_bfloat16*)planes_b);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// Zero every element of each clip's slot region outside [keep_lo, keep_hi) (both planes)
+// plus the K-overhang tail: the parts of a level buffer the FIR epilogue never writes.
+__global__ void __launch_bounds__(256) zero_margins_kernel(__nv_bfloat16* __restrict__ planes,
+                                                           int64_t plane_stride, int64_t pitch,
+                                                           int64_t keep_lo, int64_t keep_hi) {
+  const int64_t b = blockIdx.y;
+  const int64_t lo_n = keep_lo, hi_n = pitch - keep_hi;
+  const int64_t n = lo_n + hi_n;
+  const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pos = i < lo_n ? i : keep_hi + (i - lo_n);
+    planes[b * pitch + pos] = z;
+    planes[plane_stride + b * pitch + pos] = z;
+  }
+}
+
+int tc_zero_margins(void* planes_v, int64_t B, int64_t L, int K, int hop, int pad, int64_t keep_lo,
+                    int64_t keep_hi, cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  const SplitGeom g = split_geom(B, L, K, hop, pad);
+  const int hop_eff = hop * num_phases(hop);
+  __nv_bfloat16* planes = (__nv_bfloat16*)planes_v;
+  int rc = zero_tail(planes, g, hop_eff, stream);
+  if (rc) return rc;
+  const int64_t pitch = g.t_slots * hop_eff;
+  if (keep_hi > pitch) keep_hi = pitch;
+  if (keep_lo < 0) keep_lo = 0;
+  const int64_t n = keep_lo + (pitch - keep_hi);
+  if (n <= 0) return NNAB_OK;
+  int gx = (int)ceil_div64(n, 256);
+  if (gx > 64) gx = 64;
+  zero_margins_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(planes, g.plane_stride, pitch,
+                                                                keep_lo, keep_hi);
   NNAB_LAUNCH_CHECK();
   return NNAB_OK;
 }
@@ -338,7 +502,63 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
       const bool valid = (g < p.nv) && (tl < p.T);
       const int64_t t = tl * p.t_mul + p.t_add;  // frame index in the output
       const int f_base = n_tile * half;
-      if constexpr (FMT == 5) {
+      if constexpr (FMT == 6) {
+        // ---- FIR decimator stage: this thread holds outputs n0 .. n0 + 2*half - 1 of clip b ----
+        const DecimParams& d = p.epi.dec;
+        const int64_t n0 = tl * (2 * half);
+        __nv_bfloat16* pc = reinterpret_cast<__nv_bfloat16*>(d.pc);
+        __nv_bfloat16* pf = reinterpret_cast<__nv_bfloat16*>(d.pf);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 2 * half; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(trow + (uint32_t)c0, v);  // re half = outputs 0..half-1, im half = the rest
+          tmem_ld_wait();
+          const int64_t n = n0 + c0;
+          if (valid && n < d.len_out) {
+            __align__(16) __nv_bfloat16 hi[8];
+            __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(__uint_as_float(v[e]), hi[e], lo[e]);
+            const bool full = (n + 8 <= d.len_out);
+            if (pf != nullptr) {
+              __nv_bfloat16* q = pf + b * d.pf_pitch + 128 + n;
+              if (full) {
+                *reinterpret_cast<uint4*>(q) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(q + d.pf_plane) = *reinterpret_cast<const uint4*>(lo);
+              } else {
+                for (int e = 0; e < 8 && n + e < d.len_out; ++e) { q[e] = hi[e]; q[d.pf_plane + e] = lo[e]; }
+              }
+            }
+            if (pc != nullptr) {
+              __nv_bfloat16* q = pc + b * d.pc_pitch + d.pc_off + n;
+              if (full) {
+                *reinterpret_cast<uint4*>(q) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(q + d.pc_plane) = *reinterpret_cast<const uint4*>(lo);
+              } else {
+                for (int e = 0; e < 8 && n + e < d.len_out; ++e) { q[e] = hi[e]; q[d.pc_plane + e] = lo[e]; }
+              }
+              // nn.ReflectionPad1d margins of the next level: mirror samples 1..off and
+              // len-1-off..len-2 (cqt.py:1065-1068 pads each level's own signal)
+              if (d.pc_reflect && (n <= d.pc_off || n + 8 >= d.len_out - 1 - d.pc_off)) {
+                __nv_bfloat16* base = pc + b * d.pc_pitch + d.pc_off;
+                for (int e = 0; e < 8; ++e) {
+                  const int64_t m = n + e;
+                  if (m >= d.len_out) break;
+                  if (m >= 1 && m <= d.pc_off) { base[-m] = hi[e]; base[d.pc_plane - m] = lo[e]; }
+                  if (m >= d.len_out - 1 - d.pc_off && m <= d.len_out - 2) {
+                    const int64_t r = 2 * (d.len_out - 1) - m;
+                    base[r] = hi[e]; base[d.pc_plane + r] = lo[e];
+                  }
+                }
+              }
+            }
+            if (d.y32 != nullptr) {
+              float* q = d.y32 + b * d.y32_pitch + n;
+              for (int e = 0; e < 8 && n + e < d.len_out; ++e) q[e] = __uint_as_float(v[e]);
+            }
+          }
+        }
+      } else if constexpr (FMT == 5) {
         // ---- fused banded filterbank: two running filter sums per frame ----
         float* mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
         int cj0 = -1, cj1 = -1;
@@ -908,6 +1128,7 @@ static int launch_tc2_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const
     case NNAB_FMT_PHASE_UNIT: return launch_tc2_kernel_fmt<BK, STAGES, 3>(ma, mb, prm, n_pairs, stream);
     case FMT_POWER: return launch_tc2_kernel_fmt<BK, STAGES, 4>(ma, mb, prm, n_pairs, stream);
     case FMT_FBANK: return launch_tc2_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, n_pairs, stream);
+    case FMT_DECIM: return launch_tc2_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -922,6 +1143,7 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
     case NNAB_FMT_PHASE_UNIT: return launch_tc_kernel_fmt<BK, STAGES, 3>(ma, mb, prm, grid, stream);
     case FMT_POWER: return launch_tc_kernel_fmt<BK, STAGES, 4>(ma, mb, prm, grid, stream);
     case FMT_FBANK: return launch_tc_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, grid, stream);
+    case FMT_DECIM: return launch_tc_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, grid, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -930,8 +1152,12 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
                      cudaStream_t stream) {
   if (q.B <= 0 || q.T <= 0 || q.F <= 0) return NNAB_OK;
   if (packed == nullptr) return NNAB_EINVAL;
-  const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
-  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (q.presplit == nullptr) {
+    const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+    if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  } else if (num_phases(q.hop) != 1) {
+    return NNAB_EALIGN;  // pre-split planes exist for one frame phase only
+  }
   if (q.B > 65535) return NNAB_EUNSUPPORTED;
 
   int bk = 64;
@@ -945,14 +1171,16 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   const int n_tiles = (2 * q.F + bn - 1) / bn;
   const int rows_w = n_tiles * bn;
   __nv_bfloat16* planes =
-      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+      q.presplit != nullptr
+          ? reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(q.presplit))
+          : reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 
   // K overhang rows past the last clip must be finite zeros (the basis is zero-padded there)
   const int64_t clip_pitch = g.t_slots * hop_eff;
-  const int64_t tail = g.plane_stride - g.nv * hop_eff;
-  for (int pl = 0; pl < 2; ++pl)
-    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hop_eff, 0,
-                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
+  if (q.presplit == nullptr) {
+    const int zrc = zero_tail(planes, g, hop_eff, stream);
+    if (zrc) return zrc;
+  }
 
   // ---- tensor maps (shared by all phases) -------------------------------------------
   // CTA pairs (cta_group::2) by default when there are enough 256-frame tiles to fill the
@@ -1017,14 +1245,16 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
   prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
   prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
+  prm.epi.dec = q.dec;
   if (q.fmt == FMT_FBANK && (q.fb_table == nullptr || q.n_fb <= 0)) return NNAB_EINVAL;
+  if (q.fmt == FMT_DECIM && (bn != 128 || n_tiles != 1)) return NNAB_EINVAL;
 
   // ---- one pad/split + GEMM pass per frame phase ----------------------------------------
   for (int ph = 0; ph < n_ph; ++ph) {
     if (ph >= q.T) break;
     prm.t_add = ph;
     prm.T = (q.T - ph + n_ph - 1) / n_ph;  // frames t = ph, ph + n_ph, ... < T
-    {
+    if (q.presplit == nullptr) {
       dim3 grid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
       pad_split_kernel<<<grid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
                                                  ph * q.hop, clip_pitch, g.plane_stride, planes);

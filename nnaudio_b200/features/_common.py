@@ -97,3 +97,18 @@ class FilterbankTable:
             self._table = _C.build_filterbank_table(fb)
             self._key = key
         return self._table
+
+
+class PackedFir:
+    """Cache of the tensor-core packing of a decimation FIR buffer."""
+
+    def __init__(self):
+        self._key = None
+        self._packed = None
+
+    def get(self, fir: torch.Tensor, dec: int):
+        key = (fir.data_ptr(), fir._version, int(dec), str(fir.device))
+        if key != self._key:
+            self._packed = _C.pack_fir(fir, int(dec))
+            self._key = key
+        return self._packed

@@ -13,8 +13,8 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import (PackedBasis, as_matrix, broadcast_dim, forward_only_guard, pad_mode_id,
-                      tap_support)
+from ._common import (PackedBasis, PackedFir, as_matrix, broadcast_dim, forward_only_guard,
+                      pad_mode_id, tap_support)
 
 _FORMATS = {
     "Magnitude": _C.FMT_MAGNITUDE,
@@ -348,7 +348,12 @@ def _pyramid_forward(mod, x, output_format, normalization_type):
     for t in (lowpass, early_flat):
         if t is not None:
             _C._dev_f32(t, "filter")
+    if not hasattr(mod, "_fir_packed"):
+        mod._fir_packed = (PackedFir(), PackedFir())
+    lowpass_packed = mod._fir_packed[0].get(lowpass, 2)
+    early_packed = mod._fir_packed[1].get(early_flat, factor) if early_flat is not None else None
     return _C.cqt_pyramid_forward(
-        x, banks_real, banks_imag, packed, lowpass, early_flat, factor, mod.hop_length,
+        x, banks_real, banks_imag, packed, lowpass, lowpass_packed, early_flat, early_packed,
+        factor, mod.hop_length,
         pad_mode_id(mod.pad_mode), mod.n_bins, scale, scale_all, _FORMATS[output_format], eps, T,
     )
