@@ -42,6 +42,7 @@ void count_launch();
 constexpr int FMT_POWER = 100;  // internal: (sqrt(re^2+im^2+eps)) ** power -> (B,F,T)
 constexpr int FMT_FBANK = 101;  // internal (tcgen05 only): power -> banded filterbank -> (B,n_fb,T)
 constexpr int FMT_DECIM = 102;  // internal (tcgen05 only): FIR decimator stage of the CQT pyramid
+constexpr int FMT_RAW = 103;    // internal (tcgen05 only): split-K partial sums -> raw (re, im) scratch
 
 // FMT_DECIM epilogue target: the NEXT pyramid level, written as bf16 hi/lo planes in
 // the layout the tensor-core kernels read (sample m of clip b at b*pitch + off + m).
@@ -82,6 +83,7 @@ struct FramedProblem {
   const int32_t* h_k_end;
   const FbEntry* fb_table;   // FMT_FBANK: device table [F]; out is (B, n_fb, T), pre-zeroed
   int n_fb;
+  float* raw;                // tcgen05 split-K scratch: 2 planes (re, im) of B*F*T floats, or nullptr
   const void* presplit;      // tcgen05: already padded + split signal planes (skip pad_split)
   DecimParams dec;           // FMT_DECIM
 };
@@ -107,6 +109,7 @@ int tc_pad_split2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                   int K_b, int hop_b, int pad_b, int mode_b, void* planes_b, cudaStream_t stream);
 int tc_zero_margins(void* planes, int64_t B, int64_t L, int K, int hop, int pad, int64_t keep_lo,
                     int64_t keep_hi, cudaStream_t stream);
+size_t tc_splitk_scratch_bytes(int64_t B, int F, int64_t T, int K);
 size_t tc_packed_fir_bytes(int taps, int dec);
 int tc_fir_k(int taps, int dec);
 int tc_pack_fir(const float* fir, int taps, int dec, void* packed, cudaStream_t stream);

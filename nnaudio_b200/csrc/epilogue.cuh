@@ -22,6 +22,8 @@ struct EpiParams {
   const FbEntry* fb_table;  // FMT_FBANK
   int n_fb;
   DecimParams dec;          // FMT_DECIM
+  float* raw;               // FMT_RAW: re plane; im plane at raw + raw_plane
+  int64_t raw_plane;
 };
 
 __device__ __forceinline__ float epi_power(const EpiParams& e, float re, float im) {

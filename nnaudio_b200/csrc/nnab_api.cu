@@ -100,6 +100,14 @@ static int run_framed_inner(const FramedProblem& p, const void* packed, void* ws
   return launch_framed_simt(p, stream);
 }
 
+// The split-K scratch (long kernels only) sits behind the split-signal planes in the workspace.
+static void attach_splitk_scratch(FramedProblem& p, void* workspace, size_t ws_bytes) {
+  const size_t sk = tc_splitk_scratch_bytes(p.B, p.F, p.T, p.K);
+  if (sk == 0 || workspace == nullptr) return;
+  const size_t front = align_up(tc_workspace_bytes(p.B, p.L, p.K, p.hop, p.pad), 256);
+  if (front + sk <= ws_bytes) p.raw = reinterpret_cast<float*>((char*)workspace + front);
+}
+
 static bool wants_tc(int path, int K, int hop) {
   if (path == NNAB_PATH_SIMT) return false;
   FramedProblem q{};
@@ -164,9 +172,10 @@ int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K, void* pa
 // ------------------------------------------------------------------ STFT ----
 size_t nnab_stft_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop, int center,
                                  int path) {
-  (void)F;
   if (!wants_tc(path, n_fft, hop)) return 0;
-  return tc_workspace_bytes(B, L, n_fft, hop, center ? n_fft / 2 : 0);
+  const int pad = center ? n_fft / 2 : 0;
+  return align_up(tc_workspace_bytes(B, L, n_fft, hop, pad), 256) +
+         tc_splitk_scratch_bytes(B, F, frames_of(L, n_fft, hop, pad), n_fft);
 }
 
 int nnab_stft_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* wcos,
@@ -187,6 +196,7 @@ int nnab_stft_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch, con
   p.pad = pad; p.pad_mode = pad_mode; p.scale = nullptr; p.scale_all = 1.f;
   p.fmt = out_format; p.eps = sqrt_eps; p.power = 1.f; p.out = out; p.T = T;
   p.out_bins = F; p.bin_offset = 0;
+  attach_splitk_scratch(p, workspace, ws_bytes);
   return run_framed(p, packed, workspace, ws_bytes, path, (cudaStream_t)stream);
 }
 
@@ -327,9 +337,10 @@ int nnab_mfcc_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch, con
 // ------------------------------------------------------------- CQT1992v2 ----
 size_t nnab_cqt1992v2_workspace_bytes(int64_t B, int64_t L, int width, int n_bins, int hop,
                                       int center, int path) {
-  (void)n_bins;
   if (!wants_tc(path, width, hop)) return 0;
-  return tc_workspace_bytes(B, L, width, hop, center ? width / 2 : 0);
+  const int pad = center ? width / 2 : 0;
+  return align_up(tc_workspace_bytes(B, L, width, hop, pad), 256) +
+         tc_splitk_scratch_bytes(B, n_bins, frames_of(L, width, hop, pad), width);
 }
 
 int nnab_cqt1992v2_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch,
@@ -354,6 +365,7 @@ int nnab_cqt1992v2_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch
   p.fmt = out_format; p.eps = sqrt_eps; p.power = 1.f; p.out = out; p.T = T;
   p.out_bins = n_bins; p.bin_offset = 0;
   p.h_k_begin = h_k_begin; p.h_k_end = h_k_end;
+  attach_splitk_scratch(p, workspace, ws_bytes);
   return run_framed(p, packed, workspace, ws_bytes, path, (cudaStream_t)stream);
 }
 

@@ -486,11 +486,24 @@ struct TcParams {
   int rows_mode;   // 1: A viewed as (rows x hop) matrix (BK | hop); 0: overlapping-stride map
   int hop;          // effective hop (hop * phases)
   int t_mul, t_add;  // output frame index = t * t_mul + t_add (frame phases)
+  int k_splits;      // >1: every (m, n) tile is cut into k_splits K-chunks (FMT_RAW epilogue)
   int64_t nv, t_slots, T;  // T = valid frames of this phase
   int kb_begin[TC_MAX_N_TILES];
   int kb_end[TC_MAX_N_TILES];
   EpiParams epi;
 };
+
+// tile index -> (m tile, n tile, k-block range); K-chunks of one (m, n) tile are adjacent
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& m_tile, int& n_tile,
+                                            int& kb0, int& kb1) {
+  const int ks = tile % p.k_splits;
+  const int mn = tile / p.k_splits;
+  m_tile = mn / p.num_n_tiles;
+  n_tile = mn - m_tile * p.num_n_tiles;
+  const int lo = p.kb_begin[n_tile], n = p.kb_end[n_tile] - lo;
+  kb0 = lo + (int)(((int64_t)n * ks) / p.k_splits);
+  kb1 = lo + (int)(((int64_t)n * (ks + 1)) / p.k_splits);
+}
 
 // Read one 128-frame x bn accumulator tile out of TMEM (this warp's 32 lanes =
 // 32 consecutive frames) and emit it in the requested output format.
@@ -502,7 +515,27 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
       const bool valid = (g < p.nv) && (tl < p.T);
       const int64_t t = tl * p.t_mul + p.t_add;  // frame index in the output
       const int f_base = n_tile * half;
-      if constexpr (FMT == 6) {
+      if constexpr (FMT == 7) {
+        // ---- split-K partial sums: fp32 (round-to-nearest) atomics into the raw planes ----
+        float* rre = p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t;
+#pragma unroll 1
+        for (int c0 = 0; c0 < half; c0 += 8) {
+          uint32_t re[8], im[8];
+          tmem_ld8(trow + (uint32_t)c0, re);
+          tmem_ld8(trow + (uint32_t)(half + c0), im);
+          tmem_ld_wait();
+          if (valid) {
+            const int jmax = min(8, min(half - c0, p.epi.F - f_base - c0));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < jmax) {
+                float* q = rre + (int64_t)(f_base + c0 + j) * p.epi.T;
+                atomicAdd(q, __uint_as_float(re[j]));
+                atomicAdd(q + p.epi.raw_plane, __uint_as_float(im[j]));
+              }
+          }
+        }
+      } else if constexpr (FMT == 6) {
         // ---- FIR decimator stage: this thread holds outputs n0 .. n0 + 2*half - 1 of clip b ----
         const DecimParams& d = p.epi.dec;
         const int64_t n0 = tl * (2 * half);
@@ -696,7 +729,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const uint32_t b_tile_bytes = (uint32_t)p.bn * BK * 2;
 
   if (warp == 0) {
@@ -705,11 +738,11 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        int m_tile, n_tile, kb0, kb1;
+        decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * TC_BM;
         const int n0 = n_tile * p.bn;
-        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sb = base + stage * S::STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), 2 * S::A_BYTES + 2 * b_tile_bytes);
@@ -738,12 +771,14 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
+        int m_tile, n_tile, kb0, kb1;
+        decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
+        (void)m_tile;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
         uint32_t accumulate = 0;
-        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sb = base + stage * S::STAGE_BYTES;
@@ -773,8 +808,9 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      int m_tile, n_tile, kb0, kb1;
+      decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
+      (void)kb0; (void)kb1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const int64_t g = (int64_t)m_tile * TC_BM + quarter * 32 + lane;
@@ -927,7 +963,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-frame pairs here
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;  // num_m_tiles: 256-frame pairs
   const int halfn = p.bn >> 1;
   const uint32_t b_half_bytes = (uint32_t)halfn * BK * 2;
 
@@ -937,11 +973,11 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        int m_tile, n_tile, kb0, kb1;
+        decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
         const int n0 = n_tile * p.bn + (int)cta * halfn;
-        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sb = base + stage * S::STAGE_BYTES;
           mbar_expect_tx_remote(full_bar(stage), 0, 2 * S::A_BYTES + 2 * b_half_bytes);
@@ -969,12 +1005,14 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int n_tile = tile % p.num_n_tiles;
+        int m_tile, n_tile, kb0, kb1;
+        decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
+        (void)m_tile;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
         uint32_t accumulate = 0;
-        for (int kb = p.kb_begin[n_tile]; kb < p.kb_end[n_tile]; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sb = base + stage * S::STAGE_BYTES;
@@ -1003,8 +1041,9 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      int m_tile, n_tile, kb0, kb1;
+      decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
+      (void)kb0; (void)kb1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
@@ -1025,6 +1064,24 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     tcgen05_fence_after();
     tmem_dealloc_2sm(tmem_base, 512);
   }
+}
+
+// Split-K finalize: raw (re, im) sums -> per-bin scale + output format (generic epilogue).
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const EpiParams e, int64_t B) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (t >= e.T) return;
+  for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
+    const int64_t i = ((int64_t)b * e.F + f) * e.T + t;
+    epi_store(e, b, f, t, e.raw[i], e.raw[e.raw_plane + i]);
+  }
+}
+
+// Long kernels only: the scratch exists to bound the tensor-core accumulation length
+// (its error grows with the number of accumulated MMAs) and to even out the tile count.
+size_t tc_splitk_scratch_bytes(int64_t B, int F, int64_t T, int K) {
+  if (K < 8192) return 0;
+  return (size_t)2 * B * F * T * sizeof(float) + 256;
 }
 
 // ---------------------------------------------------------------------------
@@ -1129,6 +1186,7 @@ static int launch_tc2_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const
     case FMT_POWER: return launch_tc2_kernel_fmt<BK, STAGES, 4>(ma, mb, prm, n_pairs, stream);
     case FMT_FBANK: return launch_tc2_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, n_pairs, stream);
     case FMT_DECIM: return launch_tc2_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, n_pairs, stream);
+    case FMT_RAW: return launch_tc2_kernel_fmt<BK, STAGES, 7>(ma, mb, prm, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -1144,6 +1202,7 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
     case FMT_POWER: return launch_tc_kernel_fmt<BK, STAGES, 4>(ma, mb, prm, grid, stream);
     case FMT_FBANK: return launch_tc_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, grid, stream);
     case FMT_DECIM: return launch_tc_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, grid, stream);
+    case FMT_RAW: return launch_tc_kernel_fmt<BK, STAGES, 7>(ma, mb, prm, grid, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -1246,8 +1305,37 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
   prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
   prm.epi.dec = q.dec;
+  prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
+  prm.k_splits = 1;
   if (q.fmt == FMT_FBANK && (q.fb_table == nullptr || q.n_fb <= 0)) return NNAB_EINVAL;
   if (q.fmt == FMT_DECIM && (bn != 128 || n_tiles != 1)) return NNAB_EINVAL;
+
+  // ---- split-K (long kernels, caller supplied the raw scratch) ---------------------------
+  EpiParams final_epi = prm.epi;
+  bool split = false;
+  if (q.raw != nullptr && q.fmt != FMT_FBANK && q.fmt != FMT_DECIM && q.bin_offset == 0 &&
+      q.out_bins == q.F) {
+    int min_range = nkb;
+    for (int tl = 0; tl < n_tiles; ++tl) {
+      const int r = prm.kb_end[tl] - prm.kb_begin[tl];
+      min_range = r < min_range ? r : min_range;
+    }
+    int ks = (min_range + 63) / 64;  // <= 64 k-blocks (4096 taps) per accumulator
+    if (ks > 16) ks = 16;
+    if (ks > min_range) ks = min_range;
+    if (ks > 1) {
+      split = true;
+      prm.k_splits = ks;
+      float* raw = reinterpret_cast<float*>(((uintptr_t)q.raw + 255) & ~(uintptr_t)255);
+      const int64_t plane = (int64_t)q.B * q.F * q.T;
+      NNAB_CUDA_TRY(cudaMemsetAsync(raw, 0, (size_t)2 * plane * sizeof(float), stream));
+      prm.epi.fmt = FMT_RAW;
+      prm.epi.raw = raw;
+      prm.epi.raw_plane = plane;
+      final_epi.raw = raw;
+      final_epi.raw_plane = plane;
+    }
+  }
 
   // ---- one pad/split + GEMM pass per frame phase ----------------------------------------
   for (int ph = 0; ph < n_ph; ++ph) {
@@ -1262,17 +1350,22 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
     }
     if (cta_group == 2) {
       prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);  // 256-frame pair tiles
-      const int64_t ptiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
+      const int64_t ptiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles * prm.k_splits;
       const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
       rc = launch_tc2_kernel<64, 3>(ma, mb, prm, n_pairs, stream);
     } else {
       prm.num_m_tiles = (int)ceil_div64(g.nv, TC_BM);
-      const int64_t tiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles;
+      const int64_t tiles = (int64_t)prm.num_m_tiles * prm.num_n_tiles * prm.k_splits;
       const int grid = (int)(tiles < sms ? tiles : sms);
       rc = (bk == 64) ? launch_tc_kernel<64, 2>(ma, mb, prm, grid, stream)
                       : launch_tc_kernel<32, 4>(ma, mb, prm, grid, stream);
     }
     if (rc) return rc;
+  }
+  if (split) {
+    dim3 grid((unsigned)ceil_div64(q.T, 256), (unsigned)q.F, (unsigned)(q.B < 64 ? q.B : 64));
+    splitk_finalize_kernel<<<grid, 256, 0, stream>>>(final_epi, q.B);
+    NNAB_LAUNCH_CHECK();
   }
   return NNAB_OK;
 }
