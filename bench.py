@@ -45,6 +45,10 @@ WORKLOADS = {
 }
 
 
+# SMs left to the NCCL gather while the persistent kernels run (measured, profiles/README.md)
+DEFAULT_RESERVE = {1: 0, 2: 8, 4: 8, 8: 16}
+
+
 def frames_per_clip(w):
     hop = w["ctor"].get("hop_length", 512)
     return w["L"] // hop + 1
@@ -166,6 +170,20 @@ def cpu_arm(workload, steps, warmup, budget_s):
 
 # ----------------------------------------------------------------------------
 def main():
+    # stdout carries exactly ONE line (the JSON); libraries that print there (NCCL's version
+    # banner) are routed to stderr for the duration of the run.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+    if line is not None:
+        os.write(1, (json.dumps(line) + "\n").encode())
+
+
+def _run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -176,6 +194,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=None,
+                    help="SMs kept free for the concurrent NCCL gather (default: by world size)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="0 = NCCL default")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -192,7 +213,7 @@ def main():
     # ------------------------------------------------------------ CPU arm --
     if args.impl == "reference":
         if rank != 0:
-            return
+            return None
         res = cpu_arm(args.workload, args.steps, args.warmup, budget_s=120.0)
         line = {
             "impl": "reference", "metric": metric, "value": res["value"], "unit": "frames/s",
@@ -206,8 +227,7 @@ def main():
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
-        return
+        return line
 
     # ------------------------------------------------------------ GPU arm --
     import torch
@@ -221,6 +241,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # few CTAs for the output gather: it overlaps the next batch's kernels (which leave
+        # 8 SMs free for it, nnaudio_b200.parallel) and 99 MB per step does not need more
+        if args.nccl_max_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
         dist.init_process_group("nccl", device_id=dev)
 
     B = w["B"]
@@ -233,7 +257,9 @@ def main():
 
     from nnaudio_b200.parallel import BatchShardedTransform
 
-    sharded = BatchShardedTransform(lambda inp: mod(inp, **w["fwd"]), gather=(world > 1))
+    reserve = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
+    sharded = BatchShardedTransform(lambda inp: mod(inp, **w["fwd"]), gather=(world > 1),
+                                    reserve_sms=reserve)
 
     def sync_all():
         if world > 1:
@@ -349,6 +375,7 @@ def main():
                 "l2": f"{n_rot} rotating input batches ({n_rot * B * w['L'] * 4 / 1e6:.0f} MB > 126 MB L2), no flush; "
                       "one CUDA-event pair around all K steps",
                 "kernel_path": os.environ.get("NNAUDIO_B200_PATH", "auto"),
+                "sms_reserved_for_gather": reserve if world > 1 else 0,
             },
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -371,10 +398,12 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             res = cpu_arm(args.workload, steps=3, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+    else:
+        line = None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

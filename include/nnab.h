@@ -207,9 +207,35 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
                              float sqrt_eps, float* out, int64_t T,
                              void* workspace, size_t ws_bytes, int path, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * STFT.inverse / iSTFT.forward — features/stft.py:15-63 (inverse_stft), :318-356,
+ * :526-546; helpers utils.py:43-70 (SURVEY §8f "next" #2).
+ *   X (B, f_in, T, 2) complex spectrogram; f_in = n_fft/2+1 with onesided, else n_fft
+ *   kernel_cos / kernel_sin (n_fft, n_fft) = `kernel_cos_inv`/`kernel_sin_inv` of
+ *     STFT(iSTFT=True) or `kernel_cos`/`kernel_sin` of the iSTFT module; packed once with
+ *     nnab_pack_istft_basis (the one-sided mirroring of utils.py:63-70 is folded in)
+ *   window (n_fft) = `window_mask`;  length < 0 means None
+ *   out (B, out_len): out_len = n_fft + hop*(T-1) - 2*pad (length None, center) etc.
+ * Runs on the tensor-core kernel only (inverse-DFT GEMM + overlap-add epilogue +
+ * window-sumsquare normalisation).
+ * ------------------------------------------------------------------------- */
+size_t nnab_packed_istft_bytes(int n_fft, int f_in);
+int nnab_pack_istft_basis(const float* kernel_cos, const float* kernel_sin, int n_fft, int f_in,
+                          int onesided, void* packed, void* stream);
+size_t nnab_istft_workspace_bytes(int64_t B, int f_in, int64_t T, int n_fft, int hop);
+int nnab_istft_forward(const float* X, int64_t B, int f_in, int64_t T, const void* packed,
+                       const float* window, int n_fft, int hop, int center, int64_t length,
+                       float* out, int64_t out_len, void* workspace, size_t ws_bytes,
+                       void* stream);
+
 /* Kernel launches issued by this library since load (process wide; used by
  * bench.py for its `gpu_launches` claim). */
 uint64_t nnab_launch_count(void);
+
+/* Leave `n_sms` SMs out of the persistent tensor-core grids (process wide, default 0) so
+ * that a concurrently running collective (the NCCL output gather of the multi-GPU path)
+ * has SMs to run on; returns the previous value. */
+int nnab_set_sm_reserve(int n_sms);
 
 /* Live timing of the dominant kernel (the framed contraction) for bench.py's
  * roofline: while enabled, every framed-contraction launch is bracketed by a

@@ -29,6 +29,7 @@ SIGNATURES = {
     "nnab_strerror": (c_char_p, [c_int]),
     "nnab_last_cuda_error": (c_char_p, []),
     "nnab_launch_count": (c_uint64, []),
+    "nnab_set_sm_reserve": (c_int, [c_int]),
     "nnab_profile_enable": (None, [c_int]),
     "nnab_profile_read": (c_int, [_P, _P]),
     "nnab_pack_tile_n": (c_int, []),
@@ -63,6 +64,14 @@ SIGNATURES = {
         c_int,
         [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
          _P, c_float, c_int, c_float, _P, c_int64, _P, c_size_t, c_int, _P],
+    ),
+    "nnab_packed_istft_bytes": (c_size_t, [c_int, c_int]),
+    "nnab_pack_istft_basis": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "nnab_istft_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64, c_int, c_int]),
+    "nnab_istft_forward": (
+        c_int,
+        [_P, c_int64, c_int, c_int64, _P, _P, c_int, c_int, c_int, c_int64, _P, c_int64, _P,
+         c_size_t, _P],
     ),
     "nnab_packed_fir_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_fir": (c_int, [_P, c_int, c_int, _P, _P]),
@@ -114,6 +123,11 @@ def resolve_path(path) -> int:
 
 def launch_count() -> int:
     return int(lib().nnab_launch_count())
+
+
+def set_sm_reserve(n_sms: int) -> int:
+    """Keep ``n_sms`` SMs out of the persistent kernels' grids (for a concurrent collective)."""
+    return int(lib().nnab_set_sm_reserve(int(n_sms)))
 
 
 def profile_enable(on: bool):
@@ -341,4 +355,39 @@ def cqt_pyramid_forward(x, banks_real, banks_imag, packed, lowpass, lowpass_pack
             early_factor, hop, pad_mode, n_bins, _ptr(scale),
             scale_all, out_format, sqrt_eps, _ptr(out), T, _ptr(ws), wsb, path, _stream(x.device))
     _check(rc, "nnab_cqt_pyramid_forward")
+    return out
+
+
+def pack_istft_basis(kernel_cos: torch.Tensor, kernel_sin: torch.Tensor, f_in: int, onesided: bool):
+    """Tensor-core packing of the (n_fft, n_fft) inverse kernels; the mirroring of a
+    one-sided spectrum (utils.py:63-70) is folded into the packed rows."""
+    L = lib()
+    n_fft = kernel_cos.shape[0]
+    packed = torch.empty(L.nnab_packed_istft_bytes(n_fft, f_in), dtype=torch.uint8,
+                         device=kernel_cos.device)
+    with torch.cuda.device(kernel_cos.device):
+        _check(L.nnab_pack_istft_basis(_ptr(kernel_cos), _ptr(kernel_sin), n_fft, f_in,
+                                       int(onesided), _ptr(packed), _stream(kernel_cos.device)),
+               "nnab_pack_istft_basis")
+    return packed
+
+
+def istft_forward(X, packed, window, n_fft, hop, center, length):
+    """X (B, f_in, T, 2) fp32 CUDA -> waveform (B, out_len)."""
+    L = lib()
+    X = _dev_f32(X, "X")
+    X = X if X.is_contiguous() else X.contiguous()
+    B, f_in, T, _ = X.shape
+    ola_len = n_fft + hop * (T - 1)
+    pad = n_fft // 2
+    offset = pad if center else 0
+    want = length if length is not None else (ola_len - 2 * pad if center else ola_len)
+    want = max(0, min(want, ola_len - offset))
+    out = torch.empty((B, want), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        ws, wsb = _workspace(L.nnab_istft_workspace_bytes(B, f_in, T, n_fft, hop), X.device)
+        rc = L.nnab_istft_forward(_ptr(X), B, f_in, T, _ptr(packed), _ptr(window), n_fft, hop,
+                                  int(center), -1 if length is None else int(length), _ptr(out),
+                                  want, _ptr(ws), wsb, _stream(X.device))
+    _check(rc, "nnab_istft_forward")
     return out

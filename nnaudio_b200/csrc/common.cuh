@@ -13,6 +13,7 @@ namespace nnab {
 void set_cuda_error(const char* where, cudaError_t e);
 void set_error_text(const char* text);
 void count_launch();
+int sm_reserve();
 
 #define NNAB_CUDA_TRY(expr)                         \
   do {                                              \
@@ -43,6 +44,7 @@ constexpr int FMT_POWER = 100;  // internal: (sqrt(re^2+im^2+eps)) ** power -> (
 constexpr int FMT_FBANK = 101;  // internal (tcgen05 only): power -> banded filterbank -> (B,n_fb,T)
 constexpr int FMT_DECIM = 102;  // internal (tcgen05 only): FIR decimator stage of the CQT pyramid
 constexpr int FMT_RAW = 103;    // internal (tcgen05 only): split-K partial sums -> raw (re, im) scratch
+constexpr int FMT_OLA = 104;    // internal (tcgen05 only): inverse STFT frames -> overlap-add buffer
 
 // FMT_DECIM epilogue target: the NEXT pyramid level, written as bf16 hi/lo planes in
 // the layout the tensor-core kernels read (sample m of clip b at b*pitch + off + m).
@@ -86,6 +88,8 @@ struct FramedProblem {
   float* raw;                // tcgen05 split-K scratch: 2 planes (re, im) of B*F*T floats, or nullptr
   const void* presplit;      // tcgen05: already padded + split signal planes (skip pad_split)
   DecimParams dec;           // FMT_DECIM
+  int64_t ola_pitch;         // FMT_OLA: out = overlap-add buffer (B, ola_pitch); scale = window/n_fft
+  int ola_hop;
 };
 
 int launch_framed_simt(const FramedProblem& p, cudaStream_t stream);
@@ -109,6 +113,17 @@ int tc_pad_split2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                   int K_b, int hop_b, int pad_b, int mode_b, void* planes_b, cudaStream_t stream);
 int tc_zero_margins(void* planes, int64_t B, int64_t L, int K, int hop, int pad, int64_t keep_lo,
                     int64_t keep_hi, cudaStream_t stream);
+// inverse STFT pieces (tc_kernels.cu)
+int tc_istft_k(int f_in);
+int tc_istft_bn(int n_fft);
+size_t tc_packed_istft_bytes(int n_fft, int f_in);
+int tc_pack_istft(const float* kc, const float* ks, int n_fft, int f_in, int onesided, void* packed,
+                  cudaStream_t stream);
+size_t tc_istft_planes_bytes(int64_t B, int64_t T, int f_in);
+int tc_istft_prep(const float* X, int64_t B, int f_in, int64_t T, void* planes, cudaStream_t stream);
+int tc_istft_finalize(const float* ola, int64_t ola_pitch, int64_t B, const float* window,
+                      int n_fft, int hop, int64_t T, int64_t offset, float* out, int64_t out_len,
+                      cudaStream_t stream);
 size_t tc_splitk_scratch_bytes(int64_t B, int F, int64_t T, int K);
 size_t tc_packed_fir_bytes(int taps, int dec);
 int tc_fir_k(int taps, int dec);

@@ -24,6 +24,8 @@ struct EpiParams {
   DecimParams dec;          // FMT_DECIM
   float* raw;               // FMT_RAW: re plane; im plane at raw + raw_plane
   int64_t raw_plane;
+  int64_t ola_pitch;        // FMT_OLA
+  int ola_hop;
 };
 
 __device__ __forceinline__ float epi_power(const EpiParams& e, float re, float im) {

@@ -19,6 +19,8 @@ void set_cuda_error(const char* where, cudaError_t e) {
 }
 void set_error_text(const char* text) { snprintf(g_err, sizeof(g_err), "%s", text); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_sm_reserve{0};
+int sm_reserve() { return g_sm_reserve.load(std::memory_order_relaxed); }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -139,6 +141,12 @@ const char* nnab_strerror(int status) {
 const char* nnab_last_cuda_error(void) { return g_err; }
 
 uint64_t nnab_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nnab_set_sm_reserve(int n_sms) {
+  if (n_sms < 0) n_sms = 0;
+  if (n_sms > 64) n_sms = 64;
+  return g_sm_reserve.exchange(n_sms);
+}
 
 void nnab_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 
@@ -700,6 +708,81 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
     }
   }
   return NNAB_OK;
+}
+
+// ----------------------------------------------------------------- inverse STFT ----
+static __global__ void istft_scale_kernel(const float* __restrict__ window, float inv_n, int n,
+                                          float* __restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scale[i] = window[i] * inv_n;
+}
+
+size_t nnab_packed_istft_bytes(int n_fft, int f_in) { return tc_packed_istft_bytes(n_fft, f_in); }
+
+int nnab_pack_istft_basis(const float* kernel_cos, const float* kernel_sin, int n_fft, int f_in,
+                          int onesided, void* packed, void* stream) {
+  if (kernel_cos == nullptr || kernel_sin == nullptr || packed == nullptr || n_fft <= 0 ||
+      f_in <= 0 || f_in > n_fft)
+    return NNAB_EINVAL;
+  return tc_pack_istft(kernel_cos, kernel_sin, n_fft, f_in, onesided, packed, (cudaStream_t)stream);
+}
+
+static size_t istft_ola_bytes(int64_t B, int64_t T, int n_fft, int hop, int64_t* pitch) {
+  const int64_t len = n_fft + (int64_t)hop * (T - 1);
+  const int64_t p = (int64_t)align_up((size_t)len, 8);
+  if (pitch) *pitch = p;
+  return align_up((size_t)B * p * sizeof(float), 256);
+}
+
+size_t nnab_istft_workspace_bytes(int64_t B, int f_in, int64_t T, int n_fft, int hop) {
+  return align_up(tc_istft_planes_bytes(B, T, f_in), 256) + istft_ola_bytes(B, T, n_fft, hop, nullptr) +
+         align_up((size_t)n_fft * sizeof(float), 256) + 256;
+}
+
+int nnab_istft_forward(const float* X, int64_t B, int f_in, int64_t T, const void* packed,
+                       const float* window, int n_fft, int hop, int center, int64_t length,
+                       float* out, int64_t out_len, void* workspace, size_t ws_bytes,
+                       void* stream) {
+  if (X == nullptr || packed == nullptr || window == nullptr || out == nullptr || B < 0 ||
+      f_in <= 0 || T <= 0 || n_fft <= 0 || hop <= 0)
+    return NNAB_EINVAL;
+  int rc = check_arch();
+  if (rc) return rc;
+  const size_t need = nnab_istft_workspace_bytes(B, f_in, T, n_fft, hop);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  const int64_t ola_len = n_fft + (int64_t)hop * (T - 1);
+  const int pad = n_fft / 2;
+  const int64_t offset = center ? pad : 0;
+  int64_t want = length >= 0 ? length : (center ? ola_len - 2 * pad : ola_len);
+  if (offset + want > ola_len) want = ola_len - offset;  // slicing past the end just truncates
+  if (want < 0) want = 0;
+  if (out_len != want) return NNAB_EINVAL;
+  if (B == 0 || want == 0) return NNAB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  void* planes = ws;
+  int64_t ola_pitch = 0;
+  const size_t planes_b = align_up(tc_istft_planes_bytes(B, T, f_in), 256);
+  const size_t ola_b = istft_ola_bytes(B, T, n_fft, hop, &ola_pitch);
+  float* ola = (float*)(ws + planes_b);
+  float* scale = (float*)(ws + planes_b + ola_b);
+
+  if ((rc = tc_istft_prep(X, B, f_in, T, planes, s))) return rc;
+  NNAB_CUDA_TRY(cudaMemsetAsync(ola, 0, (size_t)B * ola_pitch * sizeof(float), s));
+  istft_scale_kernel<<<(n_fft + 255) / 256, 256, 0, s>>>(window, 1.0f / (float)n_fft, n_fft, scale);
+  NNAB_LAUNCH_CHECK();
+
+  const int kpad = tc_istft_k(f_in);
+  FramedProblem p{};
+  p.x = nullptr; p.B = B; p.L = T * (int64_t)kpad; p.x_pitch = 0;
+  p.F = n_fft; p.K = kpad; p.hop = kpad; p.pad = 0; p.pad_mode = NNAB_PAD_CONSTANT;
+  p.scale = scale; p.scale_all = 1.f; p.fmt = FMT_OLA; p.eps = 0.f; p.power = 1.f;
+  p.out = ola; p.T = T; p.out_bins = n_fft; p.bin_offset = 0;
+  p.presplit = planes;
+  p.ola_pitch = ola_pitch; p.ola_hop = hop;
+  if ((rc = run_framed(p, packed, nullptr, 0, NNAB_PATH_TCGEN05, s))) return rc;
+  return tc_istft_finalize(ola, ola_pitch, B, window, n_fft, hop, T, offset, out, want, s);
 }
 
 }  // extern "C"

@@ -143,7 +143,9 @@ int launch_framed_simt(const FramedProblem& q, cudaStream_t stream) {
   p.epi.fb_table = nullptr; p.epi.n_fb = 0;
   p.epi.dec = DecimParams{};
   p.epi.raw = nullptr; p.epi.raw_plane = 0;
-  if (q.fmt == FMT_FBANK || q.fmt == FMT_DECIM || q.fmt == FMT_RAW) return NNAB_EINVAL;  // fused filterbank exists on the tcgen05 path only
+  p.epi.ola_pitch = 0; p.epi.ola_hop = 0;
+  if (q.fmt == FMT_FBANK || q.fmt == FMT_DECIM || q.fmt == FMT_RAW || q.fmt == FMT_OLA)
+    return NNAB_EINVAL;  // fused filterbank exists on the tcgen05 path only
 
   const int TN = (q.F > 32) ? 4 : 2;
   const int BNB = 16 * TN;

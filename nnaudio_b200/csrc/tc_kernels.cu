@@ -340,6 +340,158 @@ int tc_zero_margins(void* planes_v, int64_t B, int64_t L, int K, int hop, int pa
 }
 
 // ---------------------------------------------------------------------------
+// inverse STFT (stft.py:15-63) as a plain GEMM on the framed kernel:
+//   frame[g, n] = sum_k A[g, k] * Winv[n, k],  g = b*T + t,  k = (re | im) x frequency
+// "hop = Kpad" rows: every frame is its own row, so the Toeplitz machinery degenerates to a
+// row-major matrix.  The FMT_OLA epilogue windows the frame and overlap-adds it.
+// ---------------------------------------------------------------------------
+int tc_istft_k(int f_in) { return round_up_i(2 * f_in, 64); }
+int tc_istft_bn(int n_fft) { return n_fft >= 256 ? 256 : (round_up_i(n_fft, 16) < 32 ? 32 : round_up_i(n_fft, 16)); }
+size_t tc_packed_istft_bytes(int n_fft, int f_in) {
+  const int bn = tc_istft_bn(n_fft);
+  const size_t rows = (size_t)((n_fft + bn - 1) / bn) * bn;
+  return 2 * rows * tc_istft_k(f_in) * sizeof(__nv_bfloat16);
+}
+
+// Winv[n][f]        = KC[n][f] (+ KC[n][N-f] for a mirrored one-sided bin)          re part
+// Winv[n][F_in + f] = -(KS[n][f] (- KS[n][N-f]))                                    im part
+// i.e. the reference's extend_fbins (utils.py:63-70) folded into the kernels.
+__global__ void __launch_bounds__(256) pack_istft_kernel(const float* __restrict__ kc,
+                                                         const float* __restrict__ ks, int n_fft,
+                                                         int f_in, int onesided, int rows, int kpad,
+                                                         __nv_bfloat16* __restrict__ packed) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)rows * kpad) return;
+  const int n = (int)(idx / kpad), k = (int)(idx % kpad);
+  float v = 0.f;
+  if (n < n_fft && k < 2 * f_in) {
+    const int part = k / f_in, f = k % f_in;
+    const bool mirror = onesided && f > 0 && f < n_fft - f && (n_fft - f) < n_fft;
+    if (part == 0) {
+      v = __ldg(kc + (int64_t)n * n_fft + f);
+      if (mirror) v += __ldg(kc + (int64_t)n * n_fft + (n_fft - f));
+    } else {
+      v = __ldg(ks + (int64_t)n * n_fft + f);
+      if (mirror) v -= __ldg(ks + (int64_t)n * n_fft + (n_fft - f));
+      v = -v;
+    }
+  }
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  packed[idx] = hi;
+  packed[(int64_t)rows * kpad + idx] = lo;
+}
+
+int tc_pack_istft(const float* kc, const float* ks, int n_fft, int f_in, int onesided, void* packed,
+                  cudaStream_t stream) {
+  const int bn = tc_istft_bn(n_fft);
+  const int rows = (n_fft + bn - 1) / bn * bn;
+  const int kpad = tc_istft_k(f_in);
+  const int64_t n = (int64_t)rows * kpad;
+  pack_istft_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(
+      kc, ks, n_fft, f_in, onesided, rows, kpad, (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+size_t tc_istft_planes_bytes(int64_t B, int64_t T, int f_in) {
+  const int kpad = tc_istft_k(f_in);
+  return tc_workspace_bytes(B, T * kpad, kpad, kpad, 0);
+}
+
+// X (B, F, T, 2) fp32 -> A planes: row g = b*T + t, column part*F + f (K-major), bf16 hi/lo.
+__global__ void __launch_bounds__(256) istft_prep_kernel(const float* __restrict__ X, int f_in,
+                                                         int64_t T, int kpad, int64_t plane_stride,
+                                                         __nv_bfloat16* __restrict__ planes) {
+  __shared__ float tile[2][32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  const int f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* __restrict__ Xb = X + b * (int64_t)f_in * T * 2;
+  for (int r = ty; r < 32; r += 8) {
+    const int f = f0 + r;
+    const int64_t t = t0 + tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (f < f_in && t < T) v = *reinterpret_cast<const float2*>(Xb + ((int64_t)f * T + t) * 2);
+    tile[0][r][tx] = v.x;
+    tile[1][r][tx] = v.y;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t t = t0 + r;
+    const int f = f0 + tx;
+    if (t < T && f < f_in) {
+      const int64_t row = (b * T + t) * kpad;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(tile[part][tx][r], hi, lo);
+        planes[row + part * f_in + f] = hi;
+        planes[plane_stride + row + part * f_in + f] = lo;
+      }
+    }
+  }
+}
+
+int tc_istft_prep(const float* X, int64_t B, int f_in, int64_t T, void* planes_v,
+                  cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  const int kpad = tc_istft_k(f_in);
+  const SplitGeom g = split_geom(B, T * kpad, kpad, kpad, 0);
+  __nv_bfloat16* planes = (__nv_bfloat16*)planes_v;
+  // zero everything once when K has padding columns, else just the overhang rows
+  if (kpad != 2 * f_in) {
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes, 0, (size_t)2 * g.plane_stride * sizeof(__nv_bfloat16), stream));
+  } else {
+    const int rc = zero_tail(planes, g, kpad, stream);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)ceil_div64(T, 32), (unsigned)((f_in + 31) / 32), (unsigned)B);
+  istft_prep_kernel<<<grid, 256, 0, stream>>>(X, f_in, T, kpad, g.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// Divide the overlap-added frames by the window sum-square (utils.py:43-49; only where it
+// exceeds 1e-10) and strip the centre padding: out[b, i] = ola[b, i + offset] / wss(i + offset).
+__global__ void __launch_bounds__(256) istft_finalize_kernel(const float* __restrict__ ola,
+                                                             int64_t ola_pitch,
+                                                             const float* __restrict__ window,
+                                                             int n_fft, int hop, int64_t T,
+                                                             int64_t offset, float* __restrict__ out,
+                                                             int64_t out_len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b = blockIdx.y;
+  if (i >= out_len) return;
+  const int64_t s = i + offset;
+  int64_t t_hi = s / hop;
+  if (t_hi > T - 1) t_hi = T - 1;
+  float wss = 0.f;
+  for (int64_t t = t_hi; t >= 0; --t) {
+    const int64_t n = s - t * hop;
+    if (n >= n_fft) break;
+    const float w = __ldg(window + n);
+    wss = fmaf(w, w, wss);
+  }
+  float v = ola[b * ola_pitch + s];
+  if (wss > 1e-10f) v = v / wss;
+  out[b * out_len + i] = v;
+}
+
+int tc_istft_finalize(const float* ola, int64_t ola_pitch, int64_t B, const float* window,
+                      int n_fft, int hop, int64_t T, int64_t offset, float* out, int64_t out_len,
+                      cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  if (out_len <= 0 || B <= 0) return NNAB_OK;
+  dim3 grid((unsigned)ceil_div64(out_len, 256), (unsigned)B);
+  istft_finalize_kernel<<<grid, 256, 0, stream>>>(ola, ola_pitch, window, n_fft, hop, T, offset,
+                                                  out, out_len);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// ---------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -515,7 +667,25 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
       const bool valid = (g < p.nv) && (tl < p.T);
       const int64_t t = tl * p.t_mul + p.t_add;  // frame index in the output
       const int f_base = n_tile * half;
-      if constexpr (FMT == 7) {
+      if constexpr (FMT == 8) {
+        // ---- inverse STFT: window the frame's samples and overlap-add them ----
+        float* dst = p.epi.out + b * p.epi.ola_pitch + t * p.epi.ola_hop;
+        const int n_base = n_tile * (2 * half);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 2 * half; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(trow + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int n = n_base + c0 + j;
+              if (n < p.epi.F)  // F = n_fft samples per frame
+                atomicAdd(dst + n, __uint_as_float(v[j]) * __ldg(p.epi.scale + n));
+            }
+          }
+        }
+      } else if constexpr (FMT == 7) {
         // ---- split-K partial sums: fp32 (round-to-nearest) atomics into the raw planes ----
         float* rre = p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t;
 #pragma unroll 1
@@ -1187,6 +1357,7 @@ static int launch_tc2_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const
     case FMT_FBANK: return launch_tc2_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, n_pairs, stream);
     case FMT_DECIM: return launch_tc2_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, n_pairs, stream);
     case FMT_RAW: return launch_tc2_kernel_fmt<BK, STAGES, 7>(ma, mb, prm, n_pairs, stream);
+    case FMT_OLA: return launch_tc2_kernel_fmt<BK, STAGES, 8>(ma, mb, prm, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -1203,6 +1374,7 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
     case FMT_FBANK: return launch_tc_kernel_fmt<BK, STAGES, 5>(ma, mb, prm, grid, stream);
     case FMT_DECIM: return launch_tc_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, grid, stream);
     case FMT_RAW: return launch_tc_kernel_fmt<BK, STAGES, 7>(ma, mb, prm, grid, stream);
+    case FMT_OLA: return launch_tc_kernel_fmt<BK, STAGES, 8>(ma, mb, prm, grid, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -1226,8 +1398,9 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   const int hop_eff = q.hop * n_ph;
   const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
   const int kpad = round_up_i(q.K, 64);
-  const int bn = choose_bn(q.F);
-  const int n_tiles = (2 * q.F + bn - 1) / bn;
+  // FMT_OLA: the N axis is the frame's n_fft output samples (q.F), not (re | im) bin pairs
+  const int bn = (q.fmt == FMT_OLA) ? tc_istft_bn(q.F) : choose_bn(q.F);
+  const int n_tiles = (q.fmt == FMT_OLA) ? (q.F + bn - 1) / bn : (2 * q.F + bn - 1) / bn;
   const int rows_w = n_tiles * bn;
   __nv_bfloat16* planes =
       q.presplit != nullptr
@@ -1247,6 +1420,8 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   int dev = 0, sms = 148;
   NNAB_CUDA_TRY(cudaGetDevice(&dev));
   NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();  // SMs left to a concurrent collective (nnab_set_sm_reserve)
+  if (sms < 2) sms = 2;
   int cta_group = (ceil_div64(g.nv, 2 * TC_BM) * n_tiles >= sms / 2) ? 2 : 1;
   if (const char* e = getenv("NNAB_TC_CTA")) cta_group = atoi(e) == 2 ? 2 : 1;
   if (cta_group == 2) bk = 64;
@@ -1306,6 +1481,7 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
   prm.epi.dec = q.dec;
   prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
+  prm.epi.ola_pitch = q.ola_pitch; prm.epi.ola_hop = q.ola_hop;
   prm.k_splits = 1;
   if (q.fmt == FMT_FBANK && (q.fb_table == nullptr || q.n_fb <= 0)) return NNAB_EINVAL;
   if (q.fmt == FMT_DECIM && (bn != 128 || n_tiles != 1)) return NNAB_EINVAL;
@@ -1313,7 +1489,8 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   // ---- split-K (long kernels, caller supplied the raw scratch) ---------------------------
   EpiParams final_epi = prm.epi;
   bool split = false;
-  if (q.raw != nullptr && q.fmt != FMT_FBANK && q.fmt != FMT_DECIM && q.bin_offset == 0 &&
+  if (q.raw != nullptr && q.fmt != FMT_FBANK && q.fmt != FMT_DECIM && q.fmt != FMT_OLA &&
+      q.bin_offset == 0 &&
       q.out_bins == q.F) {
     int min_range = nkb;
     for (int tl = 0; tl < n_tiles; ++tl) {

@@ -2,10 +2,10 @@
 
 Public names mirror ``nnAudio.features`` for the hot-path classes of
 SURVEY.md §8 (features/__init__.py:6-14 in the reference)."""
-from .stft import STFT
+from .stft import STFT, iSTFT
 from .mel import MelSpectrogram, MFCC
 from .gammatone import Gammatonegram
 from .cqt import CQT1992v2, CQT2010v2, CQT
 from .vqt import VQT
 
-__all__ = ["STFT", "MelSpectrogram", "MFCC", "Gammatonegram", "CQT1992v2", "CQT2010v2", "CQT", "VQT"]
+__all__ = ["STFT", "iSTFT", "MelSpectrogram", "MFCC", "Gammatonegram", "CQT1992v2", "CQT2010v2", "CQT", "VQT"]

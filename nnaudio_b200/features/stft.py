@@ -22,6 +22,48 @@ _FORMATS = {
 }
 
 
+class _InverseBasis:
+    """Cache of the tensor-core packing of the (n_fft, n_fft) inverse kernels per
+    (one-sided?, bins) variant."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, kc: torch.Tensor, ks: torch.Tensor, f_in: int, onesided: bool):
+        key = (kc.data_ptr(), kc._version, ks.data_ptr(), ks._version, f_in, bool(onesided),
+               str(kc.device))
+        if key not in self._cache:
+            self._cache.clear()
+            self._cache[key] = _C.pack_istft_basis(kc, ks, f_in, onesided)
+        return self._cache[key]
+
+
+def _inverse_stft(mod, X, kernel_cos, kernel_sin, window_mask, onesided, length):
+    """Shared by ``STFT.inverse`` and ``iSTFT.forward`` (STFTBase.inverse_stft, stft.py:15-63)."""
+    n_fft = mod.n_fft
+    kc = kernel_cos.detach().reshape(kernel_cos.shape[0], -1)
+    ks = kernel_sin.detach().reshape(kernel_sin.shape[0], -1)
+    _C._dev_f32(kc, "kernel_cos")
+    if kc.shape != (n_fft, n_fft) or ks.shape != (n_fft, n_fft):
+        raise RuntimeError("inverse kernels must be (n_fft, n_fft)")
+    f_in = X.shape[1]
+    expect = n_fft // 2 + 1 if onesided else n_fft
+    if f_in != expect:
+        raise RuntimeError(
+            f"expected {expect} frequency bins for onesided={onesided} and n_fft={n_fft}, got {f_in}"
+        )
+    win = window_mask.detach().reshape(-1).float()  # iSTFT keeps scipy's float64 window
+    if win.numel() != n_fft:
+        raise RuntimeError(
+            f"The size of tensor a ({n_fft}) must match the size of tensor b ({win.numel()}) "
+            "at non-singleton dimension 1"
+        )
+    if not hasattr(mod, "_inv_basis"):
+        mod._inv_basis = _InverseBasis()
+    packed = mod._inv_basis.get(kc.contiguous(), ks.contiguous(), f_in, onesided)
+    return _C.istft_forward(X, packed, win.contiguous(), n_fft, mod.stride, mod.center, length)
+
+
 class STFT(nn.Module):
     """Short-time Fourier transform of ``(L)``, ``(B, L)`` or ``(B, 1, L)``
     waveforms.  Arguments follow the reference (stft.py:153-170).
@@ -83,8 +125,7 @@ class STFT(nn.Module):
         kernel_cos = torch.tensor(kernel_cos, dtype=torch.float)
 
         if iSTFT:
-            # state_dict compatibility only; the inverse transform is not on the
-            # accelerated path.
+            # inverse kernels for STFT.inverse (stft.py:217-223)
             sin_inv = torch.cat((kernel_sin, -kernel_sin[1:-1].flip(0)), 0)
             cos_inv = torch.cat((kernel_cos, kernel_cos[1:-1].flip(0)), 0)
             self.register_buffer("kernel_sin_inv", sin_inv.unsqueeze(-1))
@@ -148,15 +189,92 @@ class STFT(nn.Module):
         )
 
     def inverse(self, X, onesided=True, length=None, refresh_win=True):
+        """Inverse STFT of a complex spectrogram ``(B, bins, T, 2)`` (stft.py:318-356);
+        needs ``iSTFT=True`` at construction.  ``refresh_win`` is accepted for signature
+        compatibility: the window sum-square is recomputed on the fly in the kernel."""
         if not (hasattr(self, "kernel_sin_inv") and hasattr(self, "kernel_cos_inv")):
             raise NameError(
                 "Please activate the iSTFT module by setting `iSTFT=True` if you want to use `inverse`"
             )
-        raise NotImplementedError(
-            "STFT.inverse is outside the accelerated hot path of nnaudio_b200 (SURVEY.md §8f #2)"
+        assert X.dim() == 4, (
+            "Inverse iSTFT only works for complex number,"
+            "make sure our tensor is in the shape of (batch, freq_bins, timesteps, 2)."
+            "\nIf you have a magnitude spectrogram, please consider using Griffin-Lim."
         )
+        forward_only_guard(self, X)
+        return _inverse_stft(self, X, self.kernel_cos_inv, self.kernel_sin_inv, self.window_mask,
+                             onesided, length)
 
     def extra_repr(self) -> str:
         return "n_fft={}, Fourier Kernel size={}, iSTFT={}, trainable={}".format(
             self.n_fft, (*self.wsin.shape,), self.iSTFT, self.trainable
         )
+
+
+class iSTFT(nn.Module):
+    """Inverse STFT module — drop-in for ``nnAudio.features.stft.iSTFT`` (stft.py:364-546).
+    Buffers: ``kernel_sin``, ``kernel_cos`` ``(n_fft, 1, n_fft, 1)`` (un-windowed inverse
+    kernels) and ``window_mask`` ``(1, win_length, 1)``.  ``forward(X, onesided=False,
+    length=None, refresh_win=None)`` takes ``(B, bins, T, 2)`` and returns ``(B, samples)``."""
+
+    def __init__(
+        self,
+        n_fft=2048,
+        win_length=None,
+        freq_bins=None,
+        hop_length=None,
+        window="hann",
+        freq_scale="no",
+        center=True,
+        fmin=50,
+        fmax=6000,
+        sr=22050,
+        trainable_kernels=False,
+        trainable_window=False,
+        verbose=True,
+        refresh_win=True,
+    ):
+        super().__init__()
+        if win_length is None:
+            win_length = n_fft
+        if hop_length is None:
+            hop_length = int(win_length // 4)
+        self.n_fft = n_fft
+        self.win_length = win_length
+        self.stride = hop_length
+        self.center = center
+        self.pad_amount = self.n_fft // 2
+        self.refresh_win = refresh_win
+        start = time()
+
+        kernel_sin, kernel_cos, _, _, _ = design.fourier_basis(
+            n_fft, win_length=win_length, freq_bins=n_fft, window=window, freq_scale=freq_scale,
+            fmin=fmin, fmax=fmax, sr=sr, verbose=False,
+        )
+        from scipy.signal import get_window
+
+        window_mask = torch.tensor(get_window(window, int(win_length), fftbins=True))
+        window_mask = window_mask.unsqueeze(0).unsqueeze(-1)
+        kernel_sin = torch.tensor(kernel_sin, dtype=torch.float).unsqueeze(-1)
+        kernel_cos = torch.tensor(kernel_cos, dtype=torch.float).unsqueeze(-1)
+        if trainable_kernels:
+            self.register_parameter("kernel_sin", nn.Parameter(kernel_sin, requires_grad=True))
+            self.register_parameter("kernel_cos", nn.Parameter(kernel_cos, requires_grad=True))
+        else:
+            self.register_buffer("kernel_sin", kernel_sin)
+            self.register_buffer("kernel_cos", kernel_cos)
+        if trainable_window:
+            self.register_parameter("window_mask", nn.Parameter(window_mask, requires_grad=True))
+        else:
+            self.register_buffer("window_mask", window_mask)
+        if verbose:
+            print("iSTFT kernels created, time used = {:.4f} seconds".format(time() - start))
+
+    def forward(self, X, onesided=False, length=None, refresh_win=None):
+        assert X.dim() == 4, (
+            "Inverse iSTFT only works for complex number,"
+            "make sure our tensor is in the shape of (batch, freq_bins, timesteps, 2)"
+        )
+        forward_only_guard(self, X)
+        return _inverse_stft(self, X, self.kernel_cos, self.kernel_sin, self.window_mask, onesided,
+                             length)

@@ -38,10 +38,20 @@ class BatchShardedTransform:
     """
 
     def __init__(self, transform: Callable[[torch.Tensor], torch.Tensor],
-                 group: Optional[dist.ProcessGroup] = None, gather: bool = True):
+                 group: Optional[dist.ProcessGroup] = None, gather: bool = True,
+                 reserve_sms: int = 8):
+        """``reserve_sms``: SMs kept out of the persistent tensor-core grids while a
+        gather may be in flight — the kernels otherwise occupy all 148 SMs and NCCL's
+        CTAs could only start at their tail (no overlap)."""
         self.transform = transform
         self.group = group
         self.gather = gather
+        if gather and dist.is_initialized() and dist.get_world_size(group) > 1 and reserve_sms > 0:
+            try:
+                from . import _C
+                _C.set_sm_reserve(reserve_sms)
+            except Exception:  # noqa: BLE001  (CPU-only test processes have no use for it)
+                pass
         self._buf = None
         self._slots = {}
 

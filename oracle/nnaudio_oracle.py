@@ -40,6 +40,7 @@ __all__ = [
     "cqt_octave_complex",
     "cqt2010v2",
     "vqt",
+    "istft",
 ]
 
 
@@ -335,3 +336,44 @@ def vqt(x, banks, lowpass_filter, lenghts, hop, n_bins, pad_mode="reflect",
             "The normalization_type %r is not part of our current options." % normalization_type
         )
     return _cqt_format(real, imag, output_format, trainable, dtype)
+
+
+# --------------------------------------------------------------------------- #
+# inverse STFT  
+# --------------------------------------------------------------------------- #
+def istft(X, kernel_cos, kernel_sin, window_mask, hop, center=True, onesided=True, length=None,
+          dtype=np.float64):
+    """STFTBase.inverse_stft (stft.py:15-63).
+
+    X (B, F, T, 2); kernel_cos / kernel_sin: the (n_fft, 1, n_fft[, 1]) inverse kernels
+    (``kernel_cos_inv`` of STFT(iSTFT=True) or ``kernel_cos`` of the iSTFT module);
+    window_mask: (1, n_fft, 1).  Steps: mirror the one-sided spectrum
+    (utils.py:63-70), contract with the kernels over the frequency axis, window and
+    divide by n_fft, overlap-add with stride ``hop`` (utils.py:52-56), divide by the
+    window sum-square where it exceeds 1e-10 (utils.py:43-49), strip the centre padding.
+    """
+    X = np.asarray(X).astype(dtype)
+    kc = np.asarray(kernel_cos).astype(dtype).reshape(kernel_cos.shape[0], -1)
+    ks = np.asarray(kernel_sin).astype(dtype).reshape(kernel_sin.shape[0], -1)
+    win = np.asarray(window_mask).astype(dtype).reshape(-1)
+    n_fft = kc.shape[0]
+    if onesided:
+        upper = X[:, 1:-1][:, ::-1].copy()
+        upper[..., 1] = -upper[..., 1]
+        X = np.concatenate((X, upper), axis=1)
+    Xr, Xi = X[..., 0], X[..., 1]                      # (B, n_fft, T)
+    real = np.einsum("of,bft->bot", kc, Xr) - np.einsum("of,bft->bot", ks, Xi)
+    real = real * win[None, :, None] / n_fft
+    B, _, T = real.shape
+    out_len = n_fft + hop * (T - 1)
+    y = np.zeros((B, out_len), dtype=dtype)
+    wss = np.zeros(out_len, dtype=dtype)
+    for t in range(T):
+        y[:, t * hop: t * hop + n_fft] += real[:, :, t]
+        wss[t * hop: t * hop + n_fft] += win ** 2
+    nz = wss > 1e-10
+    y[:, nz] = y[:, nz] / wss[nz]
+    pad = n_fft // 2
+    if length is None:
+        return y[:, pad:-pad] if center else y
+    return y[:, pad: pad + length] if center else y[:, :length]

@@ -116,6 +116,17 @@ REF_GROUND_TRUTHS = {
 SWEEP_CTOR = dict(sr=44100, fmin=55, n_bins=207, bins_per_octave=24)
 
 
+# Inverse STFT cases: id, n_fft, hop, window, kind, spec
+#   'roundtrip': X = reference STFT(iSTFT=True)(x), y = .inverse(X, onesided=True, length=L|None)
+#   'module'   : y = reference iSTFT(...)(X_random, onesided=False)
+ISTFT_CASES = [
+    ("istft_roundtrip_512", 512, 128, "hann", "roundtrip", dict(seed=70, shape=(2, 4000), length=4000)),
+    ("istft_roundtrip_1024_nolen", 1024, 256, "hamming", "roundtrip", dict(seed=71, shape=(2, 8000), length=None)),
+    ("istft_roundtrip_2048", 2048, 512, "hann", "roundtrip", dict(seed=72, shape=(1, 22050), length=22050)),
+    ("istft_module_256_full", 256, 64, "hann", "module", dict(seed=73, shape=(2, 256, 40, 2))),
+]
+
+
 def out_key(case_id: str, fwd_kwargs: dict) -> str:
     tag = "_".join(f"{k[:3]}-{v}" for k, v in sorted(fwd_kwargs.items()))
     return f"{case_id}|{tag}" if tag else case_id

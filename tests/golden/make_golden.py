@@ -28,7 +28,7 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
-from cases import CASES, REF_GROUND_TRUTHS, SWEEP_CTOR, make_input, out_key  # noqa: E402
+from cases import CASES, ISTFT_CASES, REF_GROUND_TRUTHS, SWEEP_CTOR, make_input, out_key  # noqa: E402
 
 from nnAudio import features as ref_features  # noqa: E402
 
@@ -56,6 +56,25 @@ def main():
                 y = mod(x, **kw)
             outputs[out_key(cid, kw)] = y.numpy().astype(np.float32)
             print(f"{out_key(cid, kw):60s} {tuple(y.shape)}")
+    # inverse STFT: spectrogram inputs AND waveform outputs of the reference
+    for cid, n_fft, hop, win, kind, spec in ISTFT_CASES:
+        rng = np.random.RandomState(spec["seed"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if kind == "roundtrip":
+                st = ref_features.STFT(n_fft=n_fft, hop_length=hop, window=win, iSTFT=True, verbose=False)
+                x = torch.from_numpy(rng.standard_normal(spec["shape"]).astype(np.float32))
+                with torch.no_grad():
+                    X = st(x)
+                    y = st.inverse(X, onesided=True, length=spec["length"])
+            else:
+                im = ref_features.iSTFT(n_fft=n_fft, hop_length=hop, window=win, verbose=False)
+                X = torch.from_numpy(rng.standard_normal(spec["shape"]).astype(np.float32))
+                with torch.no_grad():
+                    y = im(X, onesided=False)
+        outputs[cid + "|X"] = X.numpy().astype(np.float32)
+        outputs[cid + "|y"] = y.numpy().astype(np.float32)
+        print(f"{cid:60s} X{tuple(X.shape)} -> y{tuple(y.shape)}")
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **outputs)
     with open(os.path.join(HERE, "ref_buffers.json"), "w") as f:
         json.dump(buffers, f, indent=1, sort_keys=True)
