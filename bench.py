@@ -45,8 +45,10 @@ WORKLOADS = {
 }
 
 
-# SMs left to the NCCL gather while the persistent kernels run (measured, profiles/README.md)
-DEFAULT_RESERVE = {1: 0, 2: 8, 4: 8, 8: 16}
+# SMs left to the NCCL gather while the persistent kernels run, and the matching NCCL CTA cap
+# (the gather of (N-1) x 14 MB must hide under one ~0.47 ms transform; measured ~14.5 GB/s per
+# NCCL CTA next to the kernels: 8 CTAs suffice at N=4, not at N=8 — profiles/README.md)
+DEFAULT_RESERVE = {1: 0, 2: 4, 4: 8, 8: 16}
 
 
 def frames_per_clip(w):
@@ -196,7 +198,8 @@ def _run():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs kept free for the concurrent NCCL gather (default: by world size)")
-    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="0 = NCCL default")
+    ap.add_argument("--nccl-max-ctas", type=int, default=-1,
+                    help="-1 = same as the SM reserve (default), 0 = NCCL's own default")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -243,8 +246,10 @@ def _run():
     if world > 1:
         # few CTAs for the output gather: it overlaps the next batch's kernels (which leave
         # 8 SMs free for it, nnaudio_b200.parallel) and 99 MB per step does not need more
-        if args.nccl_max_ctas > 0:
-            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
+        reserve_plan = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
+        max_ctas = args.nccl_max_ctas if args.nccl_max_ctas >= 0 else reserve_plan
+        if max_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(max_ctas)
         dist.init_process_group("nccl", device_id=dev)
 
     B = w["B"]
