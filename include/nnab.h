@@ -228,6 +228,23 @@ int nnab_istft_forward(const float* X, int64_t B, int f_in, int64_t T, const voi
                        float* out, int64_t out_len, void* workspace, size_t ws_bytes,
                        void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Input gradient of the framed complex contraction (SURVEY §8f "next" #1, the dX half;
+ * the reference gets it from autograd through conv1d, stft.py:290-293 / cqt.py:749-750):
+ *   g   (B, F, T, 2)  gradient w.r.t. (real, imag) = (conv(x, w_re), -conv(x, w_im))
+ *   dx  (B, L)        = pad^T ( overlap_add_t ( g_re[., t] @ w_re - g_im[., t] @ w_im ) )
+ * `packed_adj` = nnab_pack_adjoint_basis(w_re, w_im) (W^T rows, bf16 hi/lo).  One GEMM on
+ * the tensor-core kernel with the overlap-add epilogue, then the padding adjoint.
+ * ------------------------------------------------------------------------- */
+size_t nnab_packed_adjoint_bytes(int K, int F);
+int nnab_pack_adjoint_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
+                            void* stream);
+size_t nnab_framed_backward_input_workspace_bytes(int64_t B, int64_t L, int K, int F, int hop,
+                                                  int center);
+int nnab_framed_backward_input(const float* g, int64_t B, int F, int64_t T, const void* packed_adj,
+                               int K, int hop, int center, int pad_mode, float* dx, int64_t L,
+                               void* workspace, size_t ws_bytes, void* stream);
+
 /* Kernel launches issued by this library since load (process wide; used by
  * bench.py for its `gpu_launches` claim). */
 uint64_t nnab_launch_count(void);

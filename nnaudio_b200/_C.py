@@ -73,6 +73,14 @@ SIGNATURES = {
         [_P, c_int64, c_int, c_int64, _P, _P, c_int, c_int, c_int, c_int64, _P, c_int64, _P,
          c_size_t, _P],
     ),
+    "nnab_packed_adjoint_bytes": (c_size_t, [c_int, c_int]),
+    "nnab_pack_adjoint_basis": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "nnab_framed_backward_input_workspace_bytes": (
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
+    "nnab_framed_backward_input": (
+        c_int,
+        [_P, c_int64, c_int, c_int64, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P, c_size_t, _P],
+    ),
     "nnab_packed_fir_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_fir": (c_int, [_P, c_int, c_int, _P, _P]),
     "nnab_cqt_pyramid_workspace_bytes": (
@@ -391,3 +399,31 @@ def istft_forward(X, packed, window, n_fft, hop, center, length):
                                   want, _ptr(ws), wsb, _stream(X.device))
     _check(rc, "nnab_istft_forward")
     return out
+
+
+def pack_adjoint_basis(w_re: torch.Tensor, w_im: torch.Tensor):
+    """W^T packing of an (F, K) forward basis pair for the input-gradient GEMM."""
+    L = lib()
+    F, K = w_re.shape
+    packed = torch.empty(L.nnab_packed_adjoint_bytes(K, F), dtype=torch.uint8, device=w_re.device)
+    with torch.cuda.device(w_re.device):
+        _check(L.nnab_pack_adjoint_basis(_ptr(w_re), _ptr(w_im), F, K, _ptr(packed),
+                                         _stream(w_re.device)), "nnab_pack_adjoint_basis")
+    return packed
+
+
+def framed_backward_input(g, packed_adj, K, hop, center, pad_mode, L_in):
+    """g (B, F, T, 2) -> dx (B, L_in)."""
+    L = lib()
+    g = _dev_f32(g, "grad")
+    g = g if g.is_contiguous() else g.contiguous()
+    B, F, T, _ = g.shape
+    dx = torch.empty((B, L_in), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        ws, wsb = _workspace(
+            L.nnab_framed_backward_input_workspace_bytes(B, L_in, K, F, hop, int(center)), g.device)
+        rc = L.nnab_framed_backward_input(_ptr(g), B, F, T, _ptr(packed_adj), K, hop, int(center),
+                                          pad_mode, _ptr(dx), L_in, _ptr(ws), wsb,
+                                          _stream(g.device))
+    _check(rc, "nnab_framed_backward_input")
+    return dx

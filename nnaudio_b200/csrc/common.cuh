@@ -118,7 +118,9 @@ int tc_istft_k(int f_in);
 int tc_istft_bn(int n_fft);
 size_t tc_packed_istft_bytes(int n_fft, int f_in);
 int tc_pack_istft(const float* kc, const float* ks, int n_fft, int f_in, int onesided, void* packed,
-                  cudaStream_t stream);
+                  cudaStream_t stream, int transposed = 0);
+int tc_unpad_adjoint(const float* gp, int64_t gp_pitch, int64_t gp_len, int64_t B, int pad,
+                     int pad_mode, int64_t L, float* dx, cudaStream_t stream);
 size_t tc_istft_planes_bytes(int64_t B, int64_t T, int f_in);
 int tc_istft_prep(const float* X, int64_t B, int f_in, int64_t T, void* planes, cudaStream_t stream);
 int tc_istft_finalize(const float* ola, int64_t ola_pitch, int64_t B, const float* window,

@@ -785,4 +785,57 @@ int nnab_istft_forward(const float* X, int64_t B, int f_in, int64_t T, const voi
   return tc_istft_finalize(ola, ola_pitch, B, window, n_fft, hop, T, offset, out, want, s);
 }
 
+// ------------------------------------------------------------- input gradient ----
+size_t nnab_packed_adjoint_bytes(int K, int F) { return tc_packed_istft_bytes(K, F); }
+
+int nnab_pack_adjoint_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
+                            void* stream) {
+  if (w_re == nullptr || w_im == nullptr || packed == nullptr || F <= 0 || K <= 0) return NNAB_EINVAL;
+  return tc_pack_istft(w_re, w_im, K, F, 0, packed, (cudaStream_t)stream, /*transposed=*/1);
+}
+
+size_t nnab_framed_backward_input_workspace_bytes(int64_t B, int64_t L, int K, int F, int hop,
+                                                  int center) {
+  const int pad = center ? K / 2 : 0;
+  const int64_t T = frames_of(L, K, hop, pad);
+  const int64_t pitch = (int64_t)align_up((size_t)(L + 2 * (int64_t)pad + K), 8);
+  return align_up(tc_istft_planes_bytes(B, T, F), 256) +
+         align_up((size_t)B * pitch * sizeof(float), 256) + 256;
+}
+
+int nnab_framed_backward_input(const float* g, int64_t B, int F, int64_t T, const void* packed_adj,
+                               int K, int hop, int center, int pad_mode, float* dx, int64_t L,
+                               void* workspace, size_t ws_bytes, void* stream) {
+  if (g == nullptr || packed_adj == nullptr || dx == nullptr || B < 0 || F <= 0 || K <= 0 ||
+      hop <= 0 || L <= 0)
+    return NNAB_EINVAL;
+  const int pad = center ? K / 2 : 0;
+  if (T != frames_of(L, K, hop, pad) || T <= 0) return NNAB_EINVAL;
+  int rc = check_arch();
+  if (rc) return rc;
+  const size_t need = nnab_framed_backward_input_workspace_bytes(B, L, K, F, hop, center);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (B == 0) return NNAB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  void* planes = ws;
+  const size_t planes_b = align_up(tc_istft_planes_bytes(B, T, F), 256);
+  const int64_t gp_len = L + 2 * (int64_t)pad;
+  const int64_t pitch = (int64_t)align_up((size_t)(gp_len + K), 8);
+  float* gp = (float*)(ws + planes_b);
+
+  if ((rc = tc_istft_prep(g, B, F, T, planes, s))) return rc;
+  NNAB_CUDA_TRY(cudaMemsetAsync(gp, 0, (size_t)B * pitch * sizeof(float), s));
+  const int kpad = tc_istft_k(F);
+  FramedProblem p{};
+  p.x = nullptr; p.B = B; p.L = T * (int64_t)kpad; p.x_pitch = 0;
+  p.F = K; p.K = kpad; p.hop = kpad; p.pad = 0; p.pad_mode = NNAB_PAD_CONSTANT;
+  p.scale = nullptr; p.scale_all = 1.f; p.fmt = FMT_OLA; p.eps = 0.f; p.power = 1.f;
+  p.out = gp; p.T = T; p.out_bins = K; p.bin_offset = 0;
+  p.presplit = planes;
+  p.ola_pitch = pitch; p.ola_hop = hop;
+  if ((rc = run_framed(p, packed_adj, nullptr, 0, NNAB_PATH_TCGEN05, s))) return rc;
+  return tc_unpad_adjoint(gp, pitch, gp_len, B, pad, pad_mode, L, dx, s);
+}
+
 }  // extern "C"

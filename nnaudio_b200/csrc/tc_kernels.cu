@@ -356,9 +356,12 @@ size_t tc_packed_istft_bytes(int n_fft, int f_in) {
 // Winv[n][f]        = KC[n][f] (+ KC[n][N-f] for a mirrored one-sided bin)          re part
 // Winv[n][F_in + f] = -(KS[n][f] (- KS[n][N-f]))                                    im part
 // i.e. the reference's extend_fbins (utils.py:63-70) folded into the kernels.
+// With `transposed` the inputs are the FORWARD bases (f_in, n_fft) = wcos / wsin and the rows
+// become W^T (the adjoint used by the input gradient): Winv[n][f] = wcos[f][n], -wsin[f][n].
 __global__ void __launch_bounds__(256) pack_istft_kernel(const float* __restrict__ kc,
                                                          const float* __restrict__ ks, int n_fft,
-                                                         int f_in, int onesided, int rows, int kpad,
+                                                         int f_in, int onesided, int transposed,
+                                                         int rows, int kpad,
                                                          __nv_bfloat16* __restrict__ packed) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)rows * kpad) return;
@@ -366,8 +369,10 @@ __global__ void __launch_bounds__(256) pack_istft_kernel(const float* __restrict
   float v = 0.f;
   if (n < n_fft && k < 2 * f_in) {
     const int part = k / f_in, f = k % f_in;
-    const bool mirror = onesided && f > 0 && f < n_fft - f && (n_fft - f) < n_fft;
-    if (part == 0) {
+    const bool mirror = onesided && !transposed && f > 0 && f < n_fft - f && (n_fft - f) < n_fft;
+    if (transposed) {
+      v = part == 0 ? __ldg(kc + (int64_t)f * n_fft + n) : -__ldg(ks + (int64_t)f * n_fft + n);
+    } else if (part == 0) {
       v = __ldg(kc + (int64_t)n * n_fft + f);
       if (mirror) v += __ldg(kc + (int64_t)n * n_fft + (n_fft - f));
     } else {
@@ -383,13 +388,13 @@ __global__ void __launch_bounds__(256) pack_istft_kernel(const float* __restrict
 }
 
 int tc_pack_istft(const float* kc, const float* ks, int n_fft, int f_in, int onesided, void* packed,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int transposed) {
   const int bn = tc_istft_bn(n_fft);
   const int rows = (n_fft + bn - 1) / bn * bn;
   const int kpad = tc_istft_k(f_in);
   const int64_t n = (int64_t)rows * kpad;
   pack_istft_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(
-      kc, ks, n_fft, f_in, onesided, rows, kpad, (__nv_bfloat16*)packed);
+      kc, ks, n_fft, f_in, onesided, transposed, rows, kpad, (__nv_bfloat16*)packed);
   NNAB_LAUNCH_CHECK();
   return NNAB_OK;
 }
@@ -449,6 +454,35 @@ int tc_istft_prep(const float* X, int64_t B, int f_in, int64_t T, void* planes_v
   }
   dim3 grid((unsigned)ceil_div64(T, 32), (unsigned)((f_in + 31) / 32), (unsigned)B);
   istft_prep_kernel<<<grid, 256, 0, stream>>>(X, f_in, T, kpad, g.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// Adjoint of nn.ReflectionPad1d / ConstantPad1d(pad): fold the gradient of the padded signal
+// back onto the clip (mirror margins add onto samples 1..pad and L-1-pad..L-2).
+__global__ void __launch_bounds__(256) unpad_adjoint_kernel(const float* __restrict__ gp,
+                                                            int64_t gp_pitch, int64_t gp_len,
+                                                            int pad, int pad_mode, int64_t L,
+                                                            float* __restrict__ dx) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b = blockIdx.y;
+  if (j >= L) return;
+  const float* __restrict__ g = gp + b * gp_pitch;
+  auto at = [&](int64_t i) { return (i >= 0 && i < gp_len) ? g[i] : 0.f; };
+  float v = at(pad + j);
+  if (pad > 0 && pad_mode == NNAB_PAD_REFLECT) {
+    if (j >= 1 && j <= pad) v += at(pad - j);
+    if (j >= L - 1 - pad && j <= L - 2) v += at(pad + 2 * (L - 1) - j);
+  }
+  dx[b * L + j] = v;
+}
+
+int tc_unpad_adjoint(const float* gp, int64_t gp_pitch, int64_t gp_len, int64_t B, int pad,
+                     int pad_mode, int64_t L, float* dx, cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  if (B <= 0 || L <= 0) return NNAB_OK;
+  dim3 grid((unsigned)ceil_div64(L, 256), (unsigned)B);
+  unpad_adjoint_kernel<<<grid, 256, 0, stream>>>(gp, gp_pitch, gp_len, pad, pad_mode, L, dx);
   NNAB_LAUNCH_CHECK();
   return NNAB_OK;
 }
@@ -681,7 +715,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
             for (int j = 0; j < 8; ++j) {
               const int n = n_base + c0 + j;
               if (n < p.epi.F)  // F = n_fft samples per frame
-                atomicAdd(dst + n, __uint_as_float(v[j]) * __ldg(p.epi.scale + n));
+                atomicAdd(dst + n, p.epi.scale != nullptr
+                                       ? __uint_as_float(v[j]) * __ldg(p.epi.scale + n)
+                                       : __uint_as_float(v[j]));
             }
           }
         }

@@ -35,15 +35,54 @@ def pad_mode_id(pad_mode: str) -> int:
 
 
 def forward_only_guard(module: torch.nn.Module, x: torch.Tensor):
-    """The fused kernels are forward-only in this round:
-    refuse loudly rather than return a silently non-differentiable result."""
+    """Gradients w.r.t. the *input* are supported (``wants_input_grad``); gradients w.r.t.
+    trainable bases / filterbanks (dW) are not built yet: refuse loudly
+    rather than return a result whose parameters silently receive no gradient."""
     if not torch.is_grad_enabled():
         return
-    if x.requires_grad or any(p.requires_grad for p in module.parameters()):
+    if any(p.requires_grad for p in module.parameters()):
         raise NotImplementedError(
-            "nnaudio_b200 kernels are forward-only: run under torch.no_grad() "
-            "(autograd through the fused kernels is not implemented yet)"
+            "nnaudio_b200 kernels are forward-only for trainable kernels: run under "
+            "torch.no_grad() (autograd w.r.t. the bases is not implemented yet; gradients "
+            "w.r.t. the input waveform are)"
         )
+
+
+def wants_input_grad(x: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and x.requires_grad
+
+
+class FramedComplexFn(torch.autograd.Function):
+    """Differentiable-w.r.t.-input complex framed contraction ``x -> (B, F, T, 2)``:
+    forward = the fused kernel, backward = ``nnab_framed_backward_input`` (one GEMM with the
+    transposed basis + overlap-add, then the adjoint of the centre padding)."""
+
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        ctx.in_shape = x.shape
+        with torch.no_grad():
+            return fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        dx = ctx.bwd(g.contiguous(), ctx.in_shape[-1])
+        return dx.reshape(ctx.in_shape), None, None
+
+
+class AdjointBasis:
+    """Cache of the W^T packing used by the input-gradient GEMM."""
+
+    def __init__(self):
+        self._key = None
+        self._packed = None
+
+    def get(self, w_re: torch.Tensor, w_im: torch.Tensor):
+        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, str(w_re.device))
+        if key != self._key:
+            self._packed = _C.pack_adjoint_basis(w_re, w_im)
+            self._key = key
+        return self._packed
 
 
 class PackedBasis:

@@ -13,8 +13,9 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import (PackedBasis, PackedFir, as_matrix, broadcast_dim, forward_only_guard,
-                      pad_mode_id, tap_support)
+from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, PackedFir, as_matrix,
+                      broadcast_dim, forward_only_guard, pad_mode_id, tap_support,
+                      wants_input_grad)
 
 _FORMATS = {
     "Magnitude": _C.FMT_MAGNITUDE,
@@ -145,6 +146,34 @@ class CQT1992v2(nn.Module):
         elif normalization_type == "wrap":
             scale_all = 2.0
         eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
+        if wants_input_grad(x):
+            # un-normalised complex CQT through the fused kernel + dX kernel; normalisation and
+            # output format (cqt.py:752-780) composed in torch for autograd
+            if not hasattr(self, "_adjoint"):
+                self._adjoint = AdjointBasis()
+
+            def fwd(t):
+                return _C.cqt1992v2_forward(t, k_real, k_imag, packed, k_begin, k_end,
+                                            self.hop_length, self.center,
+                                            pad_mode_id(self.pad_mode), None, 1.0,
+                                            _C.FMT_COMPLEX, 0.0)
+
+            def bwd(g, L):
+                return _C.framed_backward_input(g, self._adjoint.get(k_real, k_imag),
+                                                self.kernel_width, self.hop_length, self.center,
+                                                pad_mode_id(self.pad_mode), L)
+
+            c = FramedComplexFn.apply(x, fwd, bwd)
+            if scale is not None:
+                c = c * scale.view(1, -1, 1, 1)
+            elif scale_all != 1.0:
+                c = c * scale_all
+            if output_format == "Complex":
+                return c
+            if output_format == "Magnitude":
+                return torch.sqrt(c[..., 0].pow(2) + c[..., 1].pow(2) + eps)
+            ang = torch.atan2(c[..., 1], c[..., 0])
+            return torch.stack((torch.cos(ang), torch.sin(ang)), -1)
         return _C.cqt1992v2_forward(
             x, k_real, k_imag, packed, k_begin, k_end, self.hop_length, self.center,
             pad_mode_id(self.pad_mode), scale, scale_all, _FORMATS[output_format], eps,
@@ -318,6 +347,11 @@ class CQT2010v2(nn.Module):
 def _pyramid_forward(mod, x, output_format, normalization_type):
     """Shared by CQT2010v2 and VQT: plan the octave lengths on the host (for the
     reference's warnings / errors), then one C call."""
+    if wants_input_grad(x):
+        raise NotImplementedError(
+            "gradients through the CQT2010v2 / VQT pyramid are not implemented yet; "
+            "run under torch.no_grad()"
+        )
     banks_real, banks_imag, packed = mod._banks()
     early = mod.early_downsample_filter if mod.earlydownsample else None
     factor = int(mod.downsample_factor) if mod.earlydownsample else 1

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import FilterbankTable, as_matrix, forward_only_guard, pad_mode_id
+from ._common import FilterbankTable, as_matrix, forward_only_guard, pad_mode_id, wants_input_grad
 from .stft import STFT
 
 
@@ -81,6 +81,8 @@ class MelSpectrogram(nn.Module):
     def forward(self, x):
         x = self.stft._checked_input(x)
         forward_only_guard(self, x)
+        if wants_input_grad(x):  # mel.py:186-188 on top of the differentiable STFT magnitude
+            return torch.matmul(self._filterbank().detach(), self.stft._magnitude_diff(x) ** self.power)
         wcos, wsin, packed = self.stft._bases()
         fb = self._filterbank().detach()
         _C._dev_f32(fb, "filterbank")
@@ -133,6 +135,15 @@ class MFCC(nn.Module):
         mel = self.melspec_layer
         x = mel.stft._checked_input(x)
         forward_only_guard(self, x)
+        if wants_input_grad(x):  # mel.py:263-279, :281-307 composed in torch for autograd
+            S = mel(x)
+            amin = torch.tensor(self._amin_host, device=S.device)
+            log_spec = 10.0 * torch.log10(torch.clamp(S, min=self._amin_host))
+            log_spec = log_spec - 10.0 * torch.log10(torch.clamp(amin, min=self._ref_host))
+            if self.top_db is not None:
+                peak = log_spec.flatten(1).max(1)[0][:, None, None]
+                log_spec = torch.max(log_spec, peak - self.top_db)
+            return torch.matmul(self._dct_rows, log_spec)
         wcos, wsin, packed = mel.stft._bases()
         fb = mel.mel_basis.detach()
         _C._dev_f32(fb, "mel_basis")

@@ -13,7 +13,8 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import PackedBasis, as_matrix, broadcast_dim, forward_only_guard, pad_mode_id
+from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, as_matrix, broadcast_dim,
+                      forward_only_guard, pad_mode_id, wants_input_grad)
 
 _FORMATS = {
     "Magnitude": _C.FMT_MAGNITUDE,
@@ -173,6 +174,30 @@ class STFT(nn.Module):
             wcos, wsin = wcos[: self.freq_bins], wsin[: self.freq_bins]
         return wcos, wsin, self._packed.get(wcos, wsin)
 
+    def _run(self, x, output_format):
+        wcos, wsin, packed = self._bases()
+        eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
+        return _C.stft_forward(
+            x, wcos, wsin, packed, self.n_fft, self.stride, self.center,
+            pad_mode_id(self.pad_mode), _FORMATS[output_format], eps,
+        )
+
+    def _backward_input(self, g, L):
+        wcos, wsin, _ = self._bases()
+        if not hasattr(self, "_adjoint"):
+            self._adjoint = AdjointBasis()
+        return _C.framed_backward_input(g, self._adjoint.get(wcos, wsin), self.n_fft, self.stride,
+                                        self.center, pad_mode_id(self.pad_mode), L)
+
+    def _complex_diff(self, x):
+        """(B, F, T, 2) with a gradient path back to ``x``."""
+        return FramedComplexFn.apply(x, lambda t: self._run(t, "Complex"), self._backward_input)
+
+    def _magnitude_diff(self, x):
+        c = self._complex_diff(x)
+        spec = c[..., 0].pow(2) + c[..., 1].pow(2)
+        return torch.sqrt(spec + 1e-8) if self.trainable else torch.sqrt(spec)
+
     def forward(self, x, output_format=None):
         output_format = output_format or self.output_format
         if output_format not in _FORMATS:
@@ -181,12 +206,16 @@ class STFT(nn.Module):
             )
         x = self._checked_input(x)
         forward_only_guard(self, x)
-        wcos, wsin, packed = self._bases()
-        eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
-        return _C.stft_forward(
-            x, wcos, wsin, packed, self.n_fft, self.stride, self.center,
-            pad_mode_id(self.pad_mode), _FORMATS[output_format], eps,
-        )
+        if wants_input_grad(x):
+            # training through the layer: fused complex contraction + dX kernel, the light
+            # element-wise tail (stft.py:299-316) composed in torch for autograd
+            if output_format == "Complex":
+                return self._complex_diff(x)
+            if output_format == "Magnitude":
+                return self._magnitude_diff(x)
+            c = self._complex_diff(x)
+            return torch.atan2(c[..., 1] + 0.0, c[..., 0])
+        return self._run(x, output_format)
 
     def inverse(self, X, onesided=True, length=None, refresh_win=True):
         """Inverse STFT of a complex spectrogram ``(B, bins, T, 2)`` (stft.py:318-356);

@@ -127,6 +127,34 @@ ISTFT_CASES = [
 ]
 
 
+# Input-gradient cases (dX): loss = sum(out * w), w ~ N(0,1) seeded;
+# the fixture holds the reference's x.grad (autograd through its conv1d path on CPU).
+GRAD_CASES = [
+    ("grad_stft_complex", "STFT", dict(n_fft=512, hop_length=128), ("randn", 80, (2, 4000)),
+     dict(output_format="Complex")),
+    ("grad_stft_magnitude", "STFT", dict(n_fft=512, hop_length=128), ("randn", 81, (2, 4000)),
+     dict(output_format="Magnitude")),
+    ("grad_stft_oddhop_constant", "STFT", dict(n_fft=256, hop_length=100, pad_mode="constant"),
+     ("randn", 82, (1, 3000)), dict(output_format="Magnitude")),
+    ("grad_mel", "MelSpectrogram", dict(sr=16000, n_fft=512, hop_length=128, n_mels=40),
+     ("randn", 83, (2, 8000)), dict()),
+    ("grad_mfcc", "MFCC", dict(sr=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=13),
+     ("randn", 84, (2, 6000)), dict()),
+    ("grad_gammatone", "Gammatonegram", dict(sr=22050, n_fft=1024, n_bins=32, hop_length=256),
+     ("randn", 85, (1, 8000)), dict()),
+    ("grad_cqt1992v2_mag", "CQT1992v2", dict(sr=22050, fmin=220, n_bins=48, hop_length=256),
+     ("randn", 86, (2, 16000)), dict(output_format="Magnitude")),
+    ("grad_cqt1992v2_complex_wrap", "CQT1992v2",
+     dict(sr=22050, fmin=440, n_bins=24, hop_length=128, center=False),
+     ("randn", 87, (1, 8000)), dict(output_format="Complex", normalization_type="wrap")),
+]
+
+
+def loss_weights(case_id: str, shape) -> np.ndarray:
+    seed = 1000 + sum(ord(c) for c in case_id) % 1000
+    return np.random.RandomState(seed).standard_normal(shape).astype(np.float32)
+
+
 def out_key(case_id: str, fwd_kwargs: dict) -> str:
     tag = "_".join(f"{k[:3]}-{v}" for k, v in sorted(fwd_kwargs.items()))
     return f"{case_id}|{tag}" if tag else case_id

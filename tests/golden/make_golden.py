@@ -28,7 +28,8 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
-from cases import CASES, ISTFT_CASES, REF_GROUND_TRUTHS, SWEEP_CTOR, make_input, out_key  # noqa: E402
+from cases import (CASES, GRAD_CASES, ISTFT_CASES, REF_GROUND_TRUTHS, SWEEP_CTOR,  # noqa: E402
+                   loss_weights, make_input, out_key)
 
 from nnAudio import features as ref_features  # noqa: E402
 
@@ -75,6 +76,17 @@ def main():
         outputs[cid + "|X"] = X.numpy().astype(np.float32)
         outputs[cid + "|y"] = y.numpy().astype(np.float32)
         print(f"{cid:60s} X{tuple(X.shape)} -> y{tuple(y.shape)}")
+    # input gradients through the reference's own autograd path
+    for cid, cls, ctor, inp, kw in GRAD_CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = getattr(ref_features, cls)(verbose=False, **ctor)
+        x = torch.from_numpy(make_input(inp)).requires_grad_(True)
+        y = mod(x, **kw)
+        w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
+        (y * w).sum().backward()
+        outputs["grad|" + cid] = x.grad.numpy().astype(np.float32)
+        print(f"{'grad|' + cid:60s} out{tuple(y.shape)} -> dx{tuple(x.grad.shape)}")
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **outputs)
     with open(os.path.join(HERE, "ref_buffers.json"), "w") as f:
         json.dump(buffers, f, indent=1, sort_keys=True)

@@ -48,6 +48,9 @@ def test_forward_only_guard():
     assert isinstance(m.wsin, torch.nn.Parameter) and m.wsin.requires_grad
     with pytest.raises(NotImplementedError, match="forward-only"):
         m(torch.randn(1, 4000))
+    q = nb.CQT2010v2(verbose=False)
+    with pytest.raises(NotImplementedError, match="pyramid"):
+        q(torch.randn(1, 40000, requires_grad=True))
 
 
 def test_attribute_surface_matches_reference():
