@@ -48,7 +48,7 @@ WORKLOADS = {
 # SMs left to the NCCL gather while the persistent kernels run, and the matching NCCL CTA cap
 # (the gather of (N-1) x 14 MB must hide under one ~0.47 ms transform; measured ~14.5 GB/s per
 # NCCL CTA next to the kernels: 8 CTAs suffice at N=4, not at N=8 — profiles/README.md)
-DEFAULT_RESERVE = {1: 0, 2: 4, 4: 8, 8: 16}
+DEFAULT_RESERVE = {1: 0, 2: 8, 4: 8, 8: 16}
 
 
 def frames_per_clip(w):

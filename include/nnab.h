@@ -245,6 +245,17 @@ int nnab_framed_backward_input(const float* g, int64_t B, int F, int64_t T, cons
                                int K, int hop, int center, int pad_mode, float* dx, int64_t L,
                                void* workspace, size_t ws_bytes, void* stream);
 
+/* Weight gradient of the framed complex contraction (the dW half of SURVEY §8f #1):
+ *   dw (2F, K) fp32:  rows [0, F)  = sum_{b,t} g_re[b,f,t] * frame_{b,t}   (= d loss / d w_re)
+ *                     rows [F, 2F) = sum_{b,t} g_im[b,f,t] * frame_{b,t}   (= -d loss / d w_im)
+ * One split-K GEMM on the tensor-core kernel: gradient rows x transposed frame matrix. */
+size_t nnab_framed_backward_weight_workspace_bytes(int64_t B, int64_t L, int K, int F, int hop,
+                                                   int center);
+int nnab_framed_backward_weight(const float* g, const float* x, int64_t B, int64_t L,
+                                int64_t x_pitch, int F, int64_t T, int K, int hop, int center,
+                                int pad_mode, float* dw, void* workspace, size_t ws_bytes,
+                                void* stream);
+
 /* Kernel launches issued by this library since load (process wide; used by
  * bench.py for its `gpu_launches` claim). */
 uint64_t nnab_launch_count(void);

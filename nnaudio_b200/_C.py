@@ -81,6 +81,13 @@ SIGNATURES = {
         c_int,
         [_P, c_int64, c_int, c_int64, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P, c_size_t, _P],
     ),
+    "nnab_framed_backward_weight_workspace_bytes": (
+        c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
+    "nnab_framed_backward_weight": (
+        c_int,
+        [_P, _P, c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_int, c_int, _P, _P,
+         c_size_t, _P],
+    ),
     "nnab_packed_fir_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_fir": (c_int, [_P, c_int, c_int, _P, _P]),
     "nnab_cqt_pyramid_workspace_bytes": (
@@ -427,3 +434,21 @@ def framed_backward_input(g, packed_adj, K, hop, center, pad_mode, L_in):
                                           _stream(g.device))
     _check(rc, "nnab_framed_backward_input")
     return dx
+
+
+def framed_backward_weight(g, x, K, hop, center, pad_mode):
+    """g (B, F, T, 2), x (B, L) -> (d w_re, d w_im), each (F, K)."""
+    L = lib()
+    g = _dev_f32(g, "grad")
+    g = g if g.is_contiguous() else g.contiguous()
+    x, B, Ln, pitch = _rows(x)
+    _, F, T, _ = g.shape
+    dw = torch.empty((2 * F, K), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        ws, wsb = _workspace(
+            L.nnab_framed_backward_weight_workspace_bytes(B, Ln, K, F, hop, int(center)), g.device)
+        rc = L.nnab_framed_backward_weight(_ptr(g), _ptr(x), B, Ln, pitch, F, T, K, hop,
+                                           int(center), pad_mode, _ptr(dw), _ptr(ws), wsb,
+                                           _stream(g.device))
+    _check(rc, "nnab_framed_backward_weight")
+    return dw[:F], -dw[F:]

@@ -90,6 +90,7 @@ struct FramedProblem {
   DecimParams dec;           // FMT_DECIM
   int64_t ola_pitch;         // FMT_OLA: out = overlap-add buffer (B, ola_pitch); scale = window/n_fft
   int ola_hop;
+  int k_splits_hint;         // FMT_OLA only (its atomics already accumulate): cut K into chunks
 };
 
 int launch_framed_simt(const FramedProblem& p, cudaStream_t stream);
@@ -119,6 +120,13 @@ int tc_istft_bn(int n_fft);
 size_t tc_packed_istft_bytes(int n_fft, int f_in);
 int tc_pack_istft(const float* kc, const float* ks, int n_fft, int f_in, int onesided, void* packed,
                   cudaStream_t stream, int transposed = 0);
+// weight-gradient operands (tc_kernels.cu)
+int64_t tc_dw_gpad(int64_t B, int64_t T);
+size_t tc_dw_grad_planes_bytes(int64_t B, int64_t T, int F);
+size_t tc_dw_frames_bytes(int64_t B, int64_t T, int K);
+int tc_dw_prep_grad(const float* g, int64_t B, int F, int64_t T, void* planes, cudaStream_t stream);
+int tc_dw_prep_frames(const float* x, int64_t B, int64_t L, int64_t x_pitch, int K, int hop, int pad,
+                      int pad_mode, int64_t T, void* packed, cudaStream_t stream);
 int tc_unpad_adjoint(const float* gp, int64_t gp_pitch, int64_t gp_len, int64_t B, int pad,
                      int pad_mode, int64_t L, float* dx, cudaStream_t stream);
 size_t tc_istft_planes_bytes(int64_t B, int64_t T, int f_in);

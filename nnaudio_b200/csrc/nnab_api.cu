@@ -838,4 +838,48 @@ int nnab_framed_backward_input(const float* g, int64_t B, int F, int64_t T, cons
   return tc_unpad_adjoint(gp, pitch, gp_len, B, pad, pad_mode, L, dx, s);
 }
 
+size_t nnab_framed_backward_weight_workspace_bytes(int64_t B, int64_t L, int K, int F, int hop,
+                                                   int center) {
+  const int pad = center ? K / 2 : 0;
+  const int64_t T = frames_of(L, K, hop, pad);
+  return align_up(tc_dw_grad_planes_bytes(B, T, F), 256) + align_up(tc_dw_frames_bytes(B, T, K), 256) +
+         512;
+}
+
+int nnab_framed_backward_weight(const float* g, const float* x, int64_t B, int64_t L,
+                                int64_t x_pitch, int F, int64_t T, int K, int hop, int center,
+                                int pad_mode, float* dw, void* workspace, size_t ws_bytes,
+                                void* stream) {
+  if (g == nullptr || x == nullptr || dw == nullptr || B <= 0 || L <= 0 || x_pitch < L || F <= 0 ||
+      K <= 0 || hop <= 0)
+    return NNAB_EINVAL;
+  const int pad = center ? K / 2 : 0;
+  if (T != frames_of(L, K, hop, pad) || T <= 0) return NNAB_EINVAL;
+  int rc = check_arch();
+  if (rc) return rc;
+  const size_t need = nnab_framed_backward_weight_workspace_bytes(B, L, K, F, hop, center);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  void* gplanes = ws;
+  void* frames = ws + align_up(tc_dw_grad_planes_bytes(B, T, F), 256);
+  const int64_t gpad = tc_dw_gpad(B, T);
+  if (gpad >= (1ll << 31)) return NNAB_EUNSUPPORTED;
+
+  if ((rc = tc_dw_prep_grad(g, B, F, T, gplanes, s))) return rc;
+  if ((rc = tc_dw_prep_frames(x, B, L, x_pitch, K, hop, pad, pad_mode, T, frames, s))) return rc;
+  NNAB_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)2 * F * K * sizeof(float), s));
+
+  FramedProblem p{};
+  p.x = nullptr; p.B = 1; p.L = (int64_t)2 * F * gpad; p.x_pitch = 0;
+  p.F = K; p.K = (int)gpad; p.hop = (int)gpad; p.pad = 0; p.pad_mode = NNAB_PAD_CONSTANT;
+  p.scale = nullptr; p.scale_all = 1.f; p.fmt = FMT_OLA; p.eps = 0.f; p.power = 1.f;
+  p.out = dw; p.T = 2 * F; p.out_bins = K; p.bin_offset = 0;
+  p.presplit = gplanes;
+  p.ola_pitch = 0; p.ola_hop = K;        // row m of dW starts at m * K
+  p.k_splits_hint = (int)((gpad / 64 + 63) / 64);  // <= 64 k-blocks per accumulator chunk
+  if (p.k_splits_hint > 64) p.k_splits_hint = 64;
+  return run_framed(p, frames, nullptr, 0, NNAB_PATH_TCGEN05, s);
+}
+
 }  // extern "C"

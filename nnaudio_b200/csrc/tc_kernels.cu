@@ -458,6 +458,104 @@ int tc_istft_prep(const float* X, int64_t B, int f_in, int64_t T, void* planes_v
   return NNAB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Weight gradient dW[m, k] = sum_{b,t} G[m, (b,t)] * frame_{b,t}[k]   (m = re rows then im rows)
+// as a GEMM on the same kernel: the gradient rows are the "signal" (plain-matrix rows of
+// length G = B*T), the transposed frame matrix FT[k][(b,t)] takes the packed-basis slot.
+// ---------------------------------------------------------------------------
+int64_t tc_dw_gpad(int64_t B, int64_t T) { return (B * T + 63) / 64 * 64; }
+
+size_t tc_dw_grad_planes_bytes(int64_t B, int64_t T, int F) {
+  const int64_t gpad = tc_dw_gpad(B, T);
+  return tc_workspace_bytes(1, (int64_t)2 * F * gpad, (int)gpad, (int)gpad, 0);
+}
+size_t tc_dw_frames_bytes(int64_t B, int64_t T, int K) {
+  const int bn = tc_istft_bn(K);
+  const size_t rows = (size_t)((K + bn - 1) / bn) * bn;
+  return 2 * rows * (size_t)tc_dw_gpad(B, T) * sizeof(__nv_bfloat16) + 256;
+}
+
+// g (B, F, T, 2) -> rows part*F + f, columns b*T + t (bf16 hi/lo planes)
+__global__ void __launch_bounds__(256) dw_prep_grad_kernel(const float* __restrict__ g, int F,
+                                                           int64_t T, int64_t gpad,
+                                                           int64_t plane_stride,
+                                                           __nv_bfloat16* __restrict__ planes) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  if (t >= T) return;
+  const float2 v = *reinterpret_cast<const float2*>(g + (((int64_t)b * F + f) * T + t) * 2);
+  const int64_t col = b * T + t;
+  __nv_bfloat16 hi, lo;
+  split_bf16(v.x, hi, lo);
+  planes[(int64_t)f * gpad + col] = hi;
+  planes[plane_stride + (int64_t)f * gpad + col] = lo;
+  split_bf16(v.y, hi, lo);
+  planes[(int64_t)(F + f) * gpad + col] = hi;
+  planes[plane_stride + (int64_t)(F + f) * gpad + col] = lo;
+}
+
+int tc_dw_prep_grad(const float* g, int64_t B, int F, int64_t T, void* planes_v, cudaStream_t stream) {
+  if (B > 65535 || F > 65535) return NNAB_EUNSUPPORTED;
+  const int64_t gpad = tc_dw_gpad(B, T);
+  const SplitGeom geo = split_geom(1, (int64_t)2 * F * gpad, (int)gpad, (int)gpad, 0);
+  __nv_bfloat16* planes = (__nv_bfloat16*)planes_v;
+  NNAB_CUDA_TRY(cudaMemsetAsync(planes, 0, (size_t)2 * geo.plane_stride * sizeof(__nv_bfloat16), stream));
+  dim3 grid((unsigned)ceil_div64(T, 256), (unsigned)F, (unsigned)B);
+  dw_prep_grad_kernel<<<grid, 256, 0, stream>>>(g, F, T, gpad, geo.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// FT[k][b*T + t] = xpad[b, t*hop + k]   (packed-basis layout: [plane][rows][gpad])
+__global__ void __launch_bounds__(256) dw_prep_frames_kernel(
+    const float* __restrict__ x, int64_t L, int64_t x_pitch, int K, int hop, int pad, int pad_mode,
+    int64_t T, int64_t G, int64_t gpad, int64_t rows, __nv_bfloat16* __restrict__ packed) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {  // r: column (frame) index in the tile, tx: k
+    const int64_t c = c0 + r;
+    const int k = k0 + tx;
+    float v = 0.f;
+    if (c < G && k < K) {
+      const int64_t b = c / T, t = c - b * T;
+      int64_t j = t * hop + k - pad;
+      if (j < 0) j = (pad_mode == NNAB_PAD_REFLECT) ? -j : -1;
+      else if (j >= L) j = (pad_mode == NNAB_PAD_REFLECT) ? 2 * (L - 1) - j : -1;
+      if (j >= 0 && j < L) v = __ldg(x + b * x_pitch + j);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {  // r: k index in the tile, tx: frame
+    const int k = k0 + r;
+    const int64_t c = c0 + tx;
+    if (k < K && c < G) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(tile[tx][r], hi, lo);
+      packed[(int64_t)k * gpad + c] = hi;
+      packed[rows * gpad + (int64_t)k * gpad + c] = lo;
+    }
+  }
+}
+
+int tc_dw_prep_frames(const float* x, int64_t B, int64_t L, int64_t x_pitch, int K, int hop, int pad,
+                      int pad_mode, int64_t T, void* packed_v, cudaStream_t stream) {
+  const int64_t G = B * T, gpad = tc_dw_gpad(B, T);
+  const int bn = tc_istft_bn(K);
+  const int64_t rows = (int64_t)((K + bn - 1) / bn) * bn;
+  __nv_bfloat16* packed = (__nv_bfloat16*)packed_v;
+  NNAB_CUDA_TRY(cudaMemsetAsync(packed, 0, (size_t)2 * rows * gpad * sizeof(__nv_bfloat16), stream));
+  if ((K + 31) / 32 > 65535) return NNAB_EUNSUPPORTED;
+  dim3 grid((unsigned)ceil_div64(G, 32), (unsigned)((K + 31) / 32));
+  dw_prep_frames_kernel<<<grid, 256, 0, stream>>>(x, L, x_pitch, K, hop, pad, pad_mode, T, G, gpad,
+                                                  rows, packed);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
 // Adjoint of nn.ReflectionPad1d / ConstantPad1d(pad): fold the gradient of the padded signal
 // back onto the clip (mirror margins add onto samples 1..pad and L-1-pad..L-2).
 __global__ void __launch_bounds__(256) unpad_adjoint_kernel(const float* __restrict__ gp,
@@ -1521,6 +1619,16 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.k_splits = 1;
   if (q.fmt == FMT_FBANK && (q.fb_table == nullptr || q.n_fb <= 0)) return NNAB_EINVAL;
   if (q.fmt == FMT_DECIM && (bn != 128 || n_tiles != 1)) return NNAB_EINVAL;
+
+  if (q.fmt == FMT_OLA && q.k_splits_hint > 1) {  // the OLA atomics accumulate K chunks as is
+    int min_range = nkb;
+    for (int tl = 0; tl < n_tiles; ++tl) {
+      const int r = prm.kb_end[tl] - prm.kb_begin[tl];
+      min_range = r < min_range ? r : min_range;
+    }
+    prm.k_splits = q.k_splits_hint < min_range ? q.k_splits_hint : min_range;
+    if (prm.k_splits < 1) prm.k_splits = 1;
+  }
 
   // ---- split-K (long kernels, caller supplied the raw scratch) ---------------------------
   EpiParams final_epi = prm.epi;

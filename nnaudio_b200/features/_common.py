@@ -35,17 +35,22 @@ def pad_mode_id(pad_mode: str) -> int:
 
 
 def forward_only_guard(module: torch.nn.Module, x: torch.Tensor):
-    """Gradients w.r.t. the *input* are supported (``wants_input_grad``); gradients w.r.t.
-    trainable bases / filterbanks (dW) are not built yet: refuse loudly
-    rather than return a result whose parameters silently receive no gradient."""
+    """Kept for the modules without a training path (CQT2010v2 / VQT pyramid, iSTFT):
+    refuse loudly rather than return a result whose parameters silently get no gradient."""
     if not torch.is_grad_enabled():
         return
     if any(p.requires_grad for p in module.parameters()):
         raise NotImplementedError(
-            "nnaudio_b200 kernels are forward-only for trainable kernels: run under "
-            "torch.no_grad() (autograd w.r.t. the bases is not implemented yet; gradients "
-            "w.r.t. the input waveform are)"
+            "nnaudio_b200: this module is forward-only for trainable kernels; run under "
+            "torch.no_grad()"
         )
+
+
+def wants_grad(module: torch.nn.Module, x: torch.Tensor) -> bool:
+    """True when autograd needs a graph through this call (input and/or trainable bases)."""
+    if not torch.is_grad_enabled():
+        return False
+    return x.requires_grad or any(p.requires_grad for p in module.parameters())
 
 
 def wants_input_grad(x: torch.Tensor) -> bool:
@@ -53,21 +58,32 @@ def wants_input_grad(x: torch.Tensor) -> bool:
 
 
 class FramedComplexFn(torch.autograd.Function):
-    """Differentiable-w.r.t.-input complex framed contraction ``x -> (B, F, T, 2)``:
-    forward = the fused kernel, backward = ``nnab_framed_backward_input`` (one GEMM with the
-    transposed basis + overlap-add, then the adjoint of the centre padding)."""
+    """Differentiable complex framed contraction ``(x, w_re, w_im) -> (B, F, T, 2)``:
+    forward = the fused kernel; backward = ``nnab_framed_backward_input`` (GEMM with the
+    transposed basis + overlap-add + padding adjoint) for ``x`` and
+    ``nnab_framed_backward_weight`` (split-K GEMM over all frames) for the bases
+    (the reference gets both from autograd through conv1d, stft.py:290-293)."""
 
     @staticmethod
-    def forward(ctx, x, fwd, bwd):
-        ctx.bwd = bwd
+    def forward(ctx, x, w_re, w_im, fwd, bwd_x, bwd_w):
+        ctx.bwd_x, ctx.bwd_w = bwd_x, bwd_w
         ctx.in_shape = x.shape
+        ctx.w_shape = w_re.shape
+        ctx.save_for_backward(x)
         with torch.no_grad():
             return fwd(x)
 
     @staticmethod
     def backward(ctx, g):
-        dx = ctx.bwd(g.contiguous(), ctx.in_shape[-1])
-        return dx.reshape(ctx.in_shape), None, None
+        (x,) = ctx.saved_tensors
+        g = g.contiguous()
+        dx = dre = dim = None
+        if ctx.needs_input_grad[0]:
+            dx = ctx.bwd_x(g, ctx.in_shape[-1]).reshape(ctx.in_shape)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dre, dim = ctx.bwd_w(g, x)
+            dre, dim = dre.reshape(ctx.w_shape), dim.reshape(ctx.w_shape)
+        return dx, dre, dim, None, None, None
 
 
 class AdjointBasis:

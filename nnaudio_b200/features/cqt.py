@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from .. import _C, design
 from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, PackedFir, as_matrix,
-                      broadcast_dim, forward_only_guard, pad_mode_id, tap_support,
+                      broadcast_dim, forward_only_guard, pad_mode_id, tap_support, wants_grad,
                       wants_input_grad)
 
 _FORMATS = {
@@ -135,7 +135,6 @@ class CQT1992v2(nn.Module):
             )
         if x.shape[-1] + 2 * pad < self.kernel_width:
             raise RuntimeError("Kernel size can't be greater than actual input size")
-        forward_only_guard(self, x)
 
         k_real, k_imag = as_matrix(self.cqt_kernels_real), as_matrix(self.cqt_kernels_imag)
         packed = self._packed.get(k_real, k_imag)
@@ -146,8 +145,8 @@ class CQT1992v2(nn.Module):
         elif normalization_type == "wrap":
             scale_all = 2.0
         eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
-        if wants_input_grad(x):
-            # un-normalised complex CQT through the fused kernel + dX kernel; normalisation and
+        if wants_grad(self, x):
+            # un-normalised complex CQT through the fused kernel + dX / dW kernels; normalisation and
             # output format (cqt.py:752-780) composed in torch for autograd
             if not hasattr(self, "_adjoint"):
                 self._adjoint = AdjointBasis()
@@ -163,7 +162,12 @@ class CQT1992v2(nn.Module):
                                                 self.kernel_width, self.hop_length, self.center,
                                                 pad_mode_id(self.pad_mode), L)
 
-            c = FramedComplexFn.apply(x, fwd, bwd)
+            def bwd_w(g, xin):
+                return _C.framed_backward_weight(g, xin, self.kernel_width, self.hop_length,
+                                                 self.center, pad_mode_id(self.pad_mode))
+
+            c = FramedComplexFn.apply(x, self.cqt_kernels_real, self.cqt_kernels_imag, fwd, bwd,
+                                      bwd_w)
             if scale is not None:
                 c = c * scale.view(1, -1, 1, 1)
             elif scale_all != 1.0:

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import FilterbankTable, forward_only_guard, pad_mode_id, wants_input_grad
+from ._common import FilterbankTable, pad_mode_id, wants_grad
 from .stft import STFT
 
 
@@ -75,10 +75,8 @@ class Gammatonegram(nn.Module):
 
     def forward(self, x):
         x = self.stft._checked_input(x)
-        forward_only_guard(self, x)
-        if wants_input_grad(x):
-            return torch.matmul(self.gammatone_basis.detach(),
-                                self.stft._magnitude_diff(x) ** self.power)
+        if wants_grad(self, x):
+            return torch.matmul(self.gammatone_basis, self.stft._magnitude_diff(x) ** self.power)
         wcos, wsin, packed = self.stft._bases()
         fb = self.gammatone_basis.detach()
         _C._dev_f32(fb, "gammatone_basis")

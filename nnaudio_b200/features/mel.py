@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import FilterbankTable, as_matrix, forward_only_guard, pad_mode_id, wants_input_grad
+from ._common import FilterbankTable, as_matrix, pad_mode_id, wants_grad
 from .stft import STFT
 
 
@@ -80,9 +80,8 @@ class MelSpectrogram(nn.Module):
 
     def forward(self, x):
         x = self.stft._checked_input(x)
-        forward_only_guard(self, x)
-        if wants_input_grad(x):  # mel.py:186-188 on top of the differentiable STFT magnitude
-            return torch.matmul(self._filterbank().detach(), self.stft._magnitude_diff(x) ** self.power)
+        if wants_grad(self, x):  # mel.py:186-188 on top of the differentiable STFT magnitude
+            return torch.matmul(self._filterbank(), self.stft._magnitude_diff(x) ** self.power)
         wcos, wsin, packed = self.stft._bases()
         fb = self._filterbank().detach()
         _C._dev_f32(fb, "filterbank")
@@ -134,8 +133,7 @@ class MFCC(nn.Module):
             raise design.ParameterError("top_db must be non-negative")
         mel = self.melspec_layer
         x = mel.stft._checked_input(x)
-        forward_only_guard(self, x)
-        if wants_input_grad(x):  # mel.py:263-279, :281-307 composed in torch for autograd
+        if wants_grad(self, x):  # mel.py:263-279, :281-307 composed in torch for autograd
             S = mel(x)
             amin = torch.tensor(self._amin_host, device=S.device)
             log_spec = 10.0 * torch.log10(torch.clamp(S, min=self._amin_host))

@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from .. import _C, design
 from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, as_matrix, broadcast_dim,
-                      forward_only_guard, pad_mode_id, wants_input_grad)
+                      forward_only_guard, pad_mode_id, wants_grad)
 
 _FORMATS = {
     "Magnitude": _C.FMT_MAGNITUDE,
@@ -189,9 +189,14 @@ class STFT(nn.Module):
         return _C.framed_backward_input(g, self._adjoint.get(wcos, wsin), self.n_fft, self.stride,
                                         self.center, pad_mode_id(self.pad_mode), L)
 
+    def _backward_weight(self, g, x):
+        return _C.framed_backward_weight(g, x, self.n_fft, self.stride, self.center,
+                                         pad_mode_id(self.pad_mode))
+
     def _complex_diff(self, x):
-        """(B, F, T, 2) with a gradient path back to ``x``."""
-        return FramedComplexFn.apply(x, lambda t: self._run(t, "Complex"), self._backward_input)
+        """(B, F, T, 2) with gradient paths back to ``x`` and to trainable ``wcos`` / ``wsin``."""
+        return FramedComplexFn.apply(x, self.wcos, self.wsin, lambda t: self._run(t, "Complex"),
+                                     self._backward_input, self._backward_weight)
 
     def _magnitude_diff(self, x):
         c = self._complex_diff(x)
@@ -205,8 +210,7 @@ class STFT(nn.Module):
                 f"output_format must be 'Magnitude', 'Complex' or 'Phase', got {output_format!r}"
             )
         x = self._checked_input(x)
-        forward_only_guard(self, x)
-        if wants_input_grad(x):
+        if wants_grad(self, x):
             # training through the layer: fused complex contraction + dX kernel, the light
             # element-wise tail (stft.py:299-316) composed in torch for autograd
             if output_format == "Complex":

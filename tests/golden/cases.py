@@ -150,6 +150,20 @@ GRAD_CASES = [
 ]
 
 
+# Trainable-kernel cases: the fixture holds the reference's gradients of the listed parameters.
+WGRAD_CASES = [
+    ("wgrad_stft", "STFT", dict(n_fft=256, hop_length=64, trainable=True), ("randn", 90, (3, 4000)),
+     dict(output_format="Magnitude"), ["wsin", "wcos"]),
+    ("wgrad_mel", "MelSpectrogram",
+     dict(sr=16000, n_fft=256, hop_length=64, n_mels=20, trainable_mel=True, trainable_STFT=True),
+     ("randn", 91, (2, 4000)), dict(), ["mel_basis", "stft.wsin", "stft.wcos"]),
+    ("wgrad_cqt1992v2", "CQT1992v2",
+     dict(sr=22050, fmin=880, n_bins=24, hop_length=128, trainable=True),
+     ("randn", 92, (2, 8000)), dict(output_format="Magnitude"),
+     ["cqt_kernels_real", "cqt_kernels_imag"]),
+]
+
+
 def loss_weights(case_id: str, shape) -> np.ndarray:
     seed = 1000 + sum(ord(c) for c in case_id) % 1000
     return np.random.RandomState(seed).standard_normal(shape).astype(np.float32)

@@ -29,7 +29,7 @@ sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
 from cases import (CASES, GRAD_CASES, ISTFT_CASES, REF_GROUND_TRUTHS, SWEEP_CTOR,  # noqa: E402
-                   loss_weights, make_input, out_key)
+                   WGRAD_CASES, loss_weights, make_input, out_key)
 
 from nnAudio import features as ref_features  # noqa: E402
 
@@ -87,6 +87,19 @@ def main():
         (y * w).sum().backward()
         outputs["grad|" + cid] = x.grad.numpy().astype(np.float32)
         print(f"{'grad|' + cid:60s} out{tuple(y.shape)} -> dx{tuple(x.grad.shape)}")
+    # gradients of trainable kernels / filterbanks
+    for cid, cls, ctor, inp, kw, names in WGRAD_CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = getattr(ref_features, cls)(verbose=False, **ctor)
+        x = torch.from_numpy(make_input(inp))
+        y = mod(x, **kw)
+        w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
+        (y * w).sum().backward()
+        params = dict(mod.named_parameters())
+        for n in names:
+            outputs[f"wgrad|{cid}|{n}"] = params[n].grad.numpy().astype(np.float32)
+            print(f"{'wgrad|' + cid + '|' + n:60s} {tuple(params[n].grad.shape)}")
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **outputs)
     with open(os.path.join(HERE, "ref_buffers.json"), "w") as f:
         json.dump(buffers, f, indent=1, sort_keys=True)
