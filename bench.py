@@ -196,6 +196,8 @@ def _run():
     ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-copy-streams", type=int, default=1)
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs kept free for the concurrent NCCL gather (default: by world size)")
     ap.add_argument("--nccl-max-ctas", type=int, default=-1,
@@ -318,7 +320,8 @@ def _run():
 
             x_host = torch.randn(B, w["L"], dtype=torch.float32).pin_memory()
             y_host = torch.empty(out_shape, dtype=torch.float32).pin_memory()
-            pipe = HostPipeline(mod, chunk_clips=max(1, B // 8), **w["fwd"])
+            pipe = HostPipeline(mod, chunk_clips=max(1, B // args.e2e_chunks),
+                                copy_streams=args.e2e_copy_streams, **w["fwd"])
 
             def e2e_step():
                 pipe(x_host, y_host, device=dev)

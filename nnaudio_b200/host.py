@@ -14,9 +14,13 @@ import torch
 
 
 class HostPipeline:
-    def __init__(self, module: torch.nn.Module, chunk_clips: int = 8, **forward_kwargs):
+    def __init__(self, module: torch.nn.Module, chunk_clips: int = 8, copy_streams: int = 1,
+                 **forward_kwargs):
+        """``copy_streams`` > 1 splits each chunk's host->device copy over several streams
+        (several DMA engines can then drive the PCIe link together)."""
         self.module = module
         self.chunk = int(chunk_clips)
+        self.n_in = max(1, int(copy_streams))
         self.kw = forward_kwargs
         self._dev = None
         self._in = None
@@ -26,6 +30,7 @@ class HostPipeline:
         if self._dev != (device, L):
             self._in = [torch.empty((self.chunk, L), dtype=torch.float32, device=device) for _ in range(2)]
             self._streams = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+            self._extra_in = [torch.cuda.Stream(device) for _ in range(self.n_in - 1)]
             self._dev = (device, L)
 
     @torch.no_grad()
@@ -47,18 +52,26 @@ class HostPipeline:
         cur = torch.cuda.current_stream(device)
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
+        for se in self._extra_in:
+            se.wait_stream(cur)
         done_compute = [None, None]
         n_chunks = (B + self.chunk - 1) // self.chunk
         for c in range(n_chunks):
             lo, hi = c * self.chunk, min(B, (c + 1) * self.chunk)
             buf = self._in[c & 1][: hi - lo]
-            with torch.cuda.stream(s_in):
-                if done_compute[c & 1] is not None:
-                    s_in.wait_event(done_compute[c & 1])  # buffer still being read by chunk c-2
-                buf.copy_(x_host[lo:hi], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
-            cur.wait_event(ev_in)
+            in_streams = [s_in] + self._extra_in
+            n_rows = hi - lo
+            parts = min(len(in_streams), n_rows)
+            for pi in range(parts):
+                r0, r1 = (n_rows * pi) // parts, (n_rows * (pi + 1)) // parts
+                st = in_streams[pi]
+                with torch.cuda.stream(st):
+                    if done_compute[c & 1] is not None:
+                        st.wait_event(done_compute[c & 1])  # buffer still read by chunk c-2
+                    buf[r0:r1].copy_(x_host[lo + r0: lo + r1], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(st)
+                cur.wait_event(ev_in)
             y = self.module(buf, **self.kw)
             ev_c = torch.cuda.Event()
             ev_c.record(cur)
