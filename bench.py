@@ -196,7 +196,7 @@ def _run():
     ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--e2e-copy-streams", type=int, default=1)
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs kept free for the concurrent NCCL gather (default: by world size)")
@@ -379,7 +379,7 @@ def _run():
                 "global_batch": world * B, "frames_per_clip": T,
                 "parallelism": f"batch-sharded x{world}" + (
                     " + NCCL all_gather of outputs (gather of step i overlaps transform of step i+1)" if world > 1 else ""),
-                "e2e_path": "nnaudio_b200.host.HostPipeline: pinned host -> 8 chunks, H2D/compute/D2H on 3 streams",
+                "e2e_path": "nnaudio_b200.host.HostPipeline: pinned host -> 4 chunks, H2D/compute/D2H on 3 streams",
                 "l2": f"{n_rot} rotating input batches ({n_rot * B * w['L'] * 4 / 1e6:.0f} MB > 126 MB L2), no flush; "
                       "one CUDA-event pair around all K steps",
                 "kernel_path": os.environ.get("NNAUDIO_B200_PATH", "auto"),

@@ -80,11 +80,12 @@ const char* nnab_last_cuda_error(void);
  * bf16 hi/lo planes (x = hi + lo to ~2^-17) laid out for TMA/UMMA:
  *   packed[plane][tile*BN + part*BN/2 + j][k]   plane 0 = hi, 1 = lo
  *   part 0 = re rows, part 1 = NEGATED im rows, j < BN/2 bins per tile
- * with K padded to a multiple of 64 and bins zero-padded to a multiple of BN/2
- * (BN = nnab_pack_tile_n()).  Negation folds the reference's minus signs
+ * with K padded to a multiple of 64 and bins zero-padded to a multiple of BN/2.
+ * BN = nnab_pack_tile_n(F) is chosen per basis to minimise padded columns (208
+ * for F = 1025; <= 256).  Negation folds the reference's minus signs
  * (stft.py:308-311 `-spec_imag`, cqt.py:750 `-conv1d(...)`) into the basis.
  * ------------------------------------------------------------------------- */
-int nnab_pack_tile_n(void);
+int nnab_pack_tile_n(int F);
 size_t nnab_packed_basis_bytes(int F, int K);
 int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K,
                     void* packed, void* stream);

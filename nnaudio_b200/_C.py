@@ -32,7 +32,7 @@ SIGNATURES = {
     "nnab_set_sm_reserve": (c_int, [c_int]),
     "nnab_profile_enable": (None, [c_int]),
     "nnab_profile_read": (c_int, [_P, _P]),
-    "nnab_pack_tile_n": (c_int, []),
+    "nnab_pack_tile_n": (c_int, [c_int]),
     "nnab_packed_basis_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_basis": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "nnab_stft_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int]),

@@ -168,7 +168,7 @@ int nnab_profile_read(double* framed_ms, uint64_t* framed_launches) {
   return NNAB_OK;
 }
 
-int nnab_pack_tile_n(void) { return tc_tile_n(); }
+int nnab_pack_tile_n(int F) { return tc_tile_n(F); }
 size_t nnab_packed_basis_bytes(int F, int K) { return tc_packed_bytes(F, K); }
 int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                     void* stream) {

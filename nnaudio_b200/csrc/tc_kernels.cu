@@ -45,7 +45,7 @@ static int choose_bn(int F) {
   return best;
 }
 
-int tc_tile_n() { return 256; }
+int tc_tile_n(int F) { return choose_bn(F > 0 ? F : 1); }
 
 size_t tc_packed_bytes(int F, int K) {
   const int bn = choose_bn(F);

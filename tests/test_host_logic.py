@@ -101,3 +101,19 @@ def test_legacy_spectrogram_alias_warns():
         warnings.simplefilter("always")
         mod = importlib.import_module("nnaudio_b200.Spectrogram")
     assert mod.STFT is nb.STFT and any("deprecated" in str(x.message) for x in w)
+
+
+def test_nnaudio_import_shim():
+    """`from nnAudio import features` resolves to this engine when <repo>/shim is on sys.path."""
+    import importlib, os, sys
+    from helpers import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "shim"))
+    for k in [k for k in sys.modules if k == "nnAudio" or k.startswith("nnAudio.")]:
+        del sys.modules[k]
+    try:
+        feats = importlib.import_module("nnAudio.features")
+        assert feats.MelSpectrogram is nb.MelSpectrogram and feats.CQT1992v2 is nb.CQT1992v2
+    finally:
+        sys.path.remove(os.path.join(ROOT, "shim"))
+        for k in [k for k in sys.modules if k == "nnAudio" or k.startswith("nnAudio.")]:
+            del sys.modules[k]
