@@ -7,5 +7,7 @@ from .mel import MelSpectrogram, MFCC
 from .gammatone import Gammatonegram
 from .cqt import CQT1992v2, CQT2010v2, CQT
 from .vqt import VQT
+from .cqt_v1 import CQT1992, CQT2010
 
-__all__ = ["STFT", "iSTFT", "MelSpectrogram", "MFCC", "Gammatonegram", "CQT1992v2", "CQT2010v2", "CQT", "VQT"]
+__all__ = ["STFT", "iSTFT", "MelSpectrogram", "MFCC", "Gammatonegram", "CQT1992v2", "CQT2010v2", "CQT", "VQT",
+           "CQT1992", "CQT2010"]

@@ -14,8 +14,7 @@ import torch.nn as nn
 
 from .. import _C, design
 from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, PackedFir, as_matrix,
-                      broadcast_dim, forward_only_guard, pad_mode_id, tap_support, wants_grad,
-                      wants_input_grad)
+                      broadcast_dim, pad_mode_id, tap_support, wants_grad)
 
 _FORMATS = {
     "Magnitude": _C.FMT_MAGNITUDE,
@@ -340,22 +339,37 @@ class CQT2010v2(nn.Module):
         packed = self._packed.get(k_real, k_imag)  # one bank shared by every octave
         return [k_real] * self.n_octaves, [k_imag] * self.n_octaves, [packed] * self.n_octaves
 
+    def _bank_tensors(self):
+        """Per-octave (real, imag) bank tensors as autograd sees them (one shared, possibly
+        trainable, bank: its gradient is the sum over the octaves)."""
+        return [(self.cqt_kernels_real, self.cqt_kernels_imag)] * self.n_octaves
+
     def forward(self, x, output_format=None, normalization_type="librosa"):
         output_format = output_format or self.output_format
         _check_format_and_norm(output_format, normalization_type)
         x = broadcast_dim(x)
-        forward_only_guard(self, x)
-        return _pyramid_forward(self, x, output_format, normalization_type)
+        return _pyramid_forward(self, x, output_format,
+                                _v2_normalization(self, normalization_type, output_format))
 
 
-def _pyramid_forward(mod, x, output_format, normalization_type):
-    """Shared by CQT2010v2 and VQT: plan the octave lengths on the host (for the
-    reference's warnings / errors), then one C call."""
-    if wants_input_grad(x):
-        raise NotImplementedError(
-            "gradients through the CQT2010v2 / VQT pyramid are not implemented yet; "
-            "run under torch.no_grad()"
-        )
+def _v2_normalization(mod, normalization_type, output_format):
+    """cqt.py:1112-1124 / vqt.py:190-200: (per-bin scale tensor or None, global factor, sqrt eps)."""
+    scale, scale_all = None, 1.0
+    dsf = float(mod.downsample_factor)
+    if normalization_type == "librosa":
+        scale = mod._scale.get(mod.lenghts, dsf)
+    elif normalization_type == "wrap":
+        scale_all = 2.0 * dsf
+    else:
+        scale_all = dsf
+    eps = 1e-8 if (mod.trainable and output_format == "Magnitude") else 0.0
+    return scale, scale_all, eps
+
+
+def _pyramid_forward(mod, x, output_format, normalization):
+    """Shared by CQT2010v2, VQT and CQT2010: plan the octave lengths on the host (for the
+    reference's warnings / errors), then one C call.  ``normalization`` = (scale, scale_all, eps)."""
+    scale, scale_all, eps = normalization
     banks_real, banks_imag, packed = mod._banks()
     early = mod.early_downsample_filter if mod.earlydownsample else None
     factor = int(mod.downsample_factor) if mod.earlydownsample else 1
@@ -372,15 +386,9 @@ def _pyramid_forward(mod, x, output_format, normalization_type):
                 "padding with reflection mode might not be the best choice, try using constant padding",
                 UserWarning,
             )
-    scale, scale_all = None, 1.0
-    dsf = float(mod.downsample_factor)
-    if normalization_type == "librosa":
-        scale = mod._scale.get(mod.lenghts, dsf)
-    elif normalization_type == "wrap":
-        scale_all = 2.0 * dsf
-    else:
-        scale_all = dsf
-    eps = 1e-8 if (mod.trainable and output_format == "Magnitude") else 0.0
+    if wants_grad(mod, x):
+        return _pyramid_forward_autograd(mod, x, output_format, fallbacks, factor, scale, scale_all,
+                                         eps)
     lowpass = mod.lowpass_filter.detach().reshape(-1)
     early_flat = early.detach().reshape(-1) if early is not None else None
     for t in (lowpass, early_flat):
@@ -395,3 +403,70 @@ def _pyramid_forward(mod, x, output_format, normalization_type):
         factor, mod.hop_length,
         pad_mode_id(mod.pad_mode), mod.n_bins, scale, scale_all, _FORMATS[output_format], eps, T,
     )
+
+
+def _framed_complex_autograd(mod, tag, sig, w_re, w_im, hop, center, pad_mode):
+    """One differentiable framed contraction ``sig (B, L) -> (B, F, T, 2)`` through the fused
+    forward kernel and the dX / dW kernels; ``tag`` keys the packed-basis caches on ``mod``."""
+    caches = mod.__dict__.setdefault("_grad_caches", {})
+    if tag not in caches:
+        caches[tag] = (PackedBasis(), AdjointBasis())
+    k_re, k_im = as_matrix(w_re), as_matrix(w_im)
+    packed = caches[tag][0].get(k_re, k_im)
+    width = int(k_re.shape[1])
+
+    def fwd(t):
+        return _C.cqt1992v2_forward(t, k_re, k_im, packed, None, None, hop, center, pad_mode,
+                                    None, 1.0, _C.FMT_COMPLEX, 0.0)
+
+    def bwd(g, L):
+        return _C.framed_backward_input(g, caches[tag][1].get(k_re, k_im), width, hop, center,
+                                        pad_mode, L)
+
+    def bwd_w(g, xin):
+        return _C.framed_backward_weight(g, xin, width, hop, center, pad_mode)
+
+    return FramedComplexFn.apply(sig, w_re, w_im, fwd, bwd, bwd_w)
+
+
+def _decimate_autograd(mod, tag, sig, fir, n):
+    """utils.py:73-100 (``downsampling_by_n`` / ``_by_2``): zero-pad (taps-1)//2 each side, FIR,
+    keep every n-th sample — as a one-row framed contraction so the same forward / dX kernels
+    carry the gradient."""
+    taps = fir.numel()
+    w_re = fir.detach().reshape(1, taps)
+    zeros = mod.__dict__.setdefault("_fir_zeros", {})
+    if tag not in zeros or zeros[tag].shape != w_re.shape or zeros[tag].device != w_re.device:
+        zeros[tag] = torch.zeros_like(w_re)
+    half = (taps - 1) // 2
+    padded = torch.nn.functional.pad(sig, (half, half))
+    c = _framed_complex_autograd(mod, tag, padded, w_re, zeros[tag], n, False, _C.PAD_CONSTANT)
+    return c[:, 0, :, 0].contiguous()
+
+
+def _pyramid_forward_autograd(mod, x, output_format, fallbacks, factor, scale, scale_all, eps):
+    """cqt.py:1085-1139 / vqt.py:160-215 octave by octave with autograd-visible stages
+    (training path; inference uses the single fused C call above)."""
+    if factor > 1:
+        x = _decimate_autograd(mod, "early", x, mod.early_downsample_filter, factor)
+    hop = mod.hop_length
+    octaves = []
+    cur = x
+    for i, (w_re, w_im) in enumerate(mod._bank_tensors()):
+        if i > 0:
+            hop //= 2
+            cur = _decimate_autograd(mod, "lowpass", cur, mod.lowpass_filter, 2)
+        mode = _C.PAD_CONSTANT if fallbacks[i] else pad_mode_id(mod.pad_mode)
+        octaves.insert(0, _framed_complex_autograd(mod, f"bank{i}", cur, w_re, w_im, hop, True,
+                                                   mode))
+    c = torch.cat(octaves, 1)[:, -mod.n_bins:]
+    if scale is not None:  # sqrt(lenghts) * downsample_factor
+        c = c * scale.view(1, -1, 1, 1)
+    elif scale_all != 1.0:
+        c = c * scale_all
+    if output_format == "Complex":
+        return c
+    if output_format == "Magnitude":
+        return torch.sqrt(c[..., 0].pow(2) + c[..., 1].pow(2) + eps)
+    ang = torch.atan2(c[..., 1], c[..., 0])
+    return torch.stack((torch.cos(ang), torch.sin(ang)), -1)

@@ -39,6 +39,50 @@ class _InverseBasis:
         return self._cache[key]
 
 
+class _InverseAdjoint:
+    """Cache of the forward-shaped basis that carries the iSTFT input gradient:
+    ``w[f, o] = kernel[o, f] * window[o] / n_fft`` with the Hermitian mirror rows of a one-sided
+    spectrum (utils.py:63-70) folded in, plus its tensor-core packing."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, kc, ks, win, onesided):
+        key = (kc.data_ptr(), kc._version, ks.data_ptr(), ks._version, win.data_ptr(),
+               win._version, bool(onesided), str(kc.device))
+        if key != self._key:
+            n_fft = kc.shape[0]
+            w_re = (kc * (win / n_fft)[:, None]).t().contiguous()   # (f, o)
+            w_im = (ks * (win / n_fft)[:, None]).t().contiguous()
+            if onesided:
+                half = n_fft // 2
+                lo_re, lo_im = w_re[:half + 1].clone(), w_im[:half + 1].clone()
+                mirror = torch.arange(n_fft - 1, half, -1, device=kc.device)  # rows n_fft-f, f=1..half-1
+                lo_re[1:half] += w_re[mirror]
+                lo_im[1:half] -= w_im[mirror]
+                w_re, w_im = lo_re.contiguous(), lo_im.contiguous()
+            self._val = (w_re, w_im, _C.pack_basis(w_re, w_im))
+            self._key = key
+        return self._val
+
+
+class _InverseSTFTFn(torch.autograd.Function):
+    """iSTFT with a gradient for the spectrogram input (the reference gets it from autograd
+    through conv2d + fold, stft.py:15-63)."""
+
+    @staticmethod
+    def forward(ctx, X, run, grad_spec):
+        ctx.grad_spec = grad_spec
+        ctx.T = X.shape[2]
+        with torch.no_grad():
+            return run(X)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return ctx.grad_spec(gy.contiguous().float(), ctx.T), None, None
+
+
 def _inverse_stft(mod, X, kernel_cos, kernel_sin, window_mask, onesided, length):
     """Shared by ``STFT.inverse`` and ``iSTFT.forward`` (STFTBase.inverse_stft, stft.py:15-63)."""
     n_fft = mod.n_fft
@@ -62,7 +106,33 @@ def _inverse_stft(mod, X, kernel_cos, kernel_sin, window_mask, onesided, length)
     if not hasattr(mod, "_inv_basis"):
         mod._inv_basis = _InverseBasis()
     packed = mod._inv_basis.get(kc.contiguous(), ks.contiguous(), f_in, onesided)
-    return _C.istft_forward(X, packed, win.contiguous(), n_fft, mod.stride, mod.center, length)
+    win = win.contiguous()
+
+    def run(spec):
+        return _C.istft_forward(spec, packed, win, n_fft, mod.stride, mod.center, length)
+
+    if not (torch.is_grad_enabled() and X.requires_grad):
+        return run(X)
+    if not hasattr(mod, "_inv_adjoint"):
+        mod._inv_adjoint = _InverseAdjoint()
+    w_re, w_im, w_packed = mod._inv_adjoint.get(kc, ks, win, onesided)
+    hop, offset = mod.stride, (n_fft // 2 if mod.center else 0)
+
+    def grad_spec(gy, T):
+        """Adjoint of the inverse: undo the window-sum-square division, put the waveform gradient
+        back at its place in the overlap-add buffer, then one forward framed contraction with the
+        transposed, windowed inverse kernels (one-sided mirroring folded into the rows)."""
+        ola_len = n_fft + hop * (T - 1)
+        wss = torch.nn.functional.fold((win * win)[None, :, None].expand(1, n_fft, T).contiguous(),
+                                       (1, ola_len), (1, n_fft), stride=(1, hop)).reshape(-1)
+        inv = torch.where(wss > 1e-10, 1.0 / wss, torch.ones_like(wss))
+        G = torch.zeros((gy.shape[0], ola_len), dtype=torch.float32, device=gy.device)
+        G[:, offset:offset + gy.shape[1]] = gy
+        G *= inv
+        return _C.cqt1992v2_forward(G, w_re, w_im, w_packed, None, None, hop, False,
+                                    _C.PAD_CONSTANT, None, 1.0, _C.FMT_COMPLEX, 0.0)
+
+    return _InverseSTFTFn.apply(X, run, grad_spec)
 
 
 class STFT(nn.Module):

@@ -12,8 +12,8 @@ import torch
 import torch.nn as nn
 
 from .. import design
-from ._common import PackedBasis, as_matrix, broadcast_dim, forward_only_guard
-from .cqt import _ScaleCache, _check_format_and_norm, _pyramid_forward
+from ._common import PackedBasis, as_matrix, broadcast_dim
+from .cqt import _ScaleCache, _check_format_and_norm, _pyramid_forward, _v2_normalization
 
 
 class VQT(nn.Module):
@@ -140,9 +140,13 @@ class VQT(nn.Module):
         packed = [self._packed[i].get(re[i], im[i]) for i in range(self.n_octaves)]
         return re, im, packed
 
+    def _bank_tensors(self):
+        return [(getattr(self, f"cqt_kernels_real_{i}"), getattr(self, f"cqt_kernels_imag_{i}"))
+                for i in range(self.n_octaves)]
+
     def forward(self, x, output_format=None, normalization_type="librosa"):
         output_format = output_format or self.output_format
         _check_format_and_norm(output_format, normalization_type)
         x = broadcast_dim(x)
-        forward_only_guard(self, x)
-        return _pyramid_forward(self, x, output_format, normalization_type)
+        return _pyramid_forward(self, x, output_format,
+                                _v2_normalization(self, normalization_type, output_format))

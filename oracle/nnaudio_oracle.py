@@ -266,7 +266,8 @@ def cqt_octave_complex(x, kr, ki, hop, pad, pad_mode):
     return both[:, : kr.shape[0]], -both[:, kr.shape[0]:]
 
 
-def _pyramid(x, banks, hop, n_bins, lowpass, pads, pad_mode, early_fir, early_factor, dtype):
+def _pyramid(x, banks, hop, n_bins, lowpass, pads, pad_mode, early_fir, early_factor, dtype,
+             octave_fn=None):
     """Shared octave pyramid of CQT2010v2 (one bank reused) and VQT (one bank
     per octave): top octave on x, then repeatedly halve with the 256-tap FIR
     and halve the hop; octaves are stacked low -> high and the lowest surplus
@@ -280,9 +281,12 @@ def _pyramid(x, banks, hop, n_bins, lowpass, pads, pad_mode, early_fir, early_fa
         if i > 0:
             x_down = downsample_by_n(x_down, lowpass, 2)
             hop = hop // 2
-        kr2 = np.asarray(kr)[:, 0, :].astype(dtype)
-        ki2 = np.asarray(ki)[:, 0, :].astype(dtype)
-        r, im = cqt_octave_complex(x_down, kr2, ki2, hop, pads[i], pad_mode)
+        if octave_fn is not None:
+            r, im = octave_fn(x_down, kr, ki, hop, pads[i], pad_mode)
+        else:
+            kr2 = np.asarray(kr)[:, 0, :].astype(dtype)
+            ki2 = np.asarray(ki)[:, 0, :].astype(dtype)
+            r, im = cqt_octave_complex(x_down, kr2, ki2, hop, pads[i], pad_mode)
         reals.insert(0, r)
         imags.insert(0, im)
     real = np.concatenate(reals, axis=1)[:, -n_bins:, :]
@@ -336,6 +340,84 @@ def vqt(x, banks, lowpass_filter, lenghts, hop, n_bins, pad_mode="reflect",
             "The normalization_type %r is not part of our current options." % normalization_type
         )
     return _cqt_format(real, imag, output_format, trainable, dtype)
+
+
+# --------------------------------------------------------------------------- #
+# first-generation, frequency-domain CQTs  
+# --------------------------------------------------------------------------- #
+def _spectral_cqt(xp, spec_real, spec_imag, wcos, wsin, hop, dtype):
+    """The two stages of cqt.py:211-219 / utils.py:551-557 on an already padded signal:
+    un-windowed DFT rows (``conv1d`` with wcos / wsin), then ``complex_mul`` (utils.py:175-203)
+    with the spectral CQT kernels.  Returns (CQT_real, CQT_imag), each (B, n_bins, T)."""
+    wc = np.asarray(wcos)[:, 0, :].astype(dtype)
+    ws = np.asarray(wsin)[:, 0, :].astype(dtype)
+    both = framed_contraction(xp, np.concatenate((wc, ws), 0), hop, max_rows=512)
+    f_re, f_im = both[:, : wc.shape[0]], both[:, wc.shape[0]:]
+    kr = np.asarray(spec_real).astype(dtype)
+    ki = np.asarray(spec_imag).astype(dtype)
+    real = np.einsum("nf,bft->bnt", kr, f_re) - np.einsum("nf,bft->bnt", ki, f_im)
+    imag = np.einsum("nf,bft->bnt", kr, f_im) + np.einsum("nf,bft->bnt", ki, f_re)
+    return real, imag
+
+
+def cqt1992(x, spec_real, spec_imag, wcos, wsin, lenghts, hop, center=True, pad_mode="reflect",
+            output_format="Magnitude", normalization_type="librosa", dtype=np.float64):
+    """CQT1992.forward (cqt.py:189-251).  The stacked result is (real, -imag) (cqt.py:222) but
+    'Phase' takes atan2 of the un-negated imaginary part (cqt.py:246-249)."""
+    x = broadcast_dim(np.asarray(x)).astype(dtype)
+    width = np.asarray(wcos).shape[-1]
+    if center:
+        x = pad_signal(x, width // 2, pad_mode)
+    real, imag = _spectral_cqt(x, spec_real, spec_imag, wcos, wsin, hop, dtype)
+    if normalization_type == "librosa":
+        s = (np.sqrt(np.asarray(lenghts).astype(np.float32)).astype(dtype) / width).reshape(-1, 1)
+    elif normalization_type == "convolutional":
+        s = dtype(1.0)
+    elif normalization_type == "wrap":
+        s = dtype(2.0 / width)
+    else:
+        raise ValueError(
+            "The normalization_type %r is not part of our current options." % normalization_type
+        )
+    if output_format == "Phase":  # normalisation is positive: it does not move the angle
+        ang = np.arctan2(imag, real)
+        return np.stack((np.cos(ang), np.sin(ang)), -1)
+    return _cqt_format(real * s, -imag * s, output_format, False, dtype)
+
+
+def cqt2010(x, spec_real, spec_imag, wcos, wsin, lowpass_filter, lenghts, hop, n_bins, n_octaves,
+            pad_mode="reflect", early_downsample_filter=None, downsample_factor=1,
+            output_format="Magnitude", normalization_type="librosa", dtype=np.float64):
+    """CQT2010.forward (cqt.py:475-553): the /2 pyramid with ``get_cqt_complex2``
+    (utils.py:524-559) per octave — imaginary part NOT negated, no downsample_factor gain,
+    'librosa' / 'wrap' divide by n_fft."""
+    n_fft = np.asarray(wcos).shape[-1]
+
+    def octave(x_down, kr, ki, hop_i, pad, mode):
+        try:
+            xp = pad_signal(x_down, pad, mode)
+        except RuntimeError:
+            warnings.warn(
+                "padding with reflection mode might not be the best choice, try using constant padding",
+                UserWarning,
+            )
+            xp = np.pad(x_down, ((0, 0), (pad, pad)), mode="constant")
+        return _spectral_cqt(xp, kr, ki, wcos, wsin, hop_i, dtype)
+
+    banks = [(spec_real, spec_imag)] * n_octaves
+    real, imag = _pyramid(x, banks, hop, n_bins, lowpass_filter, [n_fft // 2] * n_octaves,
+                          pad_mode, early_downsample_filter, downsample_factor, dtype,
+                          octave_fn=octave)
+    if normalization_type == "librosa":
+        s = (np.sqrt(np.asarray(lenghts).astype(np.float32)).astype(dtype) / n_fft).reshape(-1, 1)
+        real, imag = real * s, imag * s
+    elif normalization_type == "wrap":
+        real, imag = real * (2.0 / n_fft), imag * (2.0 / n_fft)
+    elif normalization_type != "convolutional":
+        raise ValueError(
+            "The normalization_type %r is not part of our current options." % normalization_type
+        )
+    return _cqt_format(real, imag, output_format, False, dtype)
 
 
 # --------------------------------------------------------------------------- #

@@ -96,6 +96,18 @@ CASES = [
      [dict(output_format="Magnitude")]),
     ("vqt_gamma5", "VQT", dict(sr=22050, gamma=5, n_bins=60), ("randn", 61, (1, 32768)),
      [dict(output_format="Complex")]),
+    # ---- first-generation (frequency-domain) CQTs, SURVEY §8f next #3 ---------
+    ("cqt1992_fmin220", "CQT1992", dict(sr=22050, fmin=220, n_bins=60), ("randn", 62, (2, 16384)),
+     [dict(output_format="Magnitude"), dict(output_format="Complex", normalization_type="wrap"),
+      dict(output_format="Phase", normalization_type="convolutional")]),
+    ("cqt1992_nocenter_constant", "CQT1992",
+     dict(sr=16000, fmin=110, n_bins=36, hop_length=256, center=False, pad_mode="constant"),
+     ("randn", 63, (1, 12000)), [dict(output_format="Complex")]),
+    ("cqt2010_default", "CQT2010", dict(sr=22050, n_bins=84), ("randn", 64, (2, 32768)),
+     [dict(output_format="Magnitude"), dict(output_format="Complex", normalization_type="wrap"),
+      dict(output_format="Phase", normalization_type="convolutional")]),
+    ("cqt2010_early_downsample", "CQT2010", dict(sr=44100, n_bins=72, fmin=32.7),
+     ("randn", 65, (1, 40000)), [dict(output_format="Complex")]),
 ]
 
 # The reference's own golden vectors (Installation/tests/ground-truths/*.npy) and
@@ -147,6 +159,19 @@ GRAD_CASES = [
     ("grad_cqt1992v2_complex_wrap", "CQT1992v2",
      dict(sr=22050, fmin=440, n_bins=24, hop_length=128, center=False),
      ("randn", 87, (1, 8000)), dict(output_format="Complex", normalization_type="wrap")),
+    # the /2 pyramid: gradients flow back through every FIR decimation stage
+    ("grad_cqt2010v2_mag", "CQT2010v2", dict(sr=22050, n_bins=84), ("randn", 88, (2, 32768)),
+     dict(output_format="Magnitude")),
+    ("grad_cqt2010v2_early_complex", "CQT2010v2", dict(sr=44100, n_bins=72, fmin=32.7),
+     ("randn", 89, (1, 65536)), dict(output_format="Complex", normalization_type="convolutional")),
+    ("grad_cqt2010v2_reflect_fallback", "CQT2010v2", dict(sr=22050, n_bins=84),
+     ("randn", 93, (1, 8192)), dict(output_format="Magnitude")),
+    ("grad_cqt1992", "CQT1992", dict(sr=22050, fmin=220, n_bins=48, hop_length=256),
+     ("randn", 99, (2, 12000)), dict(output_format="Magnitude")),
+    ("grad_cqt2010", "CQT2010", dict(sr=22050, n_bins=60), ("randn", 100, (1, 32768)),
+     dict(output_format="Complex")),
+    ("grad_vqt_gamma5", "VQT", dict(sr=22050, gamma=5, n_bins=60), ("randn", 94, (1, 32768)),
+     dict(output_format="Magnitude")),
 ]
 
 
@@ -161,6 +186,30 @@ WGRAD_CASES = [
      dict(sr=22050, fmin=880, n_bins=24, hop_length=128, trainable=True),
      ("randn", 92, (2, 8000)), dict(output_format="Magnitude"),
      ["cqt_kernels_real", "cqt_kernels_imag"]),
+    # one trainable bank shared by all octaves: its gradient is the sum over the pyramid levels
+    ("wgrad_cqt2010v2", "CQT2010v2", dict(sr=22050, n_bins=48, fmin=110, trainable=True),
+     ("randn", 95, (2, 16384)), dict(output_format="Magnitude"),
+     ["cqt_kernels_real", "cqt_kernels_imag"]),
+]
+
+WGRAD_CASES += [
+    # gradients reach the reference's own parameters (DFT rows and spectral kernels) through the fold
+    ("wgrad_cqt1992", "CQT1992",
+     dict(sr=22050, fmin=880, n_bins=24, hop_length=128, trainable_STFT=True, trainable_CQT=True),
+     ("randn", 101, (2, 6000)), dict(output_format="Magnitude"),
+     ["wsin", "wcos", "cqt_kernels_real", "cqt_kernels_imag"]),
+    ("wgrad_cqt2010", "CQT2010", dict(sr=22050, n_bins=36, fmin=110, trainable_CQT=True),
+     ("randn", 102, (1, 16384)), dict(output_format="Magnitude"),
+     ["cqt_kernels_real", "cqt_kernels_imag"]),
+]
+
+
+# Gradients w.r.t. the spectrogram through the inverse STFT (reference autograd on CPU):
+#   (id, n_fft, hop, window, kind, spec) as ISTFT_CASES; loss = sum(y * w)
+ISTFT_GRAD_CASES = [
+    ("grad_istft_onesided_512", 512, 128, "hann", "roundtrip", dict(seed=96, shape=(2, 4000), length=4000)),
+    ("grad_istft_onesided_nolen", 256, 64, "hamming", "roundtrip", dict(seed=97, shape=(1, 3000), length=None)),
+    ("grad_istft_module_full", 256, 64, "hann", "module", dict(seed=98, shape=(2, 256, 40, 2))),
 ]
 
 

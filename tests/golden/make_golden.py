@@ -28,10 +28,23 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
-from cases import (CASES, GRAD_CASES, ISTFT_CASES, REF_GROUND_TRUTHS, SWEEP_CTOR,  # noqa: E402
-                   WGRAD_CASES, loss_weights, make_input, out_key)
+from cases import (CASES, GRAD_CASES, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
+                   SWEEP_CTOR, WGRAD_CASES, loss_weights, make_input, out_key)
 
 from nnAudio import features as ref_features  # noqa: E402
+
+
+def make_module(namespace, cls, ctor):
+    """CQT1992 has no ``verbose`` argument (and always prints)."""
+    import contextlib
+    import inspect
+    import io
+    klass = getattr(namespace, cls)
+    kw = dict(ctor)
+    if "verbose" in inspect.signature(klass.__init__).parameters:
+        kw["verbose"] = False
+    with contextlib.redirect_stdout(io.StringIO()):
+        return klass(**kw)
 
 
 def sha(t: torch.Tensor) -> str:
@@ -45,7 +58,7 @@ def main():
     for cid, cls, ctor, inp, fwds in CASES:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            mod = getattr(ref_features, cls)(verbose=False, **ctor)
+            mod = make_module(ref_features, cls, ctor)
         buffers[cid] = {k: [list(v.shape), sha(v)] for k, v in mod.state_dict().items()
                         if v is not None}
         x = torch.from_numpy(make_input(inp))
@@ -76,11 +89,33 @@ def main():
         outputs[cid + "|X"] = X.numpy().astype(np.float32)
         outputs[cid + "|y"] = y.numpy().astype(np.float32)
         print(f"{cid:60s} X{tuple(X.shape)} -> y{tuple(y.shape)}")
+    # gradient of the inverse STFT w.r.t. its spectrogram input
+    for cid, n_fft, hop, win, kind, spec in ISTFT_GRAD_CASES:
+        rng = np.random.RandomState(spec["seed"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if kind == "roundtrip":
+                st = ref_features.STFT(n_fft=n_fft, hop_length=hop, window=win, iSTFT=True, verbose=False)
+                x = torch.from_numpy(rng.standard_normal(spec["shape"]).astype(np.float32))
+                with torch.no_grad():
+                    X = st(x)
+                X = X.clone().requires_grad_(True)
+                y = st.inverse(X, onesided=True, length=spec["length"])
+            else:
+                im = ref_features.iSTFT(n_fft=n_fft, hop_length=hop, window=win, verbose=False)
+                X = torch.from_numpy(rng.standard_normal(spec["shape"]).astype(np.float32))
+                X.requires_grad_(True)
+                y = im(X, onesided=False)
+        w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
+        (y * w).sum().backward()
+        outputs[cid + "|X"] = X.detach().numpy().astype(np.float32)
+        outputs[cid + "|dX"] = X.grad.numpy().astype(np.float32)
+        print(f"{cid:60s} X{tuple(X.shape)} y{tuple(y.shape)} -> dX{tuple(X.grad.shape)}")
     # input gradients through the reference's own autograd path
     for cid, cls, ctor, inp, kw in GRAD_CASES:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            mod = getattr(ref_features, cls)(verbose=False, **ctor)
+            mod = make_module(ref_features, cls, ctor)
         x = torch.from_numpy(make_input(inp)).requires_grad_(True)
         y = mod(x, **kw)
         w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
@@ -91,7 +126,7 @@ def main():
     for cid, cls, ctor, inp, kw, names in WGRAD_CASES:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            mod = getattr(ref_features, cls)(verbose=False, **ctor)
+            mod = make_module(ref_features, cls, ctor)
         x = torch.from_numpy(make_input(inp))
         y = mod(x, **kw)
         w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
@@ -111,7 +146,7 @@ def main():
     for key, (cls, method, kw, transform) in REF_GROUND_TRUTHS.items():
         gt = np.load(os.path.join(gt_dir, key + "-ground-truth.npy"))
         gts[key] = gt.astype(np.float32)
-        mod = getattr(ref_features, cls)(verbose=False, **SWEEP_CTOR)
+        mod = make_module(ref_features, cls, SWEEP_CTOR)
         with torch.no_grad(), warnings.catch_warnings():
             warnings.simplefilter("ignore")
             y = mod(torch.from_numpy(make_input(("chirp", method))), **kw)

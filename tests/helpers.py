@@ -2,6 +2,9 @@
 buffers, and the parity metrics of SURVEY.md §7 step 0 / BASELINE.md §4."""
 from __future__ import annotations
 
+import contextlib
+import inspect
+import io
 import json
 import os
 import sys
@@ -51,7 +54,12 @@ def ref_buffers():
 def build(cls: str, ctor: dict):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return getattr(nb.features, cls)(verbose=False, **ctor)
+        klass = getattr(nb.features, cls)
+        kw = dict(ctor)
+        if "verbose" in inspect.signature(klass.__init__).parameters:
+            kw["verbose"] = False
+        with contextlib.redirect_stdout(io.StringIO()):  # CQT1992 always prints, like the reference
+            return klass(**kw)
 
 
 def rel_errors(a: np.ndarray, b: np.ndarray):
@@ -105,6 +113,16 @@ def run_oracle(cls: str, mod, x: np.ndarray, kw: dict, dtype=np.float64):
         return oracle.vqt(x, banks, _np(mod.lowpass_filter), _np(mod.lenghts), mod.hop_length,
                           mod.n_bins, mod.pad_mode, early, mod.downsample_factor,
                           fmt or mod.output_format, norm, mod.trainable, dtype)
+    if cls == "CQT1992":
+        return oracle.cqt1992(x, _np(mod.cqt_kernels_real), _np(mod.cqt_kernels_imag), _np(mod.wcos),
+                              _np(mod.wsin), _np(mod.lenghts), mod.hop_length, mod.center,
+                              mod.pad_mode, fmt or mod.output_format, norm, dtype)
+    if cls == "CQT2010":
+        early = _np(mod.early_downsample_filter) if mod.earlydownsample else None
+        return oracle.cqt2010(x, _np(mod.cqt_kernels_real), _np(mod.cqt_kernels_imag), _np(mod.wcos),
+                              _np(mod.wsin), _np(mod.lowpass_filter), _np(mod.lenghts),
+                              mod.hop_length, mod.n_bins, mod.n_octaves, mod.pad_mode, early,
+                              mod.downsample_factor, fmt or mod.output_format, norm, dtype)
     raise ValueError(cls)
 
 

@@ -11,6 +11,28 @@ from cases import GRAD_CASES, WGRAD_CASES, loss_weights, make_input
 
 pytestmark = pytest.mark.gpu
 
+_ERRORS = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_errors():
+    """Leave the measured gradient errors next to the other GPU evidence (gpurun_out/)."""
+    yield
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "backward_errors.json"), "w") as f:
+            json.dump(_ERRORS, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _tol(cls):
+    # MFCC: dB + top_db clamp amplify; pyramid: up to 7 chained bf16x3 stages (FIR + octave CQT)
+    return 4e-4 if cls == "MFCC" else 2e-4 if cls in ("CQT2010v2", "VQT") else 1e-4
+
 
 @pytest.mark.parametrize("case", GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
 def test_input_gradient_matches_reference_autograd(case):
@@ -27,7 +49,8 @@ def test_input_gradient_matches_reference_autograd(case):
     got = x.grad.cpu().numpy()
     assert got.shape == want.shape
     emax, el2 = rel_errors(got, want)
-    tol = 4e-4 if cls == "MFCC" else 1e-4
+    _ERRORS[cid] = {"max_rel": emax, "l2_rel": el2}
+    tol = _tol(cls)
     assert emax < tol and el2 < tol, (cid, emax, el2)
     # the differentiable path and the fused inference path must agree on the forward value
     with torch.no_grad():
@@ -66,7 +89,8 @@ def test_trainable_kernel_gradients_match_reference_autograd(case):
         got = params[n].grad.cpu().numpy()
         assert got.shape == want.shape, n
         emax, el2 = rel_errors(got, want)
-        assert emax < 1e-4 and el2 < 1e-4, (cid, n, emax, el2)
+        _ERRORS[f"{cid}|{n}"] = {"max_rel": emax, "l2_rel": el2}
+        assert emax < _tol(cls) and el2 < _tol(cls), (cid, n, emax, el2)
 
 
 def test_training_step_reduces_loss_with_trainable_stft():

@@ -1,0 +1,95 @@
+"""CPU checks of the differentiable host compositions: the CQT2010v2 /
+VQT octave loop and the iSTFT adjoint, with float64 torch stand-ins in place of the C entry points
+(tests/cpu_kernels.py).  What is verified here is the wiring — stage order, per-stage padding,
+octave concatenation, shared-bank gradient accumulation, one-sided mirror fold, window-sum-square
+adjoint — against the gradients the reference's autograd produced (tests/golden/ref_outputs.npz).
+The same cases run through the real kernels in tests/test_backward.py / tests/test_istft.py (gpu)."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build, ref_outputs, rel_errors  # noqa: E402 (sets sys.path)
+import cpu_kernels  # noqa: E402
+from cases import CASES, GRAD_CASES, ISTFT_GRAD_CASES, WGRAD_CASES, loss_weights, make_input, out_key
+
+HOST_COMPOSED = ("CQT2010v2", "VQT", "CQT1992", "CQT2010")
+PYRAMID_GRAD = [c for c in GRAD_CASES if c[1] in HOST_COMPOSED]
+PYRAMID_WGRAD = [c for c in WGRAD_CASES if c[1] in HOST_COMPOSED]
+V1_FORWARD = [c for c in CASES if c[1] in ("CQT1992", "CQT2010")]
+
+
+@pytest.mark.parametrize("case", PYRAMID_GRAD, ids=[c[0] for c in PYRAMID_GRAD])
+def test_pyramid_input_gradient_wiring(case, monkeypatch):
+    cpu_kernels.install(monkeypatch)
+    cid, cls, ctor, inp, kw = case
+    mod = build(cls, ctor)
+    x = torch.from_numpy(make_input(inp)).requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        y = mod(x, **kw)
+    w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
+    (y * w).sum().backward()
+    want = ref_outputs()["grad|" + cid]
+    emax, el2 = rel_errors(x.grad.numpy(), want)
+    assert x.grad.shape == want.shape and emax < 2e-5 and el2 < 2e-5, (cid, emax, el2)
+
+
+@pytest.mark.parametrize("case", PYRAMID_WGRAD, ids=[c[0] for c in PYRAMID_WGRAD])
+def test_pyramid_shared_bank_gradient_wiring(case, monkeypatch):
+    cpu_kernels.install(monkeypatch)
+    cid, cls, ctor, inp, kw, names = case
+    mod = build(cls, ctor)
+    x = torch.from_numpy(make_input(inp))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        y = mod(x, **kw)
+    w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
+    (y * w).sum().backward()
+    params = dict(mod.named_parameters())
+    for n in names:
+        want = ref_outputs()[f"wgrad|{cid}|{n}"]
+        emax, el2 = rel_errors(params[n].grad.numpy(), want)
+        assert params[n].grad.shape == want.shape and emax < 2e-5 and el2 < 2e-5, (cid, n, emax, el2)
+
+
+@pytest.mark.parametrize("case", ISTFT_GRAD_CASES, ids=[c[0] for c in ISTFT_GRAD_CASES])
+def test_istft_spectrogram_gradient_wiring(case, monkeypatch):
+    cpu_kernels.install(monkeypatch)
+    cid, n_fft, hop, win, kind, spec = case
+    ref = ref_outputs()
+    X = torch.from_numpy(ref[cid + "|X"]).requires_grad_(True)
+    if kind == "roundtrip":
+        st = build("STFT", dict(n_fft=n_fft, hop_length=hop, window=win, iSTFT=True))
+        y = st.inverse(X, onesided=True, length=spec["length"])
+    else:
+        y = build("iSTFT", dict(n_fft=n_fft, hop_length=hop, window=win))(X, onesided=False)
+    w = torch.from_numpy(loss_weights(cid, tuple(y.shape)))
+    (y * w).sum().backward()
+    want = ref[cid + "|dX"]
+    emax, el2 = rel_errors(X.grad.numpy(), want)
+    assert X.grad.shape == want.shape and emax < 2e-5 and el2 < 2e-5, (cid, emax, el2)
+
+
+@pytest.mark.parametrize("case", V1_FORWARD, ids=[c[0] for c in V1_FORWARD])
+def test_folded_bank_reproduces_two_stage_reference(case, monkeypatch):
+    """CQT1992 / CQT2010: the single folded time-domain bank (DFT rows x spectral kernels) gives the
+    reference's two-stage result — values, sign conventions of each output format, normalisation."""
+    cpu_kernels.install(monkeypatch)
+    cid, cls, ctor, inp, fwds = case
+    mod = build(cls, ctor)
+    x = torch.from_numpy(make_input(inp)).requires_grad_(True)  # routes through the octave loop
+    for kw in fwds:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            y = mod(x, **kw).detach().numpy()
+        want = ref_outputs()[out_key(cid, kw)]
+        assert y.shape == want.shape
+        if kw.get("output_format") == "Phase":
+            mag = np.hypot(*np.moveaxis(mod(x, **dict(kw, output_format="Complex")).detach().numpy(), -1, 0))
+            keep = mag > 1e-3 * mag.max()
+            assert np.abs(y[keep] - want[keep]).max() < 2e-3, (cid, kw)
+            continue
+        emax, el2 = rel_errors(y, want)
+        assert emax < 2e-5 and el2 < 2e-5, (cid, kw, emax, el2)

@@ -49,12 +49,14 @@ def test_forward_only_guard():
     # the training path exists (tests/test_backward.py, GPU); on CPU it still fails loudly
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(1, 4000))
-    q = nb.CQT2010v2(verbose=False)
-    with pytest.raises(NotImplementedError, match="pyramid"):
-        q(torch.randn(1, 40000, requires_grad=True))
+    # the pyramid trains too (octave loop over the same kernels); CPU tensors are still refused
     qt = nb.CQT2010v2(trainable=True, verbose=False)
-    with pytest.raises(NotImplementedError, match="forward-only"):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         qt(torch.randn(1, 40000))
+    # trainable inverse kernels / window have no dW path: refuse instead of silently not training
+    inv = nb.iSTFT(n_fft=256, trainable_kernels=True, verbose=False)
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        inv(torch.zeros(1, 256, 10, 2))
 
 
 def test_attribute_surface_matches_reference():

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from helpers import build, oracle, ref_outputs, rel_errors
-from cases import ISTFT_CASES
+from cases import ISTFT_CASES, ISTFT_GRAD_CASES, loss_weights
 
 import nnaudio_b200 as nb
 
@@ -69,6 +69,27 @@ def test_stft_inverse_round_trip_recovers_waveform():
             y = st.inverse(st(x, output_format="Complex"), onesided=True, length=x.shape[-1])
         assert y.shape == x.shape
         assert torch.allclose(y, x, rtol=1e-5, atol=1e-3), (y - x).abs().max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ISTFT_GRAD_CASES, ids=[c[0] for c in ISTFT_GRAD_CASES])
+def test_cuda_istft_spectrogram_gradient_matches_reference_autograd(case):
+    """dL/dX through the inverse (reference: autograd through conv2d + fold, stft.py:15-63)."""
+    cid, n_fft, hop, win, kind, spec = case
+    mod = _module(n_fft, hop, win, kind).cuda()
+    X = torch.from_numpy(ref_outputs()[cid + "|X"]).cuda().requires_grad_(True)
+    if kind == "roundtrip":
+        y = mod.inverse(X, onesided=True, length=spec["length"])
+    else:
+        y = mod(X, onesided=False)
+    w = torch.from_numpy(loss_weights(cid, tuple(y.shape))).cuda()
+    (y * w).sum().backward()
+    torch.cuda.synchronize()
+    want = ref_outputs()[cid + "|dX"]
+    got = X.grad.cpu().numpy()
+    assert got.shape == want.shape
+    emax, el2 = rel_errors(got, want)
+    assert emax < 1e-4 and el2 < 1e-4, (cid, emax, el2)
 
 
 def test_inverse_requires_istft_flag_and_complex_input():
