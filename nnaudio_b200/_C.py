@@ -194,6 +194,25 @@ def _workspace(nbytes: int, device):
     return ws, nbytes
 
 
+MAX_BATCH = 65535  # clips per C call (the pre-pass kernels put the clip index in gridDim.y)
+
+
+def _batch_chunked(fn):
+    """Forward wrappers take any batch size: more than ``MAX_BATCH`` clips are run as several C
+    calls on the same stream and concatenated (every op of the path is per-clip, including the
+    MFCC ``top_db`` clamp)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(x, *args, **kwargs):
+        if x.dim() != 2 or x.shape[0] <= MAX_BATCH:
+            return fn(x, *args, **kwargs)
+        return torch.cat([fn(x[i:i + MAX_BATCH], *args, **kwargs)
+                          for i in range(0, x.shape[0], MAX_BATCH)], 0)
+
+    return wrapper
+
+
 def _rows(x: torch.Tensor):
     """(B, L) view with unit inner stride -> (tensor, B, L, pitch)."""
     x = _dev_f32(x, "x")
@@ -251,6 +270,7 @@ def build_filterbank_table(fb: torch.Tensor):
 # --------------------------------------------------------------------------- #
 # forward calls
 # --------------------------------------------------------------------------- #
+@_batch_chunked
 def stft_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, out_format, sqrt_eps,
                  path=None):
     L = lib()
@@ -271,6 +291,7 @@ def stft_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, out_format
     return out
 
 
+@_batch_chunked
 def stft_filterbank_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, power,
                             fb, fb_table=None, path=None):
     L = lib()
@@ -294,6 +315,7 @@ def stft_filterbank_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode,
     return out
 
 
+@_batch_chunked
 def mfcc_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, power, mel_basis,
                  amin, ref, top_db, dct, fb_table=None, path=None):
     L = lib()
@@ -318,6 +340,7 @@ def mfcc_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, 
     return out
 
 
+@_batch_chunked
 def cqt1992v2_forward(x, k_real, k_imag, packed, k_begin, k_end, hop, center, pad_mode, scale,
                       scale_all, out_format, sqrt_eps, path=None):
     """k_begin / k_end: host int32 numpy arrays (per-bin support) or None."""
@@ -343,6 +366,7 @@ def cqt1992v2_forward(x, k_real, k_imag, packed, k_begin, k_end, hop, center, pa
     return out
 
 
+@_batch_chunked
 def cqt_pyramid_forward(x, banks_real, banks_imag, packed, lowpass, lowpass_packed, early_filter,
                         early_packed, early_factor, hop, pad_mode, n_bins, scale, scale_all,
                         out_format, sqrt_eps, T, path=None):

@@ -41,6 +41,9 @@ __all__ = [
     "cqt2010v2",
     "vqt",
     "istft",
+    "cqt1992",
+    "cqt2010",
+    "griffin_lim",
 ]
 
 
@@ -459,3 +462,55 @@ def istft(X, kernel_cos, kernel_sin, window_mask, hop, center=True, onesided=Tru
     if length is None:
         return y[:, pad:-pad] if center else y
     return y[:, pad: pad + length] if center else y[:, :length]
+
+
+# --------------------------------------------------------------------------- #
+# Griffin-Lim  
+# --------------------------------------------------------------------------- #
+def griffin_lim(S, rand_phase, n_fft, n_iter=32, hop=None, win_length=None, window="hann",
+                center=True, pad_mode="reflect", momentum=0.99, dtype=np.float64):
+    """Griffin_Lim.forward (griffin_lim.py:89-148) with the initial ``randn`` phase passed in.
+
+    PARITY UNPINNED: the reference module does not execute under torch >= 2.0 (its real-view
+    ``torch.istft`` / ``torch.stft`` calls are rejected), so this restatement follows the source
+    and the documented semantics of those two calls: ``torch.stft`` = reflect/constant centre
+    padding, window zero-padded to n_fft, one-sided DFT (always ``center=True`` in the loop,
+    griffin_lim.py:120-127); ``torch.istft`` = inverse real DFT, window, overlap-add, division by
+    the overlap-added squared window, trim n_fft//2 when ``center``."""
+    from scipy.signal import get_window
+
+    S = np.asarray(S).astype(dtype)
+    win_length = n_fft if win_length is None else win_length
+    hop = n_fft // 4 if hop is None else hop
+    w = get_window(window, int(win_length), fftbins=True).astype(np.float32).astype(dtype)
+    lpad = (n_fft - win_length) // 2
+    w = np.pad(w, (lpad, n_fft - win_length - lpad))
+    B, F, T = S.shape
+
+    def inverse(X):
+        frames = np.fft.irfft(X, n=n_fft, axis=1) * w[None, :, None]
+        out_len = n_fft + hop * (T - 1)
+        y = np.zeros((B, out_len), dtype=dtype)
+        wss = np.zeros(out_len, dtype=dtype)
+        for t in range(T):
+            y[:, t * hop: t * hop + n_fft] += frames[:, :, t]
+            wss[t * hop: t * hop + n_fft] += w ** 2
+        if center:
+            y, wss = y[:, n_fft // 2: out_len - n_fft // 2], wss[n_fft // 2: out_len - n_fft // 2]
+        return y / wss
+
+    def forward(y):
+        yp = pad_signal(y, n_fft // 2, pad_mode)
+        n_frames = (yp.shape[-1] - n_fft) // hop + 1
+        idx = np.arange(n_fft)[:, None] + hop * np.arange(n_frames)[None, :]
+        return np.fft.rfft(yp[:, idx] * w[None, :, None], axis=1)
+
+    ph = np.asarray(rand_phase).astype(np.float32).astype(dtype)
+    angles = np.cos(2 * np.pi * ph) + 1j * np.sin(2 * np.pi * ph)
+    rebuilt = np.zeros_like(angles)
+    for _ in range(n_iter):
+        tprev = rebuilt
+        rebuilt = forward(inverse(S * angles))
+        angles = rebuilt - (momentum / (1 + momentum)) * tprev
+        angles = angles / (np.abs(angles) + 1e-16)
+    return inverse(S * angles)

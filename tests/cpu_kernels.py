@@ -35,6 +35,12 @@ def cqt1992v2_forward(x, k_real, k_imag, packed, k_begin, k_end, hop, center, pa
     return _framed(x, k_real, k_imag, hop, center, pad_mode).float()
 
 
+def stft_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, out_format, sqrt_eps, path=None):
+    assert out_format == _C.FMT_COMPLEX
+    return _framed(x, wcos.reshape(wcos.shape[0], -1), wsin.reshape(wsin.shape[0], -1), hop, center,
+                   pad_mode).float()
+
+
 def framed_backward_input(g, packed_adj, K, hop, center, pad_mode, L_in):
     w_re, w_im = packed_adj
     x = torch.zeros((g.shape[0], L_in), dtype=torch.float64, requires_grad=True)
@@ -71,6 +77,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_C, "pack_istft_basis",
                         lambda kc, ks, f_in, onesided: (kc.clone(), ks.clone(), bool(onesided)))
     monkeypatch.setattr(_C, "cqt1992v2_forward", cqt1992v2_forward)
+    monkeypatch.setattr(_C, "stft_forward", stft_forward)
     monkeypatch.setattr(_C, "framed_backward_input", framed_backward_input)
     monkeypatch.setattr(_C, "framed_backward_weight", framed_backward_weight)
     monkeypatch.setattr(_C, "istft_forward", istft_forward)

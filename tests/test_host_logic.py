@@ -119,3 +119,22 @@ def test_nnaudio_import_shim():
         sys.path.remove(os.path.join(ROOT, "shim"))
         for k in [k for k in sys.modules if k == "nnAudio" or k.startswith("nnAudio.")]:
             del sys.modules[k]
+
+
+def test_batches_beyond_the_per_call_limit_are_chunked(monkeypatch):
+    """More than _C.MAX_BATCH clips: several C calls on the same stream, concatenated."""
+    from nnaudio_b200 import _C
+
+    monkeypatch.setattr(_C, "MAX_BATCH", 3)
+    calls = []
+
+    @_C._batch_chunked
+    def fake_forward(x, gain):
+        calls.append(x.shape[0])
+        return x * gain
+
+    x = torch.arange(16.0).reshape(8, 2)
+    assert torch.equal(fake_forward(x, 2.0), x * 2.0) and calls == [3, 3, 2]
+    for name in ("stft_forward", "stft_filterbank_forward", "mfcc_forward", "cqt1992v2_forward",
+                 "cqt_pyramid_forward"):
+        assert hasattr(getattr(_C, name), "__wrapped__"), name
