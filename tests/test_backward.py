@@ -23,7 +23,8 @@ def _dump_errors():
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     try:
         os.makedirs(out, exist_ok=True)
-        with open(os.path.join(out, "backward_errors.json"), "w") as f:
+        family = os.environ.get("NNAUDIO_B200_PATH", "auto")  # forward kernel family of this run
+        with open(os.path.join(out, f"backward_errors_{family}.json"), "w") as f:
             json.dump(_ERRORS, f, indent=1, sort_keys=True)
     except OSError:
         pass
