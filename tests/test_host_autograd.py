@@ -93,3 +93,30 @@ def test_folded_bank_reproduces_two_stage_reference(case, monkeypatch):
             continue
         emax, el2 = rel_errors(y, want)
         assert emax < 2e-5 and el2 < 2e-5, (cid, kw, emax, el2)
+
+
+@pytest.mark.parametrize("taps,n,L", [(256, 2, 1000), (256, 2, 1001), (256, 4, 4099), (255, 3, 777),
+                                      (16, 5, 64), (9, 2, 9)])
+def test_polyphase_decimation_adjoint_equals_conv1d_autograd(taps, n, L, monkeypatch):
+    """The backward of a decimating FIR stage is computed as n interleaved stride-1 FIRs with the
+    polyphase components (no overlap-add): identical to autograd through
+    conv1d(stride=n, padding=(taps-1)//2) (utils.py:73-100), for even/odd taps and lengths."""
+    from nnaudio_b200.features.cqt import _decimate_autograd
+
+    cpu_kernels.install(monkeypatch)
+    g = torch.Generator().manual_seed(taps * 131 + n)
+    fir = torch.randn(1, 1, taps, generator=g)
+    x = torch.randn(3, L, generator=g)
+    holder = torch.nn.Module()
+
+    a = x.clone().requires_grad_(True)
+    y = _decimate_autograd(holder, "t", a, fir, n)
+    b = x.clone().requires_grad_(True)
+    y_ref = torch.nn.functional.conv1d(b[:, None, :].double(), fir.double(), stride=n,
+                                       padding=(taps - 1) // 2)[:, 0, :]
+    assert y.shape == y_ref.shape
+    w = torch.randn(y.shape, generator=g)
+    (y * w).sum().backward()
+    (y_ref * w.double()).sum().backward()
+    assert torch.allclose(y.double(), y_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(a.grad.double(), b.grad.double(), rtol=1e-5, atol=1e-5)
