@@ -468,7 +468,25 @@ class _DecimateFn(torch.autograd.Function):
 
 
 def _decimate_autograd(mod, tag, sig, fir, n):
-    """Differentiable ``downsampling_by_n`` / ``_by_2`` stage of the training path."""
+    """Differentiable ``downsampling_by_n`` / ``_by_2`` stage of the training path.
+
+    ``NNAUDIO_B200_DECIM_BWD`` picks the adjoint (round-1 measurements, CQT2010v2 32 x 30 s forward +
+    backward, worst dX error of the pyramid cases vs the reference's autograd):
+    ``simt`` (default) polyphase FIRs on the CUDA-core kernel — 42.0 ms, 6.1e-5 (2.2e-5 on the
+    Magnitude case); ``tc`` the same on the tensor-core kernel (8 frame phases) — 30.1 ms, 6.1e-5;
+    ``ola`` a K=1 adjoint GEMM + overlap-add atomics (256 atomics per input sample) — 24.4 ms but
+    1.04e-4 on the Magnitude case, i.e. over the parity bar.  A dedicated FIR-adjoint kernel is
+    the open item."""
+    if os.environ.get("NNAUDIO_B200_DECIM_BWD", "simt") == "ola":
+        taps = fir.numel()
+        w_re = fir.detach().reshape(1, taps)
+        zeros = mod.__dict__.setdefault("_fir_zeros", {})
+        if tag not in zeros or zeros[tag].shape != w_re.shape or zeros[tag].device != w_re.device:
+            zeros[tag] = torch.zeros_like(w_re)
+        half = (taps - 1) // 2
+        padded = torch.nn.functional.pad(sig, (half, half))
+        c = _framed_complex_autograd(mod, tag, padded, w_re, zeros[tag], n, False, _C.PAD_CONSTANT)
+        return c[:, 0, :, 0].contiguous()
     cache = mod.__dict__.setdefault("_decim_cache", {})
     key = (fir.data_ptr(), fir._version, int(n), str(fir.device))
     if tag not in cache or cache[tag][0] != key:

@@ -31,8 +31,9 @@ def _dump_errors():
 
 
 def _tol(cls):
-    # MFCC: dB + top_db clamp amplify; pyramid: up to 7 chained bf16x3 stages (FIR + octave CQT)
-    return 4e-4 if cls == "MFCC" else 2e-4 if cls in ("CQT2010v2", "VQT", "CQT2010") else 1e-4
+    # MFCC: the dB + top_db clamp amplifies; everything else holds the 1e-4 bar (measured worst
+    # case of the pyramid training path: 6.1e-5, profiles/r01_backward_errors_auto.json)
+    return 4e-4 if cls == "MFCC" else 1e-4
 
 
 @pytest.mark.parametrize("case", GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
