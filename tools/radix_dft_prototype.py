@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Numerical prototype (CPU, numpy) of the next step for the STFT-family kernel: one or two
+decimation-in-time steps in front of the dense DFT contraction.
+
+Today the kernel contracts each n_fft-sample frame with the full windowed basis:
+N x (N + 2) MACs per frame (N = n_fft, one-sided, re + im).  Splitting the frame into its R
+sample phases (n = R m + r) gives R windowed sub-DFTs of length N/R whose real-input Hermitian
+symmetry leaves N/(2R) + 1 unique bins each:
+
+    S_r[k] = sum_m x[R m + r] w[R m + r] exp(-2 pi i k m / (N/R)),      k = 0 .. N/(2R)
+    X[k]   = sum_r exp(-2 pi i r k / N) S_r[k mod N/R]                   (S_r[N/R - k] = conj S_r[k])
+
+i.e. R GEMMs with K = N/R and N/(2R)+1 complex columns: N (N/R + 2) MACs per frame, 1/R of
+the dense count, plus R complex multiply-adds per output bin in the epilogue (done from TMEM in
+registers: all R sub-DFT accumulators of a frame sit in the same TMEM lane).  The A operand of
+sub-DFT r is the r-th sample phase of the signal, which TMA can read from R de-interleaved planes
+as long as R divides the hop.
+
+This script checks the algebra against the dense contraction in float64 and measures what the
+shorter contractions do to the split-bf16 (3-term) error.  It is a design aid, not product code.
+
+    python tools/radix_dft_prototype.py [--n-fft 2048] [--hop 512] [--radix 2 4]
+"""
+import argparse
+
+import numpy as np
+
+
+def bf16(v):
+    """Round-to-nearest-even float32 -> bfloat16 -> float32 (numpy)."""
+    u = np.asarray(v, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+def split3(a, b):
+    """a @ b.T with the 3-term bf16 hi/lo split, products accumulated in float64 (the tensor
+    core accumulates in fp32; float64 here isolates the operand-rounding error)."""
+    ah = bf16(a); al = bf16(a - ah)
+    bh = bf16(b); bl = bf16(b - bh)
+    f = np.float64
+    return ah.astype(f) @ bh.astype(f).T + al.astype(f) @ bh.astype(f).T + ah.astype(f) @ bl.astype(f).T
+
+
+def dense_basis(N, window):
+    k = np.arange(N // 2 + 1)[:, None]
+    n = np.arange(N)[None, :]
+    ang = 2 * np.pi * k * n / N
+    return (np.cos(ang) * window).astype(np.float32), (np.sin(ang) * window).astype(np.float32)
+
+
+def radix_bases(N, R, window):
+    """Per sample phase r: (cos, sin) rows for k = 0 .. N/(2R), over m = 0 .. N/R - 1."""
+    Ns = N // R
+    k = np.arange(Ns // 2 + 1)[:, None]
+    m = np.arange(Ns)[None, :]
+    ang = 2 * np.pi * k * m / Ns
+    return [((np.cos(ang) * window[r::R]).astype(np.float32),
+             (np.sin(ang) * window[r::R]).astype(np.float32)) for r in range(R)]
+
+
+def combine(S, N, R):
+    """Epilogue: X[k] for k = 0 .. N/2 from the R half-spectra S[r] (complex, (T, N/(2R)+1))."""
+    Ns = N // R
+    k = np.arange(N // 2 + 1)
+    kk = k % Ns
+    X = np.zeros((S[0].shape[0], N // 2 + 1), dtype=np.complex128)
+    for r in range(R):
+        full = np.where(kk <= Ns // 2, S[r][:, np.minimum(kk, Ns // 2)],
+                        np.conj(S[r][:, np.minimum(Ns - kk, Ns // 2)]))
+        X += np.exp(-2j * np.pi * r * k / N)[None, :] * full
+    return X
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-fft", type=int, default=2048)
+    ap.add_argument("--hop", type=int, default=512)
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--radix", type=int, nargs="+", default=[2, 4, 8])
+    args = ap.parse_args()
+    N, hop, T = args.n_fft, args.hop, args.frames
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal(hop * (T - 1) + N).astype(np.float32)
+    frames = np.lib.stride_tricks.sliding_window_view(x, N)[::hop][:T]
+    from scipy.signal import get_window
+    window = get_window("hann", N, fftbins=True)
+
+    wc, ws = dense_basis(N, window)
+    f = np.float64
+    exact = frames.astype(f) @ wc.astype(f).T - 1j * (frames.astype(f) @ ws.astype(f).T)
+    scale = np.abs(exact).max()
+    d3 = split3(frames, wc) - 1j * split3(frames, ws)
+    print(f"n_fft {N}, hop {hop}, {T} frames of white noise; errors are max|d| / max|X|")
+    print(f"dense   : MACs/frame {N * (N + 2):>9d}   split-bf16 error {np.abs(d3 - exact).max() / scale:.2e}")
+    for R in args.radix:
+        if N % (2 * R) or hop % R:
+            print(f"radix {R}: needs 2R | n_fft and R | hop — skipped")
+            continue
+        bases = radix_bases(N, R, window)
+        S64, S3 = [], []
+        for r, (bc, bs) in enumerate(bases):
+            a = np.ascontiguousarray(frames[:, r::R])
+            S64.append(a.astype(f) @ bc.astype(f).T - 1j * (a.astype(f) @ bs.astype(f).T))
+            S3.append(split3(a, bc) - 1j * split3(a, bs))
+        X64, X3 = combine(S64, N, R), combine(S3, N, R)
+        macs = R * (N // R) * 2 * (N // (2 * R) + 1)
+        print(f"radix {R:<2d}: MACs/frame {macs:>9d} ({N * (N + 2) / macs:.2f}x fewer)   "
+              f"algebra error {np.abs(X64 - exact).max() / scale:.1e}   "
+              f"split-bf16 error {np.abs(X3 - exact).max() / scale:.2e}   "
+              f"epilogue {R} complex MADs per bin")
+
+
+if __name__ == "__main__":
+    main()
