@@ -11,7 +11,12 @@ against (i) the reference's own golden vectors
 (``Installation/tests/ground-truths/*cqt*.npy``, replayed from
 ``tests/golden/ref_ground_truths.npz``) and (ii) outputs of the unmodified
 reference imported in the build container (``tests/golden/make_golden.py`` ->
-``tests/golden/ref_outputs.npz``).
+``tests/golden/ref_outputs.npz``) — this covers STFT, the inverse STFT, Mel,
+MFCC, Gammatone, CQT1992v2, CQT2010v2, VQT and the first-generation
+``cqt1992`` / ``cqt2010``.  ONE EXCEPTION, PARITY UNPINNED: ``griffin_lim`` — the
+reference module does not execute under torch >= 2.0 (its ``torch.istft`` /
+``torch.stft`` calls are rejected), so that function follows the source and the
+documented semantics of the two torch calls without reference outputs to check.
 
 All functions take the module's *buffers* (float32 arrays, exactly what
 ``state_dict()`` holds) plus scalar configuration, and compute in ``dtype``
@@ -44,6 +49,8 @@ __all__ = [
     "cqt1992",
     "cqt2010",
     "griffin_lim",
+    "torch_stft_restated",
+    "torch_istft_restated",
 ]
 
 
@@ -467,50 +474,63 @@ def istft(X, kernel_cos, kernel_sin, window_mask, hop, center=True, onesided=Tru
 # --------------------------------------------------------------------------- #
 # Griffin-Lim  
 # --------------------------------------------------------------------------- #
+def _padded_window(window, win_length, n_fft, dtype):
+    from scipy.signal import get_window
+
+    w = get_window(window, int(win_length), fftbins=True).astype(np.float32).astype(dtype)
+    lpad = (n_fft - win_length) // 2
+    return np.pad(w, (lpad, n_fft - win_length - lpad))
+
+
+def torch_istft_restated(X, n_fft, hop, w, center=True):
+    """``torch.istft(X, n_fft, hop, win_length, window, center)`` for one-sided complex
+    ``X (B, n_fft//2+1, T)`` and a window already padded to n_fft: inverse real DFT, window,
+    overlap-add, divide by the overlap-added squared window, trim n_fft//2 when centred.
+    Pinned against torch itself in tests/test_griffin_lim.py."""
+    B, _, T = X.shape
+    frames = np.fft.irfft(X, n=n_fft, axis=1) * w[None, :, None]
+    out_len = n_fft + hop * (T - 1)
+    y = np.zeros((B, out_len), dtype=frames.dtype)
+    wss = np.zeros(out_len, dtype=frames.dtype)
+    for t in range(T):
+        y[:, t * hop: t * hop + n_fft] += frames[:, :, t]
+        wss[t * hop: t * hop + n_fft] += w ** 2
+    if center:
+        y, wss = y[:, n_fft // 2: out_len - n_fft // 2], wss[n_fft // 2: out_len - n_fft // 2]
+    return y / wss
+
+
+def torch_stft_restated(y, n_fft, hop, w, pad_mode="reflect"):
+    """``torch.stft(y, n_fft, hop, win_length, window, center=True, pad_mode, onesided=True)``
+    as complex ``(B, n_fft//2+1, T)``.  Pinned against torch itself in tests/test_griffin_lim.py."""
+    yp = pad_signal(y, n_fft // 2, pad_mode)
+    n_frames = (yp.shape[-1] - n_fft) // hop + 1
+    idx = np.arange(n_fft)[:, None] + hop * np.arange(n_frames)[None, :]
+    return np.fft.rfft(yp[:, idx] * w[None, :, None], axis=1)
+
+
 def griffin_lim(S, rand_phase, n_fft, n_iter=32, hop=None, win_length=None, window="hann",
                 center=True, pad_mode="reflect", momentum=0.99, dtype=np.float64):
     """Griffin_Lim.forward (griffin_lim.py:89-148) with the initial ``randn`` phase passed in.
 
-    PARITY UNPINNED: the reference module does not execute under torch >= 2.0 (its real-view
-    ``torch.istft`` / ``torch.stft`` calls are rejected), so this restatement follows the source
-    and the documented semantics of those two calls: ``torch.stft`` = reflect/constant centre
-    padding, window zero-padded to n_fft, one-sided DFT (always ``center=True`` in the loop,
-    griffin_lim.py:120-127); ``torch.istft`` = inverse real DFT, window, overlap-add, division by
-    the overlap-added squared window, trim n_fft//2 when ``center``."""
-    from scipy.signal import get_window
-
+    PARITY UNPINNED for the loop as a whole: the reference module does not execute under
+    torch >= 2.0 (its real-view ``torch.istft`` / ``torch.stft`` calls are rejected).  The two
+    library calls it makes are restated above and pinned against torch; the glue below (initial
+    phase, momentum rule griffin_lim.py:129-137, final inverse) follows the source.  In the loop
+    ``torch.stft`` runs with its default ``center=True`` (griffin_lim.py:120-127); only the
+    inverse honours ``center``."""
     S = np.asarray(S).astype(dtype)
     win_length = n_fft if win_length is None else win_length
     hop = n_fft // 4 if hop is None else hop
-    w = get_window(window, int(win_length), fftbins=True).astype(np.float32).astype(dtype)
-    lpad = (n_fft - win_length) // 2
-    w = np.pad(w, (lpad, n_fft - win_length - lpad))
-    B, F, T = S.shape
-
-    def inverse(X):
-        frames = np.fft.irfft(X, n=n_fft, axis=1) * w[None, :, None]
-        out_len = n_fft + hop * (T - 1)
-        y = np.zeros((B, out_len), dtype=dtype)
-        wss = np.zeros(out_len, dtype=dtype)
-        for t in range(T):
-            y[:, t * hop: t * hop + n_fft] += frames[:, :, t]
-            wss[t * hop: t * hop + n_fft] += w ** 2
-        if center:
-            y, wss = y[:, n_fft // 2: out_len - n_fft // 2], wss[n_fft // 2: out_len - n_fft // 2]
-        return y / wss
-
-    def forward(y):
-        yp = pad_signal(y, n_fft // 2, pad_mode)
-        n_frames = (yp.shape[-1] - n_fft) // hop + 1
-        idx = np.arange(n_fft)[:, None] + hop * np.arange(n_frames)[None, :]
-        return np.fft.rfft(yp[:, idx] * w[None, :, None], axis=1)
+    w = _padded_window(window, win_length, n_fft, dtype)
 
     ph = np.asarray(rand_phase).astype(np.float32).astype(dtype)
     angles = np.cos(2 * np.pi * ph) + 1j * np.sin(2 * np.pi * ph)
     rebuilt = np.zeros_like(angles)
     for _ in range(n_iter):
         tprev = rebuilt
-        rebuilt = forward(inverse(S * angles))
+        inverse = torch_istft_restated(S * angles, n_fft, hop, w, center)
+        rebuilt = torch_stft_restated(inverse, n_fft, hop, w, pad_mode)
         angles = rebuilt - (momentum / (1 + momentum)) * tprev
         angles = angles / (np.abs(angles) + 1e-16)
-    return inverse(S * angles)
+    return torch_istft_restated(S * angles, n_fft, hop, w, center)

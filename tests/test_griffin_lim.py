@@ -47,6 +47,30 @@ def test_host_loop_matches_oracle(cfg, monkeypatch):
     assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
 
 
+@pytest.mark.parametrize("n_fft,hop,win_length,window,pad_mode", [
+    (256, 64, 256, "hann", "reflect"), (512, 128, 400, "hamming", "reflect"),
+    (256, 64, 256, "hann", "constant"), (256, 64, 256, "hamming", "reflect")])
+def test_oracle_transform_pair_is_pinned_to_torch(n_fft, hop, win_length, window, pad_mode):
+    """The reference's loop calls torch.stft / torch.istft; the oracle's restatements of those two
+    calls are held to torch itself (the modern complex API of the same functions)."""
+    rng = np.random.RandomState(3)
+    y = rng.standard_normal((2, hop * 30)).astype(np.float64)
+    w = oracle._padded_window(window, win_length, n_fft, np.float64)
+    w_t = torch.from_numpy(w[(n_fft - win_length) // 2: (n_fft - win_length) // 2 + win_length].copy())
+    X_t = torch.stft(torch.from_numpy(y), n_fft, hop, win_length=win_length, window=w_t, center=True,
+                     pad_mode=pad_mode, return_complex=True)
+    X_o = oracle.torch_stft_restated(y, n_fft, hop, w, pad_mode)
+    assert X_o.shape == tuple(X_t.shape)
+    assert np.abs(X_o - X_t.numpy()).max() < 1e-10 * np.abs(X_o).max()
+    for center in (True, False):
+        if not center and (window == "hann" or win_length < n_fft):
+            continue  # torch rejects a window sum-square that touches zero at the uncut edges
+        y_t = torch.istft(X_t, n_fft, hop, win_length=win_length, window=w_t, center=center)
+        y_o = oracle.torch_istft_restated(X_t.numpy(), n_fft, hop, w, center)
+        assert y_o.shape == tuple(y_t.shape)
+        assert np.abs(y_o - y_t.numpy()).max() < 1e-10 * np.abs(y_o).max()
+
+
 def test_module_surface():
     g = nb.Griffin_Lim(n_fft=512)
     assert g.hop_length == 128 and g.win_length == 512 and g.n_iter == 32 and g.momentum == 0.99
