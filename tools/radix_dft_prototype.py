@@ -72,6 +72,48 @@ def combine(S, N, R):
     return X
 
 
+def radix2_kernel_layout_check(frames, N, window, exact):
+    """Executable spec of the planned R = 2 kernel data layout.
+
+    Basis per sample phase r (even / odd samples), 2 * (N/4) rows of length N/2:
+        row 2k   : w[2m + r] *  cos(2 pi k m / (N/2))        k = 0 .. N/4 - 1
+        row 2k+1 : w[2m + r] * -sin(2 pi k m / (N/2))        k = 1 .. N/4 - 1
+        row 1    : w[2m + r] * (-1)^m      <- the sub-DFT's Nyquist bin (k = N/4, real) stored in
+                                              the always-zero imaginary slot of k = 0
+    so N/4 (re, im) column pairs cover all N/4 + 1 unique bins and tile evenly (512 -> 8 x 64).
+    Epilogue per frame and k (all four accumulators sit in the same TMEM lane):
+        U = W_N^k * S1[k]                    X[k]       = S0[k] + U
+                                             X[N/2 - k] = conj(S0[k] - U)
+        k = 0:  X[0] = S0re + S1re,  X[N/2] = S0re - S1re,
+                X[N/4] = S0nyq - i * S1nyq   (W_N^{N/4} = -i)
+    Returns max |X - exact| / max |exact| in float64."""
+    f = np.float64
+    Ns, Q = N // 2, N // 4
+    m = np.arange(Ns)
+    acc = []
+    for r in range(2):
+        rows = np.zeros((2 * Q, Ns), dtype=f)
+        wr = window[r::2]
+        for k in range(Q):
+            rows[2 * k] = wr * np.cos(2 * np.pi * k * m / Ns)
+            rows[2 * k + 1] = -wr * np.sin(2 * np.pi * k * m / Ns)
+        rows[1] = wr * (-1.0) ** m
+        acc.append(frames[:, r::2].astype(f) @ rows.astype(np.float32).astype(f).T)   # (T, 2Q)
+    T = frames.shape[0]
+    X = np.zeros((T, N // 2 + 1), dtype=np.complex128)
+    S0, S1 = acc
+    for k in range(1, Q):
+        s0 = S0[:, 2 * k] + 1j * S0[:, 2 * k + 1]
+        s1 = S1[:, 2 * k] + 1j * S1[:, 2 * k + 1]
+        u = np.exp(-2j * np.pi * k / N) * s1
+        X[:, k] = s0 + u
+        X[:, N // 2 - k] = np.conj(s0 - u)
+    X[:, 0] = S0[:, 0] + S1[:, 0]
+    X[:, N // 2] = S0[:, 0] - S1[:, 0]
+    X[:, Q] = S0[:, 1] - 1j * S1[:, 1]
+    return np.abs(X - exact).max() / np.abs(exact).max()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-fft", type=int, default=2048)
@@ -109,6 +151,8 @@ def main():
               f"algebra error {np.abs(X64 - exact).max() / scale:.1e}   "
               f"split-bf16 error {np.abs(X3 - exact).max() / scale:.2e}   "
               f"epilogue {R} complex MADs per bin")
+    print(f"radix 2 kernel layout (Nyquist packed into the k = 0 imaginary slot, butterfly epilogue): "
+          f"error {radix2_kernel_layout_check(frames, N, window, exact):.1e}")
 
 
 if __name__ == "__main__":
