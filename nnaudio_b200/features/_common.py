@@ -35,7 +35,7 @@ def pad_mode_id(pad_mode: str) -> int:
 
 
 def forward_only_guard(module: torch.nn.Module, x: torch.Tensor):
-    """Kept for the modules without a training path (CQT2010v2 / VQT pyramid, iSTFT):
+    """For parameters without a dW path (trainable inverse kernels / window of iSTFT):
     refuse loudly rather than return a result whose parameters silently get no gradient."""
     if not torch.is_grad_enabled():
         return
@@ -51,10 +51,6 @@ def wants_grad(module: torch.nn.Module, x: torch.Tensor) -> bool:
     if not torch.is_grad_enabled():
         return False
     return x.requires_grad or any(p.requires_grad for p in module.parameters())
-
-
-def wants_input_grad(x: torch.Tensor) -> bool:
-    return torch.is_grad_enabled() and x.requires_grad
 
 
 class FramedComplexFn(torch.autograd.Function):
