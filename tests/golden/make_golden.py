@@ -28,7 +28,7 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
-from cases import (CASES, GRAD_CASES, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
+from cases import (CASES, DESIGN_CASES, GRAD_CASES, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
                    SWEEP_CTOR, WGRAD_CASES, loss_weights, make_input, out_key)
 
 from nnAudio import features as ref_features  # noqa: E402
@@ -70,6 +70,13 @@ def main():
                 y = mod(x, **kw)
             outputs[out_key(cid, kw)] = y.numpy().astype(np.float32)
             print(f"{out_key(cid, kw):60s} {tuple(y.shape)}")
+    for cid, cls, ctor in DESIGN_CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = make_module(ref_features, cls, ctor)
+        buffers[cid] = {k: [list(v.shape), sha(v)] for k, v in mod.state_dict().items()
+                        if v is not None}
+        print(f"{cid:60s} {len(buffers[cid])} buffers")
     # inverse STFT: spectrogram inputs AND waveform outputs of the reference
     for cid, n_fft, hop, win, kind, spec in ISTFT_CASES:
         rng = np.random.RandomState(spec["seed"])
