@@ -167,6 +167,31 @@ DESIGN_CASES = [
 ]
 
 
+# Error-behaviour scenarios: what the reference raises (exception type) for malformed constructor
+# arguments and inputs; recorded into ref_errors.json.  ("ctor",) | ("forward", shape, kwargs) |
+# ("inverse", shape, kwargs)
+ERROR_CASES = [
+    ("e_stft_short_reflect", "STFT", dict(n_fft=512), ("forward", (1, 100), {})),
+    ("e_stft_4d_input", "STFT", dict(n_fft=256), ("forward", (1, 1, 2, 4000), {})),
+    ("e_stft_two_channels", "STFT", dict(n_fft=256), ("forward", (2, 2, 4000), {})),
+    ("e_stft_inverse_without_flag", "STFT", dict(n_fft=256), ("inverse", (1, 129, 10, 2), {})),
+    ("e_stft_inverse_3d", "STFT", dict(n_fft=256, iSTFT=True), ("inverse", (1, 129, 10), {})),
+    ("e_istft_3d", "iSTFT", dict(n_fft=256), ("forward", (1, 256, 10), {})),
+    ("e_mel_short_reflect", "MelSpectrogram", dict(sr=16000, n_fft=1024), ("forward", (2, 300), {})),
+    ("e_cqt1992v2_nyquist", "CQT1992v2", dict(sr=8000, fmin=220, n_bins=84), ("ctor",)),
+    ("e_cqt1992v2_short_reflect", "CQT1992v2", dict(sr=22050, fmin=220, n_bins=12), ("forward", (1, 100), {})),
+    ("e_cqt1992v2_bad_norm", "CQT1992v2", dict(sr=22050, fmin=220, n_bins=12),
+     ("forward", (1, 8000), dict(normalization_type="bogus"))),
+    ("e_cqt2010v2_nyquist", "CQT2010v2", dict(sr=8000, n_bins=96), ("ctor",)),
+    ("e_cqt2010v2_bad_norm", "CQT2010v2", dict(sr=22050, n_bins=24, fmin=220),
+     ("forward", (1, 8000), dict(normalization_type="bogus"))),
+    ("e_cqt2010v2_4d_input", "CQT2010v2", dict(sr=22050, n_bins=24, fmin=220), ("forward", (1, 1, 1, 8000), {})),
+    ("e_vqt_nyquist", "VQT", dict(sr=8000, n_bins=96), ("ctor",)),
+    ("e_cqt1992_nyquist", "CQT1992", dict(sr=8000, fmin=220, n_bins=84), ("ctor",)),
+    ("e_cqt2010_nyquist", "CQT2010", dict(sr=8000, n_bins=96), ("ctor",)),
+]
+
+
 # Input-gradient cases (dX): loss = sum(out * w), w ~ N(0,1) seeded;
 # the fixture holds the reference's x.grad (autograd through its conv1d path on CPU).
 GRAD_CASES = [

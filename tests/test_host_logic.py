@@ -138,3 +138,35 @@ def test_batches_beyond_the_per_call_limit_are_chunked(monkeypatch):
     for name in ("stft_forward", "stft_filterbank_forward", "mfcc_forward", "cqt1992v2_forward",
                  "cqt_pyramid_forward"):
         assert hasattr(getattr(_C, name), "__wrapped__"), name
+
+
+def _ref_errors():
+    import json
+    import os
+    from helpers import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_errors.json")) as f:
+        return json.load(f)
+
+
+from cases import ERROR_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ERROR_CASES, ids=[c[0] for c in ERROR_CASES])
+def test_same_exception_type_as_the_reference(case):
+    """Malformed constructor arguments / inputs raise the exception TYPE the reference raises
+    (recorded from the unmodified reference in tests/golden/ref_errors.json), and they do so before
+    the C call — so the check also holds for CPU tensors."""
+    from helpers import build
+    cid, cls, ctor, call = case
+    want = _ref_errors()[cid]
+    assert want != "ok"
+    exc = {"AssertionError": AssertionError, "ValueError": ValueError, "RuntimeError": RuntimeError,
+           "NameError": NameError}[want]
+    with pytest.raises(exc) as info, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = build(cls, ctor)
+        if call[0] == "forward":
+            mod(torch.zeros(call[1]), **call[2])
+        elif call[0] == "inverse":
+            mod.inverse(torch.zeros(call[1]), **call[2])
+    assert "no CPU fallback" not in str(info.value), "the reference-type error must come first"
