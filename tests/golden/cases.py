@@ -269,6 +269,30 @@ ISTFT_GRAD_CASES = [
 ]
 
 
+def attribute_surface(module) -> dict:
+    """JSON-able view of a module's public, non-tensor attributes (what user code reads:
+    ``n_fft``, ``stride``, ``frequencies``, ``kernel_width`` ...).  Used on the reference by
+    make_golden.py and on ours by tests/test_host_logic.py."""
+    import torch
+
+    base = set(vars(torch.nn.Module()))
+    out = {}
+    for k, v in vars(module).items():
+        if k.startswith("_") or k in base:
+            continue
+        if isinstance(v, (bool, int, float, str, type(None))):
+            out[k] = v
+        elif isinstance(v, (np.floating, np.integer)):
+            out[k] = float(v)
+        elif isinstance(v, np.ndarray):
+            out[k] = ["ndarray", list(v.shape), str(v.dtype), float(np.abs(v).sum())]
+        elif isinstance(v, (list, tuple)):
+            out[k] = [type(v).__name__, len(v)]
+        else:
+            out[k] = type(v).__name__
+    return out
+
+
 def loss_weights(case_id: str, shape) -> np.ndarray:
     seed = 1000 + sum(ord(c) for c in case_id) % 1000
     return np.random.RandomState(seed).standard_normal(shape).astype(np.float32)

@@ -29,7 +29,7 @@ sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
 from cases import (CASES, DESIGN_CASES, ERROR_CASES, GRAD_CASES, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
-                   SWEEP_CTOR, WGRAD_CASES, loss_weights, make_input, out_key)
+                   SWEEP_CTOR, WGRAD_CASES, attribute_surface, loss_weights, make_input, out_key)
 
 from nnAudio import features as ref_features  # noqa: E402
 
@@ -77,6 +77,13 @@ def main():
         buffers[cid] = {k: [list(v.shape), sha(v)] for k, v in mod.state_dict().items()
                         if v is not None}
         print(f"{cid:60s} {len(buffers[cid])} buffers")
+    attributes = {}
+    for cid, cls, ctor in [(c[0], c[1], c[2]) for c in CASES] + list(DESIGN_CASES):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            attributes[cid] = attribute_surface(make_module(ref_features, cls, ctor))
+    with open(os.path.join(HERE, "ref_attributes.json"), "w") as f:
+        json.dump(attributes, f, indent=1, sort_keys=True)
     errors = {}
     for cid, cls, ctor, call in ERROR_CASES:
         try:

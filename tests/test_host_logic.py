@@ -170,3 +170,35 @@ def test_same_exception_type_as_the_reference(case):
         elif call[0] == "inverse":
             mod.inverse(torch.zeros(call[1]), **call[2])
     assert "no CPU fallback" not in str(info.value), "the reference-type error must come first"
+
+
+def _ref_attributes():
+    import json
+    import os
+    from helpers import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_attributes.json")) as f:
+        return json.load(f)
+
+
+from cases import CASES as _CASES, DESIGN_CASES, attribute_surface  # noqa: E402
+
+_ATTR_CASES = [(c[0], c[1], c[2]) for c in _CASES] + list(DESIGN_CASES)
+
+
+@pytest.mark.parametrize("case", _ATTR_CASES, ids=[c[0] for c in _ATTR_CASES])
+def test_public_attribute_surface_matches_reference(case):
+    """Every public non-tensor attribute of the reference module (n_fft, stride, frequencies,
+    kernel_width, downsample_factor, ...) exists on ours with the same value (fixture recorded from
+    the unmodified reference); ours may carry more."""
+    from helpers import build
+    cid, cls, ctor = case
+    ours = attribute_surface(build(cls, ctor))
+    for name, want in _ref_attributes()[cid].items():
+        assert name in ours, f"{cls}.{name} missing"
+        got = ours[name]
+        if isinstance(want, float) and isinstance(got, (int, float)):
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-12), name
+        elif isinstance(want, list) and want and want[0] == "ndarray":
+            assert got[:3] == want[:3] and got[3] == pytest.approx(want[3], rel=1e-9), name
+        else:
+            assert got == want, (name, got, want)
