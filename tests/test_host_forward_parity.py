@@ -38,3 +38,26 @@ def test_module_to_library_contract_reproduces_reference(case, monkeypatch):
         tol = 2e-4 if cls == "MFCC" else 2e-5   # dB of near-zero mel powers amplifies the reference's fp32 noise
         emax, el2 = rel_errors(got, want)
         assert emax < tol and el2 < tol, (cid, kw, emax, el2)
+
+
+from cases import ISTFT_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ISTFT_CASES, ids=[c[0] for c in ISTFT_CASES])
+def test_inverse_modules_reproduce_reference(case, monkeypatch):
+    """STFT.inverse / iSTFT host layer (kernel selection, one-sided flag, length slicing)."""
+    import nnaudio_b200 as nb
+
+    cpu_kernels.install(monkeypatch)
+    cid, n_fft, hop, win, kind, spec = case
+    X = torch.from_numpy(ref_outputs()[cid + "|X"])
+    with torch.no_grad():
+        if kind == "roundtrip":
+            st = nb.STFT(n_fft=n_fft, hop_length=hop, window=win, iSTFT=True, verbose=False)
+            y = st.inverse(X, onesided=True, length=spec["length"])
+        else:
+            y = nb.iSTFT(n_fft=n_fft, hop_length=hop, window=win, verbose=False)(X, onesided=False)
+    want = ref_outputs()[cid + "|y"]
+    assert tuple(y.shape) == want.shape
+    emax, el2 = rel_errors(y.numpy(), want)
+    assert emax < 2e-5 and el2 < 2e-5, (cid, emax, el2)
