@@ -28,6 +28,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to its workers.  The CPU arm is meant to use the host cores
+# ("all the host threads it can use"), and BLAS sizes its pool when it is first loaded, so put the
+# count back before numpy / torch are imported.  Only for --impl reference: the GPU arm does no
+# host compute worth threading.
+if "--impl" in sys.argv and "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1" \
+        and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    try:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 # ----------------------------------------------------------------------------
 # workloads (BASELINE.json configs; shapes from SURVEY.md §8 config table)
 # ----------------------------------------------------------------------------
@@ -135,7 +146,25 @@ class ClockSampler:
 # ----------------------------------------------------------------------------
 def cpu_arm(workload, steps, warmup, budget_s):
     """Times the NumPy oracle (fp32, all host threads through BLAS) on a bounded
-    sample of the workload: as many clips per step as fit ``budget_s`` overall."""
+    sample of the workload: as many clips per step as fit ``budget_s`` overall.
+    torchrun exports OMP_NUM_THREADS=1 to its workers; the BLAS pool is raised back to the
+    cores this process may use, so the CPU arm is not timed single-threaded at N > 1."""
+    import contextlib
+
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=cores)
+    except Exception:  # noqa: BLE001  (no threadpoolctl: keep whatever the environment set)
+        limiter = contextlib.nullcontext()
+    with limiter:
+        return _cpu_arm(workload, steps, warmup, budget_s, cores)
+
+
+def _cpu_arm(workload, steps, warmup, budget_s, cores):
     import numpy as np
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -161,10 +190,6 @@ def cpu_arm(workload, steps, warmup, budget_s):
     for _ in range(steps):
         run_oracle(w["cls"], mod, x, w["fwd"], dtype=np.float32)
     dt = time.perf_counter() - t0
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count()
     return {
         "value": clips * T * steps / dt, "unit": "frames/s", "cores": cores, "kind": "port",
         "sample": f"{clips} clip(s) x {w['L']} samples of {workload} per step, {steps} steps, "
