@@ -93,6 +93,20 @@ def main():
             attributes[cid] = attribute_surface(make_module(ref_features, cls, ctor))
     with open(os.path.join(HERE, "ref_attributes.json"), "w") as f:
         json.dump(attributes, f, indent=1, sort_keys=True)
+    import inspect
+    signatures = {}
+    for cls in ("STFT", "iSTFT", "MelSpectrogram", "MFCC", "Gammatonegram", "CQT1992v2", "CQT", "CQT2010v2", "VQT",
+                "CQT1992", "CQT2010", "Griffin_Lim"):
+        klass = getattr(ref_features, cls)
+        entry = {}
+        for meth in ("__init__", "forward", "inverse"):
+            if hasattr(klass, meth) and (meth != "inverse" or "inverse" in klass.__dict__):
+                params = list(inspect.signature(getattr(klass, meth)).parameters.values())[1:]
+                entry[meth] = [[q.name, None if q.default is inspect.Parameter.empty else repr(q.default)]
+                               for q in params]
+        signatures[cls] = entry
+    with open(os.path.join(HERE, "ref_signatures.json"), "w") as f:
+        json.dump(signatures, f, indent=1, sort_keys=True)
     errors = {}
     for cid, cls, ctor, call in ERROR_CASES:
         try:

@@ -202,3 +202,23 @@ def test_public_attribute_surface_matches_reference(case):
             assert got[:3] == want[:3] and got[3] == pytest.approx(want[3], rel=1e-9), name
         else:
             assert got == want, (name, got, want)
+
+
+def test_signatures_match_the_reference():
+    """Constructor / forward / inverse parameter names, order and defaults of every class, against
+    the signatures recorded from the unmodified reference (tests/golden/ref_signatures.json).  The
+    only extension: Griffin_Lim.forward's optional trailing ``rand_phase``."""
+    import inspect
+    import json
+    import os
+    from helpers import GOLDEN
+
+    with open(os.path.join(GOLDEN, "ref_signatures.json")) as f:
+        ref = json.load(f)
+    extra = {("Griffin_Lim", "forward"): [["rand_phase", "None"]]}
+    for cls, methods in ref.items():
+        klass = getattr(nb.features, cls)
+        for meth, want in methods.items():
+            params = list(inspect.signature(getattr(klass, meth)).parameters.values())[1:]
+            got = [[q.name, None if q.default is inspect.Parameter.empty else repr(q.default)] for q in params]
+            assert got == want + extra.get((cls, meth), []), (cls, meth, got, want)
