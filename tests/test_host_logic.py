@@ -115,6 +115,13 @@ def test_nnaudio_import_shim():
     try:
         feats = importlib.import_module("nnAudio.features")
         assert feats.MelSpectrogram is nb.MelSpectrogram and feats.CQT1992v2 is nb.CQT1992v2
+        # the reference's per-file import paths (`from nnAudio.features.stft import STFT`, ...)
+        for sub, names in (("stft", ["STFT", "iSTFT"]), ("mel", ["MelSpectrogram", "MFCC"]),
+                           ("gammatone", ["Gammatonegram"]), ("vqt", ["VQT"]), ("griffin_lim", ["Griffin_Lim"]),
+                           ("cqt", ["CQT1992v2", "CQT2010v2", "CQT", "CQT1992", "CQT2010"])):
+            m = importlib.import_module("nnAudio.features." + sub)
+            for n in names:
+                assert getattr(m, n) is getattr(nb.features, n), (sub, n)
     finally:
         sys.path.remove(os.path.join(ROOT, "shim"))
         for k in [k for k in sys.modules if k == "nnAudio" or k.startswith("nnAudio.")]:
