@@ -123,7 +123,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)  # the default timed region is ~10 ms: a few samples inside it
 
     def start(self):
         if self.nv is not None:
