@@ -18,6 +18,8 @@
 //                coalesced stores in the reference's (B, F, T[,2]) layout
 //   smem full/empty mbarrier ring + double-buffered TMEM accumulators.
 #include <cuda.h>
+#include <mutex>
+#include <unordered_set>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -83,9 +85,17 @@ static SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad) {
   return g;
 }
 
+size_t tc_radix2_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad);
+bool tc_radix2_enabled();
+
 size_t tc_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
   const SplitGeom g = split_geom(B, L, K, hop, pad);
-  return (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+  size_t n = (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+  if (tc_radix2_enabled() && hop % 2 == 0 && K % 256 == 0) {
+    const size_t r2 = tc_radix2_workspace_bytes(B, L, K, hop, pad);
+    if (r2 > n) n = r2;
+  }
+  return n;
 }
 
 bool tc_supported(const FramedProblem& p) {
@@ -201,8 +211,16 @@ __global__ void __launch_bounds__(256) pack_basis_kernel(
   *reinterpret_cast<uint4*>(packed + (int64_t)rows * kpad + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
+int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
+                         cudaStream_t stream);
+bool tc_radix2_basis_ok(int F, int K);
+void tc_forget_packed(const void* packed);
+
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream) {
+  if (tc_radix2_enabled() && tc_radix2_basis_ok(F, K))
+    return tc_pack_basis_radix2(w_re, w_im, F, K, packed, stream);
+  tc_forget_packed(packed);
   const int bn = choose_bn(F);
   const int n_tiles = (2 * F + bn - 1) / bn;
   const int rows = n_tiles * bn;
@@ -1370,6 +1388,325 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   }
 }
 
+
+// ===========================================================================
+// EXPERIMENTAL (branch radix2-wip, not GPU-verified yet): decimation-in-time
+// variant of the STFT-family contraction, R = 2.
+//
+// For a DFT-structured basis (w_re[f][n] = win[n] cos(2 pi f n / N), w_im = ... sin, F = N/2+1)
+// the frame splits into its even / odd samples:
+//   S0[k] = sum_m xe[m] (w_re - i w_im)[k][2m]         (sub-DFT of the even samples)
+//   U [k] = sum_m xo[m] (w_re - i w_im)[k][2m+1]       (sub-DFT of the odd samples, twiddle included)
+//   X[k] = S0[k] + U[k],   X[N/2 - k] = conj(S0[k] - U[k]),   k = 0 .. N/4
+// i.e. two contractions with K = N/2 over N/4 bins: half the MACs of the dense form, and the
+// epilogue is add / subtract only.  The real Nyquist bins S0[N/4], Im U[N/4] ride in the
+// always-zero imaginary slots of k = 0, so N/4 (re, im) column pairs cover everything
+// (tools/radix_dft_prototype.py is the executable spec).
+//
+// Data: 4 signal planes [r][hi|lo], plane_r[i] = xpad[2 i + r] (hop/2, K/2 Toeplitz view each);
+// packed basis [hi|lo][seg r][tile][re half | negated im half][K/2]; TMEM: segment r of a tile
+// accumulates into columns [r*bn, (r+1)*bn) of the 256-column buffer (bn = 128).
+// ===========================================================================
+constexpr int R2_BN = 128;  // columns per segment: 64 bins x (re, im)
+
+// One thread = 8 consecutive elements of BOTH sample-phase planes (16 padded samples).
+__global__ void __launch_bounds__(256) pad_split_radix2_kernel(
+    const float* __restrict__ x, int64_t L, int64_t x_pitch, int pad, int pad_mode,
+    int64_t clip_pitch, int64_t plane_stride, __nv_bfloat16* __restrict__ planes) {
+  const int64_t b = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;  // plane element
+  if (i0 >= clip_pitch) return;
+  const float* __restrict__ xb = x + b * x_pitch;
+  const int64_t padded_len = L + 2 * (int64_t)pad;
+  __align__(16) __nv_bfloat16 hi[2][8];
+  __align__(16) __nv_bfloat16 lo[2][8];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int64_t i = 2 * i0 + e;  // index into the centre-padded clip
+    float v = 0.f;
+    if (i < padded_len) {
+      int64_t j = i - pad;
+      if (j < 0) j = (pad_mode == NNAB_PAD_REFLECT) ? -j : -1;
+      else if (j >= L) j = (pad_mode == NNAB_PAD_REFLECT) ? 2 * (L - 1) - j : -1;
+      if (j >= 0 && j < L) v = __ldg(xb + j);
+    }
+    split_bf16(v, hi[e & 1][e >> 1], lo[e & 1][e >> 1]);
+  }
+  const int64_t o = b * clip_pitch + i0;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    *reinterpret_cast<uint4*>(planes + (2 * r) * plane_stride + o) = *reinterpret_cast<const uint4*>(hi[r]);
+    *reinterpret_cast<uint4*>(planes + (2 * r + 1) * plane_stride + o) = *reinterpret_cast<const uint4*>(lo[r]);
+  }
+}
+
+// packed[plane][seg][tile*bn + part*half + j][k2]: bin k = tile*half + j, sample n = 2*k2 + seg.
+// part 0 = w_re rows, part 1 = negated w_im rows; the (k = 0, part 1) slot carries the sub-DFT
+// Nyquist bin: seg 0 -> +w_re[K/4][n], seg 1 -> -w_im[K/4][n].
+__global__ void __launch_bounds__(256) pack_basis_radix2_kernel(
+    const float* __restrict__ w_re, const float* __restrict__ w_im, int K, int rows_seg, int kpad2,
+    __nv_bfloat16* __restrict__ packed) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k8 = kpad2 / 8;
+  if (idx >= (int64_t)2 * rows_seg * k8) return;
+  const int row = (int)(idx / k8);  // 0 .. 2*rows_seg-1
+  const int k0 = (int)(idx % k8) * 8;
+  const int seg = row / rows_seg, r = row % rows_seg;
+  const int half = R2_BN / 2;
+  const int tile = r / R2_BN, within = r % R2_BN;
+  const int part = within / half, j = within % half;
+  const int k = tile * half + j;
+  const int nyq = K / 4;
+  __align__(16) __nv_bfloat16 hi[8];
+  __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k2 = k0 + e;
+    const int n = 2 * k2 + seg;
+    float v = 0.f;
+    if (k < nyq && n < K) {
+      if (part == 0) v = __ldg(w_re + (int64_t)k * K + n);
+      else if (k != 0) v = -__ldg(w_im + (int64_t)k * K + n);
+      else v = (seg == 0) ? __ldg(w_re + (int64_t)nyq * K + n) : -__ldg(w_im + (int64_t)nyq * K + n);
+    }
+    split_bf16(v, hi[e], lo[e]);
+  }
+  const int64_t o = (int64_t)row * kpad2 + k0;
+  *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(packed + (int64_t)2 * rows_seg * kpad2 + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// running banded-filterbank sums of one bin stream (ascending or descending bins)
+struct MelRun {
+  int cj0 = -1, cj1 = -1;
+  float a0 = 0.f, a1 = 0.f;
+  __device__ __forceinline__ void add(const EpiParams& e, float* mel, bool valid, int bin, float pw) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(e.fb_table) + bin);
+    if (raw.x != cj0) {
+      if (raw.x == cj1) {
+        const int tj = cj0; cj0 = cj1; cj1 = tj;
+        const float ta = a0; a0 = a1; a1 = ta;
+      } else {
+        if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
+        cj0 = raw.x; a0 = 0.f;
+      }
+    }
+    if (raw.y != cj1) {
+      if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
+      cj1 = raw.y; a1 = 0.f;
+    }
+    a0 = fmaf(__int_as_float(raw.z), pw, a0);
+    a1 = fmaf(__int_as_float(raw.w), pw, a1);
+  }
+  __device__ __forceinline__ void flush(const EpiParams& e, float* mel, bool valid) {
+    if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
+    if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
+  }
+};
+
+// Butterfly epilogue: TMEM columns [S0 re | S0 im | U re | U im], `half` bins each.
+// FMT: 0 Magnitude, 1 Complex, 4 POWER, 5 fused banded filterbank.
+template <int FMT>
+__device__ __forceinline__ void epilogue_tile_radix2(const TcParams& p, uint32_t trow, int64_t g,
+                                                     int n_tile, int half) {
+  const int64_t b = g / p.t_slots;
+  const int64_t tl = g - b * p.t_slots;
+  const bool valid = (g < p.nv) && (tl < p.T);
+  const int64_t t = tl * p.t_mul + p.t_add;
+  const int k_base = n_tile * half;
+  const int NH = p.epi.F - 1;  // N/2: bin k pairs with bin NH - k
+  constexpr int CH = (FMT == NNAB_FMT_COMPLEX) ? 2 : 1;
+  float* dst = nullptr;
+  float* mel = nullptr;
+  if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
+  else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+  MelRun up, down;
+  auto emit = [&](MelRun& run, int bin, float re, float im) {
+    if constexpr (FMT == 5) {
+      run.add(p.epi, mel, valid, bin, epi_power(p.epi, re, im));
+    } else {
+      if (valid) epi_store_fmt<FMT>(p.epi, dst, bin, re, im);
+    }
+  };
+#pragma unroll 1
+  for (int c0 = 0; c0 < half; c0 += 8) {
+    uint32_t s0r[8], s0i[8], ur[8], ui[8];
+    tmem_ld8(trow + (uint32_t)c0, s0r);
+    tmem_ld8(trow + (uint32_t)(half + c0), s0i);
+    tmem_ld8(trow + (uint32_t)(2 * half + c0), ur);
+    tmem_ld8(trow + (uint32_t)(3 * half + c0), ui);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k_base + c0 + j;
+      const float ar = __uint_as_float(s0r[j]), ai = __uint_as_float(s0i[j]);
+      const float br = __uint_as_float(ur[j]), bi = __uint_as_float(ui[j]);
+      if (k == 0) {
+        // DC, the mirror of DC (bin N/2) and the packed Nyquist pair (bin N/4)
+        MelRun one;
+        emit(one, 0, ar + br, 0.f);
+        emit(one, NH, ar - br, 0.f);
+        emit(one, NH / 2, ai, bi);
+        if constexpr (FMT == 5) one.flush(p.epi, mel, valid);
+      } else {
+        emit(up, k, ar + br, ai + bi);
+        emit(down, NH - k, ar - br, bi - ai);
+      }
+    }
+  }
+  if constexpr (FMT == 5) {
+    up.flush(p.epi, mel, valid);
+    down.flush(p.epi, mel, valid);
+  }
+}
+
+// CTA-pair kernel with two K segments per tile (see framed_tc2_kernel for the pipeline roles).
+template <int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const TcParams p, const int seg_rows) {
+  constexpr int BK = 64, STAGES = 3;
+  using S = Tc2Smem<BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  constexpr int halfn = R2_BN / 2;
+  constexpr uint32_t b_half_bytes = (uint32_t)halfn * BK * 2;
+  const int kb_n = p.kb_end[0];  // K/2 in 64-sample blocks, same for every tile and segment
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        for (int seg = 0; seg < 2; ++seg) {
+          const int n0 = seg * seg_rows + n_tile * R2_BN + (int)cta * halfn;
+          for (int kb = 0; kb < kb_n; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sb = base + stage * S::STAGE_BYTES;
+            mbar_expect_tx_remote(full_bar(stage), 0, 2 * S::A_BYTES + 2 * b_half_bytes);
+            const int k0 = kb * BK;
+            const int c1 = m0 + k0 / p.hop;          // rows mode: (rows x hop) view of a plane
+            const int c0 = k0 - (k0 / p.hop) * p.hop;
+            tma_load_3d_2sm(sb, &tm_a, full_bar(stage), c0, c1, 2 * seg);
+            tma_load_3d_2sm(sb + S::A_BYTES, &tm_a, full_bar(stage), c0, c1, 2 * seg + 1);
+            tma_load_3d_2sm(sb + 2 * S::A_BYTES, &tm_b, full_bar(stage), k0, n0, 0);
+            tma_load_3d_2sm(sb + 2 * S::A_BYTES + S::B_BYTES, &tm_b, full_bar(stage), k0, n0, 1);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(R2_BN >> 3) << 17) |
+                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        for (int seg = 0; seg < 2; ++seg) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE + (uint32_t)(seg * R2_BN);
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < kb_n; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sb = base + stage * S::STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t koff = (uint32_t)k * 32u;
+              const uint64_t a_hi = make_smem_desc<BK>(sb + koff);
+              const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
+              const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
+              const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+              accumulate = 1u;
+            }
+            umma_commit_2sm(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)acc * TC_ACC_STRIDE;
+      epilogue_tile_radix2<FMT>(p, trow, g, n_tile, halfn);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // Split-K finalize: raw (re, im) sums -> per-bin scale + output format (generic epilogue).
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const EpiParams e, int64_t B) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1513,10 +1850,172 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL radix-2 host side (NNAB_RADIX=2)
+// ---------------------------------------------------------------------------
+bool tc_radix2_enabled() {
+  const char* e = getenv("NNAB_RADIX");
+  return e != nullptr && atoi(e) == 2;
+}
+
+// basis shapes the radix packing accepts (the caller vouches that the basis is DFT-structured)
+bool tc_radix2_basis_ok(int F, int K) {
+  return K >= 512 && K % 256 == 0 && F == K / 2 + 1;
+}
+
+static std::mutex g_r2_mu;
+static std::unordered_set<const void*> g_r2_packed;
+
+static bool is_radix2_packed(const void* packed) {
+  std::lock_guard<std::mutex> lk(g_r2_mu);
+  return g_r2_packed.count(packed) != 0;
+}
+
+static void mark_radix2_packed(const void* packed, bool on) {
+  std::lock_guard<std::mutex> lk(g_r2_mu);
+  if (on) g_r2_packed.insert(packed);
+  else g_r2_packed.erase(packed);
+}
+
+void tc_forget_packed(const void* packed) { mark_radix2_packed(packed, false); }
+
+static SplitGeom radix2_geom(int64_t B, int64_t L, int K, int hop, int pad) {
+  const int64_t lp = L + 2 * (int64_t)pad;
+  return split_geom(B, (lp + 1) / 2, K / 2, hop / 2, 0);
+}
+
+size_t tc_radix2_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
+  const SplitGeom g = radix2_geom(B, L, K, hop, pad);
+  return (size_t)(4 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+}
+
+int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
+                         cudaStream_t stream) {
+  if (!tc_radix2_basis_ok(F, K)) return NNAB_EINVAL;
+  const int rows_seg = K / 2;  // (K/4 bins) x (re, im)
+  const int kpad2 = K / 2;     // K % 256 == 0 -> already a multiple of 64
+  const int64_t threads = (int64_t)2 * rows_seg * (kpad2 / 8);
+  pack_basis_radix2_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+      w_re, w_im, K, rows_seg, kpad2, (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  mark_radix2_packed(packed, true);
+  return NNAB_OK;
+}
+
+static bool radix2_problem_ok(const FramedProblem& q) {
+  if (!tc_radix2_basis_ok(q.F, q.K)) return false;
+  if (q.hop % 2 != 0 || num_phases(q.hop / 2) != 1 || (q.hop / 2) % 64 != 0) return false;
+  if (q.presplit != nullptr || q.h_k_begin != nullptr || q.raw != nullptr) return false;
+  if (q.bin_offset != 0 || q.out_bins < q.F) return false;
+  switch (q.fmt) {
+    case NNAB_FMT_MAGNITUDE: case NNAB_FMT_COMPLEX: case FMT_POWER: return true;
+    case FMT_FBANK: return q.fb_table != nullptr && q.n_fb > 0;
+    default: return false;
+  }
+}
+
+template <int FMT>
+static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                           int seg_rows, int n_pairs, cudaStream_t stream) {
+  using S = Tc2Smem<64, 3>;
+  static bool configured = false;
+  if (!configured) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2r_kernel<FMT>, ma, mb, prm, seg_rows));
+  count_launch();
+  return NNAB_OK;
+}
+
+static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, void* workspace,
+                                   size_t ws_bytes, cudaStream_t stream) {
+  if (!radix2_problem_ok(q)) return NNAB_EINVAL;  // the basis was packed for the radix kernel only
+  const size_t need = tc_radix2_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (q.B > 65535) return NNAB_EUNSUPPORTED;
+  const int hop2 = q.hop / 2, k2 = q.K / 2;
+  const SplitGeom g = radix2_geom(q.B, q.L, q.K, q.hop, q.pad);
+  __nv_bfloat16* planes =
+      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const int64_t clip_pitch = g.t_slots * hop2;
+  // K overhang past the last clip: finite zeros in all four planes
+  const int64_t tail = g.plane_stride - g.nv * hop2;
+  for (int pl = 0; pl < 4; ++pl)
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hop2, 0,
+                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
+  dim3 pgrid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
+  pad_split_radix2_kernel<<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
+                                                     clip_pitch, g.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();
+  if (sms < 2) sms = 2;
+
+  const int seg_rows = k2;            // rows of one segment in the packed basis
+  const int n_tiles = seg_rows / R2_BN;
+  CUtensorMap ma, mb;
+  int rc = encode_3d(&ma, planes, (uint64_t)hop2, (uint64_t)g.rows, 4, (uint64_t)hop2 * 2,
+                     (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
+  if (rc) return rc;
+  rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)k2, (uint64_t)(2 * seg_rows), 2,
+                 (uint64_t)k2 * 2, (uint64_t)(2 * seg_rows) * k2 * 2, 64, R2_BN / 2, 64);
+  if (rc) return rc;
+
+  TcParams prm{};
+  prm.num_n_tiles = n_tiles;
+  prm.bn = R2_BN;
+  prm.rows_mode = 1;
+  prm.hop = hop2;
+  prm.nv = g.nv;
+  prm.t_slots = g.t_slots;
+  prm.t_mul = 1;
+  prm.t_add = 0;
+  prm.T = q.T;
+  prm.k_splits = 1;
+  for (int tl = 0; tl < n_tiles; ++tl) { prm.kb_begin[tl] = 0; prm.kb_end[tl] = k2 / 64; }
+  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
+  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
+  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+  prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
+  prm.epi.dec = q.dec;
+  prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
+  prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
+  prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
+  const int64_t ptiles = (int64_t)prm.num_m_tiles * n_tiles;
+  const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  switch (q.fmt) {
+    case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_POWER: return launch_tc2r_fmt<4>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_FBANK: return launch_tc2r_fmt<5>(ma, mb, prm, seg_rows, n_pairs, stream);
+    default: return NNAB_EINVAL;
+  }
+}
+
 int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace, size_t ws_bytes,
                      cudaStream_t stream) {
   if (q.B <= 0 || q.T <= 0 || q.F <= 0) return NNAB_OK;
   if (packed == nullptr) return NNAB_EINVAL;
+  if (is_radix2_packed(packed))
+    return launch_framed_tc_radix2(q, packed, workspace, ws_bytes, stream);
   if (q.presplit == nullptr) {
     const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
     if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
