@@ -1907,10 +1907,10 @@ static bool radix2_problem_ok(const FramedProblem& q) {
   if (!tc_radix2_basis_ok(q.F, q.K)) return false;
   if (q.hop % 2 != 0 || num_phases(q.hop / 2) != 1 || (q.hop / 2) % 64 != 0) return false;
   if (q.presplit != nullptr || q.h_k_begin != nullptr || q.raw != nullptr) return false;
-  if (q.bin_offset != 0 || q.out_bins < q.F) return false;
   switch (q.fmt) {
-    case NNAB_FMT_MAGNITUDE: case NNAB_FMT_COMPLEX: case FMT_POWER: return true;
-    case FMT_FBANK: return q.fb_table != nullptr && q.n_fb > 0;
+    case NNAB_FMT_MAGNITUDE: case NNAB_FMT_COMPLEX: case FMT_POWER:
+      return q.bin_offset == 0 && q.out_bins >= q.F;
+    case FMT_FBANK: return q.fb_table != nullptr && q.n_fb > 0;  // out_bins = n_fb there
     default: return false;
   }
 }
