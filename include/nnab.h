@@ -189,6 +189,19 @@ int nnab_cqt1992v2_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch
 size_t nnab_packed_fir_bytes(int taps, int dec);
 int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* stream);
 
+/* EXPERIMENTAL (branch radix2-wip): one decimating-FIR stage and its adjoint, for the training path
+ * of the pyramid.  Replace `downsampling_by_n` / `downsampling_by_2` (utils.py:73-124) and what
+ * autograd derives from them.
+ *   y  (B, Ly) = conv1d(x (B, L), fir (taps), stride=factor, padding=(taps-1)/2),
+ *     Ly = (L + 2*((taps-1)/2) - taps) / factor + 1
+ *   dx (B, L)  = the gradient of that w.r.t. x for an upstream gradient g (B, Ly)
+ * All tensors fp32, contiguous rows with the given pitches. */
+int nnab_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* fir,
+                      int taps, int factor, float* y, int64_t Ly, void* stream);
+int nnab_fir_decimate_adjoint(const float* g, int64_t B, int64_t Ly, int64_t g_pitch,
+                              const float* fir, int taps, int factor, float* dx, int64_t L,
+                              void* stream);
+
 size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor,
                                         int max_width, int hop, int path);
 /*   h_packed: HOST array of n_octaves DEVICE pointers to the nnab_pack_basis() copy of

@@ -88,6 +88,9 @@ SIGNATURES = {
         [_P, _P, c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_int, c_int, _P, _P,
          c_size_t, _P],
     ),
+    "nnab_fir_decimate": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
+    "nnab_fir_decimate_adjoint": (
+        c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
     "nnab_packed_fir_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_fir": (c_int, [_P, c_int, c_int, _P, _P]),
     "nnab_cqt_pyramid_workspace_bytes": (
@@ -430,6 +433,34 @@ def istft_forward(X, packed, window, n_fft, hop, center, length):
                                   want, _ptr(ws), wsb, _stream(X.device))
     _check(rc, "nnab_istft_forward")
     return out
+
+
+def fir_decimate(x, fir, factor):
+    """EXPERIMENTAL: y = conv1d(x, fir, stride=factor, padding=(taps-1)//2) for (B, L) rows."""
+    L = lib()
+    x, B, Ln, pitch = _rows(x)
+    fir = _dev_f32(fir, "fir").reshape(-1).contiguous()
+    taps = fir.numel()
+    half = (taps - 1) // 2
+    Ly = (Ln + 2 * half - taps) // factor + 1
+    y = torch.empty((B, Ly), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(L.nnab_fir_decimate(_ptr(x), B, Ln, pitch, _ptr(fir), taps, int(factor), _ptr(y), Ly,
+                                   _stream(x.device)), "nnab_fir_decimate")
+    return y
+
+
+def fir_decimate_adjoint(g, fir, factor, L_in):
+    """EXPERIMENTAL: gradient of fir_decimate w.r.t. its input, (B, Ly) -> (B, L_in)."""
+    L = lib()
+    g, B, Ly, pitch = _rows(g)
+    fir = _dev_f32(fir, "fir").reshape(-1).contiguous()
+    dx = torch.empty((B, L_in), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _check(L.nnab_fir_decimate_adjoint(_ptr(g), B, Ly, pitch, _ptr(fir), fir.numel(), int(factor),
+                                           _ptr(dx), int(L_in), _stream(g.device)),
+               "nnab_fir_decimate_adjoint")
+    return dx
 
 
 def pack_adjoint_basis(w_re: torch.Tensor, w_im: torch.Tensor):

@@ -467,6 +467,34 @@ int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* strea
   return tc_pack_fir(fir, taps, dec, packed, (cudaStream_t)stream);
 }
 
+int nnab_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* fir,
+                      int taps, int factor, float* y, int64_t Ly, void* stream) {
+  if (x == nullptr || fir == nullptr || y == nullptr || B < 0 || L <= 0 || x_pitch < L || taps <= 0 ||
+      factor < 1)
+    return NNAB_EINVAL;
+  const int half = (taps - 1) / 2;
+  if (L + 2 * (int64_t)half < taps || Ly != (L + 2 * (int64_t)half - taps) / factor + 1)
+    return NNAB_EINVAL;
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_fir_decimate(x, B, L, x_pitch, fir, taps, factor, y, Ly, Ly, (cudaStream_t)stream);
+}
+
+int nnab_fir_decimate_adjoint(const float* g, int64_t B, int64_t Ly, int64_t g_pitch,
+                              const float* fir, int taps, int factor, float* dx, int64_t L,
+                              void* stream) {
+  if (g == nullptr || fir == nullptr || dx == nullptr || B < 0 || L <= 0 || Ly <= 0 || g_pitch < Ly ||
+      taps <= 0 || factor < 1)
+    return NNAB_EINVAL;
+  const int half = (taps - 1) / 2;
+  if (L + 2 * (int64_t)half < taps || Ly != (L + 2 * (int64_t)half - taps) / factor + 1)
+    return NNAB_EINVAL;
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_fir_decimate_adjoint(g, B, Ly, g_pitch, fir, taps, factor, dx, L, L,
+                                     (cudaStream_t)stream);
+}
+
 size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor,
                                         int max_width, int hop, int path) {
   size_t n = pyramid_level_bytes(B, L, early_factor);
