@@ -189,6 +189,13 @@ int nnab_cqt1992v2_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch
 size_t nnab_packed_fir_bytes(int taps, int dec);
 int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* stream);
 
+/* EXPERIMENTAL (branch radix2-wip), host only: the K-block plan of the per-block-width kernel
+ * (order[i] = 64-sample K block, groups[i] = 8-bin groups it reaches, widest first;
+ * chunk_begin[0..n_chunks] = split-K chunks of equal modelled cost).  Arrays: 512 / 512 / 17 ints. */
+int nnab_debug_varn_plan(const int32_t* h_k_begin, const int32_t* h_k_end, int n_bins, int width,
+                         int want_chunks, int32_t* order, int32_t* groups, int32_t* chunk_begin,
+                         int32_t* n_blocks, int32_t* n_chunks);
+
 /* EXPERIMENTAL (branch radix2-wip): one decimating-FIR stage and its adjoint, for the training path
  * of the pyramid.  Replace `downsampling_by_n` / `downsampling_by_2` (utils.py:73-124) and what
  * autograd derives from them.

@@ -88,6 +88,7 @@ SIGNATURES = {
         [_P, _P, c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_int, c_int, _P, _P,
          c_size_t, _P],
     ),
+    "nnab_debug_varn_plan": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nnab_fir_decimate": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
     "nnab_fir_decimate_adjoint": (
         c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),

@@ -147,6 +147,9 @@ int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t
 int launch_mfcc_tail(const float* mel, int64_t B, int n_mels, int64_t T, float amin, float ref,
                      float top_db, const float* dct, int n_mfcc, float* out,
                      unsigned int* scratch /* B words */, cudaStream_t stream);
+int tc_varn_plan_export(const int32_t* k_begin, const int32_t* k_end, int F, int K, int want_chunks,
+                        int32_t* order, int32_t* groups, int32_t* chunk_begin, int32_t* n_blocks,
+                        int32_t* n_chunks);
 int launch_fir_decimate_adjoint(const float* g, int64_t B, int64_t T, int64_t g_pitch,
                                 const float* fir, int taps, int factor, float* dx, int64_t L,
                                 int64_t dx_pitch, cudaStream_t stream);

@@ -467,6 +467,16 @@ int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* strea
   return tc_pack_fir(fir, taps, dec, packed, (cudaStream_t)stream);
 }
 
+int nnab_debug_varn_plan(const int32_t* h_k_begin, const int32_t* h_k_end, int n_bins, int width,
+                         int want_chunks, int32_t* order, int32_t* groups, int32_t* chunk_begin,
+                         int32_t* n_blocks, int32_t* n_chunks) {
+  if (order == nullptr || groups == nullptr || chunk_begin == nullptr || n_blocks == nullptr ||
+      n_chunks == nullptr || n_bins <= 0 || width <= 0)
+    return NNAB_EINVAL;
+  return tc_varn_plan_export(h_k_begin, h_k_end, n_bins, width, want_chunks, order, groups,
+                             chunk_begin, n_blocks, n_chunks);
+}
+
 int nnab_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* fir,
                       int taps, int factor, float* y, int64_t Ly, void* stream) {
   if (x == nullptr || fir == nullptr || y == nullptr || B < 0 || L <= 0 || x_pitch < L || taps <= 0 ||

@@ -19,7 +19,9 @@
 //   smem full/empty mbarrier ring + double-buffered TMEM accumulators.
 #include <cuda.h>
 #include <mutex>
-#include <unordered_set>
+#include <unordered_map>
+#include <algorithm>
+#include <vector>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -215,11 +217,17 @@ int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, voi
                          cudaStream_t stream);
 bool tc_radix2_basis_ok(int F, int K);
 void tc_forget_packed(const void* packed);
+bool tc_varn_enabled();
+bool tc_varn_basis_ok(int F, int K);
+int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void* packed,
+                       cudaStream_t stream);
 
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream) {
   if (tc_radix2_enabled() && tc_radix2_basis_ok(F, K))
     return tc_pack_basis_radix2(w_re, w_im, F, K, packed, stream);
+  if (tc_varn_enabled() && tc_varn_basis_ok(F, K) && K >= 4096)
+    return tc_pack_basis_varn(w_re, w_im, F, K, packed, stream);
   tc_forget_packed(packed);
   const int bn = choose_bn(F);
   const int n_tiles = (2 * F + bn - 1) / bn;
@@ -1707,6 +1715,243 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   }
 }
 
+
+// ===========================================================================
+// EXPERIMENTAL (branch radix2-wip, not GPU-verified yet): per-K-block MMA width for banks
+// whose rows have nested, centred supports (CQT1992v2).
+//
+// Packed rows are ordered in 8-bin groups, [re bins 8g..8g+7 | negated im of the same bins], so
+// basis row r is accumulator column r and a K block that only the G longest groups reach needs
+// an MMA of width N = 16 G: TMA fetches 8 G rows per CTA of the pair, the instruction descriptor
+// carries N, the accumulation still lands in TMEM columns [0, N).  K blocks are visited in order
+// of decreasing width, so the first MMA of a tile (accumulate = 0) initialises every column the
+// tile will touch, and the epilogue of a split-K chunk reads only those.
+// ===========================================================================
+constexpr int VN_MAX_BLOCKS = 512;
+struct VarNPlan {
+  int n_blocks;              // active K blocks
+  int n_chunks;              // split-K chunks (1 = none)
+  int chunk_begin[17];       // chunk c = ordered blocks [chunk_begin[c], chunk_begin[c+1])
+  uint16_t order[VN_MAX_BLOCKS];  // K block index (64 samples each), widest first
+  uint8_t groups[VN_MAX_BLOCKS];  // 8-bin groups the block reaches (N = 16 * groups)
+};
+
+// packed[plane][row][k]: row = 16 g + 8 part + j  <->  bin 8 g + j, part 0 = re, 1 = negated im
+__global__ void __launch_bounds__(256) pack_basis_varn_kernel(
+    const float* __restrict__ w_re, const float* __restrict__ w_im, int F, int K, int rows, int kpad,
+    __nv_bfloat16* __restrict__ packed) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k8 = kpad / 8;
+  if (idx >= (int64_t)rows * k8) return;
+  const int r = (int)(idx / k8);
+  const int k0 = (int)(idx % k8) * 8;
+  const int f = (r >> 4) * 8 + (r & 7);
+  const int part = (r >> 3) & 1;
+  __align__(16) __nv_bfloat16 hi[8];
+  __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    float v = 0.f;
+    if (f < F && k < K)
+      v = part == 0 ? __ldg(w_re + (int64_t)f * K + k) : -__ldg(w_im + (int64_t)f * K + k);
+    split_bf16(v, hi[e], lo[e]);
+  }
+  const int64_t o = (int64_t)r * kpad + k0;
+  *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(packed + (int64_t)rows * kpad + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// FMT: 0 Magnitude, 1 Complex, 3 PhaseUnit (direct), 7 split-K partial sums.
+template <int FMT>
+__device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t trow, int64_t g,
+                                                   int n_groups) {
+  const int64_t b = g / p.t_slots;
+  const int64_t tl = g - b * p.t_slots;
+  const bool valid = (g < p.nv) && (tl < p.T);
+  const int64_t t = tl * p.t_mul + p.t_add;
+  constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
+  float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+  float* rre = (FMT == 7) ? p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t : nullptr;
+#pragma unroll 1
+  for (int gi = 0; gi < n_groups; ++gi) {
+    uint32_t re[8], im[8];
+    tmem_ld8(trow + (uint32_t)(16 * gi), re);
+    tmem_ld8(trow + (uint32_t)(16 * gi + 8), im);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int f = 8 * gi + j;
+        if (f < p.epi.F) {
+          if constexpr (FMT == 7) {
+            float* q = rre + (int64_t)f * p.epi.T;
+            atomicAdd(q, __uint_as_float(re[j]));
+            atomicAdd(q + p.epi.raw_plane, __uint_as_float(im[j]));
+          } else {
+            epi_store_fmt<FMT>(p.epi, dst, f, __uint_as_float(re[j]), __uint_as_float(im[j]));
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b8,
+                   const __grid_constant__ CUtensorMap tm_b32, const TcParams p,
+                   const __grid_constant__ VarNPlan plan) {
+  constexpr int BK = 64, STAGES = 3;
+  using S = Tc2Smem<BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b8);
+    prefetch_tmap(&tm_b32);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_tiles * plan.n_chunks;  // one N tile
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int chunk = tile % plan.n_chunks;
+        const int m_tile = tile / plan.n_chunks;
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        for (int i = plan.chunk_begin[chunk]; i < plan.chunk_begin[chunk + 1]; ++i) {
+          const int k0 = (int)plan.order[i] * BK;
+          const int rows = 8 * (int)plan.groups[i];  // basis rows this CTA stages
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+          mbar_expect_tx_remote(full_bar(stage), 0, 2 * S::A_BYTES + 2 * (uint32_t)rows * BK * 2);
+          int c0 = k0, c1 = m0;
+          if (p.rows_mode) {
+            c1 = m0 + k0 / p.hop;
+            c0 = k0 - (k0 / p.hop) * p.hop;
+          }
+          tma_load_3d_2sm(sb, &tm_a, full_bar(stage), c0, c1, 0);
+          tma_load_3d_2sm(sb + S::A_BYTES, &tm_a, full_bar(stage), c0, c1, 1);
+          const int row0 = (int)cta * rows;
+          const uint32_t bh = sb + 2 * S::A_BYTES, bl = bh + S::B_BYTES;
+          int r = 0;
+          for (; rows - r >= 32; r += 32) {
+            tma_load_3d_2sm(bh + (uint32_t)r * BK * 2, &tm_b32, full_bar(stage), k0, row0 + r, 0);
+            tma_load_3d_2sm(bl + (uint32_t)r * BK * 2, &tm_b32, full_bar(stage), k0, row0 + r, 1);
+          }
+          for (; r < rows; r += 8) {
+            tma_load_3d_2sm(bh + (uint32_t)r * BK * 2, &tm_b8, full_bar(stage), k0, row0 + r, 0);
+            tma_load_3d_2sm(bl + (uint32_t)r * BK * 2, &tm_b8, full_bar(stage), k0, row0 + r, 1);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int chunk = tile % plan.n_chunks;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
+        uint32_t accumulate = 0;
+        for (int i = plan.chunk_begin[chunk]; i < plan.chunk_begin[chunk + 1]; ++i) {
+          const uint32_t idesc = idesc0 | ((uint32_t)(2 * (int)plan.groups[i]) << 17);  // N = 16 G
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t koff = (uint32_t)k * 32u;
+            const uint64_t a_hi = make_smem_desc<BK>(sb + koff);
+            const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
+            const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
+            const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+            umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+            umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+            accumulate = 1u;
+          }
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int chunk = tile % plan.n_chunks;
+      const int m_tile = tile / plan.n_chunks;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)acc * TC_ACC_STRIDE;
+      // widest block of the chunk = its first: the columns this tile initialised
+      epilogue_tile_varn<FMT>(p, trow, g, (int)plan.groups[plan.chunk_begin[chunk]]);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // Split-K finalize: raw (re, im) sums -> per-bin scale + output format (generic epilogue).
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const EpiParams e, int64_t B) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1864,21 +2109,30 @@ bool tc_radix2_basis_ok(int F, int K) {
   return K >= 512 && K % 256 == 0 && F == K / 2 + 1;
 }
 
+// layout of an experimental packed basis, keyed by its device pointer (WIP: a header inside the
+// packed buffer should replace this registry)
+enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2 };
 static std::mutex g_r2_mu;
-static std::unordered_set<const void*> g_r2_packed;
+static std::unordered_map<const void*, int> g_pack_kind;
 
-static bool is_radix2_packed(const void* packed) {
+static int packed_kind(const void* packed) {
   std::lock_guard<std::mutex> lk(g_r2_mu);
-  return g_r2_packed.count(packed) != 0;
+  auto it = g_pack_kind.find(packed);
+  return it == g_pack_kind.end() ? PACK_DENSE : it->second;
 }
 
+static void mark_packed(const void* packed, int kind) {
+  std::lock_guard<std::mutex> lk(g_r2_mu);
+  if (kind == PACK_DENSE) g_pack_kind.erase(packed);
+  else g_pack_kind[packed] = kind;
+}
+
+static bool is_radix2_packed(const void* packed) { return packed_kind(packed) == PACK_RADIX2; }
 static void mark_radix2_packed(const void* packed, bool on) {
-  std::lock_guard<std::mutex> lk(g_r2_mu);
-  if (on) g_r2_packed.insert(packed);
-  else g_r2_packed.erase(packed);
+  mark_packed(packed, on ? PACK_RADIX2 : PACK_DENSE);
 }
 
-void tc_forget_packed(const void* packed) { mark_radix2_packed(packed, false); }
+void tc_forget_packed(const void* packed) { mark_packed(packed, PACK_DENSE); }
 
 static SplitGeom radix2_geom(int64_t B, int64_t L, int K, int hop, int pad) {
   const int64_t lp = L + 2 * (int64_t)pad;
@@ -2010,10 +2264,231 @@ static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, v
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL per-K-block MMA width, host side (NNAB_VARN=1)
+// ---------------------------------------------------------------------------
+bool tc_varn_enabled() {
+  const char* e = getenv("NNAB_VARN");
+  return e != nullptr && atoi(e) == 1;
+}
+
+bool tc_varn_basis_ok(int F, int K) { return F >= 1 && F <= 128 && K >= 64 && K <= 64 * VN_MAX_BLOCKS; }
+
+int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void* packed,
+                       cudaStream_t stream) {
+  if (!tc_varn_basis_ok(F, K)) return NNAB_EINVAL;
+  const int rows = 16 * ((F + 7) / 8);
+  const int kpad = round_up_i(K, 64);
+  const int64_t threads = (int64_t)rows * (kpad / 8);
+  pack_basis_varn_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+      w_re, w_im, F, K, rows, kpad, (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  mark_packed(packed, PACK_VARN);
+  return NNAB_OK;
+}
+
+// Pure host: which K blocks are touched, by how many 8-bin groups, in which order, and how the
+// ordered list is cut into split-K chunks of equal modelled cost (max(N, 64) per block: below
+// N = 64 the A-operand reads, not the MMA, set the pace).  Returns NNAB_OK or NNAB_EUNSUPPORTED.
+int tc_varn_plan(const int32_t* k_begin, const int32_t* k_end, int F, int K, int want_chunks,
+                 VarNPlan* plan) {
+  const int nkb = (K + 63) / 64;
+  if (nkb > VN_MAX_BLOCKS || F > 128 || F < 1) return NNAB_EUNSUPPORTED;
+  std::vector<std::pair<int, int>> blocks;  // (groups, kb)
+  for (int kb = 0; kb < nkb; ++kb) {
+    int gmax = 0;
+    for (int f = 0; f < F; ++f) {
+      const int lo = k_begin ? k_begin[f] : 0, hi = k_end ? k_end[f] : K;
+      if (hi > lo && hi > kb * 64 && lo < kb * 64 + 64) gmax = std::max(gmax, f / 8 + 1);
+    }
+    if (gmax > 0) blocks.push_back({gmax, kb});
+  }
+  if (blocks.empty()) blocks.push_back({(F + 7) / 8, 0});
+  std::stable_sort(blocks.begin(), blocks.end(),
+                   [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+  plan->n_blocks = (int)blocks.size();
+  int64_t total = 0;
+  for (int i = 0; i < plan->n_blocks; ++i) {
+    plan->groups[i] = (uint8_t)blocks[i].first;
+    plan->order[i] = (uint16_t)blocks[i].second;
+    total += std::max(16 * blocks[i].first, 64);
+  }
+  int chunks = want_chunks < 1 ? 1 : (want_chunks > 16 ? 16 : want_chunks);
+  if (chunks > plan->n_blocks) chunks = plan->n_blocks;
+  plan->n_chunks = chunks;
+  plan->chunk_begin[0] = 0;
+  int64_t acc = 0;
+  int c = 1;
+  for (int i = 0; i < plan->n_blocks && c < chunks; ++i) {
+    acc += std::max(16 * (int)plan->groups[i], 64);
+    // close chunk c-1 once its share of the cost is reached, leaving >= 1 block per later chunk
+    if (acc * chunks >= total * c && plan->n_blocks - (i + 1) >= chunks - c) plan->chunk_begin[c++] = i + 1;
+  }
+  while (c < chunks) { plan->chunk_begin[c] = plan->n_blocks - (chunks - c); ++c; }
+  plan->chunk_begin[chunks] = plan->n_blocks;
+  for (int k = chunks + 1; k < 17; ++k) plan->chunk_begin[k] = plan->n_blocks;
+  return NNAB_OK;
+}
+
+// host-only view of the plan for tests / tooling
+int tc_varn_plan_export(const int32_t* k_begin, const int32_t* k_end, int F, int K, int want_chunks,
+                        int32_t* order, int32_t* groups, int32_t* chunk_begin, int32_t* n_blocks,
+                        int32_t* n_chunks) {
+  VarNPlan plan;
+  const int rc = tc_varn_plan(k_begin, k_end, F, K, want_chunks, &plan);
+  if (rc) return rc;
+  *n_blocks = plan.n_blocks;
+  *n_chunks = plan.n_chunks;
+  for (int i = 0; i < plan.n_blocks; ++i) { order[i] = plan.order[i]; groups[i] = plan.groups[i]; }
+  for (int c = 0; c <= plan.n_chunks; ++c) chunk_begin[c] = plan.chunk_begin[c];
+  return NNAB_OK;
+}
+
+static bool varn_problem_ok(const FramedProblem& q) {
+  if (!tc_varn_basis_ok(q.F, q.K)) return false;
+  if (num_phases(q.hop) != 1 || q.presplit != nullptr) return false;
+  if (q.bin_offset != 0 || q.out_bins != q.F) return false;
+  return q.fmt == NNAB_FMT_MAGNITUDE || q.fmt == NNAB_FMT_COMPLEX || q.fmt == NNAB_FMT_PHASE_UNIT;
+}
+
+template <int FMT>
+static int launch_tc2v_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const CUtensorMap& mb32,
+                           const TcParams& prm, const VarNPlan& plan, int n_pairs,
+                           cudaStream_t stream) {
+  using S = Tc2Smem<64, 3>;
+  static bool configured = false;
+  if (!configured) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2v_kernel<FMT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2v_kernel<FMT>, ma, mb8, mb32, prm, plan));
+  count_launch();
+  return NNAB_OK;
+}
+
+static int launch_framed_tc_varn(const FramedProblem& q, const void* packed, void* workspace,
+                                 size_t ws_bytes, cudaStream_t stream) {
+  if (!varn_problem_ok(q)) return NNAB_EINVAL;  // the basis was packed for this kernel only
+  const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (q.B > 65535) return NNAB_EUNSUPPORTED;
+  const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+  const int kpad = round_up_i(q.K, 64);
+  const int rows_w = 16 * ((q.F + 7) / 8);
+  __nv_bfloat16* planes =
+      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  int rc = zero_tail(planes, g, q.hop, stream);
+  if (rc) return rc;
+  const int64_t clip_pitch = g.t_slots * q.hop;
+  dim3 pgrid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
+  pad_split_kernel<<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode, 0, clip_pitch,
+                                              g.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+
+  // split-K only with the caller's raw scratch (long kernels): <= 64 K blocks per accumulator
+  VarNPlan plan;
+  {
+    VarNPlan probe;
+    if ((rc = tc_varn_plan(q.h_k_begin, q.h_k_end, q.F, q.K, 1, &probe))) return rc;
+    int ks = 1;
+    if (q.raw != nullptr) {
+      ks = (probe.n_blocks + 63) / 64;
+      if (ks > 16) ks = 16;
+    }
+    if ((rc = tc_varn_plan(q.h_k_begin, q.h_k_end, q.F, q.K, ks, &plan))) return rc;
+  }
+
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();
+  if (sms < 2) sms = 2;
+
+  CUtensorMap ma, mb8, mb32;
+  const int rows_mode = (q.hop % 64 == 0) ? 1 : 0;
+  if (rows_mode)
+    rc = encode_3d(&ma, planes, (uint64_t)q.hop, (uint64_t)g.rows, 2, (uint64_t)q.hop * 2,
+                   (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
+  else
+    rc = encode_3d(&ma, planes, (uint64_t)kpad, (uint64_t)g.nv, 2, (uint64_t)q.hop * 2,
+                   (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
+  if (rc) return rc;
+  if ((rc = encode_3d(&mb8, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
+                      (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, 64, 8, 64)))
+    return rc;
+  if ((rc = encode_3d(&mb32, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
+                      (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, 64, 32, 64)))
+    return rc;
+
+  TcParams prm{};
+  prm.num_n_tiles = 1;
+  prm.bn = rows_w;
+  prm.rows_mode = rows_mode;
+  prm.hop = q.hop;
+  prm.nv = g.nv;
+  prm.t_slots = g.t_slots;
+  prm.t_mul = 1;
+  prm.t_add = 0;
+  prm.T = q.T;
+  prm.k_splits = plan.n_chunks;
+  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
+  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
+  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+  prm.epi.fb_table = nullptr; prm.epi.n_fb = 0;
+  prm.epi.dec = q.dec;
+  prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
+  prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
+  EpiParams final_epi = prm.epi;
+  const bool split = plan.n_chunks > 1;
+  if (split) {
+    float* raw = reinterpret_cast<float*>(((uintptr_t)q.raw + 255) & ~(uintptr_t)255);
+    const int64_t plane = (int64_t)q.B * q.F * q.T;
+    NNAB_CUDA_TRY(cudaMemsetAsync(raw, 0, (size_t)2 * plane * sizeof(float), stream));
+    prm.epi.fmt = FMT_RAW;
+    prm.epi.raw = raw;
+    prm.epi.raw_plane = plane;
+    final_epi.raw = raw;
+    final_epi.raw_plane = plane;
+  }
+  prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
+  const int64_t ptiles = (int64_t)prm.num_m_tiles * plan.n_chunks;
+  const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  switch (prm.epi.fmt) {
+    case NNAB_FMT_MAGNITUDE: rc = launch_tc2v_fmt<0>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    case NNAB_FMT_COMPLEX: rc = launch_tc2v_fmt<1>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    case NNAB_FMT_PHASE_UNIT: rc = launch_tc2v_fmt<3>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    case FMT_RAW: rc = launch_tc2v_fmt<7>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    default: rc = NNAB_EINVAL;
+  }
+  if (rc) return rc;
+  if (split) {
+    dim3 grid((unsigned)ceil_div64(q.T, 256), (unsigned)q.F, (unsigned)(q.B < 64 ? q.B : 64));
+    splitk_finalize_kernel<<<grid, 256, 0, stream>>>(final_epi, q.B);
+    NNAB_LAUNCH_CHECK();
+  }
+  return NNAB_OK;
+}
+
 int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace, size_t ws_bytes,
                      cudaStream_t stream) {
   if (q.B <= 0 || q.T <= 0 || q.F <= 0) return NNAB_OK;
   if (packed == nullptr) return NNAB_EINVAL;
+  if (packed_kind(packed) == PACK_VARN)
+    return launch_framed_tc_varn(q, packed, workspace, ws_bytes, stream);
   if (is_radix2_packed(packed))
     return launch_framed_tc_radix2(q, packed, workspace, ws_bytes, stream);
   if (q.presplit == nullptr) {
