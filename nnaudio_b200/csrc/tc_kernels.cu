@@ -797,6 +797,7 @@ struct TcParams {
   int hop;          // effective hop (hop * phases)
   int t_mul, t_add;  // output frame index = t * t_mul + t_add (frame phases)
   int k_splits;      // >1: every (m, n) tile is cut into k_splits K-chunks (FMT_RAW epilogue)
+  int split4;        // EXPERIMENTAL (NNAB_SPLIT4=1): add the x_lo * w_lo term (4 MMAs per K16 step)
   int64_t nv, t_slots, T;  // T = valid frames of this phase
   int kb_begin[TC_MAX_N_TILES];
   int kb_end[TC_MAX_N_TILES];
@@ -1353,6 +1354,10 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
             const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
             const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+            if (p.split4) {  // smallest term first: fp32-like accuracy for the training forward
+              umma_bf16_2sm(d_tmem, a_lo, b_lo, idesc, accumulate);
+              accumulate = 1u;
+            }
             umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
             umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
             umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
@@ -2559,6 +2564,10 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.nv = g.nv;
   prm.t_slots = g.t_slots;
   prm.t_mul = n_ph;
+  {
+    const char* e4 = getenv("NNAB_SPLIT4");
+    prm.split4 = (e4 != nullptr && atoi(e4) == 1) ? 1 : 0;  // CTA-pair kernel only
+  }
   const int nkb = kpad / bk;
   const int half = bn / 2;
   for (int tl = 0; tl < n_tiles; ++tl) {
