@@ -35,7 +35,7 @@ def pad_mode_id(pad_mode: str) -> int:
 
 
 def forward_only_guard(module: torch.nn.Module, x: torch.Tensor):
-    """Kept for the modules without a training path (CQT2010v2 / VQT pyramid, iSTFT):
+    """For parameters without a dW path (trainable inverse kernels / window of iSTFT):
     refuse loudly rather than return a result whose parameters silently get no gradient."""
     if not torch.is_grad_enabled():
         return
@@ -51,10 +51,6 @@ def wants_grad(module: torch.nn.Module, x: torch.Tensor) -> bool:
     if not torch.is_grad_enabled():
         return False
     return x.requires_grad or any(p.requires_grad for p in module.parameters())
-
-
-def wants_input_grad(x: torch.Tensor) -> bool:
-    return torch.is_grad_enabled() and x.requires_grad
 
 
 class FramedComplexFn(torch.autograd.Function):
@@ -86,19 +82,34 @@ class FramedComplexFn(torch.autograd.Function):
         return dx, dre, dim, None, None, None
 
 
+class PerDeviceCache:
+    """One cached value per device, rebuilt when its key changes.  Entries are (key, value) tuples
+    replaced in one assignment and ``lookup`` returns the value it just read or built, so module
+    replicas that share this object across threads and devices (``torch.nn.DataParallel`` copies
+    ``__dict__`` shallowly) can neither hand each other a buffer of the wrong device nor evict each
+    other's entry."""
+
+    def __init__(self):
+        self._entries = {}
+
+    def lookup(self, device, key, build):
+        slot = str(device)
+        entry = self._entries.get(slot)
+        if entry is None or entry[0] != key:
+            entry = (key, build())
+            self._entries[slot] = entry
+        return entry[1]
+
+
 class AdjointBasis:
     """Cache of the W^T packing used by the input-gradient GEMM."""
 
     def __init__(self):
-        self._key = None
-        self._packed = None
+        self._cache = PerDeviceCache()
 
     def get(self, w_re: torch.Tensor, w_im: torch.Tensor):
-        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, str(w_re.device))
-        if key != self._key:
-            self._packed = _C.pack_adjoint_basis(w_re, w_im)
-            self._key = key
-        return self._packed
+        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version)
+        return self._cache.lookup(w_re.device, key, lambda: _C.pack_adjoint_basis(w_re, w_im))
 
 
 class PackedBasis:
@@ -107,15 +118,11 @@ class PackedBasis:
     optimiser steps)."""
 
     def __init__(self):
-        self._key = None
-        self._packed = None
+        self._cache = PerDeviceCache()
 
     def get(self, w_re: torch.Tensor, w_im: torch.Tensor):
-        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, str(w_re.device))
-        if key != self._key:
-            self._packed = _C.pack_basis(w_re, w_im)
-            self._key = key
-        return self._packed
+        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version)
+        return self._cache.lookup(w_re.device, key, lambda: _C.pack_basis(w_re, w_im))
 
 
 def as_matrix(buf: torch.Tensor) -> torch.Tensor:
@@ -143,27 +150,19 @@ class FilterbankTable:
     (rebuilt when the filterbank tensor changes; ``None`` for dense banks)."""
 
     def __init__(self):
-        self._key = None
-        self._table = None
+        self._cache = PerDeviceCache()
 
     def get(self, fb: torch.Tensor):
-        key = (fb.data_ptr(), fb._version, str(fb.device))
-        if key != self._key:
-            self._table = _C.build_filterbank_table(fb)
-            self._key = key
-        return self._table
+        key = (fb.data_ptr(), fb._version)
+        return self._cache.lookup(fb.device, key, lambda: _C.build_filterbank_table(fb))
 
 
 class PackedFir:
     """Cache of the tensor-core packing of a decimation FIR buffer."""
 
     def __init__(self):
-        self._key = None
-        self._packed = None
+        self._cache = PerDeviceCache()
 
     def get(self, fir: torch.Tensor, dec: int):
-        key = (fir.data_ptr(), fir._version, int(dec), str(fir.device))
-        if key != self._key:
-            self._packed = _C.pack_fir(fir, int(dec))
-            self._key = key
-        return self._packed
+        key = (fir.data_ptr(), fir._version, int(dec))
+        return self._cache.lookup(fir.device, key, lambda: _C.pack_fir(fir, int(dec)))

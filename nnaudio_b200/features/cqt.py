@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, PackedFir, as_matrix,
+from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, PackedFir, PerDeviceCache, as_matrix,
                       broadcast_dim, pad_mode_id, tap_support, wants_grad)
 
 _FORMATS = {
@@ -40,18 +40,15 @@ class _ScaleCache:
     """sqrt(lenghts) * factor on the device, recomputed when ``lenghts`` changes."""
 
     def __init__(self):
-        self._key = None
-        self._val = None
+        self._cache = PerDeviceCache()
 
     def get(self, lenghts: torch.Tensor, factor: float):
-        key = (lenghts.data_ptr(), lenghts._version, float(factor), str(lenghts.device))
-        if key != self._key:
+        def build():
             s = torch.sqrt(lenghts.detach().float())
-            if factor != 1:
-                s = s * factor
-            self._val = s.contiguous()
-            self._key = key
-        return self._val
+            return (s * factor if factor != 1 else s).contiguous()
+
+        key = (lenghts.data_ptr(), lenghts._version, float(factor))
+        return self._cache.lookup(lenghts.device, key, build)
 
 
 class CQT1992v2(nn.Module):
@@ -105,8 +102,7 @@ class CQT1992v2(nn.Module):
 
         self._packed = PackedBasis()
         self._scale = _ScaleCache()
-        self._support_key = None
-        self._support = (None, None)
+        self._support = PerDeviceCache()
         if verbose:
             print("CQT kernels created, time used = {:.4f} seconds".format(time() - start))
 
@@ -116,12 +112,13 @@ class CQT1992v2(nn.Module):
         if self.trainable:
             return None, None
         kr, ki = self.cqt_kernels_real, self.cqt_kernels_imag
-        key = (kr.data_ptr(), kr._version, ki.data_ptr(), ki._version)
-        if key != self._support_key:
+
+        def build():
             both = (kr.detach()[:, 0, :] != 0) | (ki.detach()[:, 0, :] != 0)
-            self._support = tap_support(both.cpu().numpy())
-            self._support_key = key
-        return self._support
+            return tap_support(both.cpu().numpy())
+
+        key = (kr.data_ptr(), kr._version, ki.data_ptr(), ki._version)
+        return self._support.lookup(kr.device, key, build)
 
     def forward(self, x, output_format=None, normalization_type="librosa"):
         output_format = output_format or self.output_format
@@ -504,16 +501,18 @@ def _decimate_autograd(mod, tag, sig, fir, n):
         c = _framed_complex_autograd(mod, tag, padded, w_re, zeros[tag], n, False, _C.PAD_CONSTANT)
         return c[:, 0, :, 0].contiguous()
     cache = mod.__dict__.setdefault("_decim_cache", {})
-    key = (fir.data_ptr(), fir._version, int(n), str(fir.device))
-    if tag not in cache or cache[tag][0] != key:
+
+    def build():
         taps = fir.numel()
         row = fir.detach().reshape(1, taps).contiguous()
         Q = (taps + n - 1) // n
         padded = torch.nn.functional.pad(row[0], (0, Q * n - taps))
         poly = padded.reshape(Q, n).t().flip(1).contiguous()      # poly[p, k] = fir[n*(Q-1-k) + p]
         poly_zero = torch.zeros_like(poly)
-        cache[tag] = (key, row, torch.zeros_like(row), (poly, poly_zero, _C.pack_basis(poly, poly_zero)))
-    _, row, zero_row, poly = cache[tag]
+        return row, torch.zeros_like(row), (poly, poly_zero, _C.pack_basis(poly, poly_zero))
+
+    key = (fir.data_ptr(), fir._version, int(n))
+    row, zero_row, poly = cache.setdefault(tag, PerDeviceCache()).lookup(fir.device, key, build)
     return _DecimateFn.apply(sig, row, zero_row, poly, int(n))
 
 

@@ -25,7 +25,7 @@ import torch.nn as nn
 from scipy.fftpack import fft as _fft
 
 from .. import _C, design
-from ._common import PackedBasis, broadcast_dim, pad_mode_id, wants_grad
+from ._common import PackedBasis, PerDeviceCache, broadcast_dim, pad_mode_id, wants_grad
 from .cqt import (_ScaleCache, _check_format_and_norm, _framed_complex_autograd,
                   _pyramid_forward)
 
@@ -50,27 +50,23 @@ class _FoldedBank:
     packing, for both signs of the imaginary rows."""
 
     def __init__(self):
-        self._key = None
-        self._val = None
-        self._packed = {}
+        self._cache = PerDeviceCache()
 
     def get(self, mod, negate_imag: bool):
         src = (mod.cqt_kernels_real, mod.cqt_kernels_imag, mod.wcos, mod.wsin)
-        key = tuple((t.data_ptr(), t._version) for t in src) + (str(src[0].device),)
-        if key != self._key:
+
+        def build():
             with torch.no_grad():
                 for t in src:
                     _C._dev_f32(t.detach(), "kernel")
                 e_re, e_im = _fold(*[t.detach() for t in src], torch.float64)
-                self._val = (e_re.float().contiguous(), e_im.float().contiguous(),
-                             (-e_im).float().contiguous())
-            self._packed = {}
-            self._key = key
-        e_re, e_im, e_im_neg = self._val
-        w_im = e_im_neg if negate_imag else e_im
-        if negate_imag not in self._packed:
-            self._packed[negate_imag] = PackedBasis()
-        return e_re, w_im, self._packed[negate_imag].get(e_re, w_im)
+                e_re, e_im, e_neg = (e_re.float().contiguous(), e_im.float().contiguous(),
+                                     (-e_im).float().contiguous())
+            return e_re, {False: e_im, True: e_neg}, {False: PackedBasis(), True: PackedBasis()}
+
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        e_re, w_im, packed = self._cache.lookup(src[0].device, key, build)
+        return e_re, w_im[negate_imag], packed[negate_imag].get(e_re, w_im[negate_imag])
 
     def differentiable(self, mod, negate_imag: bool):
         """Same fold under autograd (fp32), so dE reaches the trainable DFT rows / spectral kernels."""

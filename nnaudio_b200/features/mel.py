@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import FilterbankTable, as_matrix, pad_mode_id, wants_grad
+from ._common import FilterbankTable, pad_mode_id, wants_grad
 from .stft import STFT
 
 

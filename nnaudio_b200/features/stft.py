@@ -13,7 +13,8 @@ import torch
 import torch.nn as nn
 
 from .. import _C, design
-from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, as_matrix, broadcast_dim,
+from ._common import (AdjointBasis, FramedComplexFn, PackedBasis, PerDeviceCache, as_matrix,
+                      broadcast_dim,
                       forward_only_guard, pad_mode_id, wants_grad)
 
 _FORMATS = {
@@ -28,15 +29,11 @@ class _InverseBasis:
     (one-sided?, bins) variant."""
 
     def __init__(self):
-        self._cache = {}
+        self._cache = PerDeviceCache()
 
     def get(self, kc: torch.Tensor, ks: torch.Tensor, f_in: int, onesided: bool):
-        key = (kc.data_ptr(), kc._version, ks.data_ptr(), ks._version, f_in, bool(onesided),
-               str(kc.device))
-        if key not in self._cache:
-            self._cache.clear()
-            self._cache[key] = _C.pack_istft_basis(kc, ks, f_in, onesided)
-        return self._cache[key]
+        key = (kc.data_ptr(), kc._version, ks.data_ptr(), ks._version, f_in, bool(onesided))
+        return self._cache.lookup(kc.device, key, lambda: _C.pack_istft_basis(kc, ks, f_in, onesided))
 
 
 class _InverseAdjoint:
@@ -45,13 +42,10 @@ class _InverseAdjoint:
     spectrum (utils.py:63-70) folded in, plus its tensor-core packing."""
 
     def __init__(self):
-        self._key = None
-        self._val = None
+        self._cache = PerDeviceCache()
 
     def get(self, kc, ks, win, onesided):
-        key = (kc.data_ptr(), kc._version, ks.data_ptr(), ks._version, win.data_ptr(),
-               win._version, bool(onesided), str(kc.device))
-        if key != self._key:
+        def build():
             n_fft = kc.shape[0]
             w_re = (kc * (win / n_fft)[:, None]).t().contiguous()   # (f, o)
             w_im = (ks * (win / n_fft)[:, None]).t().contiguous()
@@ -62,9 +56,11 @@ class _InverseAdjoint:
                 lo_re[1:half] += w_re[mirror]
                 lo_im[1:half] -= w_im[mirror]
                 w_re, w_im = lo_re.contiguous(), lo_im.contiguous()
-            self._val = (w_re, w_im, _C.pack_basis(w_re, w_im))
-            self._key = key
-        return self._val
+            return w_re, w_im, _C.pack_basis(w_re, w_im)
+
+        key = (kc.data_ptr(), kc._version, ks.data_ptr(), ks._version, win.data_ptr(), win._version,
+               bool(onesided))
+        return self._cache.lookup(kc.device, key, build)
 
 
 class _InverseSTFTFn(torch.autograd.Function):

@@ -139,6 +139,59 @@ ISTFT_CASES = [
 ]
 
 
+# Constructor-only sweep: state_dict keys / shapes / sha256 of every buffer against the reference
+# (no forward pass; widens the "buffers are bit-identical" drop-in claim beyond the CASES configs).
+DESIGN_CASES = [
+    ("d_stft_blackman_win300", "STFT", dict(n_fft=1024, win_length=300, hop_length=100, window="blackmanharris")),
+    ("d_stft_gaussian_tuple", "STFT", dict(n_fft=512, window=("gaussian", 60))),
+    ("d_stft_linear_fmin_fmax", "STFT", dict(n_fft=1024, freq_bins=200, freq_scale="linear", fmin=100, fmax=7000, sr=16000)),
+    ("d_stft_log", "STFT", dict(n_fft=2048, freq_bins=120, freq_scale="log", fmin=55, fmax=8000, sr=22050)),
+    ("d_stft_log2", "STFT", dict(n_fft=1024, freq_bins=96, freq_scale="log2", fmin=60, fmax=6000, sr=22050)),
+    ("d_stft_istft_buffers", "STFT", dict(n_fft=256, hop_length=64, iSTFT=True, window="hamming")),
+    ("d_istft_module", "iSTFT", dict(n_fft=512, hop_length=128, window="hann")),
+    ("d_mel_htk_nonorm", "MelSpectrogram", dict(sr=16000, n_fft=400, hop_length=160, n_mels=64, htk=True, norm=None, fmin=60, fmax=7600)),
+    ("d_mel_48k", "MelSpectrogram", dict(sr=48000, n_fft=4096, n_mels=256, fmin=20)),
+    ("d_mel_power1", "MelSpectrogram", dict(sr=22050, n_fft=1024, n_mels=80, power=1.0, window="hamming")),
+    ("d_mfcc_40", "MFCC", dict(sr=22050, n_mfcc=40, n_fft=2048, n_mels=128)),
+    ("d_gammatone_96", "Gammatonegram", dict(sr=44100, n_fft=4096, n_bins=96, fmin=30, fmax=16000)),
+    ("d_gammatone_small", "Gammatonegram", dict(sr=8000, n_fft=256, n_bins=16)),
+    ("d_cqt1992v2_24bpo", "CQT1992v2", dict(sr=22050, fmin=55, n_bins=96, bins_per_octave=24, filter_scale=0.5)),
+    ("d_cqt1992v2_norm2_hamming", "CQT1992v2", dict(sr=16000, fmin=110, n_bins=60, norm=2, window="hamming")),
+    ("d_cqt1992v2_fmax", "CQT1992v2", dict(sr=22050, fmin=65.4, fmax=4000, bins_per_octave=12)),
+    ("d_cqt2010v2_noearly_24bpo", "CQT2010v2", dict(sr=22050, n_bins=120, bins_per_octave=24, earlydownsample=False)),
+    ("d_cqt2010v2_48k", "CQT2010v2", dict(sr=48000, n_bins=96, fmin=27.5, filter_scale=2)),
+    ("d_vqt_gamma20_36bpo", "VQT", dict(sr=22050, n_bins=108, bins_per_octave=36, gamma=20)),
+    ("d_vqt_noearly", "VQT", dict(sr=16000, n_bins=72, gamma=3, earlydownsample=False)),
+    ("d_cqt1992_24bpo", "CQT1992", dict(sr=44100, fmin=220, n_bins=80, bins_per_octave=24)),
+    ("d_cqt2010_24bpo", "CQT2010", dict(sr=44100, fmin=110, n_bins=160, bins_per_octave=24)),
+]
+
+
+# Error-behaviour scenarios: what the reference raises (exception type) for malformed constructor
+# arguments and inputs; recorded into ref_errors.json.  ("ctor",) | ("forward", shape, kwargs) |
+# ("inverse", shape, kwargs)
+ERROR_CASES = [
+    ("e_stft_short_reflect", "STFT", dict(n_fft=512), ("forward", (1, 100), {})),
+    ("e_stft_4d_input", "STFT", dict(n_fft=256), ("forward", (1, 1, 2, 4000), {})),
+    ("e_stft_two_channels", "STFT", dict(n_fft=256), ("forward", (2, 2, 4000), {})),
+    ("e_stft_inverse_without_flag", "STFT", dict(n_fft=256), ("inverse", (1, 129, 10, 2), {})),
+    ("e_stft_inverse_3d", "STFT", dict(n_fft=256, iSTFT=True), ("inverse", (1, 129, 10), {})),
+    ("e_istft_3d", "iSTFT", dict(n_fft=256), ("forward", (1, 256, 10), {})),
+    ("e_mel_short_reflect", "MelSpectrogram", dict(sr=16000, n_fft=1024), ("forward", (2, 300), {})),
+    ("e_cqt1992v2_nyquist", "CQT1992v2", dict(sr=8000, fmin=220, n_bins=84), ("ctor",)),
+    ("e_cqt1992v2_short_reflect", "CQT1992v2", dict(sr=22050, fmin=220, n_bins=12), ("forward", (1, 100), {})),
+    ("e_cqt1992v2_bad_norm", "CQT1992v2", dict(sr=22050, fmin=220, n_bins=12),
+     ("forward", (1, 8000), dict(normalization_type="bogus"))),
+    ("e_cqt2010v2_nyquist", "CQT2010v2", dict(sr=8000, n_bins=96), ("ctor",)),
+    ("e_cqt2010v2_bad_norm", "CQT2010v2", dict(sr=22050, n_bins=24, fmin=220),
+     ("forward", (1, 8000), dict(normalization_type="bogus"))),
+    ("e_cqt2010v2_4d_input", "CQT2010v2", dict(sr=22050, n_bins=24, fmin=220), ("forward", (1, 1, 1, 8000), {})),
+    ("e_vqt_nyquist", "VQT", dict(sr=8000, n_bins=96), ("ctor",)),
+    ("e_cqt1992_nyquist", "CQT1992", dict(sr=8000, fmin=220, n_bins=84), ("ctor",)),
+    ("e_cqt2010_nyquist", "CQT2010", dict(sr=8000, n_bins=96), ("ctor",)),
+]
+
+
 # Input-gradient cases (dX): loss = sum(out * w), w ~ N(0,1) seeded;
 # the fixture holds the reference's x.grad (autograd through its conv1d path on CPU).
 GRAD_CASES = [
@@ -214,6 +267,30 @@ ISTFT_GRAD_CASES = [
     ("grad_istft_onesided_nolen", 256, 64, "hamming", "roundtrip", dict(seed=97, shape=(1, 3000), length=None)),
     ("grad_istft_module_full", 256, 64, "hann", "module", dict(seed=98, shape=(2, 256, 40, 2))),
 ]
+
+
+def attribute_surface(module) -> dict:
+    """JSON-able view of a module's public, non-tensor attributes (what user code reads:
+    ``n_fft``, ``stride``, ``frequencies``, ``kernel_width`` ...).  Used on the reference by
+    make_golden.py and on ours by tests/test_host_logic.py."""
+    import torch
+
+    base = set(vars(torch.nn.Module()))
+    out = {}
+    for k, v in vars(module).items():
+        if k.startswith("_") or k in base:
+            continue
+        if isinstance(v, (bool, int, float, str, type(None))):
+            out[k] = v
+        elif isinstance(v, (np.floating, np.integer)):
+            out[k] = float(v)
+        elif isinstance(v, np.ndarray):
+            out[k] = ["ndarray", list(v.shape), str(v.dtype), float(np.abs(v).sum())]
+        elif isinstance(v, (list, tuple)):
+            out[k] = [type(v).__name__, len(v)]
+        else:
+            out[k] = type(v).__name__
+    return out
 
 
 def loss_weights(case_id: str, shape) -> np.ndarray:

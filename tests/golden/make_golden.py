@@ -28,8 +28,8 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
-from cases import (CASES, GRAD_CASES, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
-                   SWEEP_CTOR, WGRAD_CASES, loss_weights, make_input, out_key)
+from cases import (CASES, DESIGN_CASES, ERROR_CASES, GRAD_CASES, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
+                   SWEEP_CTOR, WGRAD_CASES, attribute_surface, loss_weights, make_input, out_key)
 
 from nnAudio import features as ref_features  # noqa: E402
 
@@ -70,6 +70,36 @@ def main():
                 y = mod(x, **kw)
             outputs[out_key(cid, kw)] = y.numpy().astype(np.float32)
             print(f"{out_key(cid, kw):60s} {tuple(y.shape)}")
+    for cid, cls, ctor in DESIGN_CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = make_module(ref_features, cls, ctor)
+        buffers[cid] = {k: [list(v.shape), sha(v)] for k, v in mod.state_dict().items()
+                        if v is not None}
+        print(f"{cid:60s} {len(buffers[cid])} buffers")
+    attributes = {}
+    for cid, cls, ctor in [(c[0], c[1], c[2]) for c in CASES] + list(DESIGN_CASES):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            attributes[cid] = attribute_surface(make_module(ref_features, cls, ctor))
+    with open(os.path.join(HERE, "ref_attributes.json"), "w") as f:
+        json.dump(attributes, f, indent=1, sort_keys=True)
+    errors = {}
+    for cid, cls, ctor, call in ERROR_CASES:
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                mod = make_module(ref_features, cls, ctor)
+                if call[0] == "forward":
+                    mod(torch.zeros(call[1]), **call[2])
+                elif call[0] == "inverse":
+                    mod.inverse(torch.zeros(call[1]), **call[2])
+            errors[cid] = "ok"
+        except Exception as e:  # noqa: BLE001  (the point is to record the type)
+            errors[cid] = type(e).__name__
+        print(f"{cid:60s} -> {errors[cid]}")
+    with open(os.path.join(HERE, "ref_errors.json"), "w") as f:
+        json.dump(errors, f, indent=1, sort_keys=True)
     # inverse STFT: spectrogram inputs AND waveform outputs of the reference
     for cid, n_fft, hop, win, kind, spec in ISTFT_CASES:
         rng = np.random.RandomState(spec["seed"])

@@ -2,7 +2,6 @@
 reference's autograd (x.grad recorded by tests/golden/make_golden.py on CPU)."""
 import warnings
 
-import numpy as np
 import pytest
 import torch
 

@@ -7,7 +7,6 @@ and the per-clip MFCC floor at scale — plus size-independent properties (linea
 complex transforms, clip permutation equivariance)."""
 import warnings
 
-import numpy as np
 import pytest
 import torch
 

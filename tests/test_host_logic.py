@@ -138,3 +138,67 @@ def test_batches_beyond_the_per_call_limit_are_chunked(monkeypatch):
     for name in ("stft_forward", "stft_filterbank_forward", "mfcc_forward", "cqt1992v2_forward",
                  "cqt_pyramid_forward"):
         assert hasattr(getattr(_C, name), "__wrapped__"), name
+
+
+def _ref_errors():
+    import json
+    import os
+    from helpers import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_errors.json")) as f:
+        return json.load(f)
+
+
+from cases import ERROR_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ERROR_CASES, ids=[c[0] for c in ERROR_CASES])
+def test_same_exception_type_as_the_reference(case):
+    """Malformed constructor arguments / inputs raise the exception TYPE the reference raises
+    (recorded from the unmodified reference in tests/golden/ref_errors.json), and they do so before
+    the C call — so the check also holds for CPU tensors."""
+    from helpers import build
+    cid, cls, ctor, call = case
+    want = _ref_errors()[cid]
+    assert want != "ok"
+    exc = {"AssertionError": AssertionError, "ValueError": ValueError, "RuntimeError": RuntimeError,
+           "NameError": NameError}[want]
+    with pytest.raises(exc) as info, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = build(cls, ctor)
+        if call[0] == "forward":
+            mod(torch.zeros(call[1]), **call[2])
+        elif call[0] == "inverse":
+            mod.inverse(torch.zeros(call[1]), **call[2])
+    assert "no CPU fallback" not in str(info.value), "the reference-type error must come first"
+
+
+def _ref_attributes():
+    import json
+    import os
+    from helpers import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_attributes.json")) as f:
+        return json.load(f)
+
+
+from cases import CASES as _CASES, DESIGN_CASES, attribute_surface  # noqa: E402
+
+_ATTR_CASES = [(c[0], c[1], c[2]) for c in _CASES] + list(DESIGN_CASES)
+
+
+@pytest.mark.parametrize("case", _ATTR_CASES, ids=[c[0] for c in _ATTR_CASES])
+def test_public_attribute_surface_matches_reference(case):
+    """Every public non-tensor attribute of the reference module (n_fft, stride, frequencies,
+    kernel_width, downsample_factor, ...) exists on ours with the same value (fixture recorded from
+    the unmodified reference); ours may carry more."""
+    from helpers import build
+    cid, cls, ctor = case
+    ours = attribute_surface(build(cls, ctor))
+    for name, want in _ref_attributes()[cid].items():
+        assert name in ours, f"{cls}.{name} missing"
+        got = ours[name]
+        if isinstance(want, float) and isinstance(got, (int, float)):
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-12), name
+        elif isinstance(want, list) and want and want[0] == "ndarray":
+            assert got[:3] == want[:3] and got[3] == pytest.approx(want[3], rel=1e-9), name
+        else:
+            assert got == want, (name, got, want)

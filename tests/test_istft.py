@@ -1,11 +1,10 @@
 """Inverse STFT: STFT.inverse / iSTFT against the reference
 outputs recorded by tests/golden/make_golden.py, the fp64 oracle, and the reference's own
 round-trip test (Installation/tests/test_stft.py:28-54: STFT -> inverse recovers x)."""
-import numpy as np
 import pytest
 import torch
 
-from helpers import build, oracle, ref_outputs, rel_errors
+from helpers import oracle, ref_outputs, rel_errors
 from cases import ISTFT_CASES, ISTFT_GRAD_CASES, loss_weights
 
 import nnaudio_b200 as nb

@@ -59,3 +59,42 @@ def test_two_rank_gather_matches_single_process(total):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), total, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _async_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mod = build("STFT", dict(n_fft=256, hop_length=64, output_format="Magnitude"))
+
+        def transform(x):
+            return torch.from_numpy(run_oracle("STFT", mod, x.numpy(), {}, dtype=np.float32))
+
+        sharded = BatchShardedTransform(transform)
+        rng = np.random.RandomState(11)
+        batches = [torch.from_numpy(rng.standard_normal((4, 2048)).astype(np.float32)) for _ in range(3)]
+        # the bench.py pattern: the gather of step i is waited for only after step i+1 was issued,
+        # with two rotating gather buffers
+        ok, pending = True, None
+        for i, xg in enumerate(batches):
+            work, buf = sharded.forward_async(sharded.local_slice(xg), slot=i & 1)
+            if pending is not None:
+                pw, pbuf, pfull = pending
+                pw.wait()
+                ok = ok and torch.equal(pbuf, pfull)
+            pending = (work, buf, transform(xg))
+        pending[0].wait()
+        ok = ok and torch.equal(pending[1], pending[2])
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_pipelined_gather_with_rotating_buffers():
+    """forward_async (what bench.py runs for N > 1): results of step i stay intact in their slot
+    while step i+1 is transformed and gathered into the other slot."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_async_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -114,6 +114,26 @@ def radix2_kernel_layout_check(frames, N, window, exact):
     return np.abs(X - exact).max() / np.abs(exact).max()
 
 
+def radix4_module_basis_check(frames, N, wc, ws, exact):
+    """R = 4 with the module's own rows (twiddles already inside the odd phases):
+        U_r[k] = sum_m x[4m + r] (w_cos - i w_sin)[k][4m + r],      k = 0 .. N/8
+        X[k]        =       U0 +   U1 + U2 +   U3        X[N/4 + k] = U0 - i U1 - U2 + i U3
+        X[N/4 - k]  = conj(U0) - i conj(U1) - conj(U2) + i conj(U3)
+        X[N/2 - k]  = conj(U0 - U1 + U2 - U3)
+    — additions, sign flips and re/im swaps only."""
+    f = np.float64
+    Q = N // 8
+    U = [frames[:, r::4].astype(f) @ wc[: Q + 1, r::4].astype(f).T
+         - 1j * (frames[:, r::4].astype(f) @ ws[: Q + 1, r::4].astype(f).T) for r in range(4)]
+    X = np.zeros_like(exact)
+    k = np.arange(Q + 1)
+    X[:, k] = U[0] + U[1] + U[2] + U[3]
+    X[:, N // 4 + k] = U[0] - 1j * U[1] - U[2] + 1j * U[3]
+    X[:, N // 4 - k] = np.conj(U[0]) - 1j * np.conj(U[1]) - np.conj(U[2]) + 1j * np.conj(U[3])
+    X[:, N // 2 - k] = np.conj(U[0] - U[1] + U[2] - U[3])
+    return np.abs(X - exact).max() / np.abs(exact).max()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-fft", type=int, default=2048)
@@ -151,6 +171,8 @@ def main():
               f"algebra error {np.abs(X64 - exact).max() / scale:.1e}   "
               f"split-bf16 error {np.abs(X3 - exact).max() / scale:.2e}   "
               f"epilogue {R} complex MADs per bin")
+    print(f"radix 4 with the module's own basis rows (add / swap butterflies only): "
+          f"error {radix4_module_basis_check(frames, N, wc, ws, exact):.1e}")
     print(f"radix 2 kernel layout (Nyquist packed into the k = 0 imaginary slot, butterfly epilogue): "
           f"error {radix2_kernel_layout_check(frames, N, window, exact):.1e}")
 
