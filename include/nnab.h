@@ -89,6 +89,20 @@ int nnab_pack_tile_n(int F);
 size_t nnab_packed_basis_bytes(int F, int K);
 int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K,
                     void* packed, void* stream);
+/* EXPERIMENTAL (branch radix2-wip): same buffer size, explicit layout request.
+ *   NNAB_LAYOUT_DENSE (0)   the layout above
+ *   NNAB_LAYOUT_RADIX2 (2)  decimation-in-time layout for a DFT-STRUCTURED basis with F = K/2 + 1,
+ *                           K % 256 == 0: the caller vouches that rows k and F-1-k mirror each other
+ *                           (w[F-1-k][n] = (-1)^n w[k][n] for cos rows, -(-1)^n for sin rows), which
+ *                           holds for create_fourier_kernels(freq_scale='no') times any window
+ *                           (utils.py:241-393) and for nothing trained;
+ *   NNAB_LAYOUT_GROUPS (3)  8-bin (re | im) row groups for the per-K-block-width kernel (F <= 128).
+ * The forward entry points recognise the layout of the buffer they are given. */
+#define NNAB_LAYOUT_DENSE 0
+#define NNAB_LAYOUT_RADIX2 2
+#define NNAB_LAYOUT_GROUPS 3
+int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int layout,
+                       void* packed, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * STFT.forward — features/stft.py:256-316.

@@ -88,6 +88,7 @@ SIGNATURES = {
         [_P, _P, c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_int, c_int, _P, _P,
          c_size_t, _P],
     ),
+    "nnab_pack_basis_ex": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "nnab_debug_varn_plan": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nnab_fir_decimate": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
     "nnab_fir_decimate_adjoint": (
@@ -231,9 +232,14 @@ def _rows(x: torch.Tensor):
 # --------------------------------------------------------------------------- #
 # basis packing (tcgen05 path)
 # --------------------------------------------------------------------------- #
-def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor):
+LAYOUT_DENSE, LAYOUT_RADIX2, LAYOUT_GROUPS = 0, 2, 3
+
+
+def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor, layout: int = LAYOUT_DENSE):
     """bf16 hi/lo split of an (F, K) fp32 basis pair in the TMA/UMMA layout, or
-    ``None`` when the library has no tcgen05 kernel for it."""
+    ``None`` when the library has no tcgen05 kernel for it.  ``layout`` (EXPERIMENTAL):
+    LAYOUT_RADIX2 for a basis the caller has checked with ``is_dft_structured``,
+    LAYOUT_GROUPS for long CQT banks."""
     L = lib()
     F, K = w_re.shape
     nbytes = L.nnab_packed_basis_bytes(F, K)
@@ -241,8 +247,12 @@ def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor):
         return None
     packed = torch.empty(nbytes, dtype=torch.uint8, device=w_re.device)
     with torch.cuda.device(w_re.device):
-        _check(L.nnab_pack_basis(_ptr(w_re), _ptr(w_im), F, K, _ptr(packed), _stream(w_re.device)),
-               "nnab_pack_basis")
+        if layout == LAYOUT_DENSE:
+            rc = L.nnab_pack_basis(_ptr(w_re), _ptr(w_im), F, K, _ptr(packed), _stream(w_re.device))
+        else:
+            rc = L.nnab_pack_basis_ex(_ptr(w_re), _ptr(w_im), F, K, int(layout), _ptr(packed),
+                                      _stream(w_re.device))
+        _check(rc, "nnab_pack_basis")
     return packed
 
 

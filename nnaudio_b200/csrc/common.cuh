@@ -104,6 +104,8 @@ size_t tc_packed_bytes(int F, int K);
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream);
 int tc_tile_n(int F);
+int tc_pack_basis_layout(const float* w_re, const float* w_im, int F, int K, int layout, void* packed,
+                         cudaStream_t stream);
 // split-signal geometry / helpers for callers that manage the planes themselves (pyramid)
 void tc_split_geometry(int64_t B, int64_t L, int K, int hop, int pad, int64_t* t_slots,
                        int64_t* plane_stride, int* hop_eff);

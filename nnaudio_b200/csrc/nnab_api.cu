@@ -177,6 +177,13 @@ int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K, void* pa
   return tc_pack_basis(w_re, w_im, F, K, packed, (cudaStream_t)stream);
 }
 
+int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int layout, void* packed,
+                       void* stream) {
+  if (w_re == nullptr || w_im == nullptr || packed == nullptr || F <= 0 || K <= 0)
+    return NNAB_EINVAL;
+  return tc_pack_basis_layout(w_re, w_im, F, K, layout, packed, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ STFT ----
 size_t nnab_stft_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop, int center,
                                  int path) {

@@ -222,8 +222,25 @@ bool tc_varn_basis_ok(int F, int K);
 int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void* packed,
                        cudaStream_t stream);
 
+// layout: 0 = dense (always valid); 2 = two-segment decimation-in-time layout — the CALLER vouches
+// that the basis is DFT-structured (rows k and F-1-k mirror each other, see
+// nnaudio_b200/features/_common.py:is_dft_structured); 3 = 8-bin-group layout for the
+// per-K-block-width kernel (any basis with F <= 128).  NNAB_RADIX=0 / NNAB_VARN=0 force dense.
+int tc_pack_basis_layout(const float* w_re, const float* w_im, int F, int K, int layout, void* packed,
+                         cudaStream_t stream) {
+  const char* er = getenv("NNAB_RADIX");
+  const char* ev = getenv("NNAB_VARN");
+  if (layout == 2 && !(er != nullptr && atoi(er) == 0) && tc_radix2_basis_ok(F, K))
+    return tc_pack_basis_radix2(w_re, w_im, F, K, packed, stream);
+  if (layout == 3 && !(ev != nullptr && atoi(ev) == 0) && tc_varn_basis_ok(F, K))
+    return tc_pack_basis_varn(w_re, w_im, F, K, packed, stream);
+  if (layout != 0 && layout != 2 && layout != 3) return NNAB_EINVAL;
+  return tc_pack_basis(w_re, w_im, F, K, packed, stream);
+}
+
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream) {
+  // legacy entry: experimental layouts only when the environment asks for them
   if (tc_radix2_enabled() && tc_radix2_basis_ok(F, K))
     return tc_pack_basis_radix2(w_re, w_im, F, K, packed, stream);
   if (tc_varn_enabled() && tc_varn_basis_ok(F, K) && K >= 4096)

@@ -112,6 +112,25 @@ class AdjointBasis:
         return self._cache.lookup(w_re.device, key, lambda: _C.pack_adjoint_basis(w_re, w_im))
 
 
+def is_dft_structured(w_re: torch.Tensor, w_im: torch.Tensor, rtol: float = 1e-6) -> bool:
+    """True when an (F, K) basis pair has the mirror structure of a one-sided windowed DFT with
+    F = K/2 + 1: ``w_re[F-1-k][n] = (-1)^n w_re[k][n]`` and ``w_im[F-1-k][n] = -(-1)^n w_im[k][n]``
+    (any window: it multiplies columns).  That is exactly what the decimation-in-time kernel relies
+    on, so it is checked on the buffers themselves — a loaded or trained basis that lost the
+    structure simply takes the dense kernel.  EXPERIMENTAL (branch radix2-wip)."""
+    F, K = w_re.shape
+    if F != K // 2 + 1 or K % 256 != 0 or K < 512:
+        return False
+    sign = 1.0 - 2.0 * (torch.arange(K, device=w_re.device) % 2).to(w_re.dtype)
+    scale = float(torch.maximum(w_re.abs().max(), w_im.abs().max()))
+    if scale == 0.0:
+        return False
+    tol = rtol * scale
+    ok_re = (w_re.flip(0) - w_re * sign).abs().max() <= tol
+    ok_im = (w_im.flip(0) + w_im * sign).abs().max() <= tol
+    return bool(ok_re) and bool(ok_im)
+
+
 class PackedBasis:
     """Cache of the (F, K) fp32 views and the bf16 hi/lo packed copy of a basis
     pair, invalidated when the source tensors change (load_state_dict, .to(),
@@ -120,9 +139,25 @@ class PackedBasis:
     def __init__(self):
         self._cache = PerDeviceCache()
 
-    def get(self, w_re: torch.Tensor, w_im: torch.Tensor):
-        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version)
-        return self._cache.lookup(w_re.device, key, lambda: _C.pack_basis(w_re, w_im))
+    def get(self, w_re: torch.Tensor, w_im: torch.Tensor, allow_radix: bool = False,
+            groups: bool = False):
+        """``allow_radix``: the module computes a plain one-sided STFT with this basis, so the
+        decimation-in-time layout may be used when the buffers pass ``is_dft_structured``;
+        ``groups``: long CQT bank for the per-K-block-width kernel.  Both EXPERIMENTAL and only
+        active with NNAUDIO_B200_EXPERIMENTAL=1."""
+        import os
+
+        def build():
+            layout = _C.LAYOUT_DENSE
+            if os.environ.get("NNAUDIO_B200_EXPERIMENTAL", "0") == "1":
+                if allow_radix and is_dft_structured(w_re, w_im):
+                    layout = _C.LAYOUT_RADIX2
+                elif groups and w_re.shape[0] <= 128 and w_re.shape[1] >= 4096:
+                    layout = _C.LAYOUT_GROUPS
+            return _C.pack_basis(w_re, w_im, layout) if layout else _C.pack_basis(w_re, w_im)
+
+        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, allow_radix, groups)
+        return self._cache.lookup(w_re.device, key, build)
 
 
 def as_matrix(buf: torch.Tensor) -> torch.Tensor:

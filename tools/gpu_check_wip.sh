@@ -12,6 +12,8 @@ for wl in stft2048 cfg2 cfg5; do
       > gpurun_out/wip_radix2_$wl.json 2>> gpurun_out/wip_err.txt
   cut -c1-260 gpurun_out/wip_radix2_$wl.json
 done
+# 1b. the same through the host layer's own selection (structure check + explicit layout request)
+NNAUDIO_B200_EXPERIMENTAL=1 run timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q --timeout 120
 # 2. per-K-block width, CQT1992v2
 NNAB_VARN=1 run timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 \
     -k "cqt1992v2 or sweep-cqt-1992"
