@@ -93,7 +93,7 @@ bool tc_radix2_enabled();
 size_t tc_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
   const SplitGeom g = split_geom(B, L, K, hop, pad);
   size_t n = (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
-  if (tc_radix2_enabled() && hop % 2 == 0 && K % 256 == 0) {
+  if (hop % 2 == 0 && K % 256 == 0) {  // either layout may be chosen at pack time
     const size_t r2 = tc_radix2_workspace_bytes(B, L, K, hop, pad);
     if (r2 > n) n = r2;
   }
