@@ -18,6 +18,7 @@
 //                coalesced stores in the reference's (B, F, T[,2]) layout
 //   smem full/empty mbarrier ring + double-buffered TMEM accumulators.
 #include <cuda.h>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 #include <algorithm>
@@ -2045,11 +2046,15 @@ template <int BK, int STAGES, int FMT>
 static int launch_tc_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                                 int grid, cudaStream_t stream) {
   using S = TcSmem<BK, STAGES>;
-  static bool configured = false;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
     NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc_kernel<BK, STAGES, FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    configured = true;
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
   framed_tc_kernel<BK, STAGES, FMT><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, prm);
   NNAB_LAUNCH_CHECK();
@@ -2060,11 +2065,15 @@ template <int BK, int STAGES, int FMT>
 static int launch_tc2_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                                  int n_pairs, cudaStream_t stream) {
   using S = Tc2Smem<BK, STAGES>;
-  static bool configured = false;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
     NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2_kernel<BK, STAGES, FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    configured = true;
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * n_pairs));
@@ -2195,11 +2204,15 @@ template <int FMT>
 static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                            int seg_rows, int n_pairs, cudaStream_t stream) {
   using S = Tc2Smem<64, 3>;
-  static bool configured = false;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
     NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    configured = true;
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * n_pairs));
@@ -2379,11 +2392,15 @@ static int launch_tc2v_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const 
                            const TcParams& prm, const VarNPlan& plan, int n_pairs,
                            cudaStream_t stream) {
   using S = Tc2Smem<64, 3>;
-  static bool configured = false;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
     NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2v_kernel<FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    configured = true;
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * n_pairs));
