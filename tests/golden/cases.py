@@ -167,6 +167,19 @@ DESIGN_CASES = [
 ]
 
 
+# Forward outputs for the constructor sweep (default output format, one short clip each): CPU
+# host-layer and oracle parity on configurations beyond CASES.  Length per class keeps the
+# fixture small; GPU runs of these configurations are round-2 work.
+def sweep_input(case_id: str, cls: str):
+    length = {"STFT": 6000, "MelSpectrogram": 12000, "MFCC": 12000, "Gammatonegram": 12000,
+              "CQT1992v2": 24000, "CQT2010v2": 40000, "VQT": 40000, "CQT1992": 24000, "CQT2010": 40000}[cls]
+    seed = 2000 + sum(ord(c) for c in case_id) % 1000
+    return ("randn", seed, (1, length))
+
+
+SWEEP_FORWARD = [c for c in DESIGN_CASES if c[1] != "iSTFT"]
+
+
 # Error-behaviour scenarios: what the reference raises (exception type) for malformed constructor
 # arguments and inputs; recorded into ref_errors.json.  ("ctor",) | ("forward", shape, kwargs) |
 # ("inverse", shape, kwargs)

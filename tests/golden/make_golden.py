@@ -28,7 +28,7 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 sys.path.insert(0, HERE)
 
-from cases import (CASES, DESIGN_CASES, ERROR_CASES, GRAD_CASES, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
+from cases import (CASES, DESIGN_CASES, ERROR_CASES, GRAD_CASES, SWEEP_FORWARD, sweep_input, ISTFT_CASES, ISTFT_GRAD_CASES, REF_GROUND_TRUTHS,  # noqa: E402
                    SWEEP_CTOR, WGRAD_CASES, attribute_surface, loss_weights, make_input, out_key)
 
 from nnAudio import features as ref_features  # noqa: E402
@@ -77,6 +77,15 @@ def main():
         buffers[cid] = {k: [list(v.shape), sha(v)] for k, v in mod.state_dict().items()
                         if v is not None}
         print(f"{cid:60s} {len(buffers[cid])} buffers")
+    for cid, cls, ctor in SWEEP_FORWARD:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = make_module(ref_features, cls, ctor)
+            x = torch.from_numpy(make_input(sweep_input(cid, cls)))
+            with torch.no_grad():
+                y = mod(x)
+        outputs["sweep|" + cid] = y.numpy().astype(np.float32)
+        print(f"{'sweep|' + cid:60s} {tuple(y.shape)}")
     attributes = {}
     for cid, cls, ctor in [(c[0], c[1], c[2]) for c in CASES] + list(DESIGN_CASES):
         with warnings.catch_warnings():

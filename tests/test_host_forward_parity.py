@@ -61,3 +61,29 @@ def test_inverse_modules_reproduce_reference(case, monkeypatch):
     assert tuple(y.shape) == want.shape
     emax, el2 = rel_errors(y.numpy(), want)
     assert emax < 2e-5 and el2 < 2e-5, (cid, emax, el2)
+
+
+from cases import SWEEP_FORWARD, make_input, sweep_input  # noqa: E402
+from helpers import run_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("case", SWEEP_FORWARD, ids=[c[0] for c in SWEEP_FORWARD])
+def test_constructor_sweep_forward_matches_reference(case, monkeypatch):
+    """21 further configurations (windows, frequency scales, htk / un-normalised mel, 24 / 36 bins per
+    octave, filter_scale, VQT gammas, no early downsampling ...): our host layer (float64 stand-ins
+    for the C wrappers) AND the oracle against the unmodified reference's default-format output."""
+    cid, cls, ctor = case
+    x = make_input(sweep_input(cid, cls))
+    want = ref_outputs()["sweep|" + cid]
+    mod = build(cls, ctor)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        orc = run_oracle(cls, mod, x, {})
+        cpu_kernels.install(monkeypatch)
+        with torch.no_grad():
+            got = mod(torch.from_numpy(x)).numpy()
+    tol = 4e-4 if cls == "MFCC" else 2e-5
+    for name, y in (("host layer", got), ("oracle", orc)):
+        assert y.shape == want.shape, (cid, name)
+        emax, el2 = rel_errors(y, want)
+        assert emax < tol and el2 < tol, (cid, name, emax, el2)
