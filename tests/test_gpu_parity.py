@@ -131,3 +131,21 @@ def test_simt_and_auto_paths_agree_on_large_shape():
     b = _run(mod, x, {}, "auto")
     emax, el2 = rel_errors(a, b)
     assert emax < TOL and el2 < TOL, (emax, el2)
+
+
+from cases import SWEEP_FORWARD, sweep_input  # noqa: E402
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("case", SWEEP_FORWARD, ids=[c[0] for c in SWEEP_FORWARD])
+def test_cuda_constructor_sweep_matches_reference(case, path):
+    """The 21-configuration constructor sweep on the GPU (first run: round 2)."""
+    cid, cls, ctor = case
+    mod = build(cls, ctor).cuda()
+    x = make_input(sweep_input(cid, cls))
+    got = _run(mod, x, {}, path)
+    want = ref_outputs()["sweep|" + cid]
+    assert got.shape == want.shape
+    tol = 4e-4 if cls == "MFCC" else TOL
+    emax, el2 = rel_errors(got, want)
+    assert emax < tol and el2 < tol, (cid, path, emax, el2)
