@@ -2137,7 +2137,8 @@ bool tc_radix2_enabled() {
 
 // basis shapes the radix packing accepts (the caller vouches that the basis is DFT-structured)
 bool tc_radix2_basis_ok(int F, int K) {
-  return K >= 512 && K % 256 == 0 && F == K / 2 + 1;
+  // K < 8192: longer kernels take the split-K path of the dense kernel (accumulation-length bound)
+  return K >= 512 && K < 8192 && K % 256 == 0 && F == K / 2 + 1;
 }
 
 // layout of an experimental packed basis, keyed by its device pointer (WIP: a header inside the

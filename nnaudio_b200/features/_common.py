@@ -119,7 +119,7 @@ def is_dft_structured(w_re: torch.Tensor, w_im: torch.Tensor, rtol: float = 1e-6
     on, so it is checked on the buffers themselves — a loaded or trained basis that lost the
     structure simply takes the dense kernel.  EXPERIMENTAL (branch radix2-wip)."""
     F, K = w_re.shape
-    if F != K // 2 + 1 or K % 256 != 0 or K < 512:
+    if F != K // 2 + 1 or K % 256 != 0 or K < 512 or K >= 8192:
         return False
     sign = 1.0 - 2.0 * (torch.arange(K, device=w_re.device) % 2).to(w_re.dtype)
     scale = float(torch.maximum(w_re.abs().max(), w_im.abs().max()))
