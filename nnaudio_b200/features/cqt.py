@@ -134,7 +134,8 @@ class CQT1992v2(nn.Module):
             raise RuntimeError("Kernel size can't be greater than actual input size")
 
         k_real, k_imag = as_matrix(self.cqt_kernels_real), as_matrix(self.cqt_kernels_imag)
-        packed = self._packed.get(k_real, k_imag, groups=not self.trainable)
+        packed = self._packed.get(k_real, k_imag,
+                                  groups=(not self.trainable) and self.hop_length % 8 == 0)
         k_begin, k_end = self._tap_support()
         scale, scale_all = None, 1.0
         if normalization_type == "librosa":
