@@ -1438,7 +1438,6 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // packed basis [hi|lo][seg r][tile][re half | negated im half][K/2]; TMEM: segment r of a tile
 // accumulates into columns [r*bn, (r+1)*bn) of the 256-column buffer (bn = 128).
 // ===========================================================================
-constexpr int R2_BN = 128;  // columns per segment: 64 bins x (re, im)
 
 // One thread = 8 consecutive elements of BOTH sample-phase planes (16 padded samples).
 __global__ void __launch_bounds__(256) pad_split_radix2_kernel(
@@ -1476,15 +1475,15 @@ __global__ void __launch_bounds__(256) pad_split_radix2_kernel(
 // Nyquist bin: seg 0 -> +w_re[K/4][n], seg 1 -> -w_im[K/4][n].
 __global__ void __launch_bounds__(256) pack_basis_radix2_kernel(
     const float* __restrict__ w_re, const float* __restrict__ w_im, int K, int rows_seg, int kpad2,
-    __nv_bfloat16* __restrict__ packed) {
+    int bn, __nv_bfloat16* __restrict__ packed) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k8 = kpad2 / 8;
   if (idx >= (int64_t)2 * rows_seg * k8) return;
   const int row = (int)(idx / k8);  // 0 .. 2*rows_seg-1
   const int k0 = (int)(idx % k8) * 8;
   const int seg = row / rows_seg, r = row % rows_seg;
-  const int half = R2_BN / 2;
-  const int tile = r / R2_BN, within = r % R2_BN;
+  const int half = bn / 2;
+  const int tile = r / bn, within = r % bn;
   const int part = within / half, j = within % half;
   const int k = tile * half + j;
   const int nyq = K / 4;
@@ -1592,11 +1591,15 @@ __device__ __forceinline__ void epilogue_tile_radix2(const TcParams& p, uint32_t
 }
 
 // CTA-pair kernel with two K segments per tile (see framed_tc2_kernel for the pipeline roles).
-template <int FMT>
+// BNS = columns per segment: 128 (64 bins; 2 x 128 columns per tile, TMEM double-buffered) or
+// 256 (128 bins; the two segments fill all 512 columns, so the epilogue of a tile is not overlapped
+// with the next tile's MMAs, but every MMA runs at the full N = 256).
+template <int FMT, int BNS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const TcParams p, const int seg_rows) {
   constexpr int BK = 64, STAGES = 3;
+  constexpr int NACC = (BNS == 128) ? 2 : 1;
   using S = Tc2Smem<BK, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1641,7 +1644,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  constexpr int halfn = R2_BN / 2;
+  constexpr int halfn = BNS / 2;
   constexpr uint32_t b_half_bytes = (uint32_t)halfn * BK * 2;
   const int kb_n = p.kb_end[0];  // K/2 in 64-sample blocks, same for every tile and segment
 
@@ -1654,7 +1657,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int n_tile = tile - m_tile * p.num_n_tiles;
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
         for (int seg = 0; seg < 2; ++seg) {
-          const int n0 = seg * seg_rows + n_tile * R2_BN + (int)cta * halfn;
+          const int n0 = seg * seg_rows + n_tile * BNS + (int)cta * halfn;
           for (int kb = 0; kb < kb_n; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sb = base + stage * S::STAGE_BYTES;
@@ -1673,7 +1676,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
   } else if (warp == 1) {
     if (cta == 0 && elect_one()) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(R2_BN >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNS >> 3) << 17) |
                              ((uint32_t)((2 * TC_BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -1683,7 +1686,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         for (int seg = 0; seg < 2; ++seg) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE + (uint32_t)(seg * R2_BN);
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE + (uint32_t)(seg * BNS);
           uint32_t accumulate = 0;
           for (int kb = 0; kb < kb_n; ++kb) {
             mbar_wait(full_bar(stage), phase);
@@ -1706,7 +1709,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           }
         }
         umma_commit_2sm(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
@@ -1725,7 +1728,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -2135,10 +2138,17 @@ bool tc_radix2_enabled() {
   return e != nullptr && atoi(e) == 2;
 }
 
+// columns per segment: 128 (default) or 256 (NNAB_RADIX_BN=256); read at pack and at launch time,
+// so it must not change while a packed basis is alive
+static int radix2_bn() {
+  const char* e = getenv("NNAB_RADIX_BN");
+  return (e != nullptr && atoi(e) == 256) ? 256 : 128;
+}
+
 // basis shapes the radix packing accepts (the caller vouches that the basis is DFT-structured)
 bool tc_radix2_basis_ok(int F, int K) {
   // K < 8192: longer kernels take the split-K path of the dense kernel (accumulation-length bound)
-  return K >= 512 && K < 8192 && K % 256 == 0 && F == K / 2 + 1;
+  return K >= 512 && K < 8192 && K % (2 * radix2_bn()) == 0 && F == K / 2 + 1;
 }
 
 // layout of an experimental packed basis, keyed by its device pointer (WIP: a header inside the
@@ -2183,7 +2193,7 @@ int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, voi
   const int kpad2 = K / 2;     // K % 256 == 0 -> already a multiple of 64
   const int64_t threads = (int64_t)2 * rows_seg * (kpad2 / 8);
   pack_basis_radix2_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
-      w_re, w_im, K, rows_seg, kpad2, (__nv_bfloat16*)packed);
+      w_re, w_im, K, rows_seg, kpad2, radix2_bn(), (__nv_bfloat16*)packed);
   NNAB_LAUNCH_CHECK();
   mark_radix2_packed(packed, true);
   return NNAB_OK;
@@ -2201,7 +2211,7 @@ static bool radix2_problem_ok(const FramedProblem& q) {
   }
 }
 
-template <int FMT>
+template <int FMT, int BNS>
 static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                            int seg_rows, int n_pairs, cudaStream_t stream) {
   using S = Tc2Smem<64, 3>;
@@ -2211,7 +2221,7 @@ static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const T
   NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
   const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
-    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT>,
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT, BNS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
     configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
@@ -2227,7 +2237,7 @@ static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const T
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2r_kernel<FMT>, ma, mb, prm, seg_rows));
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2r_kernel<FMT, BNS>, ma, mb, prm, seg_rows));
   count_launch();
   return NNAB_OK;
 }
@@ -2260,18 +2270,19 @@ static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, v
   if (sms < 2) sms = 2;
 
   const int seg_rows = k2;            // rows of one segment in the packed basis
-  const int n_tiles = seg_rows / R2_BN;
+  const int bns = radix2_bn();
+  const int n_tiles = seg_rows / bns;
   CUtensorMap ma, mb;
   int rc = encode_3d(&ma, planes, (uint64_t)hop2, (uint64_t)g.rows, 4, (uint64_t)hop2 * 2,
                      (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
   if (rc) return rc;
   rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)k2, (uint64_t)(2 * seg_rows), 2,
-                 (uint64_t)k2 * 2, (uint64_t)(2 * seg_rows) * k2 * 2, 64, R2_BN / 2, 64);
+                 (uint64_t)k2 * 2, (uint64_t)(2 * seg_rows) * k2 * 2, 64, bns / 2, 64);
   if (rc) return rc;
 
   TcParams prm{};
   prm.num_n_tiles = n_tiles;
-  prm.bn = R2_BN;
+  prm.bn = bns;
   prm.rows_mode = 1;
   prm.hop = hop2;
   prm.nv = g.nv;
@@ -2291,11 +2302,20 @@ static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, v
   prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
   const int64_t ptiles = (int64_t)prm.num_m_tiles * n_tiles;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  if (bns == 256) {
+    switch (q.fmt) {
+      case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
+      case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
+      case FMT_POWER: return launch_tc2r_fmt<4, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
+      case FMT_FBANK: return launch_tc2r_fmt<5, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
+      default: return NNAB_EINVAL;
+    }
+  }
   switch (q.fmt) {
-    case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case FMT_POWER: return launch_tc2r_fmt<4>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case FMT_FBANK: return launch_tc2r_fmt<5>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_POWER: return launch_tc2r_fmt<4, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_FBANK: return launch_tc2r_fmt<5, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
 }

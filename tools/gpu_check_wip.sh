@@ -12,6 +12,13 @@ for wl in stft2048 cfg2 cfg5; do
       > gpurun_out/wip_radix2_$wl.json 2>> gpurun_out/wip_err.txt
   cut -c1-260 gpurun_out/wip_radix2_$wl.json
 done
+# 1a. tile-width A/B: 128 bins per tile, N = 256 per MMA, TMEM single-buffered
+for wl in stft2048 cfg2; do
+  NNAB_RADIX=2 NNAB_RADIX_BN=256 timeout 150 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --no-e2e \
+      > gpurun_out/wip_radix2_bn256_$wl.json 2>> gpurun_out/wip_err.txt
+  cut -c1-260 gpurun_out/wip_radix2_bn256_$wl.json
+done
+NNAB_RADIX=2 NNAB_RADIX_BN=256 run timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "stft_2048 or mel_"
 # 1b. the same through the host layer's own selection (structure check + explicit layout request)
 NNAUDIO_B200_EXPERIMENTAL=1 run timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q --timeout 120
 # 2. per-K-block width, CQT1992v2

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import nnaudio_oracle as oracle  # noqa: E402
 import nnaudio_b200 as nb  # noqa: E402
 
-R2_BN = 128
+R2_BN = int(__import__('os').environ.get('NNAB_RADIX_BN', '128'))
 
 
 def pack_basis_radix2(w_re, w_im, K):
