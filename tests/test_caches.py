@@ -113,3 +113,29 @@ def test_tap_support_cache_follows_the_buffers():
         q.cqt_kernels_imag.zero_()
     b1, e1 = q._tap_support()
     assert (b1 == 0).all() and (e1 == 0).all()
+
+
+def test_modules_deepcopy_and_pickle_like_plain_nn_modules():
+    """Users copy / torch.save whole modules (the reference's are plain nn.Modules): the host-side
+    caches must not get in the way, and the copy must own independent buffers."""
+    import copy
+    import io
+    import pickle
+
+    mods = [nb.STFT(n_fft=256, iSTFT=True, verbose=False), nb.MelSpectrogram(sr=16000, n_fft=256, n_mels=20, verbose=False),
+            nb.MFCC(sr=16000, n_fft=256, n_mels=20, n_mfcc=8, verbose=False),
+            nb.Gammatonegram(sr=16000, n_fft=256, n_bins=8, verbose=False),
+            nb.CQT1992v2(sr=22050, fmin=220, n_bins=12, verbose=False), nb.CQT2010v2(sr=22050, n_bins=24, fmin=220, verbose=False),
+            nb.VQT(sr=22050, n_bins=24, fmin=220, gamma=3, verbose=False), nb.iSTFT(n_fft=256, verbose=False),
+            nb.CQT2010(sr=22050, n_bins=24, fmin=220, verbose=False), nb.Griffin_Lim(n_fft=256, n_iter=2)]
+    for m in mods:
+        c = copy.deepcopy(m)
+        p = pickle.loads(pickle.dumps(m))
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        for other in (c, p):
+            assert type(other) is type(m)
+            sd, so = m.state_dict(), other.state_dict()
+            assert sd.keys() == so.keys()
+            for k in sd:
+                assert torch.equal(sd[k], so[k]) and (sd[k].numel() == 0 or sd[k].data_ptr() != so[k].data_ptr())
