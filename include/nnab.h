@@ -101,6 +101,8 @@ int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K,
 #define NNAB_LAYOUT_DENSE 0
 #define NNAB_LAYOUT_RADIX2 2
 #define NNAB_LAYOUT_GROUPS 3
+#define NNAB_LAYOUT_RADIX4 4 /* as RADIX2 with four sample phases; additionally needs rows k and k + K/4
+                                related by (-i)^n (true for the same bases) and hop % 256 == 0 */
 int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int layout,
                        void* packed, void* stream);
 

@@ -232,7 +232,7 @@ def _rows(x: torch.Tensor):
 # --------------------------------------------------------------------------- #
 # basis packing (tcgen05 path)
 # --------------------------------------------------------------------------- #
-LAYOUT_DENSE, LAYOUT_RADIX2, LAYOUT_GROUPS = 0, 2, 3
+LAYOUT_DENSE, LAYOUT_RADIX2, LAYOUT_GROUPS, LAYOUT_RADIX4 = 0, 2, 3, 4
 
 
 def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor, layout: int = LAYOUT_DENSE):

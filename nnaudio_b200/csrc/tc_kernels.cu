@@ -231,11 +231,14 @@ int tc_pack_basis_layout(const float* w_re, const float* w_im, int F, int K, int
                          cudaStream_t stream) {
   const char* er = getenv("NNAB_RADIX");
   const char* ev = getenv("NNAB_VARN");
-  if (layout == 2 && !(er != nullptr && atoi(er) == 0) && tc_radix2_basis_ok(F, K))
-    return tc_pack_basis_radix2(w_re, w_im, F, K, packed, stream);
+  if ((layout == 2 || layout == 4) && !(er != nullptr && atoi(er) == 0)) {
+    int tc_pack_basis_radix(const float*, const float*, int, int, int, void*, cudaStream_t);
+    const int rc = tc_pack_basis_radix(w_re, w_im, F, K, layout, packed, stream);
+    if (rc != NNAB_EINVAL) return rc;  // shape not eligible: fall through to dense
+  }
   if (layout == 3 && !(ev != nullptr && atoi(ev) == 0) && tc_varn_basis_ok(F, K))
     return tc_pack_basis_varn(w_re, w_im, F, K, packed, stream);
-  if (layout != 0 && layout != 2 && layout != 3) return NNAB_EINVAL;
+  if (layout != 0 && layout != 2 && layout != 3 && layout != 4) return NNAB_EINVAL;
   return tc_pack_basis(w_re, w_im, F, K, packed, stream);
 }
 
@@ -1439,8 +1442,10 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // accumulates into columns [r*bn, (r+1)*bn) of the 256-column buffer (bn = 128).
 // ===========================================================================
 
-// One thread = 8 consecutive elements of BOTH sample-phase planes (16 padded samples).
-__global__ void __launch_bounds__(256) pad_split_radix2_kernel(
+// One thread = 8 consecutive elements of ALL R sample-phase planes (8 R padded samples).
+// planes: [r][hi|lo], plane_r[i] = xpad[R i + r].
+template <int R>
+__global__ void __launch_bounds__(256) pad_split_radix_kernel(
     const float* __restrict__ x, int64_t L, int64_t x_pitch, int pad, int pad_mode,
     int64_t clip_pitch, int64_t plane_stride, __nv_bfloat16* __restrict__ planes) {
   const int64_t b = blockIdx.y;
@@ -1448,11 +1453,11 @@ __global__ void __launch_bounds__(256) pad_split_radix2_kernel(
   if (i0 >= clip_pitch) return;
   const float* __restrict__ xb = x + b * x_pitch;
   const int64_t padded_len = L + 2 * (int64_t)pad;
-  __align__(16) __nv_bfloat16 hi[2][8];
-  __align__(16) __nv_bfloat16 lo[2][8];
+  __align__(16) __nv_bfloat16 hi[R][8];
+  __align__(16) __nv_bfloat16 lo[R][8];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const int64_t i = 2 * i0 + e;  // index into the centre-padded clip
+  for (int e = 0; e < 8 * R; ++e) {
+    const int64_t i = R * i0 + e;  // index into the centre-padded clip
     float v = 0.f;
     if (i < padded_len) {
       int64_t j = i - pad;
@@ -1460,50 +1465,53 @@ __global__ void __launch_bounds__(256) pad_split_radix2_kernel(
       else if (j >= L) j = (pad_mode == NNAB_PAD_REFLECT) ? 2 * (L - 1) - j : -1;
       if (j >= 0 && j < L) v = __ldg(xb + j);
     }
-    split_bf16(v, hi[e & 1][e >> 1], lo[e & 1][e >> 1]);
+    split_bf16(v, hi[e % R][e / R], lo[e % R][e / R]);
   }
   const int64_t o = b * clip_pitch + i0;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
+  for (int r = 0; r < R; ++r) {
     *reinterpret_cast<uint4*>(planes + (2 * r) * plane_stride + o) = *reinterpret_cast<const uint4*>(hi[r]);
     *reinterpret_cast<uint4*>(planes + (2 * r + 1) * plane_stride + o) = *reinterpret_cast<const uint4*>(lo[r]);
   }
 }
 
-// packed[plane][seg][tile*bn + part*half + j][k2]: bin k = tile*half + j, sample n = 2*k2 + seg.
-// part 0 = w_re rows, part 1 = negated w_im rows; the (k = 0, part 1) slot carries the sub-DFT
-// Nyquist bin: seg 0 -> +w_re[K/4][n], seg 1 -> -w_im[K/4][n].
-__global__ void __launch_bounds__(256) pack_basis_radix2_kernel(
-    const float* __restrict__ w_re, const float* __restrict__ w_im, int K, int rows_seg, int kpad2,
-    int bn, __nv_bfloat16* __restrict__ packed) {
+// packed[plane][seg][tile*bn + part*half + j][kk]: bin k = tile*half + j, sample n = R*kk + seg.
+// part 0 = w_re rows, part 1 = negated w_im rows.  The (k = 0, part 1) slot (always zero) carries
+// the real number that determines the sub-DFT's Nyquist bin U_seg[K/(2R)]:
+//   R = 2: seg 0 -> re, seg 1 -> im        R = 4: seg 0, 1, 3 -> re, seg 2 -> im
+// (tools/radix2_emulation.py, tools/radix4_emulation.py).
+__global__ void __launch_bounds__(256) pack_basis_radix_kernel(
+    const float* __restrict__ w_re, const float* __restrict__ w_im, int K, int R, int rows_seg,
+    int kpadr, int bn, __nv_bfloat16* __restrict__ packed) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int k8 = kpad2 / 8;
-  if (idx >= (int64_t)2 * rows_seg * k8) return;
-  const int row = (int)(idx / k8);  // 0 .. 2*rows_seg-1
+  const int k8 = kpadr / 8;
+  if (idx >= (int64_t)R * rows_seg * k8) return;
+  const int row = (int)(idx / k8);  // 0 .. R*rows_seg-1
   const int k0 = (int)(idx % k8) * 8;
   const int seg = row / rows_seg, r = row % rows_seg;
   const int half = bn / 2;
   const int tile = r / bn, within = r % bn;
   const int part = within / half, j = within % half;
   const int k = tile * half + j;
-  const int nyq = K / 4;
+  const int nyq = K / (2 * R);
+  const bool slot_is_im = (R == 2) ? (seg == 1) : (seg == 2);
   __align__(16) __nv_bfloat16 hi[8];
   __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int k2 = k0 + e;
-    const int n = 2 * k2 + seg;
+    const int kk = k0 + e;
+    const int n = R * kk + seg;
     float v = 0.f;
     if (k < nyq && n < K) {
       if (part == 0) v = __ldg(w_re + (int64_t)k * K + n);
       else if (k != 0) v = -__ldg(w_im + (int64_t)k * K + n);
-      else v = (seg == 0) ? __ldg(w_re + (int64_t)nyq * K + n) : -__ldg(w_im + (int64_t)nyq * K + n);
+      else v = slot_is_im ? -__ldg(w_im + (int64_t)nyq * K + n) : __ldg(w_re + (int64_t)nyq * K + n);
     }
     split_bf16(v, hi[e], lo[e]);
   }
-  const int64_t o = (int64_t)row * kpad2 + k0;
+  const int64_t o = (int64_t)row * kpadr + k0;
   *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(packed + (int64_t)2 * rows_seg * kpad2 + o) = *reinterpret_cast<const uint4*>(lo);
+  *reinterpret_cast<uint4*>(packed + (int64_t)R * rows_seg * kpadr + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // running banded-filterbank sums of one bin stream (ascending or descending bins)
@@ -1591,15 +1599,94 @@ __device__ __forceinline__ void epilogue_tile_radix2(const TcParams& p, uint32_t
 }
 
 // CTA-pair kernel with two K segments per tile (see framed_tc2_kernel for the pipeline roles).
+// Radix-4 butterfly epilogue: TMEM columns of segment s at [s*bns, (s+1)*bns) = [re | im], `half`
+// bins each.  With the module's own basis rows the twiddles are inside the accumulators, so
+//   X[k]       =      U0 +   U1 + U2 +   U3        X[N/4 + k] = U0 - i U1 - U2 + i U3
+//   X[N/4 - k] = conj(U0) - i conj(U1) - conj(U2) + i conj(U3)
+//   X[N/2 - k] = conj(U0 - U1 + U2 - U3)
+// are additions, sign flips and re/im swaps (tools/radix4_emulation.py is the executable spec,
+// including the k = 0 column that also carries the sub-DFT Nyquist bins).
+template <int FMT>
+__device__ __forceinline__ void epilogue_tile_radix4(const TcParams& p, uint32_t trow, int64_t g,
+                                                     int n_tile, int half) {
+  const int64_t b = g / p.t_slots;
+  const int64_t tl = g - b * p.t_slots;
+  const bool valid = (g < p.nv) && (tl < p.T);
+  const int64_t t = tl * p.t_mul + p.t_add;
+  const int k_base = n_tile * half;
+  const int NH = p.epi.F - 1;  // N/2
+  const int NQ = NH / 2;       // N/4
+  const int NE = NH / 4;       // N/8: Nyquist bin of the sub-DFTs
+  const int bns = 2 * half;
+  constexpr int CH = (FMT == NNAB_FMT_COMPLEX) ? 2 : 1;
+  float* dst = nullptr;
+  float* mel = nullptr;
+  if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
+  else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+  MelRun up0, up1, dn0, dn1;
+  auto emit = [&](MelRun& run, int bin, float re, float im) {
+    if constexpr (FMT == 5) {
+      run.add(p.epi, mel, valid, bin, epi_power(p.epi, re, im));
+    } else {
+      if (valid) epi_store_fmt<FMT>(p.epi, dst, bin, re, im);
+    }
+  };
+#pragma unroll 1
+  for (int c0 = 0; c0 < half; c0 += 8) {
+    uint32_t r0[8], i0[8], r1[8], i1[8], r2[8], i2[8], r3[8], i3[8];
+    tmem_ld8(trow + (uint32_t)(0 * bns + c0), r0);
+    tmem_ld8(trow + (uint32_t)(0 * bns + half + c0), i0);
+    tmem_ld8(trow + (uint32_t)(1 * bns + c0), r1);
+    tmem_ld8(trow + (uint32_t)(1 * bns + half + c0), i1);
+    tmem_ld8(trow + (uint32_t)(2 * bns + c0), r2);
+    tmem_ld8(trow + (uint32_t)(2 * bns + half + c0), i2);
+    tmem_ld8(trow + (uint32_t)(3 * bns + c0), r3);
+    tmem_ld8(trow + (uint32_t)(3 * bns + half + c0), i3);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k_base + c0 + j;
+      const float a0 = __uint_as_float(r0[j]), b0 = __uint_as_float(i0[j]);
+      const float a1 = __uint_as_float(r1[j]), b1 = __uint_as_float(i1[j]);
+      const float a2 = __uint_as_float(r2[j]), b2 = __uint_as_float(i2[j]);
+      const float a3 = __uint_as_float(r3[j]), b3 = __uint_as_float(i3[j]);
+      if (k == 0) {
+        // U_s[0] = a_s (real); the im slots b_s hold the packed Nyquist numbers:
+        //   v0 = (b0, 0)  v1 = (b1, -b1)  v2 = (0, b2)  v3 = (b3, b3)
+        MelRun one;
+        emit(one, 0, a0 + a1 + a2 + a3, 0.f);
+        emit(one, NQ, a0 - a2, a3 - a1);
+        emit(one, NH, a0 - a1 + a2 - a3, 0.f);
+        emit(one, NE, b0 + b1 + b3, -b1 + b2 + b3);
+        emit(one, NQ + NE, b0 - b1 - b3, -b1 - b2 + b3);
+        if constexpr (FMT == 5) one.flush(p.epi, mel, valid);
+      } else {
+        emit(up0, k, a0 + a1 + a2 + a3, b0 + b1 + b2 + b3);
+        emit(up1, NQ + k, a0 + b1 - a2 - b3, b0 - a1 - b2 + a3);
+        emit(dn0, NQ - k, a0 - b1 - a2 + b3, -b0 - a1 + b2 + a3);
+        emit(dn1, NH - k, a0 - a1 + a2 - a3, -(b0 - b1 + b2 - b3));
+      }
+    }
+  }
+  if constexpr (FMT == 5) {
+    up0.flush(p.epi, mel, valid);
+    up1.flush(p.epi, mel, valid);
+    dn0.flush(p.epi, mel, valid);
+    dn1.flush(p.epi, mel, valid);
+  }
+}
+
 // BNS = columns per segment: 128 (64 bins; 2 x 128 columns per tile, TMEM double-buffered) or
 // 256 (128 bins; the two segments fill all 512 columns, so the epilogue of a tile is not overlapped
 // with the next tile's MMAs, but every MMA runs at the full N = 256).
-template <int FMT, int BNS>
+// RAD = segments (sample phases) per tile: RAD * BNS <= 256 leaves room for two accumulator buffers.
+template <int FMT, int BNS, int RAD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const TcParams p, const int seg_rows) {
   constexpr int BK = 64, STAGES = 3;
-  constexpr int NACC = (BNS == 128) ? 2 : 1;
+  constexpr int NACC = (RAD * BNS <= 256) ? 2 : 1;
+  static_assert(RAD * BNS <= 512, "segments of one tile must fit the 512 TMEM columns");
   using S = Tc2Smem<BK, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1656,7 +1743,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
-        for (int seg = 0; seg < 2; ++seg) {
+        for (int seg = 0; seg < RAD; ++seg) {
           const int n0 = seg * seg_rows + n_tile * BNS + (int)cta * halfn;
           for (int kb = 0; kb < kb_n; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -1685,7 +1772,7 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
-        for (int seg = 0; seg < 2; ++seg) {
+        for (int seg = 0; seg < RAD; ++seg) {
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE + (uint32_t)(seg * BNS);
           uint32_t accumulate = 0;
           for (int kb = 0; kb < kb_n; ++kb) {
@@ -1724,7 +1811,8 @@ framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
-      epilogue_tile_radix2<FMT>(p, trow, g, n_tile, halfn);
+      if constexpr (RAD == 2) epilogue_tile_radix2<FMT>(p, trow, g, n_tile, halfn);
+      else epilogue_tile_radix4<FMT>(p, trow, g, n_tile, halfn);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -2131,29 +2219,39 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
 
 
 // ---------------------------------------------------------------------------
-// EXPERIMENTAL radix-2 host side (NNAB_RADIX=2)
+// EXPERIMENTAL decimation-in-time host side: radix R = 2 or 4 (NNAB_RADIX=2|4, or an explicit
+// layout request through nnab_pack_basis_ex)
 // ---------------------------------------------------------------------------
-bool tc_radix2_enabled() {
+static int radix_env() {
   const char* e = getenv("NNAB_RADIX");
-  return e != nullptr && atoi(e) == 2;
+  const int r = e != nullptr ? atoi(e) : -1;
+  return r;  // -1 unset, 0 = force dense, 2 / 4
 }
+bool tc_radix2_enabled() { const int r = radix_env(); return r == 2 || r == 4; }
 
-// columns per segment: 128 (default) or 256 (NNAB_RADIX_BN=256); read at pack and at launch time,
-// so it must not change while a packed basis is alive
-static int radix2_bn() {
+// columns per segment: R = 2: 128 (default) or 256 (NNAB_RADIX_BN=256); R = 4: 64 (default) or 128.
+// Read at pack and at launch time, so it must not change while a packed basis is alive.
+static int radix_bn(int R) {
   const char* e = getenv("NNAB_RADIX_BN");
-  return (e != nullptr && atoi(e) == 256) ? 256 : 128;
+  const int v = e != nullptr ? atoi(e) : 0;
+  if (R == 2) return v == 256 ? 256 : 128;
+  return v == 128 ? 128 : 64;
 }
 
-// basis shapes the radix packing accepts (the caller vouches that the basis is DFT-structured)
+// basis shapes the radix packing accepts (the caller vouches that the basis is DFT-structured);
+// K < 8192: longer kernels take the split-K path of the dense kernel (accumulation-length bound)
+static bool radix_basis_ok(int F, int K, int R) {
+  if (R != 2 && R != 4) return false;
+  return K >= 512 && K < 8192 && K % (R * radix_bn(R)) == 0 && F == K / 2 + 1;
+}
 bool tc_radix2_basis_ok(int F, int K) {
-  // K < 8192: longer kernels take the split-K path of the dense kernel (accumulation-length bound)
-  return K >= 512 && K < 8192 && K % (2 * radix2_bn()) == 0 && F == K / 2 + 1;
+  const int r = radix_env();
+  return radix_basis_ok(F, K, r == 4 ? 4 : 2);
 }
 
 // layout of an experimental packed basis, keyed by its device pointer (WIP: a header inside the
 // packed buffer should replace this registry)
-enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2 };
+enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2, PACK_RADIX4 = 3 };
 static std::mutex g_r2_mu;
 static std::unordered_map<const void*, int> g_pack_kind;
 
@@ -2169,39 +2267,49 @@ static void mark_packed(const void* packed, int kind) {
   else g_pack_kind[packed] = kind;
 }
 
-static bool is_radix2_packed(const void* packed) { return packed_kind(packed) == PACK_RADIX2; }
-static void mark_radix2_packed(const void* packed, bool on) {
-  mark_packed(packed, on ? PACK_RADIX2 : PACK_DENSE);
+static bool is_radix2_packed(const void* packed) {
+  const int k = packed_kind(packed);
+  return k == PACK_RADIX2 || k == PACK_RADIX4;
 }
 
 void tc_forget_packed(const void* packed) { mark_packed(packed, PACK_DENSE); }
 
-static SplitGeom radix2_geom(int64_t B, int64_t L, int K, int hop, int pad) {
+static SplitGeom radix_geom(int64_t B, int64_t L, int K, int hop, int pad, int R) {
   const int64_t lp = L + 2 * (int64_t)pad;
-  return split_geom(B, (lp + 1) / 2, K / 2, hop / 2, 0);
+  return split_geom(B, (lp + R - 1) / R, K / R, hop / R, 0);
 }
 
 size_t tc_radix2_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
-  const SplitGeom g = radix2_geom(B, L, K, hop, pad);
-  return (size_t)(4 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+  size_t n = 0;
+  for (int R = 2; R <= 4; R += 2) {
+    if (hop % R != 0 || K % R != 0) continue;
+    const SplitGeom g = radix_geom(B, L, K, hop, pad, R);
+    const size_t v = (size_t)(2 * R * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+    if (v > n) n = v;
+  }
+  return n;
 }
 
-int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
-                         cudaStream_t stream) {
-  if (!tc_radix2_basis_ok(F, K)) return NNAB_EINVAL;
-  const int rows_seg = K / 2;  // (K/4 bins) x (re, im)
-  const int kpad2 = K / 2;     // K % 256 == 0 -> already a multiple of 64
-  const int64_t threads = (int64_t)2 * rows_seg * (kpad2 / 8);
-  pack_basis_radix2_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
-      w_re, w_im, K, rows_seg, kpad2, radix2_bn(), (__nv_bfloat16*)packed);
+int tc_pack_basis_radix(const float* w_re, const float* w_im, int F, int K, int R, void* packed,
+                        cudaStream_t stream) {
+  if (!radix_basis_ok(F, K, R)) return NNAB_EINVAL;
+  const int rows_seg = K / R;  // (K / (2R) bins) x (re, im)
+  const int kpadr = K / R;     // already a multiple of 64
+  const int64_t threads = (int64_t)R * rows_seg * (kpadr / 8);
+  pack_basis_radix_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+      w_re, w_im, K, R, rows_seg, kpadr, radix_bn(R), (__nv_bfloat16*)packed);
   NNAB_LAUNCH_CHECK();
-  mark_radix2_packed(packed, true);
+  mark_packed(packed, R == 4 ? PACK_RADIX4 : PACK_RADIX2);
   return NNAB_OK;
 }
+int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
+                         cudaStream_t stream) {
+  return tc_pack_basis_radix(w_re, w_im, F, K, radix_env() == 4 ? 4 : 2, packed, stream);
+}
 
-static bool radix2_problem_ok(const FramedProblem& q) {
-  if (!tc_radix2_basis_ok(q.F, q.K)) return false;
-  if (q.hop % 2 != 0 || num_phases(q.hop / 2) != 1 || (q.hop / 2) % 64 != 0) return false;
+static bool radix_problem_ok(const FramedProblem& q, int R) {
+  if (!radix_basis_ok(q.F, q.K, R)) return false;
+  if (q.hop % R != 0 || num_phases(q.hop / R) != 1 || (q.hop / R) % 64 != 0) return false;
   if (q.presplit != nullptr || q.h_k_begin != nullptr || q.raw != nullptr) return false;
   switch (q.fmt) {
     case NNAB_FMT_MAGNITUDE: case NNAB_FMT_COMPLEX: case FMT_POWER:
@@ -2211,7 +2319,7 @@ static bool radix2_problem_ok(const FramedProblem& q) {
   }
 }
 
-template <int FMT, int BNS>
+template <int FMT, int BNS, int RAD>
 static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                            int seg_rows, int n_pairs, cudaStream_t stream) {
   using S = Tc2Smem<64, 3>;
@@ -2221,7 +2329,7 @@ static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const T
   NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
   const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
-    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT, BNS>,
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT, BNS, RAD>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
     configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
@@ -2237,30 +2345,47 @@ static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const T
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2r_kernel<FMT, BNS>, ma, mb, prm, seg_rows));
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2r_kernel<FMT, BNS, RAD>, ma, mb, prm, seg_rows));
   count_launch();
   return NNAB_OK;
 }
 
+template <int BNS, int RAD>
+static int launch_tc2r(int fmt, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                       int seg_rows, int n_pairs, cudaStream_t stream) {
+  switch (fmt) {
+    case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_POWER: return launch_tc2r_fmt<4, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_FBANK: return launch_tc2r_fmt<5, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    default: return NNAB_EINVAL;
+  }
+}
+
 static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, void* workspace,
                                    size_t ws_bytes, cudaStream_t stream) {
-  if (!radix2_problem_ok(q)) return NNAB_EINVAL;  // the basis was packed for the radix kernel only
+  const int R = packed_kind(packed) == PACK_RADIX4 ? 4 : 2;
+  if (!radix_problem_ok(q, R)) return NNAB_EINVAL;  // the basis was packed for the radix kernel only
   const size_t need = tc_radix2_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
   if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
   if (q.B > 65535) return NNAB_EUNSUPPORTED;
-  const int hop2 = q.hop / 2, k2 = q.K / 2;
-  const SplitGeom g = radix2_geom(q.B, q.L, q.K, q.hop, q.pad);
+  const int hopr = q.hop / R, kr = q.K / R;
+  const SplitGeom g = radix_geom(q.B, q.L, q.K, q.hop, q.pad, R);
   __nv_bfloat16* planes =
       reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  const int64_t clip_pitch = g.t_slots * hop2;
-  // K overhang past the last clip: finite zeros in all four planes
-  const int64_t tail = g.plane_stride - g.nv * hop2;
-  for (int pl = 0; pl < 4; ++pl)
-    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hop2, 0,
+  const int64_t clip_pitch = g.t_slots * hopr;
+  // K overhang past the last clip: finite zeros in all 2R planes
+  const int64_t tail = g.plane_stride - g.nv * hopr;
+  for (int pl = 0; pl < 2 * R; ++pl)
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hopr, 0,
                                   (size_t)tail * sizeof(__nv_bfloat16), stream));
   dim3 pgrid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
-  pad_split_radix2_kernel<<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
-                                                     clip_pitch, g.plane_stride, planes);
+  if (R == 2)
+    pad_split_radix_kernel<2><<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
+                                                          clip_pitch, g.plane_stride, planes);
+  else
+    pad_split_radix_kernel<4><<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
+                                                          clip_pitch, g.plane_stride, planes);
   NNAB_LAUNCH_CHECK();
 
   int dev = 0, sms = 148;
@@ -2269,29 +2394,29 @@ static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, v
   sms -= sm_reserve();
   if (sms < 2) sms = 2;
 
-  const int seg_rows = k2;            // rows of one segment in the packed basis
-  const int bns = radix2_bn();
+  const int seg_rows = kr;            // rows of one segment in the packed basis
+  const int bns = radix_bn(R);
   const int n_tiles = seg_rows / bns;
   CUtensorMap ma, mb;
-  int rc = encode_3d(&ma, planes, (uint64_t)hop2, (uint64_t)g.rows, 4, (uint64_t)hop2 * 2,
+  int rc = encode_3d(&ma, planes, (uint64_t)hopr, (uint64_t)g.rows, (uint64_t)(2 * R), (uint64_t)hopr * 2,
                      (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
   if (rc) return rc;
-  rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)k2, (uint64_t)(2 * seg_rows), 2,
-                 (uint64_t)k2 * 2, (uint64_t)(2 * seg_rows) * k2 * 2, 64, bns / 2, 64);
+  rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)kr, (uint64_t)(R * seg_rows), 2,
+                 (uint64_t)kr * 2, (uint64_t)(R * seg_rows) * kr * 2, 64, bns / 2, 64);
   if (rc) return rc;
 
   TcParams prm{};
   prm.num_n_tiles = n_tiles;
   prm.bn = bns;
   prm.rows_mode = 1;
-  prm.hop = hop2;
+  prm.hop = hopr;
   prm.nv = g.nv;
   prm.t_slots = g.t_slots;
   prm.t_mul = 1;
   prm.t_add = 0;
   prm.T = q.T;
   prm.k_splits = 1;
-  for (int tl = 0; tl < n_tiles; ++tl) { prm.kb_begin[tl] = 0; prm.kb_end[tl] = k2 / 64; }
+  for (int tl = 0; tl < n_tiles; ++tl) { prm.kb_begin[tl] = 0; prm.kb_end[tl] = kr / 64; }
   prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
   prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
   prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
@@ -2302,22 +2427,12 @@ static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, v
   prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
   const int64_t ptiles = (int64_t)prm.num_m_tiles * n_tiles;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
-  if (bns == 256) {
-    switch (q.fmt) {
-      case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
-      case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
-      case FMT_POWER: return launch_tc2r_fmt<4, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
-      case FMT_FBANK: return launch_tc2r_fmt<5, 256>(ma, mb, prm, seg_rows, n_pairs, stream);
-      default: return NNAB_EINVAL;
-    }
+  if (R == 2) {
+    return bns == 256 ? launch_tc2r<256, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream)
+                      : launch_tc2r<128, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream);
   }
-  switch (q.fmt) {
-    case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case FMT_POWER: return launch_tc2r_fmt<4, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case FMT_FBANK: return launch_tc2r_fmt<5, 128>(ma, mb, prm, seg_rows, n_pairs, stream);
-    default: return NNAB_EINVAL;
-  }
+  return bns == 128 ? launch_tc2r<128, 4>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream)
+                    : launch_tc2r<64, 4>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream);
 }
 
 

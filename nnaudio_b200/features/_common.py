@@ -112,23 +112,34 @@ class AdjointBasis:
         return self._cache.lookup(w_re.device, key, lambda: _C.pack_adjoint_basis(w_re, w_im))
 
 
-def is_dft_structured(w_re: torch.Tensor, w_im: torch.Tensor, rtol: float = 1e-6) -> bool:
-    """True when an (F, K) basis pair has the mirror structure of a one-sided windowed DFT with
-    F = K/2 + 1: ``w_re[F-1-k][n] = (-1)^n w_re[k][n]`` and ``w_im[F-1-k][n] = -(-1)^n w_im[k][n]``
-    (any window: it multiplies columns).  That is exactly what the decimation-in-time kernel relies
-    on, so it is checked on the buffers themselves — a loaded or trained basis that lost the
-    structure simply takes the dense kernel.  EXPERIMENTAL (branch radix2-wip)."""
+def is_dft_structured(w_re: torch.Tensor, w_im: torch.Tensor, rtol: float = 1e-6, radix: int = 2) -> bool:
+    """True when an (F, K) basis pair has the structure of a one-sided windowed DFT with F = K/2 + 1
+    that the decimation-in-time kernels rely on, checked on the buffers themselves (a loaded or
+    trained basis that lost it simply takes the dense kernel).  With W = w_re - i w_im:
+      radix 2:  W[F-1-k][n] = (-1)^n conj(W[k][n])            (mirror about N/4)
+      radix 4:  additionally W[k + K/4][n] = (-i)^n W[k][n]   (quarter-period shift)
+    Any window is fine: it multiplies columns.  EXPERIMENTAL (branch radix2-wip)."""
     F, K = w_re.shape
-    if F != K // 2 + 1 or K % 256 != 0 or K < 512 or K >= 8192:
+    if F != K // 2 + 1 or K % 256 != 0 or K < 512 or K >= 8192 or radix not in (2, 4):
         return False
-    sign = 1.0 - 2.0 * (torch.arange(K, device=w_re.device) % 2).to(w_re.dtype)
     scale = float(torch.maximum(w_re.abs().max(), w_im.abs().max()))
     if scale == 0.0:
         return False
     tol = rtol * scale
-    ok_re = (w_re.flip(0) - w_re * sign).abs().max() <= tol
-    ok_im = (w_im.flip(0) + w_im * sign).abs().max() <= tol
-    return bool(ok_re) and bool(ok_im)
+    n = torch.arange(K, device=w_re.device)
+    sign = (1.0 - 2.0 * (n % 2)).to(w_re.dtype)
+    if (w_re.flip(0) - w_re * sign).abs().max() > tol or (w_im.flip(0) + w_im * sign).abs().max() > tol:
+        return False
+    if radix == 4:
+        q = K // 4
+        # (-i)^n = 1, -i, -1, i: (re - i im) * (-i)^n for n mod 4 = 0..3 -> (re, im), (-im, re), (-re, -im), (im, -re)
+        r, m = w_re[: q + 1], w_im[: q + 1]
+        ph = n % 4
+        want_re = torch.where(ph == 0, r, torch.where(ph == 1, -m, torch.where(ph == 2, -r, m)))
+        want_im = torch.where(ph == 0, m, torch.where(ph == 1, r, torch.where(ph == 2, -m, -r)))
+        if (w_re[q: 2 * q + 1] - want_re).abs().max() > tol or (w_im[q: 2 * q + 1] - want_im).abs().max() > tol:
+            return False
+    return True
 
 
 class PackedBasis:
@@ -139,10 +150,11 @@ class PackedBasis:
     def __init__(self):
         self._cache = PerDeviceCache()
 
-    def get(self, w_re: torch.Tensor, w_im: torch.Tensor, allow_radix: bool = False,
+    def get(self, w_re: torch.Tensor, w_im: torch.Tensor, allow_radix=False,
             groups: bool = False):
-        """``allow_radix``: the module computes a plain one-sided STFT with this basis, so the
-        decimation-in-time layout may be used when the buffers pass ``is_dft_structured``;
+        """``allow_radix`` (False, 2 or 4 = the largest radix the module's hop allows): the module
+        computes a plain one-sided STFT with this basis, so the decimation-in-time layout may be
+        used when the buffers pass ``is_dft_structured``;
         ``groups``: long CQT bank for the per-K-block-width kernel.  Both EXPERIMENTAL and only
         active with NNAUDIO_B200_EXPERIMENTAL=1."""
         import os
@@ -150,7 +162,10 @@ class PackedBasis:
         def build():
             layout = _C.LAYOUT_DENSE
             if os.environ.get("NNAUDIO_B200_EXPERIMENTAL", "0") == "1":
-                if allow_radix and is_dft_structured(w_re, w_im):
+                radix = 4 if os.environ.get("NNAUDIO_B200_RADIX", "2") == "4" else 2
+                if allow_radix == 4 and radix == 4 and is_dft_structured(w_re, w_im, radix=4):
+                    layout = _C.LAYOUT_RADIX4
+                elif allow_radix and is_dft_structured(w_re, w_im):
                     layout = _C.LAYOUT_RADIX2
                 elif groups and w_re.shape[0] <= 128 and w_re.shape[1] >= 4096:
                     layout = _C.LAYOUT_GROUPS

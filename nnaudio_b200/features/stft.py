@@ -241,7 +241,9 @@ class STFT(nn.Module):
         wcos, wsin = as_matrix(self.wcos), as_matrix(self.wsin)
         if self.freq_bins is not None and self.freq_bins < wcos.shape[0]:
             wcos, wsin = wcos[: self.freq_bins], wsin[: self.freq_bins]
-        allow = bool(radix_ok) and not self.trainable and self.stride % 128 == 0
+        allow = False
+        if radix_ok and not self.trainable and self.stride % 128 == 0:
+            allow = 4 if self.stride % 256 == 0 else 2
         return wcos, wsin, self._packed.get(wcos, wsin, allow_radix=allow)
 
     def _run(self, x, output_format):

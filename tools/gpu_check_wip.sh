@@ -19,6 +19,13 @@ for wl in stft2048 cfg2; do
   cut -c1-260 gpurun_out/wip_radix2_bn256_$wl.json
 done
 NNAB_RADIX=2 NNAB_RADIX_BN=256 run timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "stft_2048 or mel_"
+# 1c. radix 4 (64-column segments, add/swap butterflies)
+NNAB_RADIX=4 run timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 120 -k "stft_cfg1 or stft_2048 or mel_ or mfcc_"
+for wl in stft2048 cfg2 cfg5; do
+  NNAB_RADIX=4 timeout 150 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --no-e2e \
+      > gpurun_out/wip_radix4_$wl.json 2>> gpurun_out/wip_err.txt
+  cut -c1-260 gpurun_out/wip_radix4_$wl.json
+done
 # 1b. the same through the host layer's own selection (structure check + explicit layout request)
 NNAUDIO_B200_EXPERIMENTAL=1 run timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q --timeout 120
 # 2. per-K-block width, CQT1992v2
