@@ -236,6 +236,8 @@ def _run():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--e2e-copy-streams", type=int, default=1)
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "symm"],
+                    help="EXPERIMENTAL: symm = copy-engine pushes into symmetric memory (no SMs reserved)")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs kept free for the concurrent NCCL gather (default: by world size)")
     ap.add_argument("--nccl-max-ctas", type=int, default=-1,
@@ -303,6 +305,8 @@ def _run():
     from nnaudio_b200.parallel import BatchShardedTransform
 
     reserve = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
+    if args.gather == "symm" and args.reserve_sms is None:
+        reserve = 0  # the copy engines do the gather: the kernels keep every SM
     sharded = BatchShardedTransform(lambda inp: mod(inp, **w["fwd"]), gather=(world > 1),
                                     reserve_sms=reserve)
 
@@ -318,9 +322,14 @@ def _run():
         for i in range(n):
             if record:
                 record[0][i].record()
-            work, y = sharded.forward_async(xs[i % n_rot], slot=i & 1)
+            if args.gather == "symm" and world > 1:
+                work, y = sharded.forward_async_symm(xs[i % n_rot], slot=i & 1)
+            else:
+                work, y = sharded.forward_async(xs[i % n_rot], slot=i & 1)
             if prev is not None:
                 prev.wait()
+                if args.gather == "symm" and world > 1:
+                    sharded.release((i - 1) & 1)
             prev = work
             if record:
                 record[1][i].record()

@@ -88,6 +88,11 @@ SIGNATURES = {
         [_P, _P, c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_int, c_int, _P, _P,
          c_size_t, _P],
     ),
+    "nnab_pack_basis_ex": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "nnab_debug_varn_plan": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "nnab_fir_decimate": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
+    "nnab_fir_decimate_adjoint": (
+        c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
     "nnab_packed_fir_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_fir": (c_int, [_P, c_int, c_int, _P, _P]),
     "nnab_cqt_pyramid_workspace_bytes": (
@@ -227,9 +232,14 @@ def _rows(x: torch.Tensor):
 # --------------------------------------------------------------------------- #
 # basis packing (tcgen05 path)
 # --------------------------------------------------------------------------- #
-def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor):
+LAYOUT_DENSE, LAYOUT_RADIX2, LAYOUT_GROUPS, LAYOUT_RADIX4 = 0, 2, 3, 4
+
+
+def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor, layout: int = LAYOUT_DENSE):
     """bf16 hi/lo split of an (F, K) fp32 basis pair in the TMA/UMMA layout, or
-    ``None`` when the library has no tcgen05 kernel for it."""
+    ``None`` when the library has no tcgen05 kernel for it.  ``layout`` (EXPERIMENTAL):
+    LAYOUT_RADIX2 for a basis the caller has checked with ``is_dft_structured``,
+    LAYOUT_GROUPS for long CQT banks."""
     L = lib()
     F, K = w_re.shape
     nbytes = L.nnab_packed_basis_bytes(F, K)
@@ -237,8 +247,12 @@ def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor):
         return None
     packed = torch.empty(nbytes, dtype=torch.uint8, device=w_re.device)
     with torch.cuda.device(w_re.device):
-        _check(L.nnab_pack_basis(_ptr(w_re), _ptr(w_im), F, K, _ptr(packed), _stream(w_re.device)),
-               "nnab_pack_basis")
+        if layout == LAYOUT_DENSE:
+            rc = L.nnab_pack_basis(_ptr(w_re), _ptr(w_im), F, K, _ptr(packed), _stream(w_re.device))
+        else:
+            rc = L.nnab_pack_basis_ex(_ptr(w_re), _ptr(w_im), F, K, int(layout), _ptr(packed),
+                                      _stream(w_re.device))
+        _check(rc, "nnab_pack_basis")
     return packed
 
 
@@ -430,6 +444,34 @@ def istft_forward(X, packed, window, n_fft, hop, center, length):
                                   want, _ptr(ws), wsb, _stream(X.device))
     _check(rc, "nnab_istft_forward")
     return out
+
+
+def fir_decimate(x, fir, factor):
+    """EXPERIMENTAL: y = conv1d(x, fir, stride=factor, padding=(taps-1)//2) for (B, L) rows."""
+    L = lib()
+    x, B, Ln, pitch = _rows(x)
+    fir = _dev_f32(fir, "fir").reshape(-1).contiguous()
+    taps = fir.numel()
+    half = (taps - 1) // 2
+    Ly = (Ln + 2 * half - taps) // factor + 1
+    y = torch.empty((B, Ly), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(L.nnab_fir_decimate(_ptr(x), B, Ln, pitch, _ptr(fir), taps, int(factor), _ptr(y), Ly,
+                                   _stream(x.device)), "nnab_fir_decimate")
+    return y
+
+
+def fir_decimate_adjoint(g, fir, factor, L_in):
+    """EXPERIMENTAL: gradient of fir_decimate w.r.t. its input, (B, Ly) -> (B, L_in)."""
+    L = lib()
+    g, B, Ly, pitch = _rows(g)
+    fir = _dev_f32(fir, "fir").reshape(-1).contiguous()
+    dx = torch.empty((B, L_in), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _check(L.nnab_fir_decimate_adjoint(_ptr(g), B, Ly, pitch, _ptr(fir), fir.numel(), int(factor),
+                                           _ptr(dx), int(L_in), _stream(g.device)),
+               "nnab_fir_decimate_adjoint")
+    return dx
 
 
 def pack_adjoint_basis(w_re: torch.Tensor, w_im: torch.Tensor):

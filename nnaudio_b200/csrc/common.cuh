@@ -104,6 +104,8 @@ size_t tc_packed_bytes(int F, int K);
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream);
 int tc_tile_n(int F);
+int tc_pack_basis_layout(const float* w_re, const float* w_im, int F, int K, int layout, void* packed,
+                         cudaStream_t stream);
 // split-signal geometry / helpers for callers that manage the planes themselves (pyramid)
 void tc_split_geometry(int64_t B, int64_t L, int K, int hop, int pad, int64_t* t_slots,
                        int64_t* plane_stride, int* hop_eff);
@@ -147,6 +149,12 @@ int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t
 int launch_mfcc_tail(const float* mel, int64_t B, int n_mels, int64_t T, float amin, float ref,
                      float top_db, const float* dct, int n_mfcc, float* out,
                      unsigned int* scratch /* B words */, cudaStream_t stream);
+int tc_varn_plan_export(const int32_t* k_begin, const int32_t* k_end, int F, int K, int want_chunks,
+                        int32_t* order, int32_t* groups, int32_t* chunk_begin, int32_t* n_blocks,
+                        int32_t* n_chunks);
+int launch_fir_decimate_adjoint(const float* g, int64_t B, int64_t T, int64_t g_pitch,
+                                const float* fir, int taps, int factor, float* dx, int64_t L,
+                                int64_t dx_pitch, cudaStream_t stream);
 int launch_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* fir,
                         int taps, int factor, float* y, int64_t Ly, int64_t y_pitch,
                         cudaStream_t stream);

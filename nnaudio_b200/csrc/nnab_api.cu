@@ -177,6 +177,13 @@ int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K, void* pa
   return tc_pack_basis(w_re, w_im, F, K, packed, (cudaStream_t)stream);
 }
 
+int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int layout, void* packed,
+                       void* stream) {
+  if (w_re == nullptr || w_im == nullptr || packed == nullptr || F <= 0 || K <= 0)
+    return NNAB_EINVAL;
+  return tc_pack_basis_layout(w_re, w_im, F, K, layout, packed, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ STFT ----
 size_t nnab_stft_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop, int center,
                                  int path) {
@@ -465,6 +472,44 @@ size_t nnab_packed_fir_bytes(int taps, int dec) { return tc_packed_fir_bytes(tap
 int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* stream) {
   if (fir == nullptr || packed == nullptr || taps <= 0 || dec < 1) return NNAB_EINVAL;
   return tc_pack_fir(fir, taps, dec, packed, (cudaStream_t)stream);
+}
+
+int nnab_debug_varn_plan(const int32_t* h_k_begin, const int32_t* h_k_end, int n_bins, int width,
+                         int want_chunks, int32_t* order, int32_t* groups, int32_t* chunk_begin,
+                         int32_t* n_blocks, int32_t* n_chunks) {
+  if (order == nullptr || groups == nullptr || chunk_begin == nullptr || n_blocks == nullptr ||
+      n_chunks == nullptr || n_bins <= 0 || width <= 0)
+    return NNAB_EINVAL;
+  return tc_varn_plan_export(h_k_begin, h_k_end, n_bins, width, want_chunks, order, groups,
+                             chunk_begin, n_blocks, n_chunks);
+}
+
+int nnab_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, const float* fir,
+                      int taps, int factor, float* y, int64_t Ly, void* stream) {
+  if (x == nullptr || fir == nullptr || y == nullptr || B < 0 || L <= 0 || x_pitch < L || taps <= 0 ||
+      factor < 1)
+    return NNAB_EINVAL;
+  const int half = (taps - 1) / 2;
+  if (L + 2 * (int64_t)half < taps || Ly != (L + 2 * (int64_t)half - taps) / factor + 1)
+    return NNAB_EINVAL;
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_fir_decimate(x, B, L, x_pitch, fir, taps, factor, y, Ly, Ly, (cudaStream_t)stream);
+}
+
+int nnab_fir_decimate_adjoint(const float* g, int64_t B, int64_t Ly, int64_t g_pitch,
+                              const float* fir, int taps, int factor, float* dx, int64_t L,
+                              void* stream) {
+  if (g == nullptr || fir == nullptr || dx == nullptr || B < 0 || L <= 0 || Ly <= 0 || g_pitch < Ly ||
+      taps <= 0 || factor < 1)
+    return NNAB_EINVAL;
+  const int half = (taps - 1) / 2;
+  if (L + 2 * (int64_t)half < taps || Ly != (L + 2 * (int64_t)half - taps) / factor + 1)
+    return NNAB_EINVAL;
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_fir_decimate_adjoint(g, B, Ly, g_pitch, fir, taps, factor, dx, L, L,
+                                     (cudaStream_t)stream);
 }
 
 size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int early_factor,

@@ -457,4 +457,67 @@ int launch_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, c
   return NNAB_OK;
 }
 
+// --------------------------------------------------------------------------
+// EXPERIMENTAL (branch radix2-wip, not GPU-verified): adjoint of the decimating FIR,
+//   dx[i] = sum_j g[j] * fir[i + half - factor*j],   half = (taps-1)/2,  0 <= i < L
+// (the gradient of y = conv1d(x, fir, stride=factor, padding=half), utils.py:73-100).
+// One CTA = 1024 consecutive inputs of one clip; the g samples and the filter they touch are
+// staged in shared memory; every input is written exactly once (no atomics).
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fir_decimate_adjoint_kernel(
+    const float* __restrict__ g, int64_t T, int64_t g_pitch, const float* __restrict__ fir, int taps,
+    int factor, int g_len, float* __restrict__ dx, int64_t L, int64_t dx_pitch) {
+  extern __shared__ float asm_[];
+  float* fs = asm_;         // [taps]
+  float* gs = asm_ + taps;  // [g_len]
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.y;
+  const int64_t i0 = (int64_t)blockIdx.x * 1024;
+  const int half = (taps - 1) / 2;
+  // smallest j any output of this block can touch: factor*j >= i0 + half - (taps-1)
+  int64_t lo = i0 + half - (taps - 1);
+  const int64_t j_lo = lo <= 0 ? 0 : (lo + factor - 1) / factor;
+  const float* __restrict__ gb = g + b * g_pitch;
+  for (int idx = tid; idx < taps; idx += 256) fs[idx] = __ldg(fir + idx);
+  for (int idx = tid; idx < g_len; idx += 256) {
+    const int64_t j = j_lo + idx;
+    gs[idx] = (j < T) ? __ldg(gb + j) : 0.f;
+  }
+  __syncthreads();
+  float* __restrict__ db = dx + b * dx_pitch;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int64_t i = i0 + tid + 256 * o;
+    if (i >= L) continue;
+    const int64_t top = i + half;               // tap index at j = 0
+    int64_t ja = top - (taps - 1);
+    ja = ja <= 0 ? 0 : (ja + factor - 1) / factor;
+    int64_t jb = top / factor;                  // last j with a non-negative tap index
+    if (jb > T - 1) jb = T - 1;
+    float acc = 0.f;
+    for (int64_t j = ja; j <= jb; ++j)
+      acc = fmaf(gs[(int)(j - j_lo)], fs[(int)(top - factor * j)], acc);
+    db[i] = acc;
+  }
+}
+
+int launch_fir_decimate_adjoint(const float* g, int64_t B, int64_t T, int64_t g_pitch,
+                                const float* fir, int taps, int factor, float* dx, int64_t L,
+                                int64_t dx_pitch, cudaStream_t stream) {
+  if (B <= 0 || L <= 0) return NNAB_OK;
+  if (B > 65535 || factor < 1 || taps < 1) return NNAB_EUNSUPPORTED;
+  // j range of one block: (1023 + taps - 1) / factor + 2 values at most
+  const int g_len = (1023 + taps - 1) / factor + 3;
+  const size_t smem = (size_t)(taps + g_len) * sizeof(float);
+  if (smem > 200 * 1024) return NNAB_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(fir_decimate_adjoint_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div64(L, 1024), (unsigned)B);
+  fir_decimate_adjoint_kernel<<<grid, 256, smem, stream>>>(g, T, g_pitch, fir, taps, factor, g_len,
+                                                           dx, L, dx_pitch);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
 }  // namespace nnab

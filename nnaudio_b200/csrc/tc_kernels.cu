@@ -18,6 +18,11 @@
 //                coalesced stores in the reference's (B, F, T[,2]) layout
 //   smem full/empty mbarrier ring + double-buffered TMEM accumulators.
 #include <cuda.h>
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <algorithm>
+#include <vector>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -83,9 +88,17 @@ static SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad) {
   return g;
 }
 
+size_t tc_radix2_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad);
+bool tc_radix2_enabled();
+
 size_t tc_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
   const SplitGeom g = split_geom(B, L, K, hop, pad);
-  return (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+  size_t n = (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+  if (hop % 2 == 0 && K % 256 == 0) {  // either layout may be chosen at pack time
+    const size_t r2 = tc_radix2_workspace_bytes(B, L, K, hop, pad);
+    if (r2 > n) n = r2;
+  }
+  return n;
 }
 
 bool tc_supported(const FramedProblem& p) {
@@ -201,8 +214,42 @@ __global__ void __launch_bounds__(256) pack_basis_kernel(
   *reinterpret_cast<uint4*>(packed + (int64_t)rows * kpad + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
+int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
+                         cudaStream_t stream);
+bool tc_radix2_basis_ok(int F, int K);
+void tc_forget_packed(const void* packed);
+bool tc_varn_enabled();
+bool tc_varn_basis_ok(int F, int K);
+int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void* packed,
+                       cudaStream_t stream);
+
+// layout: 0 = dense (always valid); 2 = two-segment decimation-in-time layout — the CALLER vouches
+// that the basis is DFT-structured (rows k and F-1-k mirror each other, see
+// nnaudio_b200/features/_common.py:is_dft_structured); 3 = 8-bin-group layout for the
+// per-K-block-width kernel (any basis with F <= 128).  NNAB_RADIX=0 / NNAB_VARN=0 force dense.
+int tc_pack_basis_layout(const float* w_re, const float* w_im, int F, int K, int layout, void* packed,
+                         cudaStream_t stream) {
+  const char* er = getenv("NNAB_RADIX");
+  const char* ev = getenv("NNAB_VARN");
+  if ((layout == 2 || layout == 4) && !(er != nullptr && atoi(er) == 0)) {
+    int tc_pack_basis_radix(const float*, const float*, int, int, int, void*, cudaStream_t);
+    const int rc = tc_pack_basis_radix(w_re, w_im, F, K, layout, packed, stream);
+    if (rc != NNAB_EINVAL) return rc;  // shape not eligible: fall through to dense
+  }
+  if (layout == 3 && !(ev != nullptr && atoi(ev) == 0) && tc_varn_basis_ok(F, K))
+    return tc_pack_basis_varn(w_re, w_im, F, K, packed, stream);
+  if (layout != 0 && layout != 2 && layout != 3 && layout != 4) return NNAB_EINVAL;
+  return tc_pack_basis(w_re, w_im, F, K, packed, stream);
+}
+
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream) {
+  // legacy entry: experimental layouts only when the environment asks for them
+  if (tc_radix2_enabled() && tc_radix2_basis_ok(F, K))
+    return tc_pack_basis_radix2(w_re, w_im, F, K, packed, stream);
+  if (tc_varn_enabled() && tc_varn_basis_ok(F, K) && K >= 4096)
+    return tc_pack_basis_varn(w_re, w_im, F, K, packed, stream);
+  tc_forget_packed(packed);
   const int bn = choose_bn(F);
   const int n_tiles = (2 * F + bn - 1) / bn;
   const int rows = n_tiles * bn;
@@ -771,6 +818,7 @@ struct TcParams {
   int hop;          // effective hop (hop * phases)
   int t_mul, t_add;  // output frame index = t * t_mul + t_add (frame phases)
   int k_splits;      // >1: every (m, n) tile is cut into k_splits K-chunks (FMT_RAW epilogue)
+  int split4;        // EXPERIMENTAL (NNAB_SPLIT4=1): add the x_lo * w_lo term (4 MMAs per K16 step)
   int64_t nv, t_slots, T;  // T = valid frames of this phase
   int kb_begin[TC_MAX_N_TILES];
   int kb_end[TC_MAX_N_TILES];
@@ -1327,6 +1375,10 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
             const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
             const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+            if (p.split4) {  // smallest term first: fp32-like accuracy for the training forward
+              umma_bf16_2sm(d_tmem, a_lo, b_lo, idesc, accumulate);
+              accumulate = 1u;
+            }
             umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
             umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
             umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
@@ -1364,6 +1416,650 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still touch it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+
+// ===========================================================================
+// EXPERIMENTAL (branch radix2-wip, not GPU-verified yet): decimation-in-time
+// variant of the STFT-family contraction, R = 2.
+//
+// For a DFT-structured basis (w_re[f][n] = win[n] cos(2 pi f n / N), w_im = ... sin, F = N/2+1)
+// the frame splits into its even / odd samples:
+//   S0[k] = sum_m xe[m] (w_re - i w_im)[k][2m]         (sub-DFT of the even samples)
+//   U [k] = sum_m xo[m] (w_re - i w_im)[k][2m+1]       (sub-DFT of the odd samples, twiddle included)
+//   X[k] = S0[k] + U[k],   X[N/2 - k] = conj(S0[k] - U[k]),   k = 0 .. N/4
+// i.e. two contractions with K = N/2 over N/4 bins: half the MACs of the dense form, and the
+// epilogue is add / subtract only.  The real Nyquist bins S0[N/4], Im U[N/4] ride in the
+// always-zero imaginary slots of k = 0, so N/4 (re, im) column pairs cover everything
+// (tools/radix_dft_prototype.py is the executable spec).
+//
+// Data: 4 signal planes [r][hi|lo], plane_r[i] = xpad[2 i + r] (hop/2, K/2 Toeplitz view each);
+// packed basis [hi|lo][seg r][tile][re half | negated im half][K/2]; TMEM: segment r of a tile
+// accumulates into columns [r*bn, (r+1)*bn) of the 256-column buffer (bn = 128).
+// ===========================================================================
+
+// One thread = 8 consecutive elements of ALL R sample-phase planes (8 R padded samples).
+// planes: [r][hi|lo], plane_r[i] = xpad[R i + r].
+template <int R>
+__global__ void __launch_bounds__(256) pad_split_radix_kernel(
+    const float* __restrict__ x, int64_t L, int64_t x_pitch, int pad, int pad_mode,
+    int64_t clip_pitch, int64_t plane_stride, __nv_bfloat16* __restrict__ planes) {
+  const int64_t b = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;  // plane element
+  if (i0 >= clip_pitch) return;
+  const float* __restrict__ xb = x + b * x_pitch;
+  const int64_t padded_len = L + 2 * (int64_t)pad;
+  __align__(16) __nv_bfloat16 hi[R][8];
+  __align__(16) __nv_bfloat16 lo[R][8];
+#pragma unroll
+  for (int e = 0; e < 8 * R; ++e) {
+    const int64_t i = R * i0 + e;  // index into the centre-padded clip
+    float v = 0.f;
+    if (i < padded_len) {
+      int64_t j = i - pad;
+      if (j < 0) j = (pad_mode == NNAB_PAD_REFLECT) ? -j : -1;
+      else if (j >= L) j = (pad_mode == NNAB_PAD_REFLECT) ? 2 * (L - 1) - j : -1;
+      if (j >= 0 && j < L) v = __ldg(xb + j);
+    }
+    split_bf16(v, hi[e % R][e / R], lo[e % R][e / R]);
+  }
+  const int64_t o = b * clip_pitch + i0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    *reinterpret_cast<uint4*>(planes + (2 * r) * plane_stride + o) = *reinterpret_cast<const uint4*>(hi[r]);
+    *reinterpret_cast<uint4*>(planes + (2 * r + 1) * plane_stride + o) = *reinterpret_cast<const uint4*>(lo[r]);
+  }
+}
+
+// packed[plane][seg][tile*bn + part*half + j][kk]: bin k = tile*half + j, sample n = R*kk + seg.
+// part 0 = w_re rows, part 1 = negated w_im rows.  The (k = 0, part 1) slot (always zero) carries
+// the real number that determines the sub-DFT's Nyquist bin U_seg[K/(2R)]:
+//   R = 2: seg 0 -> re, seg 1 -> im        R = 4: seg 0, 1, 3 -> re, seg 2 -> im
+// (tools/radix2_emulation.py, tools/radix4_emulation.py).
+__global__ void __launch_bounds__(256) pack_basis_radix_kernel(
+    const float* __restrict__ w_re, const float* __restrict__ w_im, int K, int R, int rows_seg,
+    int kpadr, int bn, __nv_bfloat16* __restrict__ packed) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k8 = kpadr / 8;
+  if (idx >= (int64_t)R * rows_seg * k8) return;
+  const int row = (int)(idx / k8);  // 0 .. R*rows_seg-1
+  const int k0 = (int)(idx % k8) * 8;
+  const int seg = row / rows_seg, r = row % rows_seg;
+  const int half = bn / 2;
+  const int tile = r / bn, within = r % bn;
+  const int part = within / half, j = within % half;
+  const int k = tile * half + j;
+  const int nyq = K / (2 * R);
+  const bool slot_is_im = (R == 2) ? (seg == 1) : (seg == 2);
+  __align__(16) __nv_bfloat16 hi[8];
+  __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int kk = k0 + e;
+    const int n = R * kk + seg;
+    float v = 0.f;
+    if (k < nyq && n < K) {
+      if (part == 0) v = __ldg(w_re + (int64_t)k * K + n);
+      else if (k != 0) v = -__ldg(w_im + (int64_t)k * K + n);
+      else v = slot_is_im ? -__ldg(w_im + (int64_t)nyq * K + n) : __ldg(w_re + (int64_t)nyq * K + n);
+    }
+    split_bf16(v, hi[e], lo[e]);
+  }
+  const int64_t o = (int64_t)row * kpadr + k0;
+  *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(packed + (int64_t)R * rows_seg * kpadr + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// running banded-filterbank sums of one bin stream (ascending or descending bins)
+struct MelRun {
+  int cj0 = -1, cj1 = -1;
+  float a0 = 0.f, a1 = 0.f;
+  __device__ __forceinline__ void add(const EpiParams& e, float* mel, bool valid, int bin, float pw) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(e.fb_table) + bin);
+    if (raw.x != cj0) {
+      if (raw.x == cj1) {
+        const int tj = cj0; cj0 = cj1; cj1 = tj;
+        const float ta = a0; a0 = a1; a1 = ta;
+      } else {
+        if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
+        cj0 = raw.x; a0 = 0.f;
+      }
+    }
+    if (raw.y != cj1) {
+      if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
+      cj1 = raw.y; a1 = 0.f;
+    }
+    a0 = fmaf(__int_as_float(raw.z), pw, a0);
+    a1 = fmaf(__int_as_float(raw.w), pw, a1);
+  }
+  __device__ __forceinline__ void flush(const EpiParams& e, float* mel, bool valid) {
+    if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
+    if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
+  }
+};
+
+// Butterfly epilogue: TMEM columns [S0 re | S0 im | U re | U im], `half` bins each.
+// FMT: 0 Magnitude, 1 Complex, 4 POWER, 5 fused banded filterbank.
+template <int FMT>
+__device__ __forceinline__ void epilogue_tile_radix2(const TcParams& p, uint32_t trow, int64_t g,
+                                                     int n_tile, int half) {
+  const int64_t b = g / p.t_slots;
+  const int64_t tl = g - b * p.t_slots;
+  const bool valid = (g < p.nv) && (tl < p.T);
+  const int64_t t = tl * p.t_mul + p.t_add;
+  const int k_base = n_tile * half;
+  const int NH = p.epi.F - 1;  // N/2: bin k pairs with bin NH - k
+  constexpr int CH = (FMT == NNAB_FMT_COMPLEX) ? 2 : 1;
+  float* dst = nullptr;
+  float* mel = nullptr;
+  if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
+  else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+  MelRun up, down;
+  auto emit = [&](MelRun& run, int bin, float re, float im) {
+    if constexpr (FMT == 5) {
+      run.add(p.epi, mel, valid, bin, epi_power(p.epi, re, im));
+    } else {
+      if (valid) epi_store_fmt<FMT>(p.epi, dst, bin, re, im);
+    }
+  };
+#pragma unroll 1
+  for (int c0 = 0; c0 < half; c0 += 8) {
+    uint32_t s0r[8], s0i[8], ur[8], ui[8];
+    tmem_ld8(trow + (uint32_t)c0, s0r);
+    tmem_ld8(trow + (uint32_t)(half + c0), s0i);
+    tmem_ld8(trow + (uint32_t)(2 * half + c0), ur);
+    tmem_ld8(trow + (uint32_t)(3 * half + c0), ui);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k_base + c0 + j;
+      const float ar = __uint_as_float(s0r[j]), ai = __uint_as_float(s0i[j]);
+      const float br = __uint_as_float(ur[j]), bi = __uint_as_float(ui[j]);
+      if (k == 0) {
+        // DC, the mirror of DC (bin N/2) and the packed Nyquist pair (bin N/4)
+        MelRun one;
+        emit(one, 0, ar + br, 0.f);
+        emit(one, NH, ar - br, 0.f);
+        emit(one, NH / 2, ai, bi);
+        if constexpr (FMT == 5) one.flush(p.epi, mel, valid);
+      } else {
+        emit(up, k, ar + br, ai + bi);
+        emit(down, NH - k, ar - br, bi - ai);
+      }
+    }
+  }
+  if constexpr (FMT == 5) {
+    up.flush(p.epi, mel, valid);
+    down.flush(p.epi, mel, valid);
+  }
+}
+
+// CTA-pair kernel with two K segments per tile (see framed_tc2_kernel for the pipeline roles).
+// Radix-4 butterfly epilogue: TMEM columns of segment s at [s*bns, (s+1)*bns) = [re | im], `half`
+// bins each.  With the module's own basis rows the twiddles are inside the accumulators, so
+//   X[k]       =      U0 +   U1 + U2 +   U3        X[N/4 + k] = U0 - i U1 - U2 + i U3
+//   X[N/4 - k] = conj(U0) - i conj(U1) - conj(U2) + i conj(U3)
+//   X[N/2 - k] = conj(U0 - U1 + U2 - U3)
+// are additions, sign flips and re/im swaps (tools/radix4_emulation.py is the executable spec,
+// including the k = 0 column that also carries the sub-DFT Nyquist bins).
+template <int FMT>
+__device__ __forceinline__ void epilogue_tile_radix4(const TcParams& p, uint32_t trow, int64_t g,
+                                                     int n_tile, int half) {
+  const int64_t b = g / p.t_slots;
+  const int64_t tl = g - b * p.t_slots;
+  const bool valid = (g < p.nv) && (tl < p.T);
+  const int64_t t = tl * p.t_mul + p.t_add;
+  const int k_base = n_tile * half;
+  const int NH = p.epi.F - 1;  // N/2
+  const int NQ = NH / 2;       // N/4
+  const int NE = NH / 4;       // N/8: Nyquist bin of the sub-DFTs
+  const int bns = 2 * half;
+  constexpr int CH = (FMT == NNAB_FMT_COMPLEX) ? 2 : 1;
+  float* dst = nullptr;
+  float* mel = nullptr;
+  if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
+  else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+  MelRun up0, up1, dn0, dn1;
+  auto emit = [&](MelRun& run, int bin, float re, float im) {
+    if constexpr (FMT == 5) {
+      run.add(p.epi, mel, valid, bin, epi_power(p.epi, re, im));
+    } else {
+      if (valid) epi_store_fmt<FMT>(p.epi, dst, bin, re, im);
+    }
+  };
+#pragma unroll 1
+  for (int c0 = 0; c0 < half; c0 += 8) {
+    uint32_t r0[8], i0[8], r1[8], i1[8], r2[8], i2[8], r3[8], i3[8];
+    tmem_ld8(trow + (uint32_t)(0 * bns + c0), r0);
+    tmem_ld8(trow + (uint32_t)(0 * bns + half + c0), i0);
+    tmem_ld8(trow + (uint32_t)(1 * bns + c0), r1);
+    tmem_ld8(trow + (uint32_t)(1 * bns + half + c0), i1);
+    tmem_ld8(trow + (uint32_t)(2 * bns + c0), r2);
+    tmem_ld8(trow + (uint32_t)(2 * bns + half + c0), i2);
+    tmem_ld8(trow + (uint32_t)(3 * bns + c0), r3);
+    tmem_ld8(trow + (uint32_t)(3 * bns + half + c0), i3);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k_base + c0 + j;
+      const float a0 = __uint_as_float(r0[j]), b0 = __uint_as_float(i0[j]);
+      const float a1 = __uint_as_float(r1[j]), b1 = __uint_as_float(i1[j]);
+      const float a2 = __uint_as_float(r2[j]), b2 = __uint_as_float(i2[j]);
+      const float a3 = __uint_as_float(r3[j]), b3 = __uint_as_float(i3[j]);
+      if (k == 0) {
+        // U_s[0] = a_s (real); the im slots b_s hold the packed Nyquist numbers:
+        //   v0 = (b0, 0)  v1 = (b1, -b1)  v2 = (0, b2)  v3 = (b3, b3)
+        MelRun one;
+        emit(one, 0, a0 + a1 + a2 + a3, 0.f);
+        emit(one, NQ, a0 - a2, a3 - a1);
+        emit(one, NH, a0 - a1 + a2 - a3, 0.f);
+        emit(one, NE, b0 + b1 + b3, -b1 + b2 + b3);
+        emit(one, NQ + NE, b0 - b1 - b3, -b1 - b2 + b3);
+        if constexpr (FMT == 5) one.flush(p.epi, mel, valid);
+      } else {
+        emit(up0, k, a0 + a1 + a2 + a3, b0 + b1 + b2 + b3);
+        emit(up1, NQ + k, a0 + b1 - a2 - b3, b0 - a1 - b2 + a3);
+        emit(dn0, NQ - k, a0 - b1 - a2 + b3, -b0 - a1 + b2 + a3);
+        emit(dn1, NH - k, a0 - a1 + a2 - a3, -(b0 - b1 + b2 - b3));
+      }
+    }
+  }
+  if constexpr (FMT == 5) {
+    up0.flush(p.epi, mel, valid);
+    up1.flush(p.epi, mel, valid);
+    dn0.flush(p.epi, mel, valid);
+    dn1.flush(p.epi, mel, valid);
+  }
+}
+
+// BNS = columns per segment: 128 (64 bins; 2 x 128 columns per tile, TMEM double-buffered) or
+// 256 (128 bins; the two segments fill all 512 columns, so the epilogue of a tile is not overlapped
+// with the next tile's MMAs, but every MMA runs at the full N = 256).
+// RAD = segments (sample phases) per tile: RAD * BNS <= 256 leaves room for two accumulator buffers.
+template <int FMT, int BNS, int RAD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const TcParams p, const int seg_rows) {
+  constexpr int BK = 64, STAGES = 3;
+  constexpr int NACC = (RAD * BNS <= 256) ? 2 : 1;
+  static_assert(RAD * BNS <= 512, "segments of one tile must fit the 512 TMEM columns");
+  using S = Tc2Smem<BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  constexpr int halfn = BNS / 2;
+  constexpr uint32_t b_half_bytes = (uint32_t)halfn * BK * 2;
+  const int kb_n = p.kb_end[0];  // K/2 in 64-sample blocks, same for every tile and segment
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        for (int seg = 0; seg < RAD; ++seg) {
+          const int n0 = seg * seg_rows + n_tile * BNS + (int)cta * halfn;
+          for (int kb = 0; kb < kb_n; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sb = base + stage * S::STAGE_BYTES;
+            mbar_expect_tx_remote(full_bar(stage), 0, 2 * S::A_BYTES + 2 * b_half_bytes);
+            const int k0 = kb * BK;
+            const int c1 = m0 + k0 / p.hop;          // rows mode: (rows x hop) view of a plane
+            const int c0 = k0 - (k0 / p.hop) * p.hop;
+            tma_load_3d_2sm(sb, &tm_a, full_bar(stage), c0, c1, 2 * seg);
+            tma_load_3d_2sm(sb + S::A_BYTES, &tm_a, full_bar(stage), c0, c1, 2 * seg + 1);
+            tma_load_3d_2sm(sb + 2 * S::A_BYTES, &tm_b, full_bar(stage), k0, n0, 0);
+            tma_load_3d_2sm(sb + 2 * S::A_BYTES + S::B_BYTES, &tm_b, full_bar(stage), k0, n0, 1);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNS >> 3) << 17) |
+                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        for (int seg = 0; seg < RAD; ++seg) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE + (uint32_t)(seg * BNS);
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < kb_n; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sb = base + stage * S::STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t koff = (uint32_t)k * 32u;
+              const uint64_t a_hi = make_smem_desc<BK>(sb + koff);
+              const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
+              const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
+              const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+              accumulate = 1u;
+            }
+            umma_commit_2sm(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)acc * TC_ACC_STRIDE;
+      if constexpr (RAD == 2) epilogue_tile_radix2<FMT>(p, trow, g, n_tile, halfn);
+      else epilogue_tile_radix4<FMT>(p, trow, g, n_tile, halfn);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+
+// ===========================================================================
+// EXPERIMENTAL (branch radix2-wip, not GPU-verified yet): per-K-block MMA width for banks
+// whose rows have nested, centred supports (CQT1992v2).
+//
+// Packed rows are ordered in 8-bin groups, [re bins 8g..8g+7 | negated im of the same bins], so
+// basis row r is accumulator column r and a K block that only the G longest groups reach needs
+// an MMA of width N = 16 G: TMA fetches 8 G rows per CTA of the pair, the instruction descriptor
+// carries N, the accumulation still lands in TMEM columns [0, N).  K blocks are visited in order
+// of decreasing width, so the first MMA of a tile (accumulate = 0) initialises every column the
+// tile will touch, and the epilogue of a split-K chunk reads only those.
+// ===========================================================================
+constexpr int VN_MAX_BLOCKS = 512;
+struct VarNPlan {
+  int n_blocks;              // active K blocks
+  int n_chunks;              // split-K chunks (1 = none)
+  int chunk_begin[17];       // chunk c = ordered blocks [chunk_begin[c], chunk_begin[c+1])
+  uint16_t order[VN_MAX_BLOCKS];  // K block index (64 samples each), widest first
+  uint8_t groups[VN_MAX_BLOCKS];  // 8-bin groups the block reaches (N = 16 * groups)
+};
+
+// packed[plane][row][k]: row = 16 g + 8 part + j  <->  bin 8 g + j, part 0 = re, 1 = negated im
+__global__ void __launch_bounds__(256) pack_basis_varn_kernel(
+    const float* __restrict__ w_re, const float* __restrict__ w_im, int F, int K, int rows, int kpad,
+    __nv_bfloat16* __restrict__ packed) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k8 = kpad / 8;
+  if (idx >= (int64_t)rows * k8) return;
+  const int r = (int)(idx / k8);
+  const int k0 = (int)(idx % k8) * 8;
+  const int f = (r >> 4) * 8 + (r & 7);
+  const int part = (r >> 3) & 1;
+  __align__(16) __nv_bfloat16 hi[8];
+  __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    float v = 0.f;
+    if (f < F && k < K)
+      v = part == 0 ? __ldg(w_re + (int64_t)f * K + k) : -__ldg(w_im + (int64_t)f * K + k);
+    split_bf16(v, hi[e], lo[e]);
+  }
+  const int64_t o = (int64_t)r * kpad + k0;
+  *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(packed + (int64_t)rows * kpad + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// FMT: 0 Magnitude, 1 Complex, 3 PhaseUnit (direct), 7 split-K partial sums.
+template <int FMT>
+__device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t trow, int64_t g,
+                                                   int n_groups) {
+  const int64_t b = g / p.t_slots;
+  const int64_t tl = g - b * p.t_slots;
+  const bool valid = (g < p.nv) && (tl < p.T);
+  const int64_t t = tl * p.t_mul + p.t_add;
+  constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
+  float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+  float* rre = (FMT == 7) ? p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t : nullptr;
+#pragma unroll 1
+  for (int gi = 0; gi < n_groups; ++gi) {
+    uint32_t re[8], im[8];
+    tmem_ld8(trow + (uint32_t)(16 * gi), re);
+    tmem_ld8(trow + (uint32_t)(16 * gi + 8), im);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int f = 8 * gi + j;
+        if (f < p.epi.F) {
+          if constexpr (FMT == 7) {
+            float* q = rre + (int64_t)f * p.epi.T;
+            atomicAdd(q, __uint_as_float(re[j]));
+            atomicAdd(q + p.epi.raw_plane, __uint_as_float(im[j]));
+          } else {
+            epi_store_fmt<FMT>(p.epi, dst, f, __uint_as_float(re[j]), __uint_as_float(im[j]));
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b8,
+                   const __grid_constant__ CUtensorMap tm_b32, const TcParams p,
+                   const __grid_constant__ VarNPlan plan) {
+  constexpr int BK = 64, STAGES = 3;
+  using S = Tc2Smem<BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b8);
+    prefetch_tmap(&tm_b32);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_tiles * plan.n_chunks;  // one N tile
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int chunk = tile % plan.n_chunks;
+        const int m_tile = tile / plan.n_chunks;
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        for (int i = plan.chunk_begin[chunk]; i < plan.chunk_begin[chunk + 1]; ++i) {
+          const int k0 = (int)plan.order[i] * BK;
+          const int rows = 8 * (int)plan.groups[i];  // basis rows this CTA stages
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+          mbar_expect_tx_remote(full_bar(stage), 0, 2 * S::A_BYTES + 2 * (uint32_t)rows * BK * 2);
+          int c0 = k0, c1 = m0;
+          if (p.rows_mode) {
+            c1 = m0 + k0 / p.hop;
+            c0 = k0 - (k0 / p.hop) * p.hop;
+          }
+          tma_load_3d_2sm(sb, &tm_a, full_bar(stage), c0, c1, 0);
+          tma_load_3d_2sm(sb + S::A_BYTES, &tm_a, full_bar(stage), c0, c1, 1);
+          const int row0 = (int)cta * rows;
+          const uint32_t bh = sb + 2 * S::A_BYTES, bl = bh + S::B_BYTES;
+          int r = 0;
+          for (; rows - r >= 32; r += 32) {
+            tma_load_3d_2sm(bh + (uint32_t)r * BK * 2, &tm_b32, full_bar(stage), k0, row0 + r, 0);
+            tma_load_3d_2sm(bl + (uint32_t)r * BK * 2, &tm_b32, full_bar(stage), k0, row0 + r, 1);
+          }
+          for (; r < rows; r += 8) {
+            tma_load_3d_2sm(bh + (uint32_t)r * BK * 2, &tm_b8, full_bar(stage), k0, row0 + r, 0);
+            tma_load_3d_2sm(bl + (uint32_t)r * BK * 2, &tm_b8, full_bar(stage), k0, row0 + r, 1);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int chunk = tile % plan.n_chunks;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
+        uint32_t accumulate = 0;
+        for (int i = plan.chunk_begin[chunk]; i < plan.chunk_begin[chunk + 1]; ++i) {
+          const uint32_t idesc = idesc0 | ((uint32_t)(2 * (int)plan.groups[i]) << 17);  // N = 16 G
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sb = base + stage * S::STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t koff = (uint32_t)k * 32u;
+            const uint64_t a_hi = make_smem_desc<BK>(sb + koff);
+            const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
+            const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
+            const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
+            umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+            umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+            accumulate = 1u;
+          }
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int chunk = tile % plan.n_chunks;
+      const int m_tile = tile / plan.n_chunks;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)acc * TC_ACC_STRIDE;
+      // widest block of the chunk = its first: the columns this tile initialised
+      epilogue_tile_varn<FMT>(p, trow, g, (int)plan.groups[plan.chunk_begin[chunk]]);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc_2sm(tmem_base, 512);
@@ -1441,11 +2137,15 @@ template <int BK, int STAGES, int FMT>
 static int launch_tc_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                                 int grid, cudaStream_t stream) {
   using S = TcSmem<BK, STAGES>;
-  static bool configured = false;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
     NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc_kernel<BK, STAGES, FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    configured = true;
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
   framed_tc_kernel<BK, STAGES, FMT><<<grid, TC_THREADS, S::TOTAL, stream>>>(ma, mb, prm);
   NNAB_LAUNCH_CHECK();
@@ -1456,11 +2156,15 @@ template <int BK, int STAGES, int FMT>
 static int launch_tc2_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                                  int n_pairs, cudaStream_t stream) {
   using S = Tc2Smem<BK, STAGES>;
-  static bool configured = false;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
   if (!configured) {
     NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2_kernel<BK, STAGES, FMT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    configured = true;
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * n_pairs));
@@ -1513,10 +2217,455 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL decimation-in-time host side: radix R = 2 or 4 (NNAB_RADIX=2|4, or an explicit
+// layout request through nnab_pack_basis_ex)
+// ---------------------------------------------------------------------------
+static int radix_env() {
+  const char* e = getenv("NNAB_RADIX");
+  const int r = e != nullptr ? atoi(e) : -1;
+  return r;  // -1 unset, 0 = force dense, 2 / 4
+}
+bool tc_radix2_enabled() { const int r = radix_env(); return r == 2 || r == 4; }
+
+// columns per segment: R = 2: 128 (default) or 256 (NNAB_RADIX_BN=256); R = 4: 64 (default) or 128.
+// Read at pack and at launch time, so it must not change while a packed basis is alive.
+static int radix_bn(int R) {
+  const char* e = getenv("NNAB_RADIX_BN");
+  const int v = e != nullptr ? atoi(e) : 0;
+  if (R == 2) return v == 256 ? 256 : 128;
+  return v == 128 ? 128 : 64;
+}
+
+// basis shapes the radix packing accepts (the caller vouches that the basis is DFT-structured);
+// K < 8192: longer kernels take the split-K path of the dense kernel (accumulation-length bound)
+static bool radix_basis_ok(int F, int K, int R) {
+  if (R != 2 && R != 4) return false;
+  return K >= 512 && K < 8192 && K % (R * radix_bn(R)) == 0 && F == K / 2 + 1;
+}
+bool tc_radix2_basis_ok(int F, int K) {
+  const int r = radix_env();
+  return radix_basis_ok(F, K, r == 4 ? 4 : 2);
+}
+
+// layout of an experimental packed basis, keyed by its device pointer (WIP: a header inside the
+// packed buffer should replace this registry)
+enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2, PACK_RADIX4 = 3 };
+static std::mutex g_r2_mu;
+static std::unordered_map<const void*, int> g_pack_kind;
+
+static int packed_kind(const void* packed) {
+  std::lock_guard<std::mutex> lk(g_r2_mu);
+  auto it = g_pack_kind.find(packed);
+  return it == g_pack_kind.end() ? PACK_DENSE : it->second;
+}
+
+static void mark_packed(const void* packed, int kind) {
+  std::lock_guard<std::mutex> lk(g_r2_mu);
+  if (kind == PACK_DENSE) g_pack_kind.erase(packed);
+  else g_pack_kind[packed] = kind;
+}
+
+static bool is_radix2_packed(const void* packed) {
+  const int k = packed_kind(packed);
+  return k == PACK_RADIX2 || k == PACK_RADIX4;
+}
+
+void tc_forget_packed(const void* packed) { mark_packed(packed, PACK_DENSE); }
+
+static SplitGeom radix_geom(int64_t B, int64_t L, int K, int hop, int pad, int R) {
+  const int64_t lp = L + 2 * (int64_t)pad;
+  return split_geom(B, (lp + R - 1) / R, K / R, hop / R, 0);
+}
+
+size_t tc_radix2_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
+  size_t n = 0;
+  for (int R = 2; R <= 4; R += 2) {
+    if (hop % R != 0 || K % R != 0) continue;
+    const SplitGeom g = radix_geom(B, L, K, hop, pad, R);
+    const size_t v = (size_t)(2 * R * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
+    if (v > n) n = v;
+  }
+  return n;
+}
+
+int tc_pack_basis_radix(const float* w_re, const float* w_im, int F, int K, int R, void* packed,
+                        cudaStream_t stream) {
+  if (!radix_basis_ok(F, K, R)) return NNAB_EINVAL;
+  const int rows_seg = K / R;  // (K / (2R) bins) x (re, im)
+  const int kpadr = K / R;     // already a multiple of 64
+  const int64_t threads = (int64_t)R * rows_seg * (kpadr / 8);
+  pack_basis_radix_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+      w_re, w_im, K, R, rows_seg, kpadr, radix_bn(R), (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  mark_packed(packed, R == 4 ? PACK_RADIX4 : PACK_RADIX2);
+  return NNAB_OK;
+}
+int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
+                         cudaStream_t stream) {
+  return tc_pack_basis_radix(w_re, w_im, F, K, radix_env() == 4 ? 4 : 2, packed, stream);
+}
+
+static bool radix_problem_ok(const FramedProblem& q, int R) {
+  if (!radix_basis_ok(q.F, q.K, R)) return false;
+  if (q.hop % R != 0 || num_phases(q.hop / R) != 1 || (q.hop / R) % 64 != 0) return false;
+  if (q.presplit != nullptr || q.h_k_begin != nullptr || q.raw != nullptr) return false;
+  switch (q.fmt) {
+    case NNAB_FMT_MAGNITUDE: case NNAB_FMT_COMPLEX: case FMT_POWER:
+      return q.bin_offset == 0 && q.out_bins >= q.F;
+    case FMT_FBANK: return q.fb_table != nullptr && q.n_fb > 0;  // out_bins = n_fb there
+    default: return false;
+  }
+}
+
+template <int FMT, int BNS, int RAD>
+static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                           int seg_rows, int n_pairs, cudaStream_t stream) {
+  using S = Tc2Smem<64, 3>;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
+  if (!configured) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT, BNS, RAD>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2r_kernel<FMT, BNS, RAD>, ma, mb, prm, seg_rows));
+  count_launch();
+  return NNAB_OK;
+}
+
+template <int BNS, int RAD>
+static int launch_tc2r(int fmt, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
+                       int seg_rows, int n_pairs, cudaStream_t stream) {
+  switch (fmt) {
+    case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_POWER: return launch_tc2r_fmt<4, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    case FMT_FBANK: return launch_tc2r_fmt<5, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
+    default: return NNAB_EINVAL;
+  }
+}
+
+static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, void* workspace,
+                                   size_t ws_bytes, cudaStream_t stream) {
+  const int R = packed_kind(packed) == PACK_RADIX4 ? 4 : 2;
+  if (!radix_problem_ok(q, R)) return NNAB_EINVAL;  // the basis was packed for the radix kernel only
+  const size_t need = tc_radix2_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (q.B > 65535) return NNAB_EUNSUPPORTED;
+  const int hopr = q.hop / R, kr = q.K / R;
+  const SplitGeom g = radix_geom(q.B, q.L, q.K, q.hop, q.pad, R);
+  __nv_bfloat16* planes =
+      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const int64_t clip_pitch = g.t_slots * hopr;
+  // K overhang past the last clip: finite zeros in all 2R planes
+  const int64_t tail = g.plane_stride - g.nv * hopr;
+  for (int pl = 0; pl < 2 * R; ++pl)
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hopr, 0,
+                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
+  dim3 pgrid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
+  if (R == 2)
+    pad_split_radix_kernel<2><<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
+                                                          clip_pitch, g.plane_stride, planes);
+  else
+    pad_split_radix_kernel<4><<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
+                                                          clip_pitch, g.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();
+  if (sms < 2) sms = 2;
+
+  const int seg_rows = kr;            // rows of one segment in the packed basis
+  const int bns = radix_bn(R);
+  const int n_tiles = seg_rows / bns;
+  CUtensorMap ma, mb;
+  int rc = encode_3d(&ma, planes, (uint64_t)hopr, (uint64_t)g.rows, (uint64_t)(2 * R), (uint64_t)hopr * 2,
+                     (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
+  if (rc) return rc;
+  rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)kr, (uint64_t)(R * seg_rows), 2,
+                 (uint64_t)kr * 2, (uint64_t)(R * seg_rows) * kr * 2, 64, bns / 2, 64);
+  if (rc) return rc;
+
+  TcParams prm{};
+  prm.num_n_tiles = n_tiles;
+  prm.bn = bns;
+  prm.rows_mode = 1;
+  prm.hop = hopr;
+  prm.nv = g.nv;
+  prm.t_slots = g.t_slots;
+  prm.t_mul = 1;
+  prm.t_add = 0;
+  prm.T = q.T;
+  prm.k_splits = 1;
+  for (int tl = 0; tl < n_tiles; ++tl) { prm.kb_begin[tl] = 0; prm.kb_end[tl] = kr / 64; }
+  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
+  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
+  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+  prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
+  prm.epi.dec = q.dec;
+  prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
+  prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
+  prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
+  const int64_t ptiles = (int64_t)prm.num_m_tiles * n_tiles;
+  const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  if (R == 2) {
+    return bns == 256 ? launch_tc2r<256, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream)
+                      : launch_tc2r<128, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream);
+  }
+  return bns == 128 ? launch_tc2r<128, 4>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream)
+                    : launch_tc2r<64, 4>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream);
+}
+
+
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL per-K-block MMA width, host side (NNAB_VARN=1)
+// ---------------------------------------------------------------------------
+bool tc_varn_enabled() {
+  const char* e = getenv("NNAB_VARN");
+  return e != nullptr && atoi(e) == 1;
+}
+
+bool tc_varn_basis_ok(int F, int K) { return F >= 1 && F <= 128 && K >= 64 && K <= 64 * VN_MAX_BLOCKS; }
+
+int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void* packed,
+                       cudaStream_t stream) {
+  if (!tc_varn_basis_ok(F, K)) return NNAB_EINVAL;
+  const int rows = 16 * ((F + 7) / 8);
+  const int kpad = round_up_i(K, 64);
+  const int64_t threads = (int64_t)rows * (kpad / 8);
+  pack_basis_varn_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+      w_re, w_im, F, K, rows, kpad, (__nv_bfloat16*)packed);
+  NNAB_LAUNCH_CHECK();
+  mark_packed(packed, PACK_VARN);
+  return NNAB_OK;
+}
+
+// Pure host: which K blocks are touched, by how many 8-bin groups, in which order, and how the
+// ordered list is cut into split-K chunks of equal modelled cost (max(N, 64) per block: below
+// N = 64 the A-operand reads, not the MMA, set the pace).  Returns NNAB_OK or NNAB_EUNSUPPORTED.
+int tc_varn_plan(const int32_t* k_begin, const int32_t* k_end, int F, int K, int want_chunks,
+                 VarNPlan* plan) {
+  const int nkb = (K + 63) / 64;
+  if (nkb > VN_MAX_BLOCKS || F > 128 || F < 1) return NNAB_EUNSUPPORTED;
+  std::vector<std::pair<int, int>> blocks;  // (groups, kb)
+  for (int kb = 0; kb < nkb; ++kb) {
+    int gmax = 0;
+    for (int f = 0; f < F; ++f) {
+      const int lo = k_begin ? k_begin[f] : 0, hi = k_end ? k_end[f] : K;
+      if (hi > lo && hi > kb * 64 && lo < kb * 64 + 64) gmax = std::max(gmax, f / 8 + 1);
+    }
+    if (gmax > 0) blocks.push_back({gmax, kb});
+  }
+  if (blocks.empty()) blocks.push_back({(F + 7) / 8, 0});
+  std::stable_sort(blocks.begin(), blocks.end(),
+                   [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+  plan->n_blocks = (int)blocks.size();
+  int64_t total = 0;
+  for (int i = 0; i < plan->n_blocks; ++i) {
+    plan->groups[i] = (uint8_t)blocks[i].first;
+    plan->order[i] = (uint16_t)blocks[i].second;
+    total += std::max(16 * blocks[i].first, 64);
+  }
+  int chunks = want_chunks < 1 ? 1 : (want_chunks > 16 ? 16 : want_chunks);
+  if (chunks > plan->n_blocks) chunks = plan->n_blocks;
+  plan->n_chunks = chunks;
+  plan->chunk_begin[0] = 0;
+  int64_t acc = 0;
+  int c = 1;
+  for (int i = 0; i < plan->n_blocks && c < chunks; ++i) {
+    acc += std::max(16 * (int)plan->groups[i], 64);
+    // close chunk c-1 once its share of the cost is reached, leaving >= 1 block per later chunk
+    if (acc * chunks >= total * c && plan->n_blocks - (i + 1) >= chunks - c) plan->chunk_begin[c++] = i + 1;
+  }
+  while (c < chunks) { plan->chunk_begin[c] = plan->n_blocks - (chunks - c); ++c; }
+  plan->chunk_begin[chunks] = plan->n_blocks;
+  for (int k = chunks + 1; k < 17; ++k) plan->chunk_begin[k] = plan->n_blocks;
+  return NNAB_OK;
+}
+
+// host-only view of the plan for tests / tooling
+int tc_varn_plan_export(const int32_t* k_begin, const int32_t* k_end, int F, int K, int want_chunks,
+                        int32_t* order, int32_t* groups, int32_t* chunk_begin, int32_t* n_blocks,
+                        int32_t* n_chunks) {
+  VarNPlan plan;
+  const int rc = tc_varn_plan(k_begin, k_end, F, K, want_chunks, &plan);
+  if (rc) return rc;
+  *n_blocks = plan.n_blocks;
+  *n_chunks = plan.n_chunks;
+  for (int i = 0; i < plan.n_blocks; ++i) { order[i] = plan.order[i]; groups[i] = plan.groups[i]; }
+  for (int c = 0; c <= plan.n_chunks; ++c) chunk_begin[c] = plan.chunk_begin[c];
+  return NNAB_OK;
+}
+
+static bool varn_problem_ok(const FramedProblem& q) {
+  if (!tc_varn_basis_ok(q.F, q.K)) return false;
+  if (num_phases(q.hop) != 1 || q.presplit != nullptr) return false;
+  if (q.bin_offset != 0 || q.out_bins != q.F) return false;
+  return q.fmt == NNAB_FMT_MAGNITUDE || q.fmt == NNAB_FMT_COMPLEX || q.fmt == NNAB_FMT_PHASE_UNIT;
+}
+
+template <int FMT>
+static int launch_tc2v_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const CUtensorMap& mb32,
+                           const TcParams& prm, const VarNPlan& plan, int n_pairs,
+                           cudaStream_t stream) {
+  using S = Tc2Smem<64, 3>;
+  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
+  if (!configured) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2v_kernel<FMT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2v_kernel<FMT>, ma, mb8, mb32, prm, plan));
+  count_launch();
+  return NNAB_OK;
+}
+
+static int launch_framed_tc_varn(const FramedProblem& q, const void* packed, void* workspace,
+                                 size_t ws_bytes, cudaStream_t stream) {
+  if (!varn_problem_ok(q)) return NNAB_EINVAL;  // the basis was packed for this kernel only
+  const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (q.B > 65535) return NNAB_EUNSUPPORTED;
+  const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+  const int kpad = round_up_i(q.K, 64);
+  const int rows_w = 16 * ((q.F + 7) / 8);
+  __nv_bfloat16* planes =
+      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  int rc = zero_tail(planes, g, q.hop, stream);
+  if (rc) return rc;
+  const int64_t clip_pitch = g.t_slots * q.hop;
+  dim3 pgrid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
+  pad_split_kernel<<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode, 0, clip_pitch,
+                                              g.plane_stride, planes);
+  NNAB_LAUNCH_CHECK();
+
+  // split-K only with the caller's raw scratch (long kernels): <= 64 K blocks per accumulator
+  VarNPlan plan;
+  {
+    VarNPlan probe;
+    if ((rc = tc_varn_plan(q.h_k_begin, q.h_k_end, q.F, q.K, 1, &probe))) return rc;
+    int ks = 1;
+    if (q.raw != nullptr) {
+      ks = (probe.n_blocks + 63) / 64;
+      if (ks > 16) ks = 16;
+    }
+    if ((rc = tc_varn_plan(q.h_k_begin, q.h_k_end, q.F, q.K, ks, &plan))) return rc;
+  }
+
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();
+  if (sms < 2) sms = 2;
+
+  CUtensorMap ma, mb8, mb32;
+  const int rows_mode = (q.hop % 64 == 0) ? 1 : 0;
+  if (rows_mode)
+    rc = encode_3d(&ma, planes, (uint64_t)q.hop, (uint64_t)g.rows, 2, (uint64_t)q.hop * 2,
+                   (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
+  else
+    rc = encode_3d(&ma, planes, (uint64_t)kpad, (uint64_t)g.nv, 2, (uint64_t)q.hop * 2,
+                   (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
+  if (rc) return rc;
+  if ((rc = encode_3d(&mb8, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
+                      (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, 64, 8, 64)))
+    return rc;
+  if ((rc = encode_3d(&mb32, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
+                      (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, 64, 32, 64)))
+    return rc;
+
+  TcParams prm{};
+  prm.num_n_tiles = 1;
+  prm.bn = rows_w;
+  prm.rows_mode = rows_mode;
+  prm.hop = q.hop;
+  prm.nv = g.nv;
+  prm.t_slots = g.t_slots;
+  prm.t_mul = 1;
+  prm.t_add = 0;
+  prm.T = q.T;
+  prm.k_splits = plan.n_chunks;
+  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
+  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
+  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+  prm.epi.fb_table = nullptr; prm.epi.n_fb = 0;
+  prm.epi.dec = q.dec;
+  prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
+  prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
+  EpiParams final_epi = prm.epi;
+  const bool split = plan.n_chunks > 1;
+  if (split) {
+    float* raw = reinterpret_cast<float*>(((uintptr_t)q.raw + 255) & ~(uintptr_t)255);
+    const int64_t plane = (int64_t)q.B * q.F * q.T;
+    NNAB_CUDA_TRY(cudaMemsetAsync(raw, 0, (size_t)2 * plane * sizeof(float), stream));
+    prm.epi.fmt = FMT_RAW;
+    prm.epi.raw = raw;
+    prm.epi.raw_plane = plane;
+    final_epi.raw = raw;
+    final_epi.raw_plane = plane;
+  }
+  prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
+  const int64_t ptiles = (int64_t)prm.num_m_tiles * plan.n_chunks;
+  const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  switch (prm.epi.fmt) {
+    case NNAB_FMT_MAGNITUDE: rc = launch_tc2v_fmt<0>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    case NNAB_FMT_COMPLEX: rc = launch_tc2v_fmt<1>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    case NNAB_FMT_PHASE_UNIT: rc = launch_tc2v_fmt<3>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    case FMT_RAW: rc = launch_tc2v_fmt<7>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
+    default: rc = NNAB_EINVAL;
+  }
+  if (rc) return rc;
+  if (split) {
+    dim3 grid((unsigned)ceil_div64(q.T, 256), (unsigned)q.F, (unsigned)(q.B < 64 ? q.B : 64));
+    splitk_finalize_kernel<<<grid, 256, 0, stream>>>(final_epi, q.B);
+    NNAB_LAUNCH_CHECK();
+  }
+  return NNAB_OK;
+}
+
 int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace, size_t ws_bytes,
                      cudaStream_t stream) {
   if (q.B <= 0 || q.T <= 0 || q.F <= 0) return NNAB_OK;
   if (packed == nullptr) return NNAB_EINVAL;
+  if (packed_kind(packed) == PACK_VARN)
+    return launch_framed_tc_varn(q, packed, workspace, ws_bytes, stream);
+  if (is_radix2_packed(packed))
+    return launch_framed_tc_radix2(q, packed, workspace, ws_bytes, stream);
   if (q.presplit == nullptr) {
     const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
     if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
@@ -1585,6 +2734,10 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
   prm.nv = g.nv;
   prm.t_slots = g.t_slots;
   prm.t_mul = n_ph;
+  {
+    const char* e4 = getenv("NNAB_SPLIT4");
+    prm.split4 = (e4 != nullptr && atoi(e4) == 1) ? 1 : 0;  // CTA-pair kernel only
+  }
   const int nkb = kpad / bk;
   const int half = bn / 2;
   for (int tl = 0; tl < n_tiles; ++tl) {

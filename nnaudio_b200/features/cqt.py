@@ -134,7 +134,8 @@ class CQT1992v2(nn.Module):
             raise RuntimeError("Kernel size can't be greater than actual input size")
 
         k_real, k_imag = as_matrix(self.cqt_kernels_real), as_matrix(self.cqt_kernels_imag)
-        packed = self._packed.get(k_real, k_imag)
+        packed = self._packed.get(k_real, k_imag,
+                                  groups=(not self.trainable) and self.hop_length % 8 == 0)
         k_begin, k_end = self._tap_support()
         scale, scale_all = None, 1.0
         if normalization_type == "librosa":
@@ -464,6 +465,19 @@ class _DecimateFn(torch.autograd.Function):
         return d_padded[:, half:half + L].contiguous(), None, None, None, None
 
 
+class _FirDecimateFn(torch.autograd.Function):
+    """``nnab_fir_decimate`` / ``nnab_fir_decimate_adjoint`` (EXPERIMENTAL, branch radix2-wip)."""
+
+    @staticmethod
+    def forward(ctx, sig, fir, n):
+        ctx.fir, ctx.n, ctx.L = fir, n, sig.shape[-1]
+        return _C.fir_decimate(sig, fir, n)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _C.fir_decimate_adjoint(g.contiguous(), ctx.fir, ctx.n, ctx.L), None, None
+
+
 def _decimate_autograd(mod, tag, sig, fir, n):
     """Differentiable ``downsampling_by_n`` / ``_by_2`` stage of the training path.
 
@@ -474,6 +488,9 @@ def _decimate_autograd(mod, tag, sig, fir, n):
     ``ola`` a K=1 adjoint GEMM + overlap-add atomics (256 atomics per input sample) — 24.4 ms but
     1.04e-4 on the Magnitude case, i.e. over the parity bar.  A dedicated FIR-adjoint kernel is
     the open item."""
+    if os.environ.get("NNAUDIO_B200_DECIM_BWD", "simt") == "fir":
+        # EXPERIMENTAL (radix2-wip): dedicated CUDA-core FIR stage and adjoint, one launch each
+        return _FirDecimateFn.apply(sig, fir.detach().reshape(-1).contiguous(), int(n))
     if os.environ.get("NNAUDIO_B200_DECIM_BWD", "simt") == "ola":
         taps = fir.numel()
         w_re = fir.detach().reshape(1, taps)

@@ -234,14 +234,20 @@ class STFT(nn.Module):
             raise RuntimeError("Kernel size can't be greater than actual input size")
         return x
 
-    def _bases(self):
+    def _bases(self, radix_ok=False):
+        """``radix_ok``: the caller's output format has a decimation-in-time epilogue (Magnitude,
+        Complex, power / fused filterbank); the layout is still only used when the buffers pass
+        ``is_dft_structured`` and the hop allows the half-rate planes (EXPERIMENTAL)."""
         wcos, wsin = as_matrix(self.wcos), as_matrix(self.wsin)
         if self.freq_bins is not None and self.freq_bins < wcos.shape[0]:
             wcos, wsin = wcos[: self.freq_bins], wsin[: self.freq_bins]
-        return wcos, wsin, self._packed.get(wcos, wsin)
+        allow = False
+        if radix_ok and not self.trainable and self.stride % 128 == 0:
+            allow = 4 if self.stride % 256 == 0 else 2
+        return wcos, wsin, self._packed.get(wcos, wsin, allow_radix=allow)
 
     def _run(self, x, output_format):
-        wcos, wsin, packed = self._bases()
+        wcos, wsin, packed = self._bases(radix_ok=output_format in ("Magnitude", "Complex"))
         eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
         return _C.stft_forward(
             x, wcos, wsin, packed, self.n_fft, self.stride, self.center,

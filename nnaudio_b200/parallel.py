@@ -97,6 +97,72 @@ class BatchShardedTransform:
         return torch.cat(parts, 0)
 
     # ------------------------------------------------------------------ #
+    # EXPERIMENTAL (branch radix2-wip, needs >= 2 GPUs to run): gather without NCCL and without
+    # SMs.  Every rank owns a symmetric-memory buffer holding the WHOLE gathered output (two
+    # rotating slots); after its transform a rank pushes its shard into the same slice of every
+    # peer's buffer with plain device-to-device copies over NVLink (copy engines, so the persistent
+    # kernels keep all 148 SMs and nothing has to be reserved for a collective).  Two device-side
+    # barriers per step order the slot reuse (all ranks have consumed the slot) and the arrival of
+    # the pushes.
+    def _symm_setup(self, y: torch.Tensor):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        world = self.world
+        shape = (2, world * y.shape[0]) + tuple(y.shape[1:])
+        if getattr(self, "_symm_shape", None) != (shape, y.dtype, y.device):
+            group = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty(shape, dtype=y.dtype, device=y.device)
+            hdl = symm_mem.rendezvous(buf, group)
+            self._symm = (buf, hdl, [hdl.get_buffer(r, shape, y.dtype) for r in range(world)])
+            self._symm_stream = torch.cuda.Stream(y.device)
+            self._symm_consumed = [None, None]
+            self._symm_shape = (shape, y.dtype, y.device)
+        return self._symm
+
+    class _SymmWork:
+        def __init__(self, event):
+            self.event = event
+
+        def wait(self):
+            """Make the current stream wait for the gathered slot."""
+            torch.cuda.current_stream().wait_event(self.event)
+            return True
+
+    def release(self, slot: int):
+        """Record that the consumer is finished with ``slot`` (call after the last kernel that reads
+        the gathered tensor has been enqueued on the current stream)."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._symm_consumed[slot] = ev
+
+    def forward_async_symm(self, x_local: torch.Tensor, slot: int = 0):
+        """Like :meth:`forward_async` with the copy-engine gather described above.  Returns
+        ``(work, gathered)``; call ``work.wait()`` before reading ``gathered`` and
+        ``self.release(slot)`` when done with it."""
+        y = self.transform(x_local).contiguous()
+        world = self.world
+        if not self.gather or world == 1:
+            return None, y
+        buf, hdl, peers = self._symm_setup(y)
+        n = y.shape[0]
+        lo = self.rank * n
+        cur = torch.cuda.current_stream(y.device)
+        ev_y = torch.cuda.Event()
+        ev_y.record(cur)
+        s = self._symm_stream
+        with torch.cuda.stream(s):
+            s.wait_event(ev_y)
+            if self._symm_consumed[slot] is not None:
+                s.wait_event(self._symm_consumed[slot])
+            hdl.barrier(channel=2 * slot)          # every rank is done reading this slot
+            for r in range(world):
+                peers[(self.rank + r) % world][slot, lo:lo + n].copy_(y, non_blocking=True)
+            hdl.barrier(channel=2 * slot + 1)      # every rank's pushes into this slot have landed
+            ev_done = torch.cuda.Event()
+            ev_done.record(s)
+        y.record_stream(s)
+        return BatchShardedTransform._SymmWork(ev_done), buf[slot]
+
     def forward_async(self, x_local: torch.Tensor, slot: int = 0):
         """Pipelined variant for back-to-back batches with equal shards: transform
         the shard, enqueue the output all-gather on NCCL's stream and return

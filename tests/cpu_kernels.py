@@ -144,6 +144,22 @@ def istft_forward(X, packed, window, n_fft, hop, center, length):
     return torch.from_numpy(np.ascontiguousarray(y)).float()
 
 
+def fir_decimate(x, fir, factor):
+    taps = fir.numel()
+    return torch.nn.functional.conv1d(x[:, None, :].double(), fir.reshape(1, 1, -1).double(), stride=factor,
+                                      padding=(taps - 1) // 2)[:, 0, :].float()
+
+
+def fir_decimate_adjoint(g, fir, factor, L_in):
+    x = torch.zeros((g.shape[0], L_in), dtype=torch.float64, requires_grad=True)
+    with torch.enable_grad():
+        taps = fir.numel()
+        y = torch.nn.functional.conv1d(x[:, None, :], fir.reshape(1, 1, -1).double(), stride=factor,
+                                       padding=(taps - 1) // 2)[:, 0, :]
+        (dx,) = torch.autograd.grad(y, x, g.double())
+    return dx.float()
+
+
 def install(monkeypatch):
     """Route the calls of the differentiable host paths to the stand-ins above."""
     monkeypatch.setattr(_C, "_dev_f32", lambda t, name: t)
@@ -161,3 +177,5 @@ def install(monkeypatch):
     monkeypatch.setattr(_C, "framed_backward_input", framed_backward_input)
     monkeypatch.setattr(_C, "framed_backward_weight", framed_backward_weight)
     monkeypatch.setattr(_C, "istft_forward", istft_forward)
+    monkeypatch.setattr(_C, "fir_decimate", fir_decimate, raising=False)
+    monkeypatch.setattr(_C, "fir_decimate_adjoint", fir_decimate_adjoint, raising=False)

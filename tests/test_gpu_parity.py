@@ -131,3 +131,33 @@ def test_simt_and_auto_paths_agree_on_large_shape():
     b = _run(mod, x, {}, "auto")
     emax, el2 = rel_errors(a, b)
     assert emax < TOL and el2 < TOL, (emax, el2)
+
+
+from cases import SWEEP_FORWARD, sweep_input  # noqa: E402
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("case", SWEEP_FORWARD, ids=[c[0] for c in SWEEP_FORWARD])
+def test_cuda_constructor_sweep_matches_reference(case, path):
+    """The 21-configuration constructor sweep on the GPU (first run: round 2)."""
+    cid, cls, ctor = case
+    mod = build(cls, ctor).cuda()
+    x = make_input(sweep_input(cid, cls))
+    got = _run(mod, x, {}, path)
+    want = ref_outputs()["sweep|" + cid]
+    assert got.shape == want.shape
+    tol = 4e-4 if cls == "MFCC" else TOL
+    emax, el2 = rel_errors(got, want)
+    assert emax < tol and el2 < tol, (cid, path, emax, el2)
+
+
+def test_more_clips_than_the_per_call_limit():
+    """70 000 short clips: _C._batch_chunked runs two C calls; every clip equals its stand-alone result."""
+    mod = build("STFT", dict(n_fft=256, hop_length=64, output_format="Magnitude")).cuda()
+    x = torch.randn(70000, 600, device="cuda")
+    with torch.no_grad():
+        y = mod(x)
+        ref = torch.cat([mod(x[:8]), mod(x[65530:65540]), mod(x[-8:])])
+    assert y.shape[0] == 70000
+    got = torch.cat([y[:8], y[65530:65540], y[-8:]])
+    assert torch.equal(got, ref)
