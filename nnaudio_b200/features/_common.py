@@ -34,12 +34,14 @@ def pad_mode_id(pad_mode: str) -> int:
         raise ValueError(f"unsupported pad_mode {pad_mode!r}; use 'reflect' or 'constant'")
 
 
-def forward_only_guard(module: torch.nn.Module, x: torch.Tensor):
+def forward_only_guard(module: torch.nn.Module, x: torch.Tensor, used=None):
     """For parameters without a dW path (trainable inverse kernels / window of iSTFT):
-    refuse loudly rather than return a result whose parameters silently get no gradient."""
+    refuse loudly rather than return a result whose parameters silently get no gradient.
+    ``used``: the tensors this call reads (default: every parameter of the module)."""
     if not torch.is_grad_enabled():
         return
-    if any(p.requires_grad for p in module.parameters()):
+    tensors = module.parameters() if used is None else used
+    if any(p.requires_grad for p in tensors):
         raise NotImplementedError(
             "nnaudio_b200: this module is forward-only for trainable kernels; run under "
             "torch.no_grad()"
@@ -92,11 +94,15 @@ class PerDeviceCache:
     def __init__(self):
         self._entries = {}
 
-    def lookup(self, device, key, build):
+    def lookup(self, device, key, build, keep=()):
+        """``keep``: the tensors whose (data_ptr, _version) make up ``key``.  The entry holds a
+        reference to them, so the allocator cannot hand their address to a *different* tensor while
+        the entry is alive (a recomputed temporary, e.g. the folded v1 CQT bank, always has
+        ``_version`` 0 and would otherwise alias a stale entry after an optimiser step)."""
         slot = str(device)
         entry = self._entries.get(slot)
         if entry is None or entry[0] != key:
-            entry = (key, build())
+            entry = (key, build(), tuple(keep))
             self._entries[slot] = entry
         return entry[1]
 
@@ -109,7 +115,8 @@ class AdjointBasis:
 
     def get(self, w_re: torch.Tensor, w_im: torch.Tensor):
         key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version)
-        return self._cache.lookup(w_re.device, key, lambda: _C.pack_adjoint_basis(w_re, w_im))
+        return self._cache.lookup(w_re.device, key, lambda: _C.pack_adjoint_basis(w_re, w_im),
+                                  keep=(w_re, w_im))
 
 
 def is_dft_structured(w_re: torch.Tensor, w_im: torch.Tensor, rtol: float = 1e-6, radix: int = 2) -> bool:
@@ -172,7 +179,7 @@ class PackedBasis:
             return _C.pack_basis(w_re, w_im, layout) if layout else _C.pack_basis(w_re, w_im)
 
         key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, allow_radix, groups)
-        return self._cache.lookup(w_re.device, key, build)
+        return self._cache.lookup(w_re.device, key, build, keep=(w_re, w_im))
 
 
 def as_matrix(buf: torch.Tensor) -> torch.Tensor:
@@ -204,7 +211,7 @@ class FilterbankTable:
 
     def get(self, fb: torch.Tensor):
         key = (fb.data_ptr(), fb._version)
-        return self._cache.lookup(fb.device, key, lambda: _C.build_filterbank_table(fb))
+        return self._cache.lookup(fb.device, key, lambda: _C.build_filterbank_table(fb), keep=(fb,))
 
 
 class PackedFir:
@@ -215,4 +222,4 @@ class PackedFir:
 
     def get(self, fir: torch.Tensor, dec: int):
         key = (fir.data_ptr(), fir._version, int(dec))
-        return self._cache.lookup(fir.device, key, lambda: _C.pack_fir(fir, int(dec)))
+        return self._cache.lookup(fir.device, key, lambda: _C.pack_fir(fir, int(dec)), keep=(fir,))

@@ -407,10 +407,19 @@ def _pyramid_forward(mod, x, output_format, normalization):
 def _framed_complex_autograd(mod, tag, sig, w_re, w_im, hop, center, pad_mode):
     """One differentiable framed contraction ``sig (B, L) -> (B, F, T, 2)`` through the fused
     forward kernel and the dX / dW kernels; ``tag`` keys the packed-basis caches on ``mod``."""
-    caches = mod.__dict__.setdefault("_grad_caches", {})
-    if tag not in caches:
-        caches[tag] = (PackedBasis(), AdjointBasis())
     k_re, k_im = as_matrix(w_re), as_matrix(w_im)
+    if w_re.grad_fn is not None or w_im.grad_fn is not None:
+        # recomputed temporaries (the folded v1 bank under autograd): every call gets a fresh
+        # tensor with _version 0 whose address the allocator may recycle from the previous step,
+        # so a (data_ptr, _version) key cannot tell them apart -> pack per call, never cache.
+        # The packing rides on the temporary itself (shared by the octaves of one forward, freed
+        # with it).
+        caches = w_re.__dict__.setdefault("_nnab_grad_caches", {})
+        caches.setdefault(tag, (PackedBasis(), AdjointBasis()))
+    else:
+        caches = mod.__dict__.setdefault("_grad_caches", {})
+        if tag not in caches:
+            caches[tag] = (PackedBasis(), AdjointBasis())
     packed = caches[tag][0].get(k_re, k_im)
     width = int(k_re.shape[1])
 

@@ -61,6 +61,10 @@ class Griffin_Lim(nn.Module):
         # the reference module owns no state_dict entries: keep the kernels out of checkpoints
         self._stft._non_persistent_buffers_set.update(self._stft._buffers.keys())
         self._inv = types.SimpleNamespace(n_fft=n_fft, stride=self.hop_length, center=center)
+        # the reference creates its window on ``device`` (griffin_lim.py:85-87), so
+        # Griffin_Lim(n_fft, device='cuda')(S_cuda) works without a .to()
+        if device is not None and torch.device(device).type != "cpu":
+            self.to(device)
 
     def _inverse(self, spec):
         st = self._stft

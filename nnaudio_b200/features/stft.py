@@ -306,7 +306,9 @@ class STFT(nn.Module):
             "make sure our tensor is in the shape of (batch, freq_bins, timesteps, 2)."
             "\nIf you have a magnitude spectrogram, please consider using Griffin-Lim."
         )
-        forward_only_guard(self, X)
+        # only the tensors the inverse actually uses decide (a trainable *forward* STFT may call
+        # .inverse() in training mode, as in the reference: trainable STFT -> process -> inverse)
+        forward_only_guard(self, X, (self.kernel_cos_inv, self.kernel_sin_inv, self.window_mask))
         return _inverse_stft(self, X, self.kernel_cos_inv, self.kernel_sin_inv, self.window_mask,
                              onesided, length)
 

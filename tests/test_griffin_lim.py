@@ -129,3 +129,15 @@ def test_cuda_spectral_convergence():
 
     start, end = sc(0), sc(32)   # ~0.65 -> ~0.12 with float64 transforms
     assert end < 0.25 and end < 0.4 * start, (start, end)
+
+
+@pytest.mark.gpu
+def test_device_argument_places_the_module():
+    """the reference builds its window on ``device`` (griffin_lim.py:85-87), so
+    ``Griffin_Lim(n_fft, device='cuda')(S_cuda)`` works without ``.to()``."""
+    cfg = CFG[0]
+    S, ph = _problem(cfg, 3)
+    mod = nb.Griffin_Lim(**cfg, device="cuda")
+    assert mod.w.is_cuda and mod._stft.wsin.is_cuda
+    y = mod(torch.from_numpy(S).cuda(), rand_phase=torch.from_numpy(ph).cuda())
+    assert y.is_cuda and torch.isfinite(y).all()

@@ -12,6 +12,7 @@ import torch
 
 from helpers import build, ref_outputs, rel_errors  # noqa: E402 (sets sys.path)
 import cpu_kernels  # noqa: E402
+import nnaudio_b200.features as nb  # noqa: E402
 from cases import CASES, GRAD_CASES, ISTFT_GRAD_CASES, WGRAD_CASES, loss_weights, make_input, out_key
 
 HOST_COMPOSED = ("CQT2010v2", "VQT", "CQT1992", "CQT2010")
@@ -120,3 +121,79 @@ def test_polyphase_decimation_adjoint_equals_conv1d_autograd(taps, n, L, monkeyp
     (y_ref * w.double()).sum().backward()
     assert torch.allclose(y.double(), y_ref, rtol=1e-5, atol=1e-5)
     assert torch.allclose(a.grad.double(), b.grad.double(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("cls,ctor", [
+    ("CQT1992", dict(sr=8000, hop_length=64, fmin=200, n_bins=12, trainable_CQT=True)),
+    ("CQT2010", dict(sr=8000, hop_length=64, fmin=200, n_bins=24, trainable_CQT=True, earlydownsample=False)),
+], ids=["cqt1992", "cqt2010"])
+def test_sgd_loop_never_reuses_a_stale_packed_bank(cls, ctor, monkeypatch):
+    """ADVICE r1 (high): the folded v1 bank is a recomputed temporary (``_version`` 0 every step);
+    after an optimiser step the allocator may give the new fold the old address, and a cache keyed
+    on (data_ptr, _version) alone would then hand back the packing of the *previous* parameters.
+    Every step's dx must equal that of a fresh module holding the same parameters."""
+    import copy
+
+    cpu_kernels.install(monkeypatch)
+    torch.manual_seed(0)
+    mod = build(cls, ctor)
+    opt = torch.optim.SGD(mod.parameters(), lr=5e-2)
+    x0 = torch.randn(2, 4096)
+    for step in range(5):
+        x = x0.clone().requires_grad_(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            y = mod(x)
+        opt.zero_grad()
+        y.square().sum().backward()
+        fresh = build(cls, ctor)
+        fresh.load_state_dict(copy.deepcopy(mod.state_dict()))
+        xf = x0.clone().requires_grad_(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            yf = fresh(xf)
+        yf.square().sum().backward()
+        emax, el2 = rel_errors(x.grad.numpy(), xf.grad.numpy())
+        assert el2 < 1e-6, (cls, step, emax, el2)
+        opt.step()
+
+
+def test_recomputed_bank_with_recycled_address_is_repacked(monkeypatch):
+    """Direct form of the above: different non-leaf banks that land on the SAME address with
+    ``_version`` 0 must not share a cached packing.  The collision is forced by making every tensor
+    report one address (the float64 stand-ins never look at addresses)."""
+    from nnaudio_b200.features.cqt import _framed_complex_autograd
+
+    cpu_kernels.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "data_ptr", lambda self: 0x1234)
+    mod = torch.nn.Module()
+    p = torch.nn.Parameter(torch.randn(6, 64))
+    q = torch.nn.Parameter(torch.randn(6, 64))
+    x0 = torch.randn(1, 1024)
+    grads = []
+    for scale in (1.0, 3.0, -2.0, 0.5):
+        w_re, w_im = p * scale, q * scale          # fresh temporaries, _version 0
+        x = x0.clone().requires_grad_(True)
+        c = _framed_complex_autograd(mod, "t", x, w_re, w_im, 32, True, 0)
+        c.square().sum().backward()
+        grads.append(x.grad.clone() / scale ** 2)   # dx of |c|^2 is quadratic in the bank
+    for g in grads[1:]:
+        emax, el2 = rel_errors(g.numpy(), grads[0].numpy())
+        assert el2 < 1e-6, (emax, el2)
+
+
+def test_trainable_forward_stft_can_call_inverse_in_training_mode(monkeypatch):
+    """``inverse`` only reads kernel_*_inv / window_mask (buffers), so a
+    STFT(trainable=True, iSTFT=True) must be able to invert under autograd; a trainable iSTFT
+    kernel (no dW path) still refuses."""
+    cpu_kernels.install(monkeypatch)
+    st = nb.STFT(n_fft=128, hop_length=32, trainable=True, iSTFT=True, verbose=False)
+    x = torch.randn(2, 1024)
+    X = st(x, output_format="Complex")
+    y = st.inverse(X, length=1024)
+    assert y.shape == (2, 1024)
+    y.square().sum().backward()
+    assert st.wsin.grad is not None and torch.isfinite(st.wsin.grad).all()
+    inv = nb.iSTFT(n_fft=128, hop_length=32, trainable_kernels=True, verbose=False)
+    with pytest.raises(NotImplementedError):
+        inv(X.detach(), onesided=True)
