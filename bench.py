@@ -208,6 +208,113 @@ def cpu_arm(workload, steps, warmup, budget_s):
     }
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "nnAudio"))
+
+
+def _reference_module(workload):
+    """The UNMODIFIED reference module of a workload, imported from baseline/_ref
+    (baseline/install_ref.sh; pip --target install of /root/reference/Installation)."""
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import importlib
+
+    feats = importlib.import_module("nnAudio.features")
+    assert os.path.realpath(feats.__file__).startswith(os.path.realpath(REF_DIR)), feats.__file__
+    w = WORKLOADS[workload]
+    return getattr(feats, w["cls"])(verbose=False, **w["ctor"])
+
+
+def reference_cpu_arm(workload, steps, warmup, budget_s):
+    """The reference's own CPU path (torch conv1d -> oneDNN, every host thread): a bounded sample
+    of the workload per step, sized from a calibration run so the whole arm fits ``budget_s``."""
+    import torch
+
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(avail)
+    w = WORKLOADS[workload]
+    T = frames_per_clip(w)
+    mod = _reference_module(workload)
+    gen = torch.Generator().manual_seed(1234)
+
+    def timed(x, n):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for _ in range(n):
+                mod(x, **w["fwd"])
+        return time.perf_counter() - t0
+
+    n_cal = int(min(4, w["B"]))
+    xc = torch.randn(n_cal, w["L"], generator=gen)
+    timed(xc, 1)
+    per_clip = max(min(timed(xc, 1) for _ in range(2)) / n_cal, 1e-4)
+    clips = int(max(1, min(w["B"], budget_s / ((steps + warmup) * per_clip))))
+    x = torch.randn(clips, w["L"], generator=gen)
+    timed(x, warmup)
+    dt = timed(x, steps)
+    return {
+        "value": clips * T * steps / dt, "unit": "frames/s", "cores": avail, "kind": "reference",
+        "sample": f"{clips} clip(s) x {w['L']} samples of {workload} per step, {steps} steps, unmodified "
+                  f"nnAudio 0.3.3 {w['cls']} (baseline/_ref) on CPU, torch {torch.__version__} conv1d, "
+                  f"{avail} threads, {dt:.1f}s",
+        "ms_per_step": 1e3 * dt / steps,
+    }
+
+
+def reference_gpu_leg(workload, dev, budget_s=20.0):
+    """the reference's own modules (cuDNN conv1d) on the SAME B200, inputs
+    resident, CUDA events.  The batch is halved until the reference fits in memory / its time
+    budget; frames/s is reported for the batch that ran."""
+    import torch
+
+    w = WORKLOADS[workload]
+    T = frames_per_clip(w)
+    mod = _reference_module(workload).to(dev)
+    B = w["B"]
+    gen = torch.Generator(device=dev).manual_seed(99)
+    last_err = None
+    while B >= 1:
+        try:
+            x = torch.randn(B, w["L"], generator=gen, device=dev)
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                mod(x, **w["fwd"])
+                torch.cuda.synchronize(dev)
+                first = time.perf_counter() - t0
+                mod(x, **w["fwd"])
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                mod(x, **w["fwd"])
+                torch.cuda.synchronize(dev)
+                one = time.perf_counter() - t0
+                n = int(max(3, min(20, budget_s / max(one, 1e-4) / 2)))
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    y = mod(x, **w["fwd"])
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / n
+            del x, y
+            torch.cuda.empty_cache()
+            return {"value": B * T / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "batch": B,
+                    "steps": n, "first_call_s": round(first, 3),
+                    "what": f"unmodified nnAudio 0.3.3 {w['cls']} on cuda (cuDNN conv1d, torch "
+                            f"{torch.__version__}), inputs resident, {B} of {w['B']} clips"}
+        except Exception as e:  # noqa: BLE001  (OOM / cuDNN workspace: smaller batch)
+            last_err = f"{type(e).__name__}: {str(e)[:120]}"
+            torch.cuda.empty_cache()
+            B //= 2
+    return {"value": None, "unavailable": last_err}
+
+
 # ----------------------------------------------------------------------------
 def main():
     # stdout carries exactly ONE line (the JSON); libraries that print there (NCCL's version
@@ -259,14 +366,18 @@ def _run():
     if args.impl == "reference":
         if rank != 0:
             return None
-        res = cpu_arm(args.workload, args.steps, args.warmup, budget_s=120.0)
+        if reference_available():
+            res = reference_cpu_arm(args.workload, args.steps, args.warmup, budget_s=120.0)
+            arm = "the UNMODIFIED reference (baseline/_ref, nnAudio 0.3.3) on the host cores: torch conv1d (oneDNN)"
+        else:
+            res = cpu_arm(args.workload, args.steps, args.warmup, budget_s=120.0)
+            arm = "CPU oracle port of the reference conv1d path (baseline/_ref not installed)"
         line = {
             "impl": "reference", "metric": metric, "value": res["value"], "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "arm": "CPU oracle port of the "
-                       "reference conv1d path (reference is pure Python; cannot travel)"},
+            "config": {"workload": f"{args.workload}: {w['desc']}", "arm": arm},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -457,7 +568,10 @@ def _run():
                            "ms_per_step": e2e_ms / args.steps}
         if world == 1 and not args.no_cpu_baseline:
             try:  # a reported baseline must never cost the measured line
-                res = cpu_arm(args.workload, steps=8, warmup=1, budget_s=20.0)
+                if reference_available():
+                    res = reference_cpu_arm(args.workload, steps=4, warmup=1, budget_s=20.0)
+                else:
+                    res = cpu_arm(args.workload, steps=8, warmup=1, budget_s=20.0)
                 line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
