@@ -106,6 +106,19 @@ int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K,
 int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int layout,
                        void* packed, void* stream);
 
+/* Block-partial ("sliding") layout for the STFT family: periodic Hann window of length n_fft,
+ * integer bins (freq_scale='no', F = n_fft/2 + 1) and hop = n_fft/R with R = 2 or 4, hop % 64 == 0
+ * -- the reference's defaults (stft.py:177-178, utils.py:379-384).  The contraction then runs once
+ * per hop-sized block against the UN-windowed basis (K = hop instead of n_fft: R x fewer MMA flops);
+ * the window is a 3-tap filter along the bin axis and the frame sum a combination of R consecutive
+ * block rows, both in the kernel's epilogue.  The packed rows are generated analytically (float64),
+ * so the CALLER vouches that its wcos/wsin buffers are exactly that transform
+ * (nnaudio_b200/features/_common.py:is_hann_dft checks the tensors).  `packed` needs
+ * nnab_packed_basis_bytes(n_fft/2 + 1, n_fft) bytes; the forward entry points recognise the layout.
+ * nnab_block_layout_ok() is host-only: 1 when (n_fft, hop) is eligible. */
+int nnab_block_layout_ok(int n_fft, int hop);
+int nnab_pack_basis_block(int n_fft, int hop, void* packed, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * STFT.forward — features/stft.py:256-316.
  *   x        (B, L) rows with pitch x_pitch floats

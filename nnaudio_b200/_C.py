@@ -89,6 +89,8 @@ SIGNATURES = {
          c_size_t, _P],
     ),
     "nnab_pack_basis_ex": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "nnab_block_layout_ok": (c_int, [c_int, c_int]),
+    "nnab_pack_basis_block": (c_int, [c_int, c_int, _P, _P]),
     "nnab_debug_varn_plan": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nnab_fir_decimate": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
     "nnab_fir_decimate_adjoint": (
@@ -253,6 +255,22 @@ def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor, layout: int = LAYOUT_DENS
             rc = L.nnab_pack_basis_ex(_ptr(w_re), _ptr(w_im), F, K, int(layout), _ptr(packed),
                                       _stream(w_re.device))
         _check(rc, "nnab_pack_basis")
+    return packed
+
+
+def block_layout_ok(n_fft: int, hop: int) -> bool:
+    return bool(lib().nnab_block_layout_ok(int(n_fft), int(hop)))
+
+
+def pack_basis_block(w_re: torch.Tensor, hop: int):
+    """Packed rows of the block-partial STFT kernel for an (F, n_fft) periodic-Hann DFT basis
+    (the caller has checked the buffers with ``is_hann_dft``); generated analytically on the device."""
+    L = lib()
+    F, K = w_re.shape
+    packed = torch.empty(L.nnab_packed_basis_bytes(F, K), dtype=torch.uint8, device=w_re.device)
+    with torch.cuda.device(w_re.device):
+        _check(L.nnab_pack_basis_block(int(K), int(hop), _ptr(packed), _stream(w_re.device)),
+               "nnab_pack_basis_block")
     return packed
 
 

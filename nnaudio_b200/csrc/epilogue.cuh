@@ -119,4 +119,32 @@ __device__ __forceinline__ void epi_store_fmt(const EpiParams& e, float* dst, in
   }
 }
 
+// running banded-filterbank sums of one bin stream (ascending or descending bins)
+struct MelRun {
+  int cj0 = -1, cj1 = -1;
+  float a0 = 0.f, a1 = 0.f;
+  __device__ __forceinline__ void add(const EpiParams& e, float* mel, bool valid, int bin, float pw) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(e.fb_table) + bin);
+    if (raw.x != cj0) {
+      if (raw.x == cj1) {
+        const int tj = cj0; cj0 = cj1; cj1 = tj;
+        const float ta = a0; a0 = a1; a1 = ta;
+      } else {
+        if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
+        cj0 = raw.x; a0 = 0.f;
+      }
+    }
+    if (raw.y != cj1) {
+      if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
+      cj1 = raw.y; a1 = 0.f;
+    }
+    a0 = fmaf(__int_as_float(raw.z), pw, a0);
+    a1 = fmaf(__int_as_float(raw.w), pw, a1);
+  }
+  __device__ __forceinline__ void flush(const EpiParams& e, float* mel, bool valid) {
+    if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
+    if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
+  }
+};
+
 }  // namespace nnab

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc_host.cuh"
 
 namespace nnab {
 
@@ -182,6 +183,13 @@ int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int l
   if (w_re == nullptr || w_im == nullptr || packed == nullptr || F <= 0 || K <= 0)
     return NNAB_EINVAL;
   return tc_pack_basis_layout(w_re, w_im, F, K, layout, packed, (cudaStream_t)stream);
+}
+
+int nnab_block_layout_ok(int n_fft, int hop) { return tc_block_shape_ok(n_fft, hop) ? 1 : 0; }
+
+int nnab_pack_basis_block(int n_fft, int hop, void* packed, void* stream) {
+  if (packed == nullptr) return NNAB_EINVAL;
+  return tc_pack_basis_block(n_fft, hop, packed, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ STFT ----

@@ -1,0 +1,41 @@
+// Host-side pieces shared by the tensor-core translation units (tc_kernels.cu, tcb_kernels.cu).
+#pragma once
+
+#include <cuda.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace nnab {
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+
+static inline int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
+
+// geometry of the split / padded signal workspace (tc_kernels.cu)
+struct SplitGeom {
+  int64_t t_slots;       // virtual frames per clip
+  int64_t nv;            // virtual frames in the batch
+  int64_t rows;          // rows of the (rows x hop) view incl. K overhang
+  int64_t plane_stride;  // elements per plane
+};
+SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad);
+int num_phases(int hop);
+
+// bf16 3-D tensor map {d0 (contiguous), d1, d2}, box {box0, box1, 1}, swizzle by bk (64 -> 128B)
+int encode_3d(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+              uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int bk);
+
+// layout of a packed basis, keyed by its device pointer
+enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2, PACK_RADIX4 = 3, PACK_BLOCK = 4 };
+int packed_kind(const void* packed);
+void mark_packed(const void* packed, int kind);
+
+// block-partial ("sliding") STFT kernel (tcb_kernels.cu)
+int tc_pack_basis_block(int n_fft, int hop, void* packed, cudaStream_t stream);
+bool tc_block_shape_ok(int n_fft, int hop);
+int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* workspace,
+                           size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace nnab

@@ -28,15 +28,14 @@
 
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "tc_ptx.cuh"
+#include "tc_host.cuh"
 
 namespace nnab {
 
-constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 256;
 constexpr int TC_MAX_N_TILES = 128;
 constexpr int TC_ACC_STRIDE = 256;  // TMEM columns per accumulator buffer
 
-static inline int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
 
 // N tile (columns = re + im rows of bn/2 bins): minimise padded columns.
 static int choose_bn(int F) {
@@ -63,21 +62,15 @@ size_t tc_packed_bytes(int F, int K) {
 // ---------------------------------------------------------------------------
 // geometry of the split / padded signal workspace
 // ---------------------------------------------------------------------------
-struct SplitGeom {
-  int64_t t_slots;       // virtual frames per clip
-  int64_t nv;            // virtual frames in the batch
-  int64_t rows;          // rows of the (rows x hop) view incl. K overhang
-  int64_t plane_stride;  // elements per plane
-};
 
 // Frames t = p, p + np, p + 2 np, ... (phase p of np = 8 / gcd(hop, 8)) start at
 // multiples of hop * np, which is always a multiple of 8 samples = 16 bytes in
 // bf16: every hop is served by TMA, one pass per phase over a signal shifted by
 // p * hop samples.
 static int gcd_i(int a, int b) { return b == 0 ? a : gcd_i(b, a % b); }
-static int num_phases(int hop) { return 8 / gcd_i(hop, 8); }
+int num_phases(int hop) { return 8 / gcd_i(hop, 8); }
 
-static SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad) {
+SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad) {
   const int hop_eff = hop * num_phases(hop);
   SplitGeom g;
   g.t_slots = (L + 2 * (int64_t)pad + hop_eff - 1) / hop_eff;
@@ -287,6 +280,7 @@ __global__ void __launch_bounds__(256) pack_fir_kernel(const float* __restrict__
 }
 
 int tc_pack_fir(const float* fir, int taps, int dec, void* packed, cudaStream_t stream) {
+  tc_forget_packed(packed);  // dense rows: drop any stale layout tag of a recycled address
   const int kpad = tc_fir_k(taps, dec);
   pack_fir_kernel<<<(128 * kpad + 255) / 256, 256, 0, stream>>>(fir, taps, dec, kpad,
                                                                (__nv_bfloat16*)packed);
@@ -436,6 +430,7 @@ __global__ void __launch_bounds__(256) pack_istft_kernel(const float* __restrict
 
 int tc_pack_istft(const float* kc, const float* ks, int n_fft, int f_in, int onesided, void* packed,
                   cudaStream_t stream, int transposed) {
+  tc_forget_packed(packed);
   const int bn = tc_istft_bn(n_fft);
   const int rows = (n_fft + bn - 1) / bn * bn;
   const int kpad = tc_istft_k(f_in);
@@ -594,6 +589,7 @@ int tc_dw_prep_frames(const float* x, int64_t B, int64_t L, int64_t x_pitch, int
   const int bn = tc_istft_bn(K);
   const int64_t rows = (int64_t)((K + bn - 1) / bn) * bn;
   __nv_bfloat16* packed = (__nv_bfloat16*)packed_v;
+  tc_forget_packed(packed_v);
   NNAB_CUDA_TRY(cudaMemsetAsync(packed, 0, (size_t)2 * rows * gpad * sizeof(__nv_bfloat16), stream));
   if ((K + 31) / 32 > 65535) return NNAB_EUNSUPPORTED;
   dim3 grid((unsigned)ceil_div64(G, 32), (unsigned)((K + 31) / 32));
@@ -670,144 +666,7 @@ int tc_istft_finalize(const float* ola, int64_t ola_pitch, int64_t B, const floa
   return NNAB_OK;
 }
 
-// ---------------------------------------------------------------------------
-// PTX wrappers (sm_100a)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a descriptor / barrier bug must trap, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  unsigned long long t0 = 0;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFu) == 0) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) {  // 4 s
-        printf("nnab: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n",
-               (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// K-major swizzled smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused when swizzled) | [32,46) SBO>>4 |
-//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
-template <int BK>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  constexpr uint64_t SBO = (8u * BK * 2u) >> 4;  // 8 rows of one swizzle atom
-  constexpr uint64_t LAYOUT = (BK == 64) ? 2 : 4;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (SBO << 32) | (1ull << 46) |
-         (LAYOUT << 61);
-}
+// PTX wrappers: tc_ptx.cuh
 
 // ---------------------------------------------------------------------------
 // the kernel
@@ -1193,72 +1052,6 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // accumulators in its own TMEM.  Per SM this halves the B operand reads and TMA
 // fills — the shared-memory bandwidth that bounds the 1-CTA kernel at ~76 %.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive (optionally with expect_tx) on the barrier at the same offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(cta)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t bar, uint32_t cta, uint32_t bytes) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
-      ::"r"(bar), "r"(cta), "r"(bytes)
-      : "memory");
-}
-// TMA load whose completion bytes are credited to the LEADER CTA's barrier (peer bit cleared)
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                                int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1),
-        "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish_2sm() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                              uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-      "[%0], %1;"
-      ::"r"(bar), "h"((uint16_t)3)
-      : "memory");
-}
-
 template <int BK, int STAGES>
 struct Tc2Smem {
   static constexpr uint32_t A_BYTES = TC_BM * BK * 2;
@@ -1513,34 +1306,6 @@ __global__ void __launch_bounds__(256) pack_basis_radix_kernel(
   *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
   *reinterpret_cast<uint4*>(packed + (int64_t)R * rows_seg * kpadr + o) = *reinterpret_cast<const uint4*>(lo);
 }
-
-// running banded-filterbank sums of one bin stream (ascending or descending bins)
-struct MelRun {
-  int cj0 = -1, cj1 = -1;
-  float a0 = 0.f, a1 = 0.f;
-  __device__ __forceinline__ void add(const EpiParams& e, float* mel, bool valid, int bin, float pw) {
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(e.fb_table) + bin);
-    if (raw.x != cj0) {
-      if (raw.x == cj1) {
-        const int tj = cj0; cj0 = cj1; cj1 = tj;
-        const float ta = a0; a0 = a1; a1 = ta;
-      } else {
-        if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
-        cj0 = raw.x; a0 = 0.f;
-      }
-    }
-    if (raw.y != cj1) {
-      if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
-      cj1 = raw.y; a1 = 0.f;
-    }
-    a0 = fmaf(__int_as_float(raw.z), pw, a0);
-    a1 = fmaf(__int_as_float(raw.w), pw, a1);
-  }
-  __device__ __forceinline__ void flush(const EpiParams& e, float* mel, bool valid) {
-    if (cj0 >= 0 && valid) atomicAdd(mel + (int64_t)cj0 * e.T, a0);
-    if (cj1 >= 0 && valid) atomicAdd(mel + (int64_t)cj1 * e.T, a1);
-  }
-};
 
 // Butterfly epilogue: TMEM columns [S0 re | S0 im | U re | U im], `half` bins each.
 // FMT: 0 Magnitude, 1 Complex, 4 POWER, 5 fused banded filterbank.
@@ -2105,7 +1870,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_3d(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+int encode_3d(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
                      int bk) {
   EncodeTiledFn fn = get_encode_fn();
@@ -2251,17 +2016,16 @@ bool tc_radix2_basis_ok(int F, int K) {
 
 // layout of an experimental packed basis, keyed by its device pointer (WIP: a header inside the
 // packed buffer should replace this registry)
-enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2, PACK_RADIX4 = 3 };
 static std::mutex g_r2_mu;
 static std::unordered_map<const void*, int> g_pack_kind;
 
-static int packed_kind(const void* packed) {
+int packed_kind(const void* packed) {
   std::lock_guard<std::mutex> lk(g_r2_mu);
   auto it = g_pack_kind.find(packed);
   return it == g_pack_kind.end() ? PACK_DENSE : it->second;
 }
 
-static void mark_packed(const void* packed, int kind) {
+void mark_packed(const void* packed, int kind) {
   std::lock_guard<std::mutex> lk(g_r2_mu);
   if (kind == PACK_DENSE) g_pack_kind.erase(packed);
   else g_pack_kind[packed] = kind;
@@ -2662,6 +2426,8 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
                      cudaStream_t stream) {
   if (q.B <= 0 || q.T <= 0 || q.F <= 0) return NNAB_OK;
   if (packed == nullptr) return NNAB_EINVAL;
+  if (packed_kind(packed) == PACK_BLOCK)
+    return launch_framed_tc_block(q, packed, workspace, ws_bytes, stream);
   if (packed_kind(packed) == PACK_VARN)
     return launch_framed_tc_varn(q, packed, workspace, ws_bytes, stream);
   if (is_radix2_packed(packed))

@@ -149,6 +149,29 @@ def is_dft_structured(w_re: torch.Tensor, w_im: torch.Tensor, rtol: float = 1e-6
     return True
 
 
+def is_hann_dft(w_re: torch.Tensor, w_im: torch.Tensor, atol: float = 1e-6) -> bool:
+    """True when an (F, K) basis pair IS the one-sided DFT with a periodic Hann window of length K:
+    ``w_re[k][n] = hann[n] cos(2 pi k n / K)``, ``w_im[k][n] = hann[n] sin(2 pi k n / K)``, F = K/2 + 1
+    -- what ``create_fourier_kernels(freq_scale='no', window='hann', win_length=n_fft)`` builds
+    (utils.py:241-393, stft.py:230-232).  Checked on the buffers themselves in float64, so loaded,
+    trained, sliced (``freq_bins``), linear / log-spaced or differently windowed bases keep the dense
+    kernel; only an exact match may use the block-partial layout, whose rows are generated
+    analytically."""
+    F, K = w_re.shape
+    if F != K // 2 + 1 or K % 2 != 0 or w_im.shape != w_re.shape:
+        return False
+    n = torch.arange(K, device=w_re.device, dtype=torch.float64)
+    k = torch.arange(F, device=w_re.device, dtype=torch.float64)
+    # exact phase reduction in integers before the trig call
+    m = (torch.arange(F, device=w_re.device)[:, None] * torch.arange(K, device=w_re.device)[None, :]) % K
+    ang = (2.0 * torch.pi / K) * m.to(torch.float64)
+    hann = 0.5 - 0.5 * torch.cos(2.0 * torch.pi * n / K)
+    del k
+    ok_re = bool(((torch.cos(ang) * hann) - w_re.double()).abs().max() <= atol)
+    ok_im = bool(((torch.sin(ang) * hann) - w_im.double()).abs().max() <= atol)
+    return ok_re and ok_im
+
+
 class PackedBasis:
     """Cache of the (F, K) fp32 views and the bf16 hi/lo packed copy of a basis
     pair, invalidated when the source tensors change (load_state_dict, .to(),
@@ -158,7 +181,7 @@ class PackedBasis:
         self._cache = PerDeviceCache()
 
     def get(self, w_re: torch.Tensor, w_im: torch.Tensor, allow_radix=False,
-            groups: bool = False):
+            groups: bool = False, block_hop: int = 0):
         """``allow_radix`` (False, 2 or 4 = the largest radix the module's hop allows): the module
         computes a plain one-sided STFT with this basis, so the decimation-in-time layout may be
         used when the buffers pass ``is_dft_structured``;
@@ -167,6 +190,13 @@ class PackedBasis:
         import os
 
         def build():
+            # block-partial layout (default for the STFT family): the module computes a plain
+            # one-sided STFT with hop ``block_hop`` and an output format the block kernel has an
+            # epilogue for; the buffers must BE the periodic-Hann DFT (NNAUDIO_B200_BLOCK=0: off)
+            if block_hop and os.environ.get("NNAUDIO_B200_BLOCK", "1") != "0" \
+                    and _C.block_layout_ok(int(w_re.shape[1]), int(block_hop)) \
+                    and is_hann_dft(w_re, w_im):
+                return _C.pack_basis_block(w_re, int(block_hop))
             layout = _C.LAYOUT_DENSE
             if os.environ.get("NNAUDIO_B200_EXPERIMENTAL", "0") == "1":
                 radix = 4 if os.environ.get("NNAUDIO_B200_RADIX", "2") == "4" else 2
@@ -178,7 +208,8 @@ class PackedBasis:
                     layout = _C.LAYOUT_GROUPS
             return _C.pack_basis(w_re, w_im, layout) if layout else _C.pack_basis(w_re, w_im)
 
-        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, allow_radix, groups)
+        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, allow_radix, groups,
+               int(block_hop))
         return self._cache.lookup(w_re.device, key, build, keep=(w_re, w_im))
 
 

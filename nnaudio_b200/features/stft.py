@@ -234,7 +234,7 @@ class STFT(nn.Module):
             raise RuntimeError("Kernel size can't be greater than actual input size")
         return x
 
-    def _bases(self, radix_ok=False):
+    def _bases(self, radix_ok=False, block_ok=False):
         """``radix_ok``: the caller's output format has a decimation-in-time epilogue (Magnitude,
         Complex, power / fused filterbank); the layout is still only used when the buffers pass
         ``is_dft_structured`` and the hop allows the half-rate planes (EXPERIMENTAL)."""
@@ -244,10 +244,13 @@ class STFT(nn.Module):
         allow = False
         if radix_ok and not self.trainable and self.stride % 128 == 0:
             allow = 4 if self.stride % 256 == 0 else 2
-        return wcos, wsin, self._packed.get(wcos, wsin, allow_radix=allow)
+        # block-partial kernel: forward-only modules whose buffers are the periodic-Hann DFT
+        block_hop = self.stride if (block_ok and not self.trainable) else 0
+        return wcos, wsin, self._packed.get(wcos, wsin, allow_radix=allow, block_hop=block_hop)
 
     def _run(self, x, output_format):
-        wcos, wsin, packed = self._bases(radix_ok=output_format in ("Magnitude", "Complex"))
+        wcos, wsin, packed = self._bases(radix_ok=output_format in ("Magnitude", "Complex"),
+                                         block_ok=True)
         eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
         return _C.stft_forward(
             x, wcos, wsin, packed, self.n_fft, self.stride, self.center,
