@@ -56,6 +56,11 @@ WORKLOADS = {
 }
 
 
+# which roof bounds a workload: the fused pyramid is HBM-bound, the rest tensor-bound
+WORKLOAD_BOUND = {"cfg2": "tensor", "stft2048": "tensor", "cfg3": "tensor", "cfg5": "tensor", "cfg4": "hbm"}
+# the other configurations BASELINE.json's metric names, reported inside the same JSON line
+SECONDARY = ["stft2048", "cfg3", "cfg4", "cfg5"]
+
 # SMs left to the NCCL gather while the persistent kernels run, and the matching NCCL CTA cap
 # (the gather of (N-1) x 14 MB must hide under one ~0.47 ms transform; measured ~14.5 GB/s per
 # NCCL CTA next to the kernels: 8 CTAs suffice at N=4, not at N=8 — profiles/README.md)
@@ -123,7 +128,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.004)  # the default timed region is ~10 ms: a few samples inside it
+            time.sleep(0.001)  # short timed regions still get samples
 
     def start(self):
         if self.nv is not None:
@@ -333,15 +338,19 @@ def main():
 def _run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default=None, choices=[None, "auto", "simt", "tcgen05"])
     ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--no-workloads", action="store_true", help="skip the secondary configs (stft2048, cfg3, cfg4, cfg5)")
+    ap.add_argument("--workload-steps", type=int, default=10)
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's cuDNN leg")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--e2e-copy-streams", type=int, default=1)
     ap.add_argument("--gather", default="nccl", choices=["nccl", "symm"],
                     help="EXPERIMENTAL: symm = copy-engine pushes into symmetric memory (no SMs reserved)")
@@ -391,183 +400,270 @@ def _run():
 
     import nnaudio_b200 as nb
     from nnaudio_b200 import _C
+    from nnaudio_b200.host import HostPipeline, alloc_pinned, gpu_local_cpus
+    from nnaudio_b200.parallel import BatchShardedTransform
 
     if args.path:
         os.environ["NNAUDIO_B200_PATH"] = args.path
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host threads of this rank on the GPU's NUMA node: pinned buffers are first-touched there and
+    # the launch thread does not cross sockets (the e2e copies are PCIe-bound)
+    local_cpus = gpu_local_cpus(local_rank)
+    if local_cpus and not args.no_numa_bind:
+        try:
+            os.sched_setaffinity(0, local_cpus)
+        except OSError:
+            local_cpus = None
     if world > 1:
         # few CTAs for the output gather: it overlaps the next batch's kernels (which leave
-        # 8 SMs free for it, nnaudio_b200.parallel) and 99 MB per step does not need more
+        # SMs free for it, nnaudio_b200.parallel) and 99 MB per step does not need more
         reserve_plan = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
         max_ctas = args.nccl_max_ctas if args.nccl_max_ctas >= 0 else reserve_plan
-        if max_ctas > 0:
+        if max_ctas > 0 and args.gather == "nccl":
             os.environ["NCCL_MAX_CTAS"] = str(max_ctas)
         dist.init_process_group("nccl", device_id=dev)
 
-    B = w["B"]
-    mod = getattr(nb.features, w["cls"])(verbose=False, **w["ctor"]).to(dev)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    # three rotating input batches (3 x 56 MB at cfg2 > 126 MB L2): no step re-reads a cached input
-    n_rot = max(3, int(-(-160e6 // (B * w["L"] * 4))))
-    xs = [torch.randn(B, w["L"], generator=gen, device=dev, dtype=torch.float32) for _ in range(n_rot)]
-    x = xs[0]
-
-    from nnaudio_b200.parallel import BatchShardedTransform
-
-    reserve = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
-    if args.gather == "symm" and args.reserve_sms is None:
-        reserve = 0  # the copy engines do the gather: the kernels keep every SM
-    sharded = BatchShardedTransform(lambda inp: mod(inp, **w["fwd"]), gather=(world > 1),
-                                    reserve_sms=reserve)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6500.0))
+    peak_src = ("measured (MEASURED_PEAKS.json: bf16_tflops burst, hbm_gbs)" if peaks
+                else "fallback (B200_PROFILING.md): 1590 TFLOP/s bf16, 6500 GB/s")
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run_steps(n, record=None):
-        """n steps; the NCCL gather of step i overlaps the transform of step i+1
-        (two gather buffers); every gather completes inside the timed region."""
-        prev = None
-        for i in range(n):
-            if record:
-                record[0][i].record()
-            if args.gather == "symm" and world > 1:
-                work, y = sharded.forward_async_symm(xs[i % n_rot], slot=i & 1)
-            else:
-                work, y = sharded.forward_async(xs[i % n_rot], slot=i & 1)
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    reserve = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
+    if args.gather == "symm" and args.reserve_sms is None:
+        reserve = 0  # the copy engines do the gather: the kernels keep every SM
+
+    def measure(name, steps, warmup, gather):
+        """One workload, inputs resident in HBM: ``steps`` timed steps between two CUDA events on the
+        launching stream (max over ranks), the framed contraction timed per launch with in-stream
+        events (nnab_profile_*), clocks sampled through NVML during the timed region."""
+        w = dict(WORKLOADS[name])
+        if args.batch and name == args.workload:
+            w["B"] = args.batch
+        B, T = w["B"], frames_per_clip(w)
+        mod = getattr(nb.features, w["cls"])(verbose=False, **w["ctor"]).to(dev)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        batch_bytes = B * w["L"] * 4
+        # rotating input batches, > 126 MB of L2 in total: no step re-reads a cached input
+        n_rot = 1 if batch_bytes > 160e6 else max(3, int(-(-160e6 // batch_bytes)))
+        xs = [torch.randn(B, w["L"], generator=gen, device=dev, dtype=torch.float32) for _ in range(n_rot)]
+        sharded = BatchShardedTransform(lambda inp: mod(inp, **w["fwd"]), gather=(gather and world > 1),
+                                        reserve_sms=reserve if gather else 0)
+
+        def run_steps(n):
+            """n steps; the gather of step i overlaps the transform of step i+1 (two gather buffers);
+            every gather completes inside the timed region."""
+            prev, y = None, None
+            for i in range(n):
+                if args.gather == "symm" and gather and world > 1:
+                    work, y = sharded.forward_async_symm(xs[i % n_rot], slot=i & 1)
+                else:
+                    work, y = sharded.forward_async(xs[i % n_rot], slot=i & 1)
+                if prev is not None:
+                    prev.wait()
+                    if args.gather == "symm" and gather and world > 1:
+                        sharded.release((i - 1) & 1)
+                prev = work
             if prev is not None:
                 prev.wait()
-                if args.gather == "symm" and world > 1:
-                    sharded.release((i - 1) & 1)
-            prev = work
-            if record:
-                record[1][i].record()
-        if prev is not None:
-            prev.wait()
-        return y
+            return y
 
-    with torch.no_grad():
-        y = run_steps(args.warmup)
-        sync_all()
-        out_shape = (B,) + tuple(y.shape[1:])  # this rank's own spectrograms
-        # release the warm-up output: otherwise the timed loop holds one more live output than
-        # the warm-up did and its first steps cudaMalloc (113 MB outputs: ~0.4 ms/step over 10 steps)
-        del y
-        run_steps(2)
-        sync_all()
-
-        sampler = ClockSampler(local_rank)
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        final = torch.cuda.Event(enable_timing=True)
-        _C.profile_read()
-        _C.profile_enable(True)
-        launches0 = _C.launch_count()
-        sampler.start()
-        sync_all()
-        run_steps(args.steps, (starts, ends))
-        final.record()
-        sync_all()
-        clocks = sampler.stop()
-        _C.profile_enable(False)
-        launches = _C.launch_count() - launches0
-        framed_ms, framed_n = _C.profile_read()
-        dev_ms = starts[0].elapsed_time(final)  # the whole K-step region, gathers included
-
-        # ------------------------------------------------------------ e2e --
-        e2e = None
-        if not args.no_e2e:
-            from nnaudio_b200.host import HostPipeline
-
-            x_host = torch.randn(B, w["L"], dtype=torch.float32).pin_memory()
-            y_host = torch.empty(out_shape, dtype=torch.float32).pin_memory()
-            pipe = HostPipeline(mod, chunk_clips=max(1, B // args.e2e_chunks),
-                                copy_streams=args.e2e_copy_streams, **w["fwd"])
-
-            def e2e_step():
-                pipe(x_host, y_host, device=dev)
-
-            for _ in range(3):
-                e2e_step()
+        with torch.no_grad():
+            y = run_steps(warmup)
             sync_all()
-            es = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-            ee = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-            # rotating pinned inputs as well (host side is not cached by the GPU anyway)
-            es[0].record()
-            for i in range(args.steps):
-                e2e_step()
-            ee[-1].record()
+            out_shape = (B,) + tuple(y.shape[1:])  # this rank's own spectrograms
+            out_bytes = int(torch.tensor(out_shape).prod().item()) * 4
+            del y  # else the timed loop holds one more live output than the warm-up did (cudaMalloc)
+            run_steps(2)
             sync_all()
-            e2e_ms = es[0].elapsed_time(ee[-1])
-            e2e = {"ms": e2e_ms, "h2d": x_host.numel() * 4, "d2h": y_host.numel() * 4}
-
-    # max over ranks
-    t = torch.tensor([dev_ms, e2e["ms"] if e2e else 0.0, framed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, framed_ms_max = (float(v) for v in t.tolist())
-
-    if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:  # noqa: BLE001
-            pass
-        tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
-        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1.59 PF"
-        frames_total = world * B * T * args.steps
-        value = frames_total / (dev_ms * 1e-3)
+            sampler = ClockSampler(local_rank)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            _C.profile_read()
+            _C.profile_read_exec_flops()
+            _C.profile_enable(True)
+            launches0 = _C.launch_count()
+            sampler.start()
+            sync_all()
+            e0.record()
+            run_steps(steps)
+            e1.record()
+            sync_all()
+            clocks = sampler.stop()
+            _C.profile_enable(False)
+            launches = _C.launch_count() - launches0
+            framed_ms, framed_n = _C.profile_read()
+            exec_flops = _C.profile_read_exec_flops()
+            dev_ms = e0.elapsed_time(e1)
+        dev_ms, framed_ms = reduce_max([dev_ms, framed_ms])
+        frames_total = world * B * T * steps
         flops_launch = framed_algorithmic_flops(mod, w["cls"], B, T)
         avg_launch_ms = framed_ms / max(framed_n, 1)
-        achieved = flops_launch / (avg_launch_ms * 1e-3) / 1e12 if framed_n else None
+        tensor_alg = flops_launch / (avg_launch_ms * 1e-3) / 1e12 if framed_n else None
+        tensor_exec = exec_flops / (framed_ms * 1e-3) / 1e12 if framed_ms > 0 else None
+        alg_bytes = batch_bytes + out_bytes  # per step and rank: waveform in + spectrogram out
+        hbm_ach = alg_bytes / (dev_ms / steps * 1e-3) / 1e9
+        bound = WORKLOAD_BOUND.get(name, "tensor")
+        roof = {
+            "kernel": "framed contraction (frames x basis), pad/split pre-pass included",
+            "bound": bound,
+            "achieved": tensor_alg if bound == "tensor" else hbm_ach,
+            "peak": tensor_peak if bound == "tensor" else hbm_peak,
+            "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+            "frac": ((tensor_alg / tensor_peak) if tensor_alg else None) if bound == "tensor" else hbm_ach / hbm_peak,
+            "traffic": None, "traffic_note": "see profiles/ (ncu --set full captures are static, not re-measured per run)",
+            "peak_source": peak_src,
+            "algorithmic_flops_per_launch": flops_launch, "avg_launch_ms": avg_launch_ms,
+            "launches_timed": framed_n, "share_of_step": framed_ms / dev_ms if dev_ms else None,
+            # SURVEY.md 8(d): both figures -- algorithmic (the reference's dense flops) and executed
+            "tensor_algorithmic_tflops": tensor_alg,
+            "tensor_algorithmic_frac": (tensor_alg / tensor_peak) if tensor_alg else None,
+            "tensor_pipe": {"executed_tflops": tensor_exec,
+                            "frac": (tensor_exec / tensor_peak) if tensor_exec else None,
+                            "what": "MMA flops issued (3 bf16 split terms, tile padding, structural zeros) / kernel time / peak"},
+            "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": hbm_ach, "frac": hbm_ach / hbm_peak,
+                    "what": "(waveform in + spectrogram out) per step / step time / measured copy bandwidth"},
+        }
         used_tc = (os.environ.get("NNAUDIO_B200_PATH", "auto") != "simt") and \
             _C.lib().nnab_packed_basis_bytes(8, 2048) > 0
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("framed_dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            pass
-        line = {
-            "metric": metric, "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        res = {
+            "desc": w["desc"], "value": frames_total / (dev_ms * 1e-3), "unit": "frames/s",
+            "ms_per_step": dev_ms / steps, "steps": steps, "warmup": warmup, "per_gpu_batch": B,
+            "frames_per_clip": T, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "l2": f"{n_rot} rotating input batch(es) of {batch_bytes / 1e6:.0f} MB (> 126 MB L2 in total), no flush",
             "dtype": "bf16x3 split (fp32-equivalent), f32 accumulate" if used_tc else "f32",
-            "data": "synthetic",
+        }
+        return res, mod, out_shape, w
+
+    main, mod, out_shape, w = measure(args.workload, args.steps, args.warmup, gather=True)
+    B = w["B"]
+
+    # ------------------------------------------------------------ e2e --
+    e2e, pcie = None, None
+    if not args.no_e2e:
+        with torch.no_grad():
+            # raw link rate of this box, pinned memory, one big copy per direction
+            probe_n = 64 << 20  # floats = 256 MB
+            hp, place = alloc_pinned((probe_n,), device_index=local_rank)
+            dp = torch.empty(probe_n, dtype=torch.float32, device=dev)
+            rates = {}
+            for key, (dst, src) in (("h2d", (dp, hp)), ("d2h", (hp, dp))):
+                dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize(dev)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(4):
+                    dst.copy_(src, non_blocking=True)
+                b_.record()
+                torch.cuda.synchronize(dev)
+                rates[key] = 4 * probe_n * 4 / (a.elapsed_time(b_) * 1e-3) / 1e9
+            del hp, dp
+            pcie = {"h2d_gbs": rates["h2d"], "d2h_gbs": rates["d2h"], "pinned": place,
+                    "what": "cudaMemcpyAsync of 256 MB pinned buffers, 4 copies per direction, CUDA events"}
+
+            x_hosts = [alloc_pinned((B, w["L"]), device_index=local_rank, fill="randn")[0] for _ in range(2)]
+            y_host, _ = alloc_pinned(out_shape, device_index=local_rank)
+            pipe = HostPipeline(mod, chunk_clips=max(1, B // args.e2e_chunks),
+                                copy_streams=args.e2e_copy_streams, **w["fwd"])
+            for i in range(3):
+                pipe(x_hosts[i & 1], y_host, device=dev)
+            sync_all()
+            n_e2e = max(args.steps, 20)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(n_e2e):
+                pipe(x_hosts[i & 1], y_host, device=dev)
+            b_.record()
+            sync_all()
+            (e2e_ms,) = reduce_max([a.elapsed_time(b_)])
+            h2d_b, d2h_b = x_hosts[0].numel() * 4, y_host.numel() * 4
+            T_ = frames_per_clip(w)
+            ms_step = e2e_ms / n_e2e
+            link_ms = max(h2d_b / (rates["h2d"] * 1e9), d2h_b / (rates["d2h"] * 1e9)) * 1e3
+            e2e = {"value": world * B * T_ * n_e2e / (e2e_ms * 1e-3), "unit": "frames/s",
+                   "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "ms_per_step": ms_step,
+                   "steps": n_e2e, "h2d_gbs_achieved": h2d_b / (ms_step * 1e-3) / 1e9,
+                   "link_bound_ms_per_step": link_ms, "frac_of_link": link_ms / ms_step,
+                   "path": f"nnaudio_b200.host.HostPipeline: pinned host ({place}) -> {args.e2e_chunks} chunks, "
+                           "H2D / kernels / D2H on 3 streams, copies of consecutive calls back to back"}
+            del x_hosts, y_host, pipe
+
+    # ------------------------------------------- the metric's other configs --
+    others = {}
+    if not args.no_workloads:
+        del mod
+        torch.cuda.empty_cache()
+        for name in [n for n in SECONDARY if n != args.workload]:
+            try:
+                res, m2, _, _ = measure(name, steps=args.workload_steps, warmup=3, gather=False)
+                del m2
+                others[name] = res
+            except Exception as e:  # noqa: BLE001  (never cost the headline line)
+                others[name] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.empty_cache()
+
+    # --------------------------------- the reference's own cuDNN path, same GPU --
+    ref_gpu = {}
+    if world == 1 and not args.no_reference_gpu and reference_available():
+        for name in [args.workload] + [n for n in ("stft2048", "cfg3") if n != args.workload and not args.no_workloads]:
+            try:
+                ref_gpu[name] = reference_gpu_leg(name, dev)
+            except Exception as e:  # noqa: BLE001
+                ref_gpu[name] = {"value": None, "unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.empty_cache()
+
+    if rank == 0:
+        T = frames_per_clip(w)
+        line = {
+            "metric": metric, "value": main["value"], "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": main["dtype"], "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: {w['desc']}", "per_gpu_batch": B,
                 "global_batch": world * B, "frames_per_clip": T,
                 "parallelism": f"batch-sharded x{world}" + (
-                    " + NCCL all_gather of outputs (gather of step i overlaps transform of step i+1)" if world > 1 else ""),
-                "e2e_path": "nnaudio_b200.host.HostPipeline: pinned host -> 4 chunks, H2D/compute/D2H on 3 streams",
-                "l2": f"{n_rot} rotating input batches ({n_rot * B * w['L'] * 4 / 1e6:.0f} MB > 126 MB L2), no flush; "
-                      "one CUDA-event pair around all K steps",
+                    f" + {args.gather} gather of the output spectrograms (gather of step i overlaps transform of "
+                    "step i+1)" if world > 1 else ""),
+                "l2": main["l2"] + "; one CUDA-event pair around all K steps",
                 "kernel_path": os.environ.get("NNAUDIO_B200_PATH", "auto"),
                 "sms_reserved_for_gather": reserve if world > 1 else 0,
+                "host_cpus": f"{len(local_cpus)} cpus of the GPU's NUMA node" if local_cpus else "unbound",
             },
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {
-                "kernel": "framed contraction (frames x basis)",
-                "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": (achieved / tensor_peak) if achieved else None,
-                "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_flops_per_launch": flops_launch, "avg_launch_ms": avg_launch_ms,
-                "launches_timed": framed_n, "share_of_step": framed_ms / dev_ms if dev_ms else None,
-                "note": "achieved = ALGORITHMIC flops / live CUDA-event time of the kernel; the tcgen05 "
-                        "path executes 3 bf16 MMA passes per algorithmic flop (split precision for the "
-                        "1e-4 parity bar), so the tensor pipe is ~3x busier than this fraction",
-            },
+            "gpu_launches": main["gpu_launches"],
+            "clocks": main["clocks"],
+            "roofline": main["roofline"],
         }
         if e2e:
-            line["e2e"] = {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s",
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "ms_per_step": e2e_ms / args.steps}
+            line["e2e"] = e2e
+            line["pcie"] = pcie
+        if others:
+            line["workloads"] = others
+        if ref_gpu:
+            line["reference_gpu"] = ref_gpu
         if world == 1 and not args.no_cpu_baseline:
             try:  # a reported baseline must never cost the measured line
+                if local_cpus:
+                    try:
+                        os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU arm uses every core
+                    except OSError:
+                        pass
                 if reference_available():
                     res = reference_cpu_arm(args.workload, steps=4, warmup=1, budget_s=20.0)
                 else:

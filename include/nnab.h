@@ -322,6 +322,9 @@ int nnab_set_sm_reserve(int n_sms);
  * of launches timed since the last read, and resets the accumulator. */
 void nnab_profile_enable(int on);
 int nnab_profile_read(double* framed_ms, uint64_t* framed_launches);
+/* MMA flops the tensor-core launches EXECUTED since the last read (all bf16 split terms, tile
+ * padding and structural zeros included) -> bench.py's roofline.tensor_pipe. */
+int nnab_profile_read_exec_flops(double* exec_flops);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

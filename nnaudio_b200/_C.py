@@ -32,6 +32,7 @@ SIGNATURES = {
     "nnab_set_sm_reserve": (c_int, [c_int]),
     "nnab_profile_enable": (None, [c_int]),
     "nnab_profile_read": (c_int, [_P, _P]),
+    "nnab_profile_read_exec_flops": (c_int, [_P]),
     "nnab_pack_tile_n": (c_int, [c_int]),
     "nnab_packed_basis_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_basis": (c_int, [_P, _P, c_int, c_int, _P, _P]),
@@ -162,6 +163,12 @@ def profile_read():
     n = c_uint64(0)
     _check(lib().nnab_profile_read(ctypes.byref(ms), ctypes.byref(n)), "nnab_profile_read")
     return ms.value, int(n.value)
+
+
+def profile_read_exec_flops() -> float:
+    v = ctypes.c_double(0.0)
+    _check(lib().nnab_profile_read_exec_flops(ctypes.byref(v)), "nnab_profile_read_exec_flops")
+    return float(v.value)
 
 
 def _check(rc: int, what: str):

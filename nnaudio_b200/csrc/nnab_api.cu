@@ -56,6 +56,13 @@ static std::mutex g_prof_mu;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pairs;  // recorded, unread
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
 
+static double g_exec_flops = 0.0;  // guarded by g_prof_mu
+void add_exec_flops(double flops) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_exec_flops += flops;
+}
+
 static bool prof_begin(cudaStream_t s, std::pair<cudaEvent_t, cudaEvent_t>* pr) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return false;
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -166,6 +173,13 @@ int nnab_profile_read(double* framed_ms, uint64_t* framed_launches) {
   g_prof_pairs.clear();
   if (framed_ms) *framed_ms = total;
   if (framed_launches) *framed_launches = n;
+  return NNAB_OK;
+}
+
+int nnab_profile_read_exec_flops(double* exec_flops) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (exec_flops) *exec_flops = g_exec_flops;
+  g_exec_flops = 0.0;
   return NNAB_OK;
 }
 

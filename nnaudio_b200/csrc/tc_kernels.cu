@@ -2191,6 +2191,7 @@ static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, v
   prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
   const int64_t ptiles = (int64_t)prm.num_m_tiles * n_tiles;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  add_exec_flops(3.0 * 2.0 * (double)ptiles * (2 * TC_BM) * (double)bns * R * kr);
   if (R == 2) {
     return bns == 256 ? launch_tc2r<256, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream)
                       : launch_tc2r<128, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream);
@@ -2406,6 +2407,11 @@ static int launch_framed_tc_varn(const FramedProblem& q, const void* packed, voi
   prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
   const int64_t ptiles = (int64_t)prm.num_m_tiles * plan.n_chunks;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  {
+    double cols = 0.0;
+    for (int i = 0; i < plan.n_blocks; ++i) cols += 16.0 * plan.groups[i] * 64.0;
+    add_exec_flops(3.0 * 2.0 * (double)prm.num_m_tiles * (2 * TC_BM) * cols);
+  }
   switch (prm.epi.fmt) {
     case NNAB_FMT_MAGNITUDE: rc = launch_tc2v_fmt<0>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
     case NNAB_FMT_COMPLEX: rc = launch_tc2v_fmt<1>(ma, mb8, mb32, prm, plan, n_pairs, stream); break;
@@ -2587,6 +2593,13 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
       pad_split_kernel<<<grid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
                                                  ph * q.hop, clip_pitch, g.plane_stride, planes);
       NNAB_LAUNCH_CHECK();
+    }
+    {
+      const int mrows = (cta_group == 2 ? 2 : 1) * TC_BM;
+      double kcols = 0.0;  // sum over N tiles of (k-blocks executed) x bk x bn
+      for (int tl = 0; tl < n_tiles; ++tl) kcols += (double)(prm.kb_end[tl] - prm.kb_begin[tl]) * bk * bn;
+      add_exec_flops((prm.split4 && cta_group == 2 ? 4.0 : 3.0) * 2.0 *
+                     (double)ceil_div64(g.nv, mrows) * mrows * kcols);
     }
     if (cta_group == 2) {
       prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);  // 256-frame pair tiles

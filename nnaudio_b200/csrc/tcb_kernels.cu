@@ -138,11 +138,20 @@ int tc_pack_basis_block(int n_fft, int hop, void* packed, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------
-// epilogue: one warp = one TMEM lane quarter = 32 consecutive block rows
+// epilogue: one warp = one TMEM lane quarter (32 consecutive block rows) x a range of 8-column chunks.
+// The body of a chunk is straight-line code (no branches between the TMEM load and the stores), so
+// the 8 bins' dependency chains (3-tap filter -> shuffles -> twiddles -> magnitude) interleave: with
+// one or two warps per scheduler the epilogue is latency-bound, not issue-bound.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));  // <= 1 ulp-ish: far below the 1e-4 bar
+  return r;
+}
+
 template <int FMT, int R>
 __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t trow, int64_t g,
-                                                    int lane, int n_tile) {
+                                                    int lane, int n_tile, int c_begin, int c_end) {
   const int nb = p.nb;
   const int64_t b = g / p.t_slots;
   const int64_t t = g - b * p.t_slots;  // frame index inside the clip = index of its first block
@@ -172,8 +181,16 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
 
   float wr[10], wi[10];  // packed columns 8c-2 .. 8c+7 of this row (re, im)
   wr[8] = wr[9] = wi[8] = wi[9] = 0.f;
+  if (c_begin > 0) {  // a column range that starts inside the tile: seed the two carried columns
+    uint32_t re[8], im[8];
+    tmem_ld8(trow + (uint32_t)(8 * (c_begin - 1)), re);
+    tmem_ld8(trow + (uint32_t)(nb + 8 * (c_begin - 1)), im);
+    tmem_ld_wait();
+    wr[8] = __uint_as_float(re[6]); wr[9] = __uint_as_float(re[7]);
+    wi[8] = __uint_as_float(im[6]); wi[9] = __uint_as_float(im[7]);
+  }
 #pragma unroll 1
-  for (int c = 0; c < nb / 8; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     wr[0] = wr[8]; wr[1] = wr[9]; wi[0] = wi[8]; wi[1] = wi[9];
     {
       uint32_t re[8], im[8];
@@ -183,15 +200,13 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
 #pragma unroll
       for (int e = 0; e < 8; ++e) { wr[e + 2] = __uint_as_float(re[e]); wi[e + 2] = __uint_as_float(im[e]); }
     }
+    float xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (c == 0 && e < 2) continue;  // outputs -2, -1 do not exist (warp-uniform)
-      const int k = k_tile0 + 8 * c - 2 + e;
       const float zmr = wr[e], zmi = wi[e], z0r = wr[e + 1], z0i = wi[e + 1], zpr = wr[e + 2],
                   zpi = wi[e + 2];
       const float sr = zmr + zpr, si = zmi + zpi;
       const float ar = 0.5f * z0r, ai = 0.5f * z0i;
-      float xr, xi;
       if constexpr (R == 4) {
         const float dr = zmr - zpr, di = zmi - zpi;
         const float v0r = fmaf(-0.25f, sr, ar), v0i = fmaf(-0.25f, si, ai);
@@ -203,21 +218,55 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
         v3r = __shfl_down_sync(0xffffffffu, v3r, 3); v3i = __shfl_down_sync(0xffffffffu, v3i, 3);
         const float qr = cr[e & 3], qi = ci[e & 3], q2 = c2[e & 3];
         // X = V0 + c V1 + c^2 V2 + conj(c) V3
-        xr = v0r + (qr * v1r - qi * v1i) + q2 * v2r + (qr * v3r + qi * v3i);
-        xi = v0i + (qr * v1i + qi * v1r) + q2 * v2i + (qr * v3i - qi * v3r);
+        xr[e] = v0r + (qr * v1r - qi * v1i) + q2 * v2r + (qr * v3r + qi * v3i);
+        xi[e] = v0i + (qr * v1i + qi * v1r) + q2 * v2i + (qr * v3i - qi * v3r);
       } else {
         const float v0r = fmaf(-0.25f, sr, ar), v0i = fmaf(-0.25f, si, ai);
         float v1r = fmaf(0.25f, sr, ar), v1i = fmaf(0.25f, si, ai);
         v1r = __shfl_down_sync(0xffffffffu, v1r, 1); v1i = __shfl_down_sync(0xffffffffu, v1i, 1);
         const float q2 = c2[e & 3];
-        xr = fmaf(q2, v1r, v0r);
-        xi = fmaf(q2, v1i, v0i);
+        xr[e] = fmaf(q2, v1r, v0r);
+        xi[e] = fmaf(q2, v1i, v0i);
       }
-      if (k < p.epi.F) {  // warp-uniform
-        if constexpr (FMT == 5) {
-          run.add(p.epi, mel, valid, k, epi_power(p.epi, xr, xi));
+    }
+    const int k0 = k_tile0 + 8 * c - 2;          // bin of e = 0 (outputs -2, -1 of chunk 0 do not exist)
+    const int e_lo = (c == 0) ? 2 : 0;
+    if constexpr (FMT == NNAB_FMT_MAGNITUDE || FMT == NNAB_FMT_COMPLEX || FMT == 4) {
+      float* q = dst + (int64_t)k0 * p.epi.T * CH;
+      const int64_t step = p.epi.T * CH;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool ok = valid && e >= e_lo && (k0 + e) < p.epi.F;
+        if constexpr (FMT == NNAB_FMT_COMPLEX) {
+          if (ok) *reinterpret_cast<float2*>(q) = make_float2(xr[e], xi[e]);
         } else {
-          if (valid) epi_store_fmt<FMT>(p.epi, dst, k, xr, xi);
+          float pw = __fadd_rn(__fmul_rn(xr[e], xr[e]), __fmul_rn(xi[e], xi[e]));
+          if (p.epi.eps != 0.f) pw = __fadd_rn(pw, p.epi.eps);
+          float v;
+          if constexpr (FMT == NNAB_FMT_MAGNITUDE) {
+            v = sqrt_approx(pw);
+          } else {  // |X| ** power (mel.py:186); ** 2 is the power spectrum itself to 1 ulp
+            v = (p.epi.power == 2.0f) ? pw
+                : ((p.epi.power == 1.0f) ? sqrt_approx(pw) : powf(sqrt_approx(pw), p.epi.power));
+          }
+          if (ok) *q = v;
+        }
+        q += step;
+      }
+    } else {
+      // atan2f / banded-filterbank tails: rolled per bin (code size), after the straight-line part
+#pragma unroll 1
+      for (int e = e_lo; e < 8; ++e) {
+        const int k = k0 + e;
+        if (k >= p.epi.F) break;  // warp-uniform
+        // dynamic index into xr/xi would spill: select with a short unrolled scan
+        float re = xr[0], im = xi[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { re = (e == j) ? xr[j] : re; im = (e == j) ? xi[j] : im; }
+        if constexpr (FMT == 5) {
+          run.add(p.epi, mel, valid, k, epi_power(p.epi, re, im));
+        } else {
+          if (valid) epi_store_fmt<FMT>(p.epi, dst, k, re, im);
         }
       }
     }
@@ -225,8 +274,11 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
   if constexpr (FMT == 5) run.flush(p.epi, mel, valid);
 }
 
+constexpr int TCB_EPI_WARPS = 8;                       // 2 per TMEM lane quarter (column halves)
+constexpr int TCB_THREADS = 128 + 32 * TCB_EPI_WARPS;  // warps 0-3: TMA, MMA, TMEM alloc, idle
+
 template <int FMT, int R>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCB_THREADS, 1)
 framed_tcb_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const TcbParams p) {
   constexpr int BK = TCB_BK, STAGES = TCB_STAGES;
@@ -260,7 +312,7 @@ framed_tcb_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(tempty_bar(a), 2 * TCB_EPI_WARPS);  // epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -346,7 +398,11 @@ framed_tcb_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own rows) =====================
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;             // TMEM lanes 32 * (warp % 4) .. + 31
+    constexpr int PARTS = TCB_EPI_WARPS / 4;  // warps per quarter, each a contiguous chunk range
+    const int part = (warp - 4) >> 2;
+    const int n_chunks = nb / 8;
+    const int c_begin = (n_chunks * part) / PARTS, c_end = (n_chunks * (part + 1)) / PARTS;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -357,7 +413,7 @@ framed_tcb_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const int64_t g = (int64_t)(2 * m_pair + (int)cta) * (4 * FW) + quarter * FW + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TCB_ACC_STRIDE;
-      epilogue_tile_block<FMT, R>(p, trow, g, lane, n_tile);
+      epilogue_tile_block<FMT, R>(p, trow, g, lane, n_tile, c_begin, c_end);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -391,7 +447,7 @@ static int launch_tcb_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const Tc
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * n_pairs));
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(TCB_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -487,6 +543,7 @@ int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* wor
   prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
   const int64_t ptiles = (int64_t)prm.num_m_pairs * n_tiles;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
+  add_exec_flops(3.0 * 2.0 * (double)ptiles * (2 * TC_BM) * (2 * nb) * q.hop);
   return R == 4 ? launch_tcb<4>(q.fmt, ma, mb, prm, n_pairs, stream)
                 : launch_tcb<2>(q.fmt, ma, mb, prm, n_pairs, stream);
 }
