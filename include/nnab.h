@@ -114,9 +114,10 @@ int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int l
  * block rows, both in the kernel's epilogue.  The packed rows are generated analytically (float64),
  * so the CALLER vouches that its wcos/wsin buffers are exactly that transform
  * (nnaudio_b200/features/_common.py:is_hann_dft checks the tensors).  `packed` needs
- * nnab_packed_basis_bytes(n_fft/2 + 1, n_fft) bytes; the forward entry points recognise the layout.
+ * nnab_packed_block_bytes(n_fft, hop) bytes; the forward entry points recognise the layout.
  * nnab_block_layout_ok() is host-only: 1 when (n_fft, hop) is eligible. */
 int nnab_block_layout_ok(int n_fft, int hop);
+size_t nnab_packed_block_bytes(int n_fft, int hop);
 int nnab_pack_basis_block(int n_fft, int hop, void* packed, void* stream);
 
 /* ------------------------------------------------------------------------- *

@@ -91,6 +91,7 @@ SIGNATURES = {
     ),
     "nnab_pack_basis_ex": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "nnab_block_layout_ok": (c_int, [c_int, c_int]),
+    "nnab_packed_block_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_basis_block": (c_int, [c_int, c_int, _P, _P]),
     "nnab_debug_varn_plan": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "nnab_fir_decimate": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
@@ -274,7 +275,7 @@ def pack_basis_block(w_re: torch.Tensor, hop: int):
     (the caller has checked the buffers with ``is_hann_dft``); generated analytically on the device."""
     L = lib()
     F, K = w_re.shape
-    packed = torch.empty(L.nnab_packed_basis_bytes(F, K), dtype=torch.uint8, device=w_re.device)
+    packed = torch.empty(L.nnab_packed_block_bytes(int(K), int(hop)), dtype=torch.uint8, device=w_re.device)
     with torch.cuda.device(w_re.device):
         _check(L.nnab_pack_basis_block(int(K), int(hop), _ptr(packed), _stream(w_re.device)),
                "nnab_pack_basis_block")

@@ -67,6 +67,19 @@ struct FbEntry {
   float w0, w1;
 };
 
+// Static action list of the banded-filterbank epilogue (block-partial kernel): what the two running
+// filter sums of a row do at FFT bin k -- the control flow depends on k only, so it is resolved once
+// per filterbank instead of per (row, bin).  Before accumulating bin k: a slot whose flush id is
+// >= 0 adds its sum to that filter's output and restarts from zero; then slot a += wa * P[k],
+// slot b += wb * P[k].  cur_a / cur_b = filters the slots hold after bin k (flushed at a range end).
+struct FbStep {
+  float wa, wb;
+  short flush_a, flush_b;
+  short cur_a, cur_b;
+};
+static_assert(sizeof(FbStep) == 16, "one 128-bit load per bin");
+constexpr int FB_STEP_PAD = 160;  // entries past F (a tile's last chunk may overrun the last bin)
+
 struct FramedProblem {
   const float* x;      // (B, L) rows, pitch x_pitch
   int64_t B, L, x_pitch;
@@ -87,6 +100,8 @@ struct FramedProblem {
   const int32_t* h_k_begin;  // host, per-bin support or nullptr
   const int32_t* h_k_end;
   const FbEntry* fb_table;   // FMT_FBANK: device table [F]; out is (B, n_fb, T), pre-zeroed
+  const FbStep* fb_steps;    // FMT_FBANK, block-partial kernel: [F + FB_STEP_PAD] (nullptr: MelRun path)
+  int fb_nb_mask;            // bit i: tile width nb = 32 + 8 i gives <= 2 partial sums per filter
   int n_fb;
   float* raw;                // tcgen05 split-K scratch: 2 planes (re, im) of B*F*T floats, or nullptr
   const void* presplit;      // tcgen05: already padded + split signal planes (skip pad_split)
@@ -144,6 +159,10 @@ size_t tc_packed_fir_bytes(int taps, int dec);
 int tc_fir_k(int taps, int dec);
 int tc_pack_fir(const float* fir, int taps, int dec, void* packed, cudaStream_t stream);
 int launch_fb_table(const float* fb, int n_fb, int F, FbEntry* table, int* d_max_nnz,
+                    cudaStream_t stream);
+// FbEntry[F] -> FbStep[F + FB_STEP_PAD]; d_meta[0] = widest filter support (bins), d_meta[1] = bit mask
+// of the tile widths nb = 32 + 8 i under which every filter gets <= 2 partial sums
+int launch_fb_steps(const FbEntry* table, int n_fb, int F, FbStep* steps, int* d_meta,
                     cudaStream_t stream);
 
 // filterbank / MFCC tail / FIR decimation (simt_kernels.cu)

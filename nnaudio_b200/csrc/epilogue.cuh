@@ -20,6 +20,7 @@ struct EpiParams {
   int bin_offset;
   int F;
   const FbEntry* fb_table;  // FMT_FBANK
+  const FbStep* fb_steps;   // FMT_FBANK, block-partial kernel
   int n_fb;
   DecimParams dec;          // FMT_DECIM
   float* raw;               // FMT_RAW: re plane; im plane at raw + raw_plane

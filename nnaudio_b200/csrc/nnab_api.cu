@@ -4,6 +4,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -201,6 +202,8 @@ int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int l
 
 int nnab_block_layout_ok(int n_fft, int hop) { return tc_block_shape_ok(n_fft, hop) ? 1 : 0; }
 
+size_t nnab_packed_block_bytes(int n_fft, int hop) { return tc_packed_block_bytes(n_fft, hop); }
+
 int nnab_pack_basis_block(int n_fft, int hop, void* packed, void* stream) {
   if (packed == nullptr) return NNAB_EINVAL;
   return tc_pack_basis_block(n_fft, hop, packed, (cudaStream_t)stream);
@@ -243,18 +246,43 @@ static size_t power_bytes(int64_t B, int F, int64_t T) {
   return align_up((size_t)B * F * T * sizeof(float), 256);
 }
 
-size_t nnab_filterbank_table_bytes(int F) { return (size_t)F * sizeof(FbEntry) + 64; }
+// table buffer: [FbEntry x F][pad to 64][int max_nnz, widest, ok, -][pad to 256][FbStep x (F + FB_STEP_PAD)]
+static size_t fb_meta_offset(int F) { return align_up((size_t)F * sizeof(FbEntry), 64); }
+static size_t fb_steps_offset(int F) { return align_up(fb_meta_offset(F) + 64, 256); }
+size_t nnab_filterbank_table_bytes(int F) {
+  return fb_steps_offset(F) + (size_t)(F + FB_STEP_PAD) * sizeof(FbStep);
+}
+
+// deterministic-tile-width mask per table buffer (host copy of the device meta word; read at launch time)
+static std::mutex g_fbw_mu;
+static std::unordered_map<const void*, int> g_fb_width;
+static int fb_width_of(const void* table) {
+  std::lock_guard<std::mutex> lk(g_fbw_mu);
+  auto it = g_fb_width.find(table);
+  return it == g_fb_width.end() ? 0 : it->second;
+}
 
 int nnab_build_filterbank_table(const float* fb, int n_fb, int F, void* table, int* h_max_nnz,
                                 void* stream) {
   if (fb == nullptr || table == nullptr || h_max_nnz == nullptr || n_fb <= 0 || F <= 0)
     return NNAB_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
-  int* d_max = reinterpret_cast<int*>(reinterpret_cast<char*>(table) + (size_t)F * sizeof(FbEntry));
-  int rc = launch_fb_table(fb, n_fb, F, reinterpret_cast<FbEntry*>(table), d_max, s);
+  char* base = reinterpret_cast<char*>(table);
+  int* d_meta = reinterpret_cast<int*>(base + fb_meta_offset(F));
+  int rc = launch_fb_table(fb, n_fb, F, reinterpret_cast<FbEntry*>(table), d_meta, s);
   if (rc) return rc;
-  NNAB_CUDA_TRY(cudaMemcpyAsync(h_max_nnz, d_max, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (n_fb < 32768 &&
+      (rc = launch_fb_steps(reinterpret_cast<const FbEntry*>(table), n_fb, F,
+                            reinterpret_cast<FbStep*>(base + fb_steps_offset(F)), d_meta + 1, s)))
+    return rc;
+  int h_meta[3] = {0, 0, 0};
+  NNAB_CUDA_TRY(cudaMemcpyAsync(h_meta, d_meta, sizeof(h_meta), cudaMemcpyDeviceToHost, s));
   NNAB_CUDA_TRY(cudaStreamSynchronize(s));
+  *h_max_nnz = h_meta[0];
+  {
+    std::lock_guard<std::mutex> lk(g_fbw_mu);
+    g_fb_width[table] = (n_fb < 32768) ? h_meta[2] : 0;
+  }
   return NNAB_OK;
 }
 
@@ -311,6 +339,8 @@ int nnab_stft_filterbank_forward(const float* x, int64_t B, int64_t L, int64_t x
     p.fmt = FMT_FBANK; p.eps = sqrt_eps; p.power = power; p.out = out; p.T = T;
     p.out_bins = n_fb; p.bin_offset = 0;
     p.fb_table = reinterpret_cast<const FbEntry*>(fb_table); p.n_fb = n_fb;
+    p.fb_steps = reinterpret_cast<const FbStep*>(reinterpret_cast<const char*>(fb_table) + fb_steps_offset(F));
+    p.fb_nb_mask = fb_width_of(fb_table);
     if (tc_supported(p)) {
       const size_t need = tc_workspace_bytes(B, L, n_fft, hop, pad);
       if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;

@@ -279,6 +279,72 @@ int launch_fb_table(const float* fb, int n_fb, int F, FbEntry* table, int* d_max
   return NNAB_OK;
 }
 
+// Sequential (one thread; F ~ 1e3, init time) replay of the two-slot running-sum logic over the bin
+// axis, recording the actions per bin (see FbStep).
+__global__ void fb_steps_kernel(const FbEntry* __restrict__ table, int n_fb, int F,
+                                FbStep* __restrict__ steps, int* __restrict__ meta) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int cur_a = -1, cur_b = -1;
+  for (int k = 0; k < F + FB_STEP_PAD; ++k) {
+    FbStep st{0.f, 0.f, (short)-1, (short)-1, (short)cur_a, (short)cur_b};
+    if (k < F) {
+      const FbEntry e = table[k];
+      const int js[2] = {e.j0, e.j1};
+      const float ws[2] = {e.w0, e.w1};
+      bool used_a = false, used_b = false;
+      for (int i = 0; i < 2; ++i) {  // filters already held keep their slot
+        if (js[i] < 0) continue;
+        if (js[i] == cur_a) { st.wa = ws[i]; used_a = true; }
+        else if (js[i] == cur_b) { st.wb = ws[i]; used_b = true; }
+      }
+      for (int i = 0; i < 2; ++i) {  // new filters take a free slot (its old sum is flushed first)
+        if (js[i] < 0 || js[i] == cur_a || js[i] == cur_b) continue;
+        if (!used_a) {
+          if (cur_a >= 0) st.flush_a = (short)cur_a;
+          cur_a = js[i]; st.wa = ws[i]; used_a = true;
+        } else {
+          if (cur_b >= 0) st.flush_b = (short)cur_b;
+          cur_b = js[i]; st.wb = ws[i]; used_b = true;
+        }
+      }
+    }
+    st.cur_a = (short)cur_a;
+    st.cur_b = (short)cur_b;
+    steps[k] = st;
+  }
+  // For which tile widths nb = 32 + 8 i (i = 0..12) does every filter receive at most two partial
+  // sums?  A partial sum comes from each bin range (tile x warp part, cut exactly as
+  // framed_tcb_kernel cuts them) that intersects the filter's support; with <= 2 of them the
+  // atomic adds commute and the fused filterbank is run-to-run identical.
+  int widest = 0;
+  unsigned mask = 0x1FFFu;
+  for (int j = 0; j < n_fb; ++j) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < F; ++k) {
+      const FbEntry e = table[k];
+      if (e.j0 == j || e.j1 == j) { if (lo < 0) lo = k; hi = k; }
+    }
+    if (lo < 0) continue;
+    if (hi - lo + 1 > widest) widest = hi - lo + 1;
+    for (int i = 0; i < 13; ++i) {
+      const int nb = 32 + 8 * i, outs = nb - 2, half = 8 * ((nb / 8) / 2) - 2;
+      // range index of bin k: 2 * (k / outs) + ((k % outs) >= half)
+      const int r_lo = 2 * (lo / outs) + ((lo % outs) >= half ? 1 : 0);
+      const int r_hi = 2 * (hi / outs) + ((hi % outs) >= half ? 1 : 0);
+      if (r_hi - r_lo + 1 > 2) mask &= ~(1u << i);
+    }
+  }
+  meta[0] = widest;
+  meta[1] = (int)mask;
+}
+
+int launch_fb_steps(const FbEntry* table, int n_fb, int F, FbStep* steps, int* d_meta,
+                    cudaStream_t stream) {
+  fb_steps_kernel<<<1, 32, 0, stream>>>(table, n_fb, F, steps, d_meta);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
 int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t T, int n_fb,
                       float* out, cudaStream_t stream) {
   if (B <= 0 || T <= 0 || n_fb <= 0) return NNAB_OK;

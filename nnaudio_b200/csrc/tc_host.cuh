@@ -34,6 +34,7 @@ void mark_packed(const void* packed, int kind);
 
 // block-partial ("sliding") STFT kernel (tcb_kernels.cu)
 int tc_pack_basis_block(int n_fft, int hop, void* packed, cudaStream_t stream);
+size_t tc_packed_block_bytes(int n_fft, int hop);
 bool tc_block_shape_ok(int n_fft, int hop);
 int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* workspace,
                            size_t ws_bytes, cudaStream_t stream);

@@ -684,6 +684,14 @@ struct TcParams {
   EpiParams epi;
 };
 
+// Work order of a persistent worker: its u-th unit.  All K-chunks of an (m, n) tile go to the SAME
+// worker, consecutively, so the split-K partial sums are combined by ordered read-modify-writes of
+// one thread (run-to-run identical; no atomics, no zero-fill of the scratch).
+__device__ __forceinline__ int sched_tile(int u, int worker, int n_workers, int num_mn, int ks) {
+  const int mn = worker + (u / ks) * n_workers;
+  return mn < num_mn ? mn * ks + (u % ks) : -1;
+}
+
 // tile index -> (m tile, n tile, k-block range); K-chunks of one (m, n) tile are adjacent
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& m_tile, int& n_tile,
                                             int& kb0, int& kb1) {
@@ -700,7 +708,7 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& m_
 // 32 consecutive frames) and emit it in the requested output format.
 template <int FMT>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, int64_t g,
-                                              int n_tile, int half) {
+                                              int n_tile, int half, int k_chunk) {
       const int64_t b = g / p.t_slots;
       const int64_t tl = g - b * p.t_slots;
       const bool valid = (g < p.nv) && (tl < p.T);
@@ -727,7 +735,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
           }
         }
       } else if constexpr (FMT == 7) {
-        // ---- split-K partial sums: fp32 (round-to-nearest) atomics into the raw planes ----
+        // ---- split-K partial sums: ordered read-modify-write of the raw planes (this thread owns
+        // the element for every chunk of the tile; chunk 0 stores, later chunks add) ----
         float* rre = p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t;
 #pragma unroll 1
         for (int c0 = 0; c0 < half; c0 += 8) {
@@ -741,8 +750,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
             for (int j = 0; j < 8; ++j)
               if (j < jmax) {
                 float* q = rre + (int64_t)(f_base + c0 + j) * p.epi.T;
-                atomicAdd(q, __uint_as_float(re[j]));
-                atomicAdd(q + p.epi.raw_plane, __uint_as_float(im[j]));
+                float vr = __uint_as_float(re[j]), vi = __uint_as_float(im[j]);
+                if (k_chunk > 0) { vr += q[0]; vi += q[p.epi.raw_plane]; }
+                q[0] = vr;
+                q[p.epi.raw_plane] = vi;
               }
           }
         }
@@ -940,7 +951,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+  const int num_mn = p.num_m_tiles * p.num_n_tiles;
   const uint32_t b_tile_bytes = (uint32_t)p.bn * BK * 2;
 
   if (warp == 0) {
@@ -948,7 +959,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * TC_BM;
@@ -981,7 +992,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         (void)m_tile;
@@ -1018,7 +1029,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int half = p.bn >> 1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
       int m_tile, n_tile, kb0, kb1;
       decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
       (void)kb0; (void)kb1;
@@ -1027,7 +1038,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int64_t g = (int64_t)m_tile * TC_BM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
-      epilogue_tile<FMT>(p, trow, g, n_tile, half);
+      epilogue_tile<FMT>(p, trow, g, n_tile, half, tile % p.k_splits);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -1108,7 +1119,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;  // num_m_tiles: 256-frame pairs
+  const int num_mn = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles: 256-frame pairs
   const int halfn = p.bn >> 1;
   const uint32_t b_half_bytes = (uint32_t)halfn * BK * 2;
 
@@ -1117,7 +1128,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
@@ -1149,7 +1160,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         (void)m_tile;
@@ -1189,7 +1200,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
       int m_tile, n_tile, kb0, kb1;
       decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
       (void)kb0; (void)kb1;
@@ -1198,7 +1209,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
-      epilogue_tile<FMT>(p, trow, g, n_tile, halfn);
+      epilogue_tile<FMT>(p, trow, g, n_tile, halfn, tile % p.k_splits);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -1644,7 +1655,7 @@ __global__ void __launch_bounds__(256) pack_basis_varn_kernel(
 // FMT: 0 Magnitude, 1 Complex, 3 PhaseUnit (direct), 7 split-K partial sums.
 template <int FMT>
 __device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t trow, int64_t g,
-                                                   int n_groups) {
+                                                   int n_groups, int k_chunk) {
   const int64_t b = g / p.t_slots;
   const int64_t tl = g - b * p.t_slots;
   const bool valid = (g < p.nv) && (tl < p.T);
@@ -1665,8 +1676,10 @@ __device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t t
         if (f < p.epi.F) {
           if constexpr (FMT == 7) {
             float* q = rre + (int64_t)f * p.epi.T;
-            atomicAdd(q, __uint_as_float(re[j]));
-            atomicAdd(q + p.epi.raw_plane, __uint_as_float(im[j]));
+            float vr = __uint_as_float(re[j]), vi = __uint_as_float(im[j]);
+            if (k_chunk > 0) { vr += q[0]; vi += q[p.epi.raw_plane]; }  // ordered: same thread, chunk order
+            q[0] = vr;
+            q[p.epi.raw_plane] = vi;
           } else {
             epi_store_fmt<FMT>(p.epi, dst, f, __uint_as_float(re[j]), __uint_as_float(im[j]));
           }
@@ -1726,13 +1739,12 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_tiles * plan.n_chunks;  // one N tile
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
         const int chunk = tile % plan.n_chunks;
         const int m_tile = tile / plan.n_chunks;
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
@@ -1771,7 +1783,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
         const int chunk = tile % plan.n_chunks;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
@@ -1805,7 +1817,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
       const int chunk = tile % plan.n_chunks;
       const int m_tile = tile / plan.n_chunks;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -1814,7 +1826,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
       // widest block of the chunk = its first: the columns this tile initialised
-      epilogue_tile_varn<FMT>(p, trow, g, (int)plan.groups[plan.chunk_begin[chunk]]);
+      epilogue_tile_varn<FMT>(p, trow, g, (int)plan.groups[plan.chunk_begin[chunk]], chunk);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -2397,7 +2409,6 @@ static int launch_framed_tc_varn(const FramedProblem& q, const void* packed, voi
   if (split) {
     float* raw = reinterpret_cast<float*>(((uintptr_t)q.raw + 255) & ~(uintptr_t)255);
     const int64_t plane = (int64_t)q.B * q.F * q.T;
-    NNAB_CUDA_TRY(cudaMemsetAsync(raw, 0, (size_t)2 * plane * sizeof(float), stream));
     prm.epi.fmt = FMT_RAW;
     prm.epi.raw = raw;
     prm.epi.raw_plane = plane;
@@ -2574,8 +2585,7 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
       prm.k_splits = ks;
       float* raw = reinterpret_cast<float*>(((uintptr_t)q.raw + 255) & ~(uintptr_t)255);
       const int64_t plane = (int64_t)q.B * q.F * q.T;
-      NNAB_CUDA_TRY(cudaMemsetAsync(raw, 0, (size_t)2 * plane * sizeof(float), stream));
-      prm.epi.fmt = FMT_RAW;
+        prm.epi.fmt = FMT_RAW;
       prm.epi.raw = raw;
       prm.epi.raw_plane = plane;
       final_epi.raw = raw;

@@ -72,7 +72,14 @@ static int block_choose_nb(int F) {
   return best;
 }
 static int block_n_tiles(int F, int nb) { return (F + nb - 3) / (nb - 2); }
-static int block_p_rows(int F, int nb) { return (block_n_tiles(F, nb) - 1) * (nb - 2) + nb; }
+// rows of one (plane, part) slab: bins -1 .. F plus zero rows so that the last tile of ANY nb <= 128
+// stays inside the slab (the launch picks nb, e.g. wider tiles for the fused filterbank)
+static int block_p_rows(int F) { return round_up_i(F + 2 + 128, 8); }
+
+size_t tc_packed_block_bytes(int n_fft, int hop) {
+  if (!tc_block_shape_ok(n_fft, hop)) return 0;
+  return (size_t)4 * block_p_rows(n_fft / 2 + 1) * hop * sizeof(__nv_bfloat16) + 256;
+}
 
 bool tc_block_shape_ok(int n_fft, int hop) {
   if (hop <= 0 || n_fft % hop != 0) return false;
@@ -123,8 +130,7 @@ static std::unordered_map<const void*, BlockPack> g_blk;
 int tc_pack_basis_block(int n_fft, int hop, void* packed, cudaStream_t stream) {
   if (!tc_block_shape_ok(n_fft, hop) || packed == nullptr) return NNAB_EINVAL;
   const int F = n_fft / 2 + 1;
-  const int nb = block_choose_nb(F);
-  const int p_rows = block_p_rows(F, nb);
+  const int p_rows = block_p_rows(F);
   const int64_t threads = (int64_t)p_rows * (hop / 8);
   pack_block_basis_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
       n_fft, hop, F, p_rows, (__nv_bfloat16*)packed);
@@ -163,6 +169,8 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
   if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
   else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
   MelRun run;
+  float ma = 0.f, mb = 0.f;  // FMT 5, static action list: the two running filter sums
+  int mca = -1, mcb = -1;    //   and the filters they currently belong to
 
   // twiddles c_k^j of the 4 residues the unrolled loop meets: output o = 8c - 2 + e is bin
   // k = k_tile0 + o, so k mod 4 = (k_tile0 + 2 + e) mod 4 (8c drops out).
@@ -253,8 +261,46 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
         }
         q += step;
       }
+    } else if constexpr (FMT == 5) {
+      if (p.epi.fb_steps != nullptr) {
+        // banded filterbank, static action list: straight-line, two running sums per row
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = k0 + e;
+          const bool use = (e >= e_lo) && (k < p.epi.F);  // warp-uniform
+          const int4 raw = __ldg(reinterpret_cast<const int4*>(p.epi.fb_steps) + (k < 0 ? 0 : k));
+          float pw = __fadd_rn(__fmul_rn(xr[e], xr[e]), __fmul_rn(xi[e], xi[e]));
+          if (p.epi.eps != 0.f) pw = __fadd_rn(pw, p.epi.eps);
+          if (p.epi.power != 2.0f)
+            pw = (p.epi.power == 1.0f) ? sqrt_approx(pw) : powf(sqrt_approx(pw), p.epi.power);
+          pw = use ? pw : 0.f;
+          const int fa = use ? (int)(short)(raw.z & 0xffff) : -1;
+          const int fb = use ? (int)(short)((unsigned)raw.z >> 16) : -1;
+          if (fa >= 0) {
+            if (valid) atomicAdd(mel + (int64_t)fa * p.epi.T, ma);
+            ma = 0.f;
+          }
+          if (fb >= 0) {
+            if (valid) atomicAdd(mel + (int64_t)fb * p.epi.T, mb);
+            mb = 0.f;
+          }
+          ma = fmaf(__int_as_float(raw.x), pw, ma);
+          mb = fmaf(__int_as_float(raw.y), pw, mb);
+          if (use) { mca = (int)(short)(raw.w & 0xffff); mcb = (int)(short)((unsigned)raw.w >> 16); }
+        }
+      } else {
+#pragma unroll 1
+        for (int e = e_lo; e < 8; ++e) {
+          const int k = k0 + e;
+          if (k >= p.epi.F) break;  // warp-uniform
+          float re = xr[0], im = xi[0];
+#pragma unroll
+          for (int j = 1; j < 8; ++j) { re = (e == j) ? xr[j] : re; im = (e == j) ? xi[j] : im; }
+          run.add(p.epi, mel, valid, k, epi_power(p.epi, re, im));
+        }
+      }
     } else {
-      // atan2f / banded-filterbank tails: rolled per bin (code size), after the straight-line part
+      // atan2f tail: rolled per bin (code size), after the straight-line part
 #pragma unroll 1
       for (int e = e_lo; e < 8; ++e) {
         const int k = k0 + e;
@@ -263,13 +309,13 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
         float re = xr[0], im = xi[0];
 #pragma unroll
         for (int j = 1; j < 8; ++j) { re = (e == j) ? xr[j] : re; im = (e == j) ? xi[j] : im; }
-        if constexpr (FMT == 5) {
-          run.add(p.epi, mel, valid, k, epi_power(p.epi, re, im));
-        } else {
-          if (valid) epi_store_fmt<FMT>(p.epi, dst, k, re, im);
-        }
+        if (valid) epi_store_fmt<FMT>(p.epi, dst, k, re, im);
       }
     }
+  }
+  if constexpr (FMT == 5) {
+    if (mca >= 0 && valid) atomicAdd(mel + (int64_t)mca * p.epi.T, ma);
+    if (mcb >= 0 && valid) atomicAdd(mel + (int64_t)mcb * p.epi.T, mb);
   }
   if constexpr (FMT == 5) run.flush(p.epi, mel, valid);
 }
@@ -514,9 +560,22 @@ int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* wor
   sms -= sm_reserve();
   if (sms < 2) sms = 2;
 
-  const int nb = block_choose_nb(q.F);
+  int nb = block_choose_nb(q.F);
+  if (q.fmt == FMT_FBANK && q.fb_steps != nullptr && q.fb_nb_mask != 0) {
+    // run-to-run identical filterbank sums: with at most two partial sums per filter the atomic
+    // adds commute.  The table builder replayed the range cuts for every tile width; take the
+    // cheapest width that qualifies (fewest padded columns), else keep the default.
+    int best = -1, best_cost = 1 << 30;
+    for (int i = 0; i < 13; ++i) {
+      if (!((q.fb_nb_mask >> i) & 1)) continue;
+      const int c = 32 + 8 * i;
+      const int cost = block_n_tiles(q.F, c) * (c + 6);
+      if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    if (best > 0) nb = best;
+  }
   const int n_tiles = block_n_tiles(q.F, nb);
-  const int p_rows = block_p_rows(q.F, nb);
+  const int p_rows = block_p_rows(q.F);
   CUtensorMap ma, mb;
   rc = encode_3d(&ma, planes, (uint64_t)q.hop, (uint64_t)g.rows, 2, (uint64_t)q.hop * 2,
                  (uint64_t)g.plane_stride * 2, 64, 32, 64);
@@ -538,7 +597,7 @@ int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* wor
   prm.epi.scale = nullptr; prm.epi.scale_all = 1.f; prm.epi.fmt = q.fmt;
   prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
   prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
-  prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
+  prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb; prm.epi.fb_steps = q.fb_steps;
   prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
   prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
   const int64_t ptiles = (int64_t)prm.num_m_pairs * n_tiles;

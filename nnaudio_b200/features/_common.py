@@ -185,8 +185,10 @@ class PackedBasis:
         """``allow_radix`` (False, 2 or 4 = the largest radix the module's hop allows): the module
         computes a plain one-sided STFT with this basis, so the decimation-in-time layout may be
         used when the buffers pass ``is_dft_structured``;
-        ``groups``: long CQT bank for the per-K-block-width kernel.  Both EXPERIMENTAL and only
-        active with NNAUDIO_B200_EXPERIMENTAL=1."""
+        ``groups``: long CQT bank for the per-K-block-width kernel (default);
+        ``block_hop``: STFT-family module -> block-partial layout when the buffers are the Hann DFT.
+        The radix layouts stay EXPERIMENTAL (NNAUDIO_B200_EXPERIMENTAL=1): the block-partial kernel
+        supersedes them."""
         import os
 
         def build():
@@ -204,8 +206,11 @@ class PackedBasis:
                     layout = _C.LAYOUT_RADIX4
                 elif allow_radix and is_dft_structured(w_re, w_im):
                     layout = _C.LAYOUT_RADIX2
-                elif groups and w_re.shape[0] <= 128 and w_re.shape[1] >= 4096:
-                    layout = _C.LAYOUT_GROUPS
+            # long CQT banks (CQT1992v2): per-K-block MMA width, the default since round 2
+            # (GPU-verified: reference chirp goldens + cfg3 full size; NNAUDIO_B200_VARN=0: dense)
+            if layout == _C.LAYOUT_DENSE and groups and w_re.shape[0] <= 128 and w_re.shape[1] >= 4096 \
+                    and os.environ.get("NNAUDIO_B200_VARN", "1") != "0":
+                layout = _C.LAYOUT_GROUPS
             return _C.pack_basis(w_re, w_im, layout) if layout else _C.pack_basis(w_re, w_im)
 
         key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, allow_radix, groups,

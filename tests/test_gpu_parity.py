@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import record_error
 from helpers import (CASES, REF_GROUND_TRUTHS, SWEEP_CTOR, build, case_input, is_phase, make_input,
                      out_key, phase_to_unit, ref_ground_truths, ref_outputs, rel_errors, run_oracle)
 
@@ -52,13 +53,16 @@ def test_cuda_matches_reference_and_oracle(case, path):
             mag = run_oracle(cls, mod, x, dict(kw, output_format="Magnitude"))
             keep = mag > PHASE_FLOOR[path] * mag.max()
             assert keep.sum() > 20
-            for ref in (want, orc):
+            for name, ref in (("reference", want), ("oracle", orc)):
                 d = np.abs(phase_to_unit(cls, got)[keep] - phase_to_unit(cls, ref)[keep]).max()
+                record_error("phase", f"{cid}|{kw}|{path}|{name}", max_abs_unit=float(d),
+                             floor=PHASE_FLOOR[path], kept=int(keep.sum()))
                 assert d < 2e-3, (cid, kw, path, d)
             continue
         tol = 4e-4 if cls == "MFCC" else TOL  # dB of near-zero mel powers amplifies fp32 noise
         for name, ref in (("reference", want), ("oracle", orc)):
             emax, el2 = rel_errors(got, ref)
+            record_error("cases", f"{cid}|{kw}|{path}|{name}", max_rel=emax, l2_rel=el2, tol=tol)
             assert emax < tol and el2 < tol, (cid, kw, path, name, emax, el2)
 
 
