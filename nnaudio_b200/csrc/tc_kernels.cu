@@ -678,18 +678,51 @@ struct TcParams {
   int t_mul, t_add;  // output frame index = t * t_mul + t_add (frame phases)
   int k_splits;      // >1: every (m, n) tile is cut into k_splits K-chunks (FMT_RAW epilogue)
   int split4;        // EXPERIMENTAL (NNAB_SPLIT4=1): add the x_lo * w_lo term (4 MMAs per K16 step)
+  int* sk_flags;     // split-K: one arrival counter per (m, n) tile, zeroed per launch (or nullptr)
+  int sk_warps;      // epilogue warps per unit (4, or 8 for a CTA pair)
   int64_t nv, t_slots, T;  // T = valid frames of this phase
   int kb_begin[TC_MAX_N_TILES];
   int kb_end[TC_MAX_N_TILES];
   EpiParams epi;
 };
 
-// Work order of a persistent worker: its u-th unit.  All K-chunks of an (m, n) tile go to the SAME
-// worker, consecutively, so the split-K partial sums are combined by ordered read-modify-writes of
-// one thread (run-to-run identical; no atomics, no zero-fill of the scratch).
-__device__ __forceinline__ int sched_tile(int u, int worker, int n_workers, int num_mn, int ks) {
+// Work order of a persistent worker: its u-th unit (unit = tile * ks + K-chunk), or -1 when done.
+// Split-K partial sums are combined by ORDERED read-modify-writes (run-to-run identical; no atomics,
+// no zero-fill of the scratch): chunk c of a tile adds after chunk c-1 has stored.
+//   flags != nullptr: units are dealt round-robin (balanced); the epilogue of chunk c waits until
+//     the tile's flag counts c * (epilogue warps per unit) arrivals.  Unit u-1 sits on worker
+//     (u-1) % W at a queue position <= that of unit u, so the wait cannot deadlock a persistent grid.
+//   flags == nullptr: all chunks of a tile go to the same worker, consecutively (program order).
+__device__ __forceinline__ int sched_tile(int u, int worker, int n_workers, int num_mn, int ks,
+                                          const int* flags) {
+  if (flags != nullptr) {
+    const int64_t unit = (int64_t)worker + (int64_t)u * n_workers;
+    return unit < (int64_t)num_mn * ks ? (int)unit : -1;
+  }
   const int mn = worker + (u / ks) * n_workers;
   return mn < num_mn ? mn * ks + (u % ks) : -1;
+}
+__device__ __forceinline__ void sk_wait(const int* flag, int need, int lane) {
+  if (lane == 0) {
+    int v;
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v < need && (++spins & 0x3FFFu) == 0) {  // bounded: a scheduling bug must trap, not hang
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) { printf("nnab: split-K order wait timeout\n"); __trap(); }
+      }
+    } while (v < need);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void sk_arrive(int* flag, int lane) {
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
 }
 
 // tile index -> (m tile, n tile, k-block range); K-chunks of one (m, n) tile are adjacent
@@ -708,7 +741,7 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& m_
 // 32 consecutive frames) and emit it in the requested output format.
 template <int FMT>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, int64_t g,
-                                              int n_tile, int half, int k_chunk) {
+                                              int n_tile, int half, int k_chunk, int mn_tile) {
       const int64_t b = g / p.t_slots;
       const int64_t tl = g - b * p.t_slots;
       const bool valid = (g < p.nv) && (tl < p.T);
@@ -738,6 +771,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
         // ---- split-K partial sums: ordered read-modify-write of the raw planes (this thread owns
         // the element for every chunk of the tile; chunk 0 stores, later chunks add) ----
         float* rre = p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t;
+        if (p.sk_flags != nullptr && k_chunk > 0)
+          sk_wait(p.sk_flags + mn_tile, k_chunk * p.sk_warps, threadIdx.x & 31);
 #pragma unroll 1
         for (int c0 = 0; c0 < half; c0 += 8) {
           uint32_t re[8], im[8];
@@ -751,12 +786,13 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
               if (j < jmax) {
                 float* q = rre + (int64_t)(f_base + c0 + j) * p.epi.T;
                 float vr = __uint_as_float(re[j]), vi = __uint_as_float(im[j]);
-                if (k_chunk > 0) { vr += q[0]; vi += q[p.epi.raw_plane]; }
-                q[0] = vr;
-                q[p.epi.raw_plane] = vi;
+                if (k_chunk > 0) { vr += __ldcg(q); vi += __ldcg(q + p.epi.raw_plane); }
+                __stcg(q, vr);
+                __stcg(q + p.epi.raw_plane, vi);
               }
           }
         }
+        if (p.sk_flags != nullptr) sk_arrive(p.sk_flags + mn_tile, threadIdx.x & 31);
       } else if constexpr (FMT == 6) {
         // ---- FIR decimator stage: this thread holds outputs n0 .. n0 + 2*half - 1 of clip b ----
         const DecimParams& d = p.epi.dec;
@@ -959,7 +995,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * TC_BM;
@@ -992,7 +1028,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         (void)m_tile;
@@ -1029,7 +1065,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int half = p.bn >> 1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
+    for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
       int m_tile, n_tile, kb0, kb1;
       decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
       (void)kb0; (void)kb1;
@@ -1038,7 +1074,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int64_t g = (int64_t)m_tile * TC_BM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
-      epilogue_tile<FMT>(p, trow, g, n_tile, half, tile % p.k_splits);
+      epilogue_tile<FMT>(p, trow, g, n_tile, half, tile % p.k_splits, tile / p.k_splits);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -1128,7 +1164,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
@@ -1160,7 +1196,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         (void)m_tile;
@@ -1200,7 +1236,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
+    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
       int m_tile, n_tile, kb0, kb1;
       decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
       (void)kb0; (void)kb1;
@@ -1209,7 +1245,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
-      epilogue_tile<FMT>(p, trow, g, n_tile, halfn, tile % p.k_splits);
+      epilogue_tile<FMT>(p, trow, g, n_tile, halfn, tile % p.k_splits, tile / p.k_splits);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -1655,7 +1691,7 @@ __global__ void __launch_bounds__(256) pack_basis_varn_kernel(
 // FMT: 0 Magnitude, 1 Complex, 3 PhaseUnit (direct), 7 split-K partial sums.
 template <int FMT>
 __device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t trow, int64_t g,
-                                                   int n_groups, int k_chunk) {
+                                                   int n_groups, int k_chunk, int mn_tile) {
   const int64_t b = g / p.t_slots;
   const int64_t tl = g - b * p.t_slots;
   const bool valid = (g < p.nv) && (tl < p.T);
@@ -1663,6 +1699,10 @@ __device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t t
   constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
   float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
   float* rre = (FMT == 7) ? p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t : nullptr;
+  if constexpr (FMT == 7) {
+    if (p.sk_flags != nullptr && k_chunk > 0)
+      sk_wait(p.sk_flags + mn_tile, k_chunk * p.sk_warps, threadIdx.x & 31);
+  }
 #pragma unroll 1
   for (int gi = 0; gi < n_groups; ++gi) {
     uint32_t re[8], im[8];
@@ -1677,15 +1717,18 @@ __device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t t
           if constexpr (FMT == 7) {
             float* q = rre + (int64_t)f * p.epi.T;
             float vr = __uint_as_float(re[j]), vi = __uint_as_float(im[j]);
-            if (k_chunk > 0) { vr += q[0]; vi += q[p.epi.raw_plane]; }  // ordered: same thread, chunk order
-            q[0] = vr;
-            q[p.epi.raw_plane] = vi;
+            if (k_chunk > 0) { vr += __ldcg(q); vi += __ldcg(q + p.epi.raw_plane); }  // ordered by chunk
+            __stcg(q, vr);
+            __stcg(q + p.epi.raw_plane, vi);
           } else {
             epi_store_fmt<FMT>(p.epi, dst, f, __uint_as_float(re[j]), __uint_as_float(im[j]));
           }
         }
       }
     }
+  }
+  if constexpr (FMT == 7) {
+    if (p.sk_flags != nullptr) sk_arrive(p.sk_flags + mn_tile, threadIdx.x & 31);
   }
 }
 
@@ -1744,7 +1787,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks, p.sk_flags)) >= 0; ++u) {
         const int chunk = tile % plan.n_chunks;
         const int m_tile = tile / plan.n_chunks;
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
@@ -1783,7 +1826,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks, p.sk_flags)) >= 0; ++u) {
         const int chunk = tile % plan.n_chunks;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
@@ -1817,7 +1860,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
+    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks, p.sk_flags)) >= 0; ++u) {
       const int chunk = tile % plan.n_chunks;
       const int m_tile = tile / plan.n_chunks;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -1826,7 +1869,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)acc * TC_ACC_STRIDE;
       // widest block of the chunk = its first: the columns this tile initialised
-      epilogue_tile_varn<FMT>(p, trow, g, (int)plan.groups[plan.chunk_begin[chunk]], chunk);
+      epilogue_tile_varn<FMT>(p, trow, g, (int)plan.groups[plan.chunk_begin[chunk]], chunk, m_tile);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -1856,9 +1899,22 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const EpiParams e,
 
 // Long kernels only: the scratch exists to bound the tensor-core accumulation length
 // (its error grows with the number of accumulated MMAs) and to even out the tile count.
+constexpr size_t SK_FLAG_BYTES = 1u << 20;  // arrival counters of the ordered split-K combine
 size_t tc_splitk_scratch_bytes(int64_t B, int F, int64_t T, int K) {
   if (K < 8192) return 0;
-  return (size_t)2 * B * F * T * sizeof(float) + 256;
+  return (size_t)2 * B * F * T * sizeof(float) + 512 + SK_FLAG_BYTES;
+}
+
+// flags behind the two raw planes; nullptr (-> same-worker chunk order) when there are too many tiles
+static int* sk_flags_of(float* raw, int64_t plane, int64_t num_mn, cudaStream_t stream, int* rc) {
+  *rc = NNAB_OK;
+  if (num_mn * (int64_t)sizeof(int) > (int64_t)SK_FLAG_BYTES) return nullptr;
+  int* flags = reinterpret_cast<int*>(((uintptr_t)(raw + 2 * plane) + 255) & ~(uintptr_t)255);
+  if (cudaMemsetAsync(flags, 0, (size_t)num_mn * sizeof(int), stream) != cudaSuccess) {
+    *rc = NNAB_ECUDA;
+    return nullptr;
+  }
+  return flags;
 }
 
 // ---------------------------------------------------------------------------
@@ -2416,6 +2472,12 @@ static int launch_framed_tc_varn(const FramedProblem& q, const void* packed, voi
     final_epi.raw_plane = plane;
   }
   prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
+  prm.sk_flags = nullptr;
+  prm.sk_warps = 8;
+  if (split) {
+    prm.sk_flags = sk_flags_of(prm.epi.raw, prm.epi.raw_plane, prm.num_m_tiles, stream, &rc);
+    if (rc) return rc;
+  }
   const int64_t ptiles = (int64_t)prm.num_m_tiles * plan.n_chunks;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
   {
@@ -2610,6 +2672,13 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
       for (int tl = 0; tl < n_tiles; ++tl) kcols += (double)(prm.kb_end[tl] - prm.kb_begin[tl]) * bk * bn;
       add_exec_flops((prm.split4 && cta_group == 2 ? 4.0 : 3.0) * 2.0 *
                      (double)ceil_div64(g.nv, mrows) * mrows * kcols);
+    }
+    prm.sk_flags = nullptr;
+    prm.sk_warps = cta_group == 2 ? 8 : 4;
+    if (split) {  // arrival counters are per launch: every frame phase starts from zero
+      const int64_t num_mn = ceil_div64(g.nv, (cta_group == 2 ? 2 : 1) * TC_BM) * prm.num_n_tiles;
+      prm.sk_flags = sk_flags_of(prm.epi.raw, prm.epi.raw_plane, num_mn, stream, &rc);
+      if (rc) return rc;
     }
     if (cta_group == 2) {
       prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);  // 256-frame pair tiles
