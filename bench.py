@@ -61,6 +61,9 @@ WORKLOAD_BOUND = {"cfg2": "tensor", "stft2048": "tensor", "cfg3": "tensor", "cfg
 # the other configurations BASELINE.json's metric names, reported inside the same JSON line
 SECONDARY = ["stft2048", "cfg3", "cfg4", "cfg5"]
 
+GATHER_DESC = {"symm": "copy-engine pushes into symmetric memory over NVLink, no SMs, no NCCL kernels",
+               "nccl": "ncclAllGather on reserved SMs", "none": "-", "auto": "-"}
+
 # SMs left to the NCCL gather while the persistent kernels run, and the matching NCCL CTA cap
 # (the gather of (N-1) x 14 MB must hide under one ~0.47 ms transform; measured ~14.5 GB/s per
 # NCCL CTA next to the kernels: 8 CTAs suffice at N=4, not at N=8 — profiles/README.md)
@@ -364,8 +367,11 @@ def _run():
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's cuDNN leg")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--e2e-copy-streams", type=int, default=1)
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "symm"],
-                    help="EXPERIMENTAL: symm = copy-engine pushes into symmetric memory (no SMs reserved)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "symm"],
+                    help="symm = copy-engine pushes into symmetric memory (no SMs reserved); nccl = "
+                         "all_gather_into_tensor with an SM reserve; auto = symm when it works on this box")
+    ap.add_argument("--gather-to", default="all", choices=["all", "root"],
+                    help="every rank receives the whole batch's spectrograms, or rank 0 only")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs kept free for the concurrent NCCL gather (default: by world size)")
     ap.add_argument("--nccl-max-ctas", type=int, default=-1,
@@ -427,14 +433,40 @@ def _run():
             os.sched_setaffinity(0, local_cpus)
         except OSError:
             local_cpus = None
+    gather_impl = "none"
     if world > 1:
-        # few CTAs for the output gather: it overlaps the next batch's kernels (which leave
-        # SMs free for it, nnaudio_b200.parallel) and 99 MB per step does not need more
+        # NCCL path: few CTAs for the output gather -- it overlaps the next batch's kernels (which
+        # leave SMs free for it, nnaudio_b200.parallel) and 99 MB per step does not need more
         reserve_plan = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
         max_ctas = args.nccl_max_ctas if args.nccl_max_ctas >= 0 else reserve_plan
-        if max_ctas > 0 and args.gather == "nccl":
+        if max_ctas > 0 and args.gather != "symm":
             os.environ["NCCL_MAX_CTAS"] = str(max_ctas)
         dist.init_process_group("nccl", device_id=dev)
+        gather_impl = args.gather
+        if args.gather in ("auto", "symm"):
+            # does the copy-engine gather work here?  (symmetric memory needs P2P / fabric handles);
+            # every rank must agree, so reduce the outcome
+            ok = 1
+            try:
+                probe = BatchShardedTransform(lambda t: t, gather=True, reserve_sms=0)
+                xp = torch.full((2, 8), float(rank), device=dev)
+                wk, got = probe.forward_async_symm(xp, slot=0, gather_to="all")
+                wk.wait()
+                torch.cuda.synchronize(dev)
+                want = torch.arange(world, device=dev, dtype=torch.float32).repeat_interleave(2)[:, None].expand(-1, 8)
+                ok = int(torch.equal(got, want))
+                probe.release(0)
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] rank {rank}: symmetric-memory gather unavailable: {type(e).__name__}: {e}\n")
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                gather_impl = "symm"
+            elif args.gather == "symm":
+                raise RuntimeError("--gather symm requested but the symmetric-memory gather failed its probe")
+            else:
+                gather_impl = "nccl"
 
     peaks = {}
     try:
@@ -459,7 +491,7 @@ def _run():
         return [float(v) for v in t.tolist()]
 
     reserve = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
-    if args.gather == "symm" and args.reserve_sms is None:
+    if gather_impl == "symm" and args.reserve_sms is None:
         reserve = 0  # the copy engines do the gather: the kernels keep every SM
 
     def measure(name, steps, warmup, gather):
@@ -484,13 +516,13 @@ def _run():
             every gather completes inside the timed region."""
             prev, y = None, None
             for i in range(n):
-                if args.gather == "symm" and gather and world > 1:
-                    work, y = sharded.forward_async_symm(xs[i % n_rot], slot=i & 1)
+                if gather_impl == "symm" and gather and world > 1:
+                    work, y = sharded.forward_async_symm(xs[i % n_rot], slot=i & 1, gather_to=args.gather_to)
                 else:
                     work, y = sharded.forward_async(xs[i % n_rot], slot=i & 1)
                 if prev is not None:
                     prev.wait()
-                    if args.gather == "symm" and gather and world > 1:
+                    if gather_impl == "symm" and gather and world > 1:
                         sharded.release((i - 1) & 1)
                 prev = work
             if prev is not None:
@@ -565,6 +597,12 @@ def _run():
 
     main, mod, out_shape, w = measure(args.workload, args.steps, args.warmup, gather=True)
     B = w["B"]
+    no_gather = None
+    if world > 1:  # frames/s with and without the gather
+        ng, m_ng, _, _ = measure(args.workload, args.steps, args.warmup, gather=False)
+        del m_ng
+        no_gather = {"value": ng["value"], "ms_per_step": ng["ms_per_step"],
+                     "what": "same run, transform only (shards stay on their GPUs)"}
 
     # ------------------------------------------------------------ e2e --
     e2e, pcie = None, None
@@ -651,8 +689,9 @@ def _run():
                 "workload": f"{args.workload}: {w['desc']}", "per_gpu_batch": B,
                 "global_batch": world * B, "frames_per_clip": T,
                 "parallelism": f"batch-sharded x{world}" + (
-                    f" + {args.gather} gather of the output spectrograms (gather of step i overlaps transform of "
-                    "step i+1)" if world > 1 else ""),
+                    f" + gather of the output spectrograms to {args.gather_to} ({GATHER_DESC[gather_impl]}; the "
+                    "gather of step i overlaps the transform of step i+1)" if world > 1 else ""),
+                "gather": gather_impl if world > 1 else None,
                 "l2": main["l2"] + "; one CUDA-event pair around all K steps",
                 "kernel_path": os.environ.get("NNAUDIO_B200_PATH", "auto"),
                 "sms_reserved_for_gather": reserve if world > 1 else 0,
@@ -662,6 +701,8 @@ def _run():
             "clocks": main["clocks"],
             "roofline": main["roofline"],
         }
+        if no_gather:
+            line["without_gather"] = no_gather
         if e2e:
             line["e2e"] = e2e
             line["pcie"] = pcie

@@ -1908,6 +1908,11 @@ size_t tc_splitk_scratch_bytes(int64_t B, int F, int64_t T, int K) {
 // flags behind the two raw planes; nullptr (-> same-worker chunk order) when there are too many tiles
 static int* sk_flags_of(float* raw, int64_t plane, int64_t num_mn, cudaStream_t stream, int* rc) {
   *rc = NNAB_OK;
+  // Measured on cfg3 (B200): 2.04 ms with the flag-ordered round-robin vs 1.27 ms with all chunks of
+  // a tile on one worker -- the chunks of a tile finish their MMAs together and their epilogues then
+  // run one after the other while holding TMEM buffers.  Kept for experiments (NNAB_SK_FLAGS=1).
+  static const bool use_flags = [] { const char* e = getenv("NNAB_SK_FLAGS"); return e != nullptr && atoi(e) == 1; }();
+  if (!use_flags) return nullptr;
   if (num_mn * (int64_t)sizeof(int) > (int64_t)SK_FLAG_BYTES) return nullptr;
   int* flags = reinterpret_cast<int*>(((uintptr_t)(raw + 2 * plane) + 255) & ~(uintptr_t)255);
   if (cudaMemsetAsync(flags, 0, (size_t)num_mn * sizeof(int), stream) != cudaSuccess) {

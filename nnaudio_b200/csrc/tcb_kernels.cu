@@ -155,6 +155,16 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return r;
 }
 
+// fire-and-forget fp32 add, predicated (no branch: the chunk body stays one basic block)
+__device__ __forceinline__ void red_add_if(float* addr, float v, bool on) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "@p red.global.add.f32 [%0], %1;\n\t}"
+      ::"l"(addr), "f"(v), "r"((int)on)
+      : "memory");
+}
+
 template <int FMT, int R>
 __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t trow, int64_t g,
                                                     int lane, int n_tile, int c_begin, int c_end) {
@@ -169,6 +179,9 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
   if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
   else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
   MelRun run;
+  // FMT 5 fast path: static action list and the default power 2 without eps; anything else (other
+  // powers, trainable eps, no action list) takes the rolled MelRun path below
+  const bool fast_fb = (FMT == 5) && p.epi.fb_steps != nullptr && p.epi.power == 2.0f && p.epi.eps == 0.f;
   float ma = 0.f, mb = 0.f;  // FMT 5, static action list: the two running filter sums
   int mca = -1, mcb = -1;    //   and the filters they currently belong to
 
@@ -200,6 +213,15 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     wr[0] = wr[8]; wr[1] = wr[9]; wi[0] = wi[8]; wi[1] = wi[9];
+    int4 st[8];  // FMT 5: this chunk's filterbank actions, requested before the TMEM round trip
+    if constexpr (FMT == 5) {
+      if (fast_fb) {
+        const int kq = k_tile0 + 8 * c - 2;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          st[e] = __ldg(reinterpret_cast<const int4*>(p.epi.fb_steps) + (kq + e < 0 ? 0 : kq + e));
+      }
+    }
     {
       uint32_t re[8], im[8];
       tmem_ld8(trow + (uint32_t)(8 * c), re);
@@ -262,31 +284,26 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
         q += step;
       }
     } else if constexpr (FMT == 5) {
-      if (p.epi.fb_steps != nullptr) {
-        // banded filterbank, static action list: straight-line, two running sums per row
+      if (fast_fb) {
+        // banded filterbank, static action list: branch-free, two running sums per row
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int k = k0 + e;
           const bool use = (e >= e_lo) && (k < p.epi.F);  // warp-uniform
-          const int4 raw = __ldg(reinterpret_cast<const int4*>(p.epi.fb_steps) + (k < 0 ? 0 : k));
+          const int4 raw = st[e];
+          // power == 2 (the default, mel.py:186: |X| ** 2): the power spectrum itself, to 1 ulp
           float pw = __fadd_rn(__fmul_rn(xr[e], xr[e]), __fmul_rn(xi[e], xi[e]));
-          if (p.epi.eps != 0.f) pw = __fadd_rn(pw, p.epi.eps);
-          if (p.epi.power != 2.0f)
-            pw = (p.epi.power == 1.0f) ? sqrt_approx(pw) : powf(sqrt_approx(pw), p.epi.power);
           pw = use ? pw : 0.f;
-          const int fa = use ? (int)(short)(raw.z & 0xffff) : -1;
-          const int fb = use ? (int)(short)((unsigned)raw.z >> 16) : -1;
-          if (fa >= 0) {
-            if (valid) atomicAdd(mel + (int64_t)fa * p.epi.T, ma);
-            ma = 0.f;
-          }
-          if (fb >= 0) {
-            if (valid) atomicAdd(mel + (int64_t)fb * p.epi.T, mb);
-            mb = 0.f;
-          }
+          const int fa = (int)(short)(raw.z & 0xffff), fb = (int)(short)((unsigned)raw.z >> 16);
+          const bool fla = use && fa >= 0, flb = use && fb >= 0;
+          red_add_if(mel + (int64_t)fa * p.epi.T, ma, fla && valid);
+          red_add_if(mel + (int64_t)fb * p.epi.T, mb, flb && valid);
+          ma = fla ? 0.f : ma;
+          mb = flb ? 0.f : mb;
           ma = fmaf(__int_as_float(raw.x), pw, ma);
           mb = fmaf(__int_as_float(raw.y), pw, mb);
-          if (use) { mca = (int)(short)(raw.w & 0xffff); mcb = (int)(short)((unsigned)raw.w >> 16); }
+          mca = use ? (int)(short)(raw.w & 0xffff) : mca;
+          mcb = use ? (int)(short)((unsigned)raw.w >> 16) : mcb;
         }
       } else {
 #pragma unroll 1
@@ -314,8 +331,8 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
     }
   }
   if constexpr (FMT == 5) {
-    if (mca >= 0 && valid) atomicAdd(mel + (int64_t)mca * p.epi.T, ma);
-    if (mcb >= 0 && valid) atomicAdd(mel + (int64_t)mcb * p.epi.T, mb);
+    red_add_if(mel + (int64_t)mca * p.epi.T, ma, mca >= 0 && valid);
+    red_add_if(mel + (int64_t)mcb * p.epi.T, mb, mcb >= 0 && valid);
   }
   if constexpr (FMT == 5) run.flush(p.epi, mel, valid);
 }

@@ -97,13 +97,14 @@ class BatchShardedTransform:
         return torch.cat(parts, 0)
 
     # ------------------------------------------------------------------ #
-    # EXPERIMENTAL (branch radix2-wip, needs >= 2 GPUs to run): gather without NCCL and without
-    # SMs.  Every rank owns a symmetric-memory buffer holding the WHOLE gathered output (two
-    # rotating slots); after its transform a rank pushes its shard into the same slice of every
-    # peer's buffer with plain device-to-device copies over NVLink (copy engines, so the persistent
-    # kernels keep all 148 SMs and nothing has to be reserved for a collective).  Two device-side
-    # barriers per step order the slot reuse (all ranks have consumed the slot) and the arrival of
-    # the pushes.
+    # Gather without NCCL kernels and without SMs (SURVEY.md 8(e) fusion target, first step).  Every
+    # rank owns a symmetric-memory buffer holding the WHOLE gathered output (two rotating slots);
+    # after its transform a rank pushes its shard into the same slice of every peer's buffer
+    # (``gather_to='all'``) or of the root's only (``gather_to='root'``: what the north star names;
+    # 1/world of the fabric bytes) with plain device-to-device copies over NVLink -- copy engines,
+    # so the persistent kernels keep all 148 SMs and nothing is reserved for a collective.  Two
+    # device-side barriers per step order the slot reuse (every rank has consumed the slot) and the
+    # arrival of the pushes.
     def _symm_setup(self, y: torch.Tensor):
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -114,7 +115,7 @@ class BatchShardedTransform:
             buf = symm_mem.empty(shape, dtype=y.dtype, device=y.device)
             hdl = symm_mem.rendezvous(buf, group)
             self._symm = (buf, hdl, [hdl.get_buffer(r, shape, y.dtype) for r in range(world)])
-            self._symm_stream = torch.cuda.Stream(y.device)
+            self._symm_streams = [torch.cuda.Stream(y.device) for _ in range(2)]
             self._symm_consumed = [None, None]
             self._symm_shape = (shape, y.dtype, y.device)
         return self._symm
@@ -130,15 +131,19 @@ class BatchShardedTransform:
 
     def release(self, slot: int):
         """Record that the consumer is finished with ``slot`` (call after the last kernel that reads
-        the gathered tensor has been enqueued on the current stream)."""
+        the gathered tensor has been enqueued on the current stream).  No-op for the NCCL path."""
+        if getattr(self, "_symm_consumed", None) is None:
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self._symm_consumed[slot] = ev
 
-    def forward_async_symm(self, x_local: torch.Tensor, slot: int = 0):
+    def forward_async_symm(self, x_local: torch.Tensor, slot: int = 0, gather_to: str = "all",
+                           root: int = 0):
         """Like :meth:`forward_async` with the copy-engine gather described above.  Returns
         ``(work, gathered)``; call ``work.wait()`` before reading ``gathered`` and
-        ``self.release(slot)`` when done with it."""
+        ``self.release(slot)`` when done with it.  With ``gather_to='root'`` only rank ``root``'s
+        ``gathered`` holds the other ranks' shards."""
         y = self.transform(x_local).contiguous()
         world = self.world
         if not self.gather or world == 1:
@@ -149,18 +154,31 @@ class BatchShardedTransform:
         cur = torch.cuda.current_stream(y.device)
         ev_y = torch.cuda.Event()
         ev_y.record(cur)
-        s = self._symm_stream
+        s, s2 = self._symm_streams
         with torch.cuda.stream(s):
             s.wait_event(ev_y)
             if self._symm_consumed[slot] is not None:
                 s.wait_event(self._symm_consumed[slot])
             hdl.barrier(channel=2 * slot)          # every rank is done reading this slot
-            for r in range(world):
-                peers[(self.rank + r) % world][slot, lo:lo + n].copy_(y, non_blocking=True)
+            if gather_to == "root":
+                peers[root][slot, lo:lo + n].copy_(y, non_blocking=True)
+            else:
+                # two copy streams: two DMA engines drive the NVLink ports together
+                ev_b = torch.cuda.Event()
+                ev_b.record(s)
+                s2.wait_event(ev_b)
+                for i in range(world):
+                    st = s if (i & 1) == 0 else s2
+                    with torch.cuda.stream(st):
+                        peers[(self.rank + i) % world][slot, lo:lo + n].copy_(y, non_blocking=True)
+                ev_2 = torch.cuda.Event()
+                ev_2.record(s2)
+                s.wait_event(ev_2)
             hdl.barrier(channel=2 * slot + 1)      # every rank's pushes into this slot have landed
             ev_done = torch.cuda.Event()
             ev_done.record(s)
         y.record_stream(s)
+        y.record_stream(s2)
         return BatchShardedTransform._SymmWork(ev_done), buf[slot]
 
     def forward_async(self, x_local: torch.Tensor, slot: int = 0):
