@@ -10,7 +10,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
        -I"$root/include" -I"$here")
 mkdir -p "$root/build"
 objs=()
-for src in simt_kernels tc_kernels tcb_kernels tc_probe nnab_api; do
+for src in simt_kernels tc_kernels tcb_kernels tct_kernels tc_probe nnab_api; do
   "$NVCC" "${FLAGS[@]}" ${NNAB_PTXAS_V:+-Xptxas -v} -c "$here/$src.cu" -o "$root/build/$src.o" &
   objs+=("$root/build/$src.o")
 done

@@ -79,6 +79,9 @@ struct FbStep {
 };
 static_assert(sizeof(FbStep) == 16, "one 128-bit load per bin");
 constexpr int FB_STEP_PAD = 160;  // entries past F (a tile's last chunk may overrun the last bin)
+// epilogue warps per TMEM lane quarter of the fused-filterbank block kernel: each covers a contiguous
+// range of a tile's 8-column chunks, [n_chunks * part / PARTS, n_chunks * (part + 1) / PARTS)
+constexpr int FB_EPI_PARTS = 3;
 
 struct FramedProblem {
   const float* x;      // (B, L) rows, pitch x_pitch

@@ -327,11 +327,15 @@ __global__ void fb_steps_kernel(const FbEntry* __restrict__ table, int n_fb, int
     if (lo < 0) continue;
     if (hi - lo + 1 > widest) widest = hi - lo + 1;
     for (int i = 0; i < 13; ++i) {
-      const int nb = 32 + 8 * i, outs = nb - 2, half = 8 * ((nb / 8) / 2) - 2;
-      // range index of bin k: 2 * (k / outs) + ((k % outs) >= half)
-      const int r_lo = 2 * (lo / outs) + ((lo % outs) >= half ? 1 : 0);
-      const int r_hi = 2 * (hi / outs) + ((hi % outs) >= half ? 1 : 0);
-      if (r_hi - r_lo + 1 > 2) mask &= ~(1u << i);
+      const int nb = 32 + 8 * i, outs = nb - 2, n_chunks = nb / 8;
+      // range index of bin k: tile k / outs, then the warp part that owns chunk (o + 2) / 8 of output o
+      auto range_of = [&](int k) {
+        const int c = (k % outs + 2) / 8;
+        int part = 0;
+        while (part + 1 < FB_EPI_PARTS && c >= (n_chunks * (part + 1)) / FB_EPI_PARTS) ++part;
+        return FB_EPI_PARTS * (k / outs) + part;
+      };
+      if (range_of(hi) - range_of(lo) + 1 > 2) mask &= ~(1u << i);
     }
   }
   meta[0] = widest;

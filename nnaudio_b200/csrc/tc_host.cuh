@@ -39,4 +39,8 @@ bool tc_block_shape_ok(int n_fft, int hop);
 int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* workspace,
                            size_t ws_bytes, cudaStream_t stream);
 
+// tall-A kernel for long nested banks (tct_kernels.cu); NNAB_EUNSUPPORTED = not applicable, nothing enqueued
+int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* workspace, size_t ws_bytes,
+                          cudaStream_t stream);
+
 }  // namespace nnab

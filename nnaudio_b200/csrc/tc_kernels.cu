@@ -2396,6 +2396,11 @@ static int launch_tc2v_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const 
 static int launch_framed_tc_varn(const FramedProblem& q, const void* packed, void* workspace,
                                  size_t ws_bytes, cudaStream_t stream) {
   if (!varn_problem_ok(q)) return NNAB_EINVAL;  // the basis was packed for this kernel only
+  {
+    // same packed layout, A operand read in place from one tall block per column (tct_kernels.cu)
+    const int trc = launch_framed_tc_tall(q, packed, workspace, ws_bytes, stream);
+    if (trc != NNAB_EUNSUPPORTED) return trc;
+  }
   const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
   if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
   if (q.B > 65535) return NNAB_EUNSUPPORTED;

@@ -285,26 +285,25 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
       }
     } else if constexpr (FMT == 5) {
       if (fast_fb) {
-        // banded filterbank, static action list: branch-free, two running sums per row
+        // banded filterbank, static action list: branch-free, two running sums per row.
+        // Bins past F have neutral table entries (and zero basis rows); the two columns of chunk 0
+        // that belong to the previous tile contribute with power 0.
+        if (c == 0) { xr[0] = xi[0] = xr[1] = xi[1] = 0.f; }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int k = k0 + e;
-          const bool use = (e >= e_lo) && (k < p.epi.F);  // warp-uniform
           const int4 raw = st[e];
           // power == 2 (the default, mel.py:186: |X| ** 2): the power spectrum itself, to 1 ulp
-          float pw = __fadd_rn(__fmul_rn(xr[e], xr[e]), __fmul_rn(xi[e], xi[e]));
-          pw = use ? pw : 0.f;
+          const float pw = __fadd_rn(__fmul_rn(xr[e], xr[e]), __fmul_rn(xi[e], xi[e]));
           const int fa = (int)(short)(raw.z & 0xffff), fb = (int)(short)((unsigned)raw.z >> 16);
-          const bool fla = use && fa >= 0, flb = use && fb >= 0;
-          red_add_if(mel + (int64_t)fa * p.epi.T, ma, fla && valid);
-          red_add_if(mel + (int64_t)fb * p.epi.T, mb, flb && valid);
-          ma = fla ? 0.f : ma;
-          mb = flb ? 0.f : mb;
+          red_add_if(mel + (int64_t)fa * p.epi.T, ma, fa >= 0 && valid);
+          red_add_if(mel + (int64_t)fb * p.epi.T, mb, fb >= 0 && valid);
+          ma = fa >= 0 ? 0.f : ma;
+          mb = fb >= 0 ? 0.f : mb;
           ma = fmaf(__int_as_float(raw.x), pw, ma);
           mb = fmaf(__int_as_float(raw.y), pw, mb);
-          mca = use ? (int)(short)(raw.w & 0xffff) : mca;
-          mcb = use ? (int)(short)((unsigned)raw.w >> 16) : mcb;
         }
+        mca = (int)(short)(st[7].w & 0xffff);  // filters the two sums belong to after this chunk
+        mcb = (int)(short)((unsigned)st[7].w >> 16);
       } else {
 #pragma unroll 1
         for (int e = e_lo; e < 8; ++e) {
@@ -337,11 +336,16 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
   if constexpr (FMT == 5) run.flush(p.epi, mel, valid);
 }
 
-constexpr int TCB_EPI_WARPS = 8;                       // 2 per TMEM lane quarter (column halves)
-constexpr int TCB_THREADS = 128 + 32 * TCB_EPI_WARPS;  // warps 0-3: TMA, MMA, TMEM alloc, idle
+// epilogue warps: 2 per TMEM lane quarter (column halves); 3 for the fused filterbank, whose longer
+// per-bin chain needs the extra warp per scheduler to stay under the MMA time of a tile
+template <int FMT> struct TcbCfg {
+  static constexpr int PARTS = (FMT == 5) ? FB_EPI_PARTS : 2;
+  static constexpr int EPI_WARPS = 4 * PARTS;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;  // warps 0-3: TMA, MMA, TMEM alloc, idle
+};
 
 template <int FMT, int R>
-__global__ void __launch_bounds__(TCB_THREADS, 1)
+__global__ void __launch_bounds__(TcbCfg<FMT>::THREADS, 1)
 framed_tcb_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const TcbParams p) {
   constexpr int BK = TCB_BK, STAGES = TCB_STAGES;
@@ -375,7 +379,7 @@ framed_tcb_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * TCB_EPI_WARPS);  // epilogue warps x 2 CTAs
+      mbar_init(tempty_bar(a), 2 * TcbCfg<FMT>::EPI_WARPS);  // epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -462,7 +466,7 @@ framed_tcb_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own rows) =====================
     const int quarter = warp & 3;             // TMEM lanes 32 * (warp % 4) .. + 31
-    constexpr int PARTS = TCB_EPI_WARPS / 4;  // warps per quarter, each a contiguous chunk range
+    constexpr int PARTS = TcbCfg<FMT>::PARTS;  // warps per quarter, each a contiguous chunk range
     const int part = (warp - 4) >> 2;
     const int n_chunks = nb / 8;
     const int c_begin = (n_chunks * part) / PARTS, c_end = (n_chunks * (part + 1)) / PARTS;
@@ -510,7 +514,7 @@ static int launch_tcb_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const Tc
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * n_pairs));
-  cfg.blockDim = dim3(TCB_THREADS);
+  cfg.blockDim = dim3(TcbCfg<FMT>::THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

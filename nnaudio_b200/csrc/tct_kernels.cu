@@ -1,0 +1,429 @@
+// "Tall-A" framed contraction for long, nested banks (CQT1992v2: features/cqt.py:749-750) on tcgen05.
+//
+// The A operand of the framed GEMM is a Toeplitz matrix: K block kb of frame m holds the samples
+// [m*hop + 64 kb, +64).  With 64 | hop and HB = hop / 64, block kb = HB*r + c of frame m is column
+// block c of plane row m + r -- so ONE shared-memory block of (128 + r_span) rows x 64 columns serves
+// every K block of column c: the MMA of shift r reads the same bytes through a descriptor that
+// starts r rows further down.  (Hardware probe csrc/tc_probe.cu, profiles/r02_probe_rowoffset.json:
+// a K-major SWIZZLE_128B descriptor may start at ANY 128-byte row of a TMA-written block, descriptor
+// base-offset field 0.)  Per tile the A bytes fetched from L2 drop from n_blocks * 32 KB to
+// HB * ~44 KB (cfg3: 11.4 MB -> 0.35 MB per 256-frame tile); what remains on the shared-memory port
+// is the MMA's own operand read.
+//
+// Everything else follows the per-K-block-width kernel (framed_tc2v_kernel, tc_kernels.cu): packed
+// rows in 8-bin (re | im) groups, each K block issues MMAs of width N = 16 * groups(kb), B rows by
+// 32- / 8-row TMA boxes, CTA pairs (cta_group::2), bf16 hi/lo split (3 MMAs per K16 step).
+//
+// Accuracy / determinism: the K range is cut per column block (<= 64 K blocks per TMEM accumulation
+// chain, as the split-K path of the other kernels), but the partial sums never leave the SM: the
+// epilogue warps keep the running (re, im) sums of their bins in registers across the column blocks
+// of a tile and write the final format once.  No scratch, no atomics, no finalize kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <atomic>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "tc_ptx.cuh"
+#include "tc_host.cuh"
+
+namespace nnab {
+
+constexpr int TCT_BK = 64;
+constexpr int TCT_B_STAGES = 4;
+constexpr int TCT_A_ROWS = 192;      // 128 frames + up to 64 row shifts
+constexpr int TCT_B_ROWS = 96;       // rows one CTA stages per K block (8 * groups, groups <= 12)
+constexpr int TCT_MAX_COLS = 16;     // hop / 64
+constexpr int TCT_MAX_KB = 512;
+constexpr int TCT_EPI_WARPS = 8;
+constexpr int TCT_THREADS = 128 + 32 * TCT_EPI_WARPS;
+constexpr int TCT_GROUPS_PER_PART = 6;  // 2 epilogue warps per TMEM lane quarter x 6 groups = 96 bins
+
+struct TallPlan {
+  int n_cols;                     // column blocks with work = accumulation chunks of a tile
+  int col[TCT_MAX_COLS];          // column block index c
+  int r_min[TCT_MAX_COLS];        // first active row shift of the column
+  int r_cnt[TCT_MAX_COLS];        // number of active shifts (contiguous)
+  int r_first[TCT_MAX_COLS];      // shift visited first: the column's widest block
+  int g_max[TCT_MAX_COLS];        // its width in 8-bin groups = columns the chunk initialises
+  int hb;                         // hop / 64
+  uint8_t groups[TCT_MAX_KB];     // 8-bin groups K block kb reaches (0 = inactive)
+};
+
+struct TctParams {
+  int num_m_tiles;                // 256-frame pair tiles
+  int64_t nv, t_slots, T;
+  EpiParams epi;
+};
+
+struct TctSmem {
+  static constexpr uint32_t A_PLANE = TCT_A_ROWS * TCT_BK * 2;   // 24 KB
+  static constexpr uint32_t A_BUF = 2 * A_PLANE;                 // hi + lo
+  static constexpr uint32_t B_PLANE = TCT_B_ROWS * TCT_BK * 2;   // 12 KB
+  static constexpr uint32_t B_STAGE = 2 * B_PLANE;
+  static constexpr uint32_t B_OFFSET = 2 * A_BUF;                // two A buffers
+  static constexpr uint32_t BAR_OFFSET = B_OFFSET + TCT_B_STAGES * B_STAGE;
+  static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+// i-th shift of a column in visiting order: r_first, then alternately above / below, clipped to the
+// active range.  Every shift of [r_min, r_min + r_cnt) appears exactly once.
+__device__ __forceinline__ int tct_visit(int i, int r_min, int r_cnt, int r_first) {
+  const int below = r_first - r_min;              // shifts below r_first
+  const int above = r_min + r_cnt - 1 - r_first;  // shifts above
+  if (i == 0) return r_first;
+  const int pairs = below < above ? below : above;
+  if (i <= 2 * pairs) return (i & 1) ? r_first + (i + 1) / 2 : r_first - i / 2;
+  const int rest = i - 2 * pairs;                 // one side is exhausted
+  return above > below ? r_first + pairs + rest : r_first - pairs - rest;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(TCT_THREADS, 1)
+framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b8,
+                   const __grid_constant__ CUtensorMap tm_b32, const TctParams p,
+                   const __grid_constant__ TallPlan plan) {
+  constexpr int BK = TCT_BK, BS = TCT_B_STAGES;
+  using S = TctSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  auto b_full = [&](int s) { return bar_base + 8u * s; };                // leader
+  auto b_empty = [&](int s) { return bar_base + 8u * (BS + s); };         // per CTA
+  auto a_full = [&](int a) { return bar_base + 8u * (2 * BS + a); };      // leader
+  auto a_empty = [&](int a) { return bar_base + 8u * (2 * BS + 2 + a); };  // per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * BS + 4 + a); };   // per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * BS + 6 + a); };  // leader
+  const uint32_t tmem_slot = bar_base + 8u * (2 * BS + 8);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b8);
+    prefetch_tmap(&tm_b32);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < BS; ++s) {
+      mbar_init(b_full(s), 2);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(a_full(a), 2);
+      mbar_init(a_empty(a), 1);
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * TCT_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0, abuf = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        for (int ci = 0; ci < plan.n_cols; ++ci) {
+          const int c = plan.col[ci], r_min = plan.r_min[ci], r_cnt = plan.r_cnt[ci];
+          // ---- the column's tall A block: rows m0 + r_min .. + 192, columns [64 c, 64 c + 64)
+          mbar_wait(a_empty(abuf), aphase ^ 1u);
+          const uint32_t ab = base + (uint32_t)abuf * S::A_BUF;
+          mbar_expect_tx_remote(a_full(abuf), 0, S::A_BUF);
+          tma_load_3d_2sm(ab, &tm_a, a_full(abuf), c * BK, m0 + r_min, 0);
+          tma_load_3d_2sm(ab + S::A_PLANE, &tm_a, a_full(abuf), c * BK, m0 + r_min, 1);
+          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+          // ---- the basis rows of every K block of this column
+          for (int i = 0; i < r_cnt; ++i) {
+            const int r = tct_visit(i, r_min, r_cnt, plan.r_first[ci]);
+            const int kb = r * plan.hb + c;
+            const int rows = 8 * (int)plan.groups[kb];  // basis rows this CTA stages
+            mbar_wait(b_empty(stage), phase ^ 1u);
+            const uint32_t bh = base + S::B_OFFSET + (uint32_t)stage * S::B_STAGE, bl = bh + S::B_PLANE;
+            mbar_expect_tx_remote(b_full(stage), 0, 2 * (uint32_t)rows * BK * 2);
+            const int k0 = kb * BK, row0 = (int)cta * rows;
+            int q = 0;
+            for (; rows - q >= 32; q += 32) {
+              tma_load_3d_2sm(bh + (uint32_t)q * BK * 2, &tm_b32, b_full(stage), k0, row0 + q, 0);
+              tma_load_3d_2sm(bl + (uint32_t)q * BK * 2, &tm_b32, b_full(stage), k0, row0 + q, 1);
+            }
+            for (; q < rows; q += 8) {
+              tma_load_3d_2sm(bh + (uint32_t)q * BK * 2, &tm_b8, b_full(stage), k0, row0 + q, 0);
+              tma_load_3d_2sm(bl + (uint32_t)q * BK * 2, &tm_b8, b_full(stage), k0, row0 + q, 1);
+            }
+            if (++stage == BS) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0, abuf = 0, acc = 0;
+      uint32_t phase = 0, aphase = 0, acc_phase = 0;
+      for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+        for (int ci = 0; ci < plan.n_cols; ++ci) {
+          const int c = plan.col[ci], r_min = plan.r_min[ci], r_cnt = plan.r_cnt[ci];
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          mbar_wait(a_full(abuf), aphase);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+          const uint32_t ab = base + (uint32_t)abuf * S::A_BUF;
+          uint32_t accumulate = 0;
+          for (int i = 0; i < r_cnt; ++i) {
+            const int r = tct_visit(i, r_min, r_cnt, plan.r_first[ci]);
+            const int kb = r * plan.hb + c;
+            const uint32_t idesc = idesc0 | ((uint32_t)(2 * (int)plan.groups[kb]) << 17);  // N = 16 G
+            mbar_wait(b_full(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t bh = base + S::B_OFFSET + (uint32_t)stage * S::B_STAGE;
+            const uint32_t a_row = (uint32_t)(r - r_min) * (BK * 2);  // descriptor start: r rows down
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t koff = (uint32_t)k * 32u;
+              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
+              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
+              const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
+              const uint64_t b_lo = make_smem_desc<BK>(bh + S::B_PLANE + koff);
+              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+              accumulate = 1u;
+            }
+            umma_commit_2sm(b_empty(stage));
+            if (++stage == BS) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit_2sm(a_empty(abuf));   // the column's A block is free once its MMAs retire
+          umma_commit_2sm(tfull_bar(acc));  // chunk complete -> epilogue
+          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: register-resident sums over the column blocks ==========
+    const int quarter = warp & 3;
+    const int part = (warp - 4) >> 2;  // which 6 groups of the tile's <= 12
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float sre[TCT_GROUPS_PER_PART][8], sim[TCT_GROUPS_PER_PART][8];
+    for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+#pragma unroll
+      for (int gi = 0; gi < TCT_GROUPS_PER_PART; ++gi)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sre[gi][j] = 0.f; sim[gi][j] = 0.f; }
+      for (int ci = 0; ci < plan.n_cols; ++ci) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
+        const int g_lim = plan.g_max[ci];  // columns this chunk initialised
+#pragma unroll
+        for (int gi = 0; gi < TCT_GROUPS_PER_PART; ++gi) {
+          const int g = part * TCT_GROUPS_PER_PART + gi;
+          if (g < g_lim) {  // warp-uniform
+            uint32_t re[8], im[8];
+            tmem_ld8(trow + (uint32_t)(16 * g), re);
+            tmem_ld8(trow + (uint32_t)(16 * g + 8), im);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sre[gi][j] += __uint_as_float(re[j]);
+              sim[gi][j] += __uint_as_float(im[j]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      // ---- final format, once per tile
+      const int64_t g_row = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const int64_t b = g_row / p.t_slots;
+      const int64_t t = g_row - b * p.t_slots;
+      if (g_row < p.nv && t < p.T) {
+        constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
+        float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+#pragma unroll
+        for (int gi = 0; gi < TCT_GROUPS_PER_PART; ++gi) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int f = 8 * (part * TCT_GROUPS_PER_PART + gi) + j;
+            if (f < p.epi.F) epi_store_fmt<FMT>(p.epi, dst, f, sre[gi][j], sim[gi][j]);
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+bool tc_tall_problem_ok(const FramedProblem& q) {
+  if (q.hop % 64 != 0 || q.hop / 64 > TCT_MAX_COLS) return false;
+  if (q.F > 8 * 2 * TCT_GROUPS_PER_PART || q.K > 64 * TCT_MAX_KB) return false;
+  if (q.presplit != nullptr || q.bin_offset != 0 || q.out_bins != q.F) return false;
+  if (q.h_k_begin == nullptr || q.h_k_end == nullptr) return false;
+  return q.fmt == NNAB_FMT_MAGNITUDE || q.fmt == NNAB_FMT_COMPLEX || q.fmt == NNAB_FMT_PHASE_UNIT;
+}
+
+// Returns NNAB_EUNSUPPORTED when the bank does not fit the tall layout (caller falls back).
+static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
+  const int hb = q.hop / 64;
+  const int nkb = (q.K + 63) / 64;
+  memset(plan, 0, sizeof(*plan));
+  plan->hb = hb;
+  int kb_lo = nkb, kb_hi = -1;
+  for (int kb = 0; kb < nkb; ++kb) {
+    int gmax = 0;
+    for (int f = 0; f < q.F; ++f) {
+      const int lo = q.h_k_begin[f], hi = q.h_k_end[f];
+      if (hi > lo && hi > kb * 64 && lo < kb * 64 + 64) gmax = gmax > f / 8 + 1 ? gmax : f / 8 + 1;
+    }
+    plan->groups[kb] = (uint8_t)gmax;
+    if (gmax > 0) { kb_lo = kb < kb_lo ? kb : kb_lo; kb_hi = kb; }
+  }
+  if (kb_hi < 0) return NNAB_EUNSUPPORTED;
+  // inactive blocks inside the active interval (a gap in every wavelet) still get the narrowest MMA
+  for (int kb = kb_lo; kb <= kb_hi; ++kb)
+    if (plan->groups[kb] == 0) plan->groups[kb] = 1;
+  int n = 0;
+  for (int c = 0; c < hb; ++c) {
+    const int r_lo = (kb_lo - c + hb - 1) / hb > 0 ? (kb_lo - c + hb - 1) / hb : 0;
+    const int r_hi = (kb_hi - c) >= 0 ? (kb_hi - c) / hb : -1;
+    if (r_hi < r_lo) continue;
+    if (r_hi - r_lo + 1 > 64) return NNAB_EUNSUPPORTED;  // A block rows: 128 + 63
+    int best = r_lo;
+    for (int r = r_lo; r <= r_hi; ++r)
+      if (plan->groups[r * hb + c] > plan->groups[best * hb + c]) best = r;
+    plan->col[n] = c;
+    plan->r_min[n] = r_lo;
+    plan->r_cnt[n] = r_hi - r_lo + 1;
+    plan->r_first[n] = best;
+    plan->g_max[n] = plan->groups[best * hb + c];
+    ++n;
+  }
+  plan->n_cols = n;
+  return n > 0 ? NNAB_OK : NNAB_EUNSUPPORTED;
+}
+
+template <int FMT>
+static int launch_tc2t_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const CUtensorMap& mb32,
+                           const TctParams& prm, const TallPlan& plan, int n_pairs,
+                           cudaStream_t stream) {
+  using S = TctSmem;
+  static std::atomic<uint64_t> configured_devs{0};  // the attribute is per device
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  if (!((configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u)) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2t_kernel<FMT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(TCT_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2t_kernel<FMT>, ma, mb8, mb32, prm, plan));
+  count_launch();
+  return NNAB_OK;
+}
+
+// `packed`: the 8-bin-group layout of tc_pack_basis_varn.  Returns NNAB_EUNSUPPORTED (nothing
+// enqueued) when the bank does not fit; the caller then runs framed_tc2v_kernel.
+int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* workspace, size_t ws_bytes,
+                          cudaStream_t stream) {
+  if (!tc_tall_problem_ok(q)) return NNAB_EUNSUPPORTED;
+  if (const char* e = getenv("NNAB_TALL")) {
+    if (atoi(e) == 0) return NNAB_EUNSUPPORTED;  // A/B switch: per-K-block-width kernel without A reuse
+  }
+  TallPlan plan;
+  int rc = build_tall_plan(q, &plan);
+  if (rc) return rc;
+  const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  if (q.B > 65535) return NNAB_EUNSUPPORTED;
+  const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+  const int kpad = round_up_i(q.K, 64);
+  const int rows_w = 16 * ((q.F + 7) / 8);
+  __nv_bfloat16* planes =
+      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  rc = tc_pad_split(q.x, q.B, q.L, q.x_pitch, q.K, q.hop, q.pad, q.pad_mode, planes, stream);
+  if (rc) return rc;
+
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();
+  if (sms < 2) sms = 2;
+
+  CUtensorMap ma, mb8, mb32;
+  // A: (rows x hop) view of a plane; one box = 192 rows x 64 columns (rows past the end: zero fill)
+  rc = encode_3d(&ma, planes, (uint64_t)q.hop, (uint64_t)g.rows, 2, (uint64_t)q.hop * 2,
+                 (uint64_t)g.plane_stride * 2, 64, TCT_A_ROWS, 64);
+  if (rc) return rc;
+  if ((rc = encode_3d(&mb8, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
+                      (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, 64, 8, 64)))
+    return rc;
+  if ((rc = encode_3d(&mb32, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
+                      (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, 64, 32, 64)))
+    return rc;
+
+  TctParams prm{};
+  prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
+  prm.nv = g.nv;
+  prm.t_slots = g.t_slots;
+  prm.T = q.T;
+  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
+  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
+  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+  const int n_pairs = prm.num_m_tiles < sms / 2 ? prm.num_m_tiles : sms / 2;
+  {
+    double cols = 0.0;
+    for (int kb = 0; kb < TCT_MAX_KB; ++kb) cols += 16.0 * plan.groups[kb] * 64.0;
+    add_exec_flops(3.0 * 2.0 * (double)prm.num_m_tiles * (2 * TC_BM) * cols);
+  }
+  switch (q.fmt) {
+    case NNAB_FMT_MAGNITUDE: return launch_tc2t_fmt<0>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc2t_fmt<1>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+    case NNAB_FMT_PHASE_UNIT: return launch_tc2t_fmt<3>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+    default: return NNAB_EINVAL;
+  }
+}
+
+}  // namespace nnab
