@@ -81,7 +81,9 @@ static_assert(sizeof(FbStep) == 16, "one 128-bit load per bin");
 constexpr int FB_STEP_PAD = 160;  // entries past F (a tile's last chunk may overrun the last bin)
 // epilogue warps per TMEM lane quarter of the fused-filterbank block kernel: each covers a contiguous
 // range of a tile's 8-column chunks, [n_chunks * part / PARTS, n_chunks * (part + 1) / PARTS)
-constexpr int FB_EPI_PARTS = 3;
+// (3 measured 7 % faster at cfg2 -- 0.197 vs 0.211 ms -- but then a 53-bin mel filter spans three
+// ranges, its three atomic partial sums no longer commute and results differ run to run: 2 it is.)
+constexpr int FB_EPI_PARTS = 2;
 
 struct FramedProblem {
   const float* x;      // (B, L) rows, pitch x_pitch

@@ -32,7 +32,7 @@ def _dump_errors():
 def _tol(cls):
     # MFCC: the dB + top_db clamp amplifies; everything else holds the 1e-4 bar (measured worst
     # case of the pyramid training path: 6.1e-5, profiles/r01_backward_errors_auto.json)
-    return 4e-4 if cls == "MFCC" else 1e-4
+    return 1e-4  # north_star bar for every module, MFCC included (measured: 3e-7 .. 3e-6, profiles/r02_parity_errors.json)
 
 
 @pytest.mark.parametrize("case", GRAD_CASES, ids=[c[0] for c in GRAD_CASES])

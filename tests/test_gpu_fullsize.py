@@ -21,7 +21,7 @@ CONFIGS = {
     "cfg3": ("CQT1992v2", dict(sr=44100, n_bins=84, bins_per_octave=12, fmin=32.7), 128, 441000,
              dict(output_format="Magnitude"), 1e-4),
     "cfg4": ("CQT2010v2", dict(sr=22050, n_bins=88), 256, 661500, dict(output_format="Magnitude"), 1e-4),
-    "cfg5": ("MFCC", dict(sr=16000), 1024, 80000, {}, 4e-4),
+    "cfg5": ("MFCC", dict(sr=16000), 1024, 80000, {}, 1e-4),
 }
 
 

@@ -19,8 +19,10 @@ from helpers import (CASES, REF_GROUND_TRUTHS, SWEEP_CTOR, build, case_input, is
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 PATHS = ["simt", "auto"]
-# smallest |X| / max|X| at which phases are compared (fp32 SIMT vs split-bf16 tensor path)
-PHASE_FLOOR = {"simt": 1e-3, "auto": 0.05}
+# smallest |X| / max|X| at which phases are compared.  A 1e-4 max-relative implementation is only
+# bound down to |X| >= 0.05 max|X| at the 2e-3 angle tolerance used here (angle error <= |dX| / |X|);
+# both kernel families are held to 5x / 50x more: the split-bf16 tensor path measures |dX| ~ 5e-6 max|X|.
+PHASE_FLOOR = {"simt": 1e-3, "auto": 0.01}
 
 
 def _run(mod, x, kw, path):
@@ -59,7 +61,7 @@ def test_cuda_matches_reference_and_oracle(case, path):
                              floor=PHASE_FLOOR[path], kept=int(keep.sum()))
                 assert d < 2e-3, (cid, kw, path, d)
             continue
-        tol = 4e-4 if cls == "MFCC" else TOL  # dB of near-zero mel powers amplifies fp32 noise
+        tol = TOL  # the 1e-4 bar for every module, MFCC included (measured 3e-7 .. 3e-6)
         for name, ref in (("reference", want), ("oracle", orc)):
             emax, el2 = rel_errors(got, ref)
             record_error("cases", f"{cid}|{kw}|{path}|{name}", max_rel=emax, l2_rel=el2, tol=tol)
@@ -85,9 +87,9 @@ def test_cuda_matches_reference_ground_truths(key, path):
         assert np.abs(y - lin_gt).max() < 1e-4 * np.abs(lin_gt).max()
         # log(X + eps) at the reference's own rtol/atol where the log is conditioned well
         # enough for a 1e-4 (max-relative) implementation: d(log) = dX / (X + eps).  The fp32
-        # SIMT path holds it nearly everywhere, the split-bf16 tensor-core path (|dX| up to
-        # ~5e-5 max|X| at K = 32768) from 10 % of the peak upwards.
-        floor = 1e-5 if path == "simt" else 0.1
+        # SIMT path holds it nearly everywhere, the split-bf16 tensor-core path (|dX| ~ 1.5e-5 max|X|
+        # at K = 32768 with the per-column accumulation chunks) from 3 % of the peak upwards.
+        floor = 1e-5 if path == "simt" else 0.03
         keep = y > 1e-2 * eps + floor * y.max()
         assert keep.sum() > 50
         assert np.allclose(np.log(y[keep] + eps), gt[keep], rtol=1e-3, atol=1e-3)
@@ -150,7 +152,7 @@ def test_cuda_constructor_sweep_matches_reference(case, path):
     got = _run(mod, x, {}, path)
     want = ref_outputs()["sweep|" + cid]
     assert got.shape == want.shape
-    tol = 4e-4 if cls == "MFCC" else TOL
+    tol = TOL
     emax, el2 = rel_errors(got, want)
     assert emax < tol and el2 < tol, (cid, path, emax, el2)
 
