@@ -110,6 +110,8 @@ struct FramedProblem {
   int n_fb;
   float* raw;                // tcgen05 split-K scratch: 2 planes (re, im) of B*F*T floats, or nullptr
   const void* presplit;      // tcgen05: already padded + split signal planes (skip pad_split)
+  int64_t presplit_t_slots;  // > 0: frames per clip slot of the pre-split planes (else derived)
+  int64_t presplit_plane_stride;  // elements per plane when presplit_t_slots > 0
   DecimParams dec;           // FMT_DECIM
   int64_t ola_pitch;         // FMT_OLA: out = overlap-add buffer (B, ola_pitch); scale = window/n_fft
   int ola_hop;
@@ -134,6 +136,10 @@ void tc_split_geometry(int64_t B, int64_t L, int K, int hop, int pad, int64_t* t
                        int64_t* plane_stride, int* hop_eff);
 int tc_pad_split(const float* x, int64_t B, int64_t L, int64_t x_pitch, int K, int hop, int pad,
                  int pad_mode, void* planes, cudaStream_t stream);
+int tc_pad_split_ex(const float* x, int64_t B, int64_t L, int64_t x_pitch, int pad, int pad_mode,
+                    int64_t clip_pitch, int64_t plane_stride, void* planes, cudaStream_t stream);
+int tc_zero_slots(void* planes, int64_t B, int64_t clip_pitch, int64_t plane_stride, int64_t keep_lo,
+                  int64_t keep_hi, cudaStream_t stream);
 int tc_pad_split2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                   int K_a, int hop_a, int pad_a, int mode_a, void* planes_a,
                   int K_b, int hop_b, int pad_b, int mode_b, void* planes_b, cudaStream_t stream);

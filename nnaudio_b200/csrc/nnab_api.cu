@@ -520,6 +520,75 @@ static size_t plan_pyramid(int64_t B, int64_t L, int n_octaves, int early_factor
   return off;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pyramid, second generation (round 2): ONE plane set per level, shared by the level's octave CQT
+// (reflect margins of `pad` samples, frames every `hop`) and by the FIR stage that produces the next
+// level (256-sample rows, resident taps, clip edges recomputed: launch_fir_stage_tc).  Per level and
+// sample: one 4-byte write and one read by each consumer, instead of two differently padded copies.
+// ---------------------------------------------------------------------------------------------
+struct Lvl2 {
+  int64_t len;
+  int hop, width, pad, mode;
+  bool presplit;        // the octave CQT reads the planes directly (single frame phase)
+  bool planes;          // the level has planes (CQT and / or FIR source)
+  size_t pc, y32;       // workspace offsets (SIZE_MAX = none)
+  int64_t pitch, plane, t_slots, y32_pitch;
+};
+
+static int64_t gcd64(int64_t a, int64_t b) { return b == 0 ? a : gcd64(b, a % b); }
+
+// false: the shape does not fit this plan (caller uses the first-generation pyramid)
+static bool plan_pyramid2(int64_t B, int64_t L, int n_octaves, int hop, const int32_t* widths,
+                          int fixed_width, int pad_mode, Lvl2* lv, size_t* total) {
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up(n, 256); return o; };
+  int64_t len = L;
+  int cur_hop = hop;
+  for (int i = 0; i < n_octaves; ++i) {
+    if (i > 0) { len = decimated_len(len, 2); cur_hop /= 2; }
+    Lvl2& l = lv[i];
+    l.len = len; l.hop = cur_hop;
+    l.width = widths ? widths[i] : fixed_width;
+    l.pad = l.width / 2;
+    if (len <= 0 || cur_hop <= 0) return false;
+    l.mode = (pad_mode == NNAB_PAD_REFLECT && l.pad >= len) ? NNAB_PAD_CONSTANT : pad_mode;
+    l.presplit = (cur_hop % 8) == 0;
+    const bool fir_src = i < n_octaves - 1;
+    l.planes = l.presplit || fir_src;
+    l.pc = l.y32 = SIZE_MAX;
+    l.pitch = l.plane = l.t_slots = l.y32_pitch = 0;
+    if (fir_src && (l.pad < 128 || (l.pad - 128) % 64 != 0 || (l.pad - 128) / 64 > 24)) return false;
+    if (l.planes) {
+      const int he = l.presplit ? cur_hop : 8;  // planes of multi-phase levels only feed the FIR
+      const int kpad = (l.width + 63) / 64 * 64;
+      int64_t need = len + 2 * (int64_t)l.pad + kpad;
+      if (fir_src) {
+        const int64_t FT = (decimated_len(len, 2) + 127) / 128;
+        const int64_t rows = FT + 1 + (7 + (l.pad - 128) / 64) / 4;
+        if (256 * rows > need) need = 256 * rows;
+      }
+      const int64_t gran = (int64_t)he / gcd64(he, 256) * 256;  // lcm(he, 256)
+      l.pitch = (need + gran - 1) / gran * gran;
+      l.t_slots = l.pitch / he;
+      const int64_t rows = B * l.t_slots + (kpad + he - 1) / he + 1;
+      l.plane = (rows * he + 255) / 256 * 256;
+      l.pc = take((size_t)2 * l.plane * 2);
+    }
+    if (!l.presplit && i > 0) {
+      l.y32_pitch = (int64_t)align_up((size_t)len, 8);
+      l.y32 = take((size_t)B * l.y32_pitch * sizeof(float));
+    }
+  }
+  // scratch for octaves that run from fp32 (several frame phases): sized for the first such level
+  for (int i = 0; i < n_octaves; ++i)
+    if (!lv[i].presplit) {
+      off += tc_workspace_bytes(B, lv[i].len, lv[i].width, lv[i].hop, lv[i].pad) + 256;
+      break;
+    }
+  *total = off;
+  return true;
+}
+
 size_t nnab_packed_fir_bytes(int taps, int dec) { return tc_packed_fir_bytes(taps, dec); }
 int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* stream) {
   if (fir == nullptr || packed == nullptr || taps <= 0 || dec < 1) return NNAB_EINVAL;
@@ -577,9 +646,88 @@ size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int
       const size_t full = plan_pyramid(B, L, n_octaves, early_factor, hop, nullptr, max_width,
                                        NNAB_PAD_REFLECT, lv, nullptr) + 1024;
       if (full > n) n = full;
+      Lvl2 lv2[32];
+      size_t full2 = 0;
+      if (early_factor <= 1 &&
+          plan_pyramid2(B, L, n_octaves, hop, nullptr, max_width, NNAB_PAD_REFLECT, lv2, &full2) &&
+          full2 + 1024 > n)
+        n = full2 + 1024;
     }
   }
   return n;
+}
+
+static int pyramid_fused2(const float* x, int64_t B, int64_t L, int64_t x_pitch, int n_octaves,
+                          const float* const* h_k_real, const float* const* h_k_imag,
+                          const void* const* h_packed, const int32_t* h_widths, int n_filters,
+                          const float* lowpass, const void* lowpass_packed, int hop, int pad_mode,
+                          int n_bins, const float* scale, float scale_all, int out_format,
+                          float sqrt_eps, float* out, int64_t T, void* workspace, size_t ws_bytes,
+                          cudaStream_t s) {
+  if (n_octaves > 32 || B > 65535) return NNAB_EUNSUPPORTED;
+  Lvl2 lv[32];
+  size_t need = 0;
+  if (!plan_pyramid2(B, L, n_octaves, hop, h_widths, 0, pad_mode, lv, &need)) return NNAB_EUNSUPPORTED;
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  if (need + 512 > ws_bytes) return NNAB_EUNSUPPORTED;
+  for (int i = 0; i < n_octaves; ++i)
+    if (frames_of(lv[i].len, lv[i].width, lv[i].hop, lv[i].pad) != T) return NNAB_EINVAL;
+  size_t scratch_off = need;
+  for (int i = 0; i < n_octaves; ++i)
+    if (!lv[i].presplit) {
+      scratch_off -= tc_workspace_bytes(B, lv[i].len, lv[i].width, lv[i].hop, lv[i].pad) + 256;
+      break;
+    }
+  char* scratch = ws + scratch_off;
+  const size_t scratch_bytes = ws_bytes - 256 - scratch_off;
+  int rc;
+
+  // level 0: the caller's fp32 waveform -> planes (one pass; writes the whole clip slot)
+  if (lv[0].planes) {
+    rc = tc_pad_split_ex(x, B, L, x_pitch, lv[0].pad, lv[0].mode, lv[0].pitch, lv[0].plane,
+                         ws + lv[0].pc, s);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < n_octaves; ++i) {
+    Lvl2& l = lv[i];
+    FramedProblem p{};
+    p.B = B; p.L = l.len;
+    p.w_re = h_k_real[i]; p.w_im = h_k_imag[i]; p.F = n_filters; p.K = l.width; p.hop = l.hop;
+    p.pad = l.pad; p.pad_mode = l.mode; p.scale_all = scale_all;
+    p.fmt = out_format; p.eps = sqrt_eps; p.power = 1.f; p.out = out; p.T = T;
+    p.out_bins = n_bins;
+    p.bin_offset = n_bins - n_filters * (i + 1);
+    p.scale = scale ? scale + p.bin_offset : nullptr;
+    if (l.presplit) {
+      p.presplit = ws + l.pc;
+      p.presplit_t_slots = l.t_slots;
+      p.presplit_plane_stride = l.plane;
+      if ((rc = run_framed(p, h_packed[i], nullptr, 0, NNAB_PATH_TCGEN05, s))) return rc;
+    } else {
+      const float* src = (i == 0) ? x : (const float*)(ws + l.y32);
+      p.x = src; p.x_pitch = (i == 0) ? x_pitch : l.y32_pitch;
+      if ((rc = run_framed(p, h_packed[i], scratch, scratch_bytes, NNAB_PATH_TCGEN05, s))) return rc;
+    }
+    if (i == n_octaves - 1) break;
+    // ---- FIR stage: level i -> level i + 1
+    Lvl2& d = lv[i + 1];
+    DecimParams dec{};
+    dec.len_out = d.len;
+    if (d.planes) {
+      const bool refl = d.mode == NNAB_PAD_REFLECT;
+      // what the stage's epilogue never writes: everything outside the samples (+ reflect margins)
+      rc = tc_zero_slots(ws + d.pc, B, d.pitch, d.plane, refl ? 0 : d.pad,
+                         refl ? d.len + 2 * (int64_t)d.pad : d.pad + d.len, s);
+      if (rc) return rc;
+      dec.pc = ws + d.pc; dec.pc_plane = d.plane; dec.pc_pitch = d.pitch; dec.pc_off = d.pad;
+      dec.pc_reflect = refl ? 1 : 0;
+    }
+    if (d.y32 != SIZE_MAX) { dec.y32 = (float*)(ws + d.y32); dec.y32_pitch = d.y32_pitch; }
+    rc = launch_fir_stage_tc(ws + l.pc, B, l.len, l.pitch, l.plane, l.pad, lowpass_packed, lowpass,
+                             FIR_TAPS, dec, s);
+    if (rc) return rc;  // (EUNSUPPORTED cannot happen after plan_pyramid2 accepted the shape)
+  }
+  return NNAB_OK;
 }
 
 // All-tensor-core pyramid; returns NNAB_EUNSUPPORTED when the plan cannot be used (the caller
@@ -738,6 +886,13 @@ int nnab_cqt_pyramid_forward(const float* x, int64_t B, int64_t L, int64_t x_pit
   bool all_packed = (path != NNAB_PATH_SIMT) && h_packed != nullptr && lowpass_packed != nullptr &&
                     (early_factor <= 1 || early_packed != nullptr);
   for (int i = 0; all_packed && i < n_octaves; ++i) all_packed = h_packed[i] != nullptr;
+  if (all_packed && getenv("NNAB_PYRAMID_UNFUSED") == nullptr && early_factor <= 1 &&
+      !(getenv("NNAB_PYRAMID2") != nullptr && atoi(getenv("NNAB_PYRAMID2")) == 0)) {
+    rc = pyramid_fused2(x, B, L, x_pitch, n_octaves, h_k_real, h_k_imag, h_packed, h_widths, n_filters,
+                        lowpass, lowpass_packed, hop, pad_mode, n_bins, scale, scale_all, out_format,
+                        sqrt_eps, out, T, workspace, ws_bytes, s);
+    if (rc != NNAB_EUNSUPPORTED) return rc;
+  }
   if (all_packed && getenv("NNAB_PYRAMID_UNFUSED") == nullptr) {
     rc = pyramid_fused(x, B, L, x_pitch, n_octaves, h_k_real, h_k_imag, h_packed, h_widths,
                        n_filters, lowpass_packed, early_packed, early_factor, hop, pad_mode, n_bins,

@@ -17,14 +17,17 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 }
 
 // trow: TMEM address of this warp's lane quarter / accumulator; tl: frame index inside clip b.
+// [c_lo, c_hi): the TMEM columns (= outputs of the frame) this warp handles (c_hi < 0: all 2*half).
 __device__ __forceinline__ void epilogue_decim(const DecimParams& d, uint32_t trow, int64_t b,
-                                               int64_t tl, bool valid, int half) {
+                                               int64_t tl, bool valid, int half, int c_lo = 0,
+                                               int c_hi = -1) {
         // ---- FIR decimator stage: this thread holds outputs n0 .. n0 + 2*half - 1 of clip b ----
         const int64_t n0 = tl * (2 * half);
         __nv_bfloat16* pc = reinterpret_cast<__nv_bfloat16*>(d.pc);
         __nv_bfloat16* pf = reinterpret_cast<__nv_bfloat16*>(d.pf);
+        if (c_hi < 0) c_hi = 2 * half;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 2 * half; c0 += 8) {
+        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
           uint32_t v[8];
           tmem_ld8(trow + (uint32_t)c0, v);  // re half = outputs 0..half-1, im half = the rest
           tmem_ld_wait();

@@ -318,6 +318,49 @@ int tc_pad_split(const float* x, int64_t B, int64_t L, int64_t x_pitch, int K, i
   return NNAB_OK;
 }
 
+__global__ void zero_margins_kernel(__nv_bfloat16* __restrict__ planes, int64_t plane_stride,
+                                    int64_t pitch, int64_t keep_lo, int64_t keep_hi);
+
+// pad + split into caller-defined geometry (clip pitch / plane stride in elements).  pad_split_kernel
+// writes the whole [0, clip_pitch) slot of every clip (zeros past the padded signal); the tail
+// [B * clip_pitch, plane_stride) is zeroed here.
+int tc_pad_split_ex(const float* x, int64_t B, int64_t L, int64_t x_pitch, int pad, int pad_mode,
+                    int64_t clip_pitch, int64_t plane_stride, void* planes_v, cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  if (clip_pitch % 8 != 0 || plane_stride < B * clip_pitch) return NNAB_EINVAL;
+  __nv_bfloat16* planes = (__nv_bfloat16*)planes_v;
+  const int64_t tail = plane_stride - B * clip_pitch;
+  for (int pl = 0; pl < 2 && tail > 0; ++pl)
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * plane_stride + B * clip_pitch, 0,
+                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
+  dim3 grid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)B);
+  pad_split_kernel<<<grid, 256, 0, stream>>>(x, L, x_pitch, pad, pad_mode, 0, clip_pitch, plane_stride,
+                                             planes);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
+// zero [keep_hi, clip_pitch) and [0, keep_lo) of every clip slot (both planes) + the tail of the planes
+int tc_zero_slots(void* planes_v, int64_t B, int64_t clip_pitch, int64_t plane_stride, int64_t keep_lo,
+                  int64_t keep_hi, cudaStream_t stream) {
+  if (B > 65535) return NNAB_EUNSUPPORTED;
+  __nv_bfloat16* planes = (__nv_bfloat16*)planes_v;
+  const int64_t tail = plane_stride - B * clip_pitch;
+  for (int pl = 0; pl < 2 && tail > 0; ++pl)
+    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * plane_stride + B * clip_pitch, 0,
+                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
+  if (keep_hi > clip_pitch) keep_hi = clip_pitch;
+  if (keep_lo < 0) keep_lo = 0;
+  const int64_t n = keep_lo + (clip_pitch - keep_hi);
+  if (n <= 0) return NNAB_OK;
+  int gx = (int)ceil_div64(n, 256);
+  if (gx > 64) gx = 64;
+  zero_margins_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(planes, plane_stride, clip_pitch,
+                                                                keep_lo, keep_hi);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
 int tc_pad_split2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
                   int K_a, int hop_a, int pad_a, int mode_a, void* planes_a,
                   int K_b, int hop_b, int pad_b, int mode_b, void* planes_b, cudaStream_t stream) {
@@ -2478,7 +2521,16 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
 
   const int n_ph = num_phases(q.hop);
   const int hop_eff = q.hop * n_ph;
-  const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+  SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+  if (q.presplit != nullptr && q.presplit_t_slots > 0) {
+    // caller-defined plane geometry (pyramid levels shared with the FIR stage): frame g of the batch
+    // still starts at element g * hop, with presplit_t_slots frames per clip slot
+    g.t_slots = q.presplit_t_slots;
+    g.nv = q.B * g.t_slots;
+    g.plane_stride = q.presplit_plane_stride;
+    g.rows = g.plane_stride / hop_eff;
+    if (g.rows < g.nv) return NNAB_EINVAL;
+  }
   const int kpad = round_up_i(q.K, 64);
   // FMT_OLA: the N axis is the frame's n_fft output samples (q.F), not (re | im) bin pairs
   const int bn = (q.fmt == FMT_OLA) ? tc_istft_bn(q.F) : choose_bn(q.F);

@@ -28,6 +28,7 @@
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 #include "tc_host.cuh"
+#include "tc_decim.cuh"
 
 namespace nnab {
 
@@ -424,6 +425,291 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
     case NNAB_FMT_PHASE_UNIT: return launch_tc2t_fmt<3>(ma, mb8, mb32, prm, plan, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
+}
+
+
+// ===========================================================================
+// FIR decimator stage of the CQT pyramid (utils.py:73-124: conv1d(x, lowpass(256), stride=2,
+// padding=127)) with RESIDENT taps and tall A blocks.
+//
+// As in tc_kernels.cu the stage is a framed contraction: frame t of a level covers its samples
+// [256 t - 128, 256 t + 384) and yields the 128 outputs y[128 t + j] through the banded Toeplitz rows
+// H[j][k] = fir[k - 1 - 2 j] (K = 512, N = 128).  New here:
+//   * the level lives in ONE plane set (hi / lo bf16) shared with the level's octave CQT: sample m of
+//     clip b at b * pitch + pad + m with the CQT's reflect margins.  The FIR wants ZERO margins; only
+//     the first / last 64 outputs of a clip see the margins, and fir_edge_fix_kernel recomputes
+//     those (plus their mirror copies) afterwards.  One write + one read of 4 B per sample and level
+//     instead of two differently padded copies.
+//   * the 128 x 512 tap matrix (128 KB as hi / lo halves per CTA of the pair) stays in shared memory
+//     for the whole persistent kernel; per tile only the signal moves.
+//   * the signal is read through tall A blocks (see framed_tc2t_kernel): with 256-sample rows, K block
+//     kb' = kb + off64 is column kb' % 4 of row t + kb' / 4, so 4 blocks of (128 + r_max) rows x 64
+//     columns feed all 8 K blocks.  off64 = (pad - 128) / 64 aligns the CQT's padding origin.
+// ===========================================================================
+constexpr int FIR_KBLOCKS = 8;
+constexpr int FIR_A_ROWS = 136;   // 128 frames + up to 8 row shifts
+constexpr int FIR_THREADS = 128 + 32 * 8;
+
+struct FirSmem {
+  static constexpr uint32_t B_KB = 64 * TCT_BK * 2;            // one K block, one plane, this CTA's 64 rows
+  static constexpr uint32_t B_RES = 2 * FIR_KBLOCKS * B_KB;    // hi + lo, 8 K blocks = 128 KB
+  static constexpr uint32_t A_PLANE = FIR_A_ROWS * TCT_BK * 2; // 17 KB
+  static constexpr uint32_t A_BUF = 2 * A_PLANE;
+  static constexpr uint32_t A_OFFSET = B_RES;
+  static constexpr uint32_t BAR_OFFSET = A_OFFSET + 2 * A_BUF;
+  static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+struct FirParams {
+  int num_m_tiles;       // 256-frame pair tiles over the virtual frames b * t_slots + t
+  int off64;             // (source pad - 128) / 64
+  int64_t nv, t_slots, FT;  // frames: virtual total, per clip slot, valid per clip
+  DecimParams dec;
+};
+
+__global__ void __launch_bounds__(FIR_THREADS, 1)
+fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+              const FirParams p) {
+  constexpr int BK = TCT_BK;
+  using S = FirSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  const uint32_t b_full = bar_base;                                       // leader
+  auto a_full = [&](int a) { return bar_base + 8u * (1 + a); };            // leader
+  auto a_empty = [&](int a) { return bar_base + 8u * (3 + a); };           // per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (5 + a); };         // per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (7 + a); };        // leader
+  const uint32_t tmem_slot = bar_base + 8u * 9;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(b_full, 2);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(a_full(a), 2);
+      mbar_init(a_empty(a), 1);
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 256);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // K block kb reads column (kb + off64) % 4 at row shift (kb + off64) / 4
+  const int r_max = (FIR_KBLOCKS - 1 + p.off64) / 4;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // resident taps: this CTA's 64 rows of every K block, hi then lo
+      mbar_expect_tx_remote(b_full, 0, S::B_RES);
+      for (int kb = 0; kb < FIR_KBLOCKS; ++kb) {
+        tma_load_3d_2sm(base + (uint32_t)kb * S::B_KB, &tm_b, b_full, kb * BK, (int)cta * 64, 0);
+        tma_load_3d_2sm(base + (uint32_t)(FIR_KBLOCKS + kb) * S::B_KB, &tm_b, b_full, kb * BK,
+                        (int)cta * 64, 1);
+      }
+      int abuf = 0;
+      uint32_t aphase = 0;
+      for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        for (int c = 0; c < 4; ++c) {
+          mbar_wait(a_empty(abuf), aphase ^ 1u);
+          const uint32_t ab = base + S::A_OFFSET + (uint32_t)abuf * S::A_BUF;
+          mbar_expect_tx_remote(a_full(abuf), 0, S::A_BUF);
+          tma_load_3d_2sm(ab, &tm_a, a_full(abuf), c * BK, m0, 0);
+          tma_load_3d_2sm(ab + S::A_PLANE, &tm_a, a_full(abuf), c * BK, m0, 1);
+          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) |
+                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      mbar_wait(b_full, 0);
+      int abuf = 0, acc = 0;
+      uint32_t aphase = 0, acc_phase = 0;
+      for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < 4; ++c) {
+          mbar_wait(a_full(abuf), aphase);
+          tcgen05_fence_after();
+          const uint32_t ab = base + S::A_OFFSET + (uint32_t)abuf * S::A_BUF;
+          for (int r = 0; r <= r_max; ++r) {
+            const int kb = 4 * r + c - p.off64;
+            if (kb < 0 || kb >= FIR_KBLOCKS) continue;
+            const uint32_t a_row = (uint32_t)r * (BK * 2);
+            const uint32_t bh = base + (uint32_t)kb * S::B_KB, bl = base + (uint32_t)(FIR_KBLOCKS + kb) * S::B_KB;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t koff = (uint32_t)k * 32u;
+              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
+              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
+              const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
+              const uint64_t b_lo = make_smem_desc<BK>(bl + koff);
+              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+              accumulate = 1u;
+            }
+          }
+          umma_commit_2sm(a_empty(abuf));
+          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const int part = (warp - 4) >> 2;  // column half of the 128 outputs
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const int64_t b = g / p.t_slots;
+      const int64_t tl = g - b * p.t_slots;
+      const bool valid = (g < p.nv) && (tl < p.FT);
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u;
+      epilogue_decim(p.dec, trow, b, tl, valid, 64, 64 * part, 64 * part + 64);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 256);
+  }
+}
+
+// Outputs whose taps reach past a clip edge: y[n] = sum_m fir[m] x[2 n + m - 127] with x = 0 outside
+// [0, len_src) -- n < 64 and n >= len_out - 64 -- recomputed from the source planes (hi + lo) and
+// written over what fir_tc_kernel produced from the reflect margins: the sample itself, its mirror
+// copies in the destination's reflect margins, and the fp32 copy when the level keeps one.
+__global__ void __launch_bounds__(128) fir_edge_fix_kernel(
+    const __nv_bfloat16* __restrict__ src, int64_t src_pitch, int64_t src_plane, int src_off,
+    int64_t len_src, const float* __restrict__ fir, int taps, DecimParams d) {
+  const int64_t b = blockIdx.x;
+  const int i = threadIdx.x;  // 0..63: head outputs, 64..127: tail outputs
+  int64_t n = (i < 64) ? i : d.len_out - 128 + i;
+  if (i >= 64 && n < 64) return;  // short clip: the head half already covers it
+  if (n < 0 || n >= d.len_out) return;
+  const __nv_bfloat16* sb = src + b * src_pitch + src_off;
+  float acc = 0.f;
+  for (int m = 0; m < taps; ++m) {
+    const int64_t j = 2 * n + m - (taps - 1) / 2;
+    if (j >= 0 && j < len_src)
+      acc = fmaf(__ldg(fir + m), __bfloat162float(sb[j]) + __bfloat162float(sb[src_plane + j]), acc);
+  }
+  __nv_bfloat16 hi, lo;
+  split_bf16(acc, hi, lo);
+  if (d.pc != nullptr) {
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.pc) + b * d.pc_pitch + d.pc_off;
+    base[n] = hi; base[d.pc_plane + n] = lo;
+    if (d.pc_reflect) {
+      if (n >= 1 && n <= d.pc_off) { base[-n] = hi; base[d.pc_plane - n] = lo; }
+      if (n >= d.len_out - 1 - d.pc_off && n <= d.len_out - 2) {
+        const int64_t r = 2 * (d.len_out - 1) - n;
+        base[r] = hi; base[d.pc_plane + r] = lo;
+      }
+    }
+  }
+  if (d.y32 != nullptr) d.y32[b * d.y32_pitch + n] = acc;
+}
+
+// One FIR stage: source level planes (single set, samples at offset src_pad, clip pitch a multiple of
+// 256) -> destination level through `dec` (pc planes with their own pad, optional fp32 copy).
+int launch_fir_stage_tc(const void* src_planes, int64_t B, int64_t src_len, int64_t src_pitch,
+                        int64_t src_plane_stride, int src_pad, const void* fir_packed,
+                        const float* fir, int taps, const DecimParams& dec, cudaStream_t stream) {
+  if (taps != 256 || src_pad < 128 || (src_pad - 128) % 64 != 0 || (src_pad - 128) / 64 > 24)
+    return NNAB_EUNSUPPORTED;
+  if (src_pitch % 256 != 0 || B > 65535 || dec.pf != nullptr) return NNAB_EUNSUPPORTED;
+  const int off64 = (src_pad - 128) / 64;
+  const int64_t FT = (dec.len_out + 127) / 128;
+  const int64_t t_slots = src_pitch / 256;
+  if (256 * (FT + 1 + (7 + off64) / 4) > src_pitch + 256) return NNAB_EUNSUPPORTED;  // last frame's rows
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();
+  if (sms < 2) sms = 2;
+  CUtensorMap ma, mb;
+  const int64_t rows = src_plane_stride / 256;
+  int rc = encode_3d(&ma, const_cast<void*>(src_planes), 256, (uint64_t)rows, 2, 512,
+                     (uint64_t)src_plane_stride * 2, 64, FIR_A_ROWS, 64);
+  if (rc) return rc;
+  const int kf = tc_fir_k(taps, 2);  // 512
+  if (kf != 64 * FIR_KBLOCKS) return NNAB_EUNSUPPORTED;
+  rc = encode_3d(&mb, const_cast<void*>(fir_packed), (uint64_t)kf, 128, 2, (uint64_t)kf * 2,
+                 (uint64_t)128 * kf * 2, 64, 64, 64);
+  if (rc) return rc;
+  FirParams prm{};
+  prm.nv = B * t_slots;
+  prm.t_slots = t_slots;
+  prm.FT = FT;
+  prm.off64 = off64;
+  prm.num_m_tiles = (int)ceil_div64(prm.nv, 2 * TC_BM);
+  prm.dec = dec;
+  const int n_pairs = prm.num_m_tiles < sms / 2 ? prm.num_m_tiles : sms / 2;
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  if (!((configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u)) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(fir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)FirSmem::TOTAL));
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(FIR_THREADS);
+  cfg.dynamicSmemBytes = FirSmem::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, fir_tc_kernel, ma, mb, prm));
+  count_launch();
+  add_exec_flops(3.0 * 2.0 * (double)prm.num_m_tiles * (2 * TC_BM) * 128.0 * 512.0);
+  // clip edges
+  fir_edge_fix_kernel<<<(unsigned)B, 128, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src_planes), src_pitch, src_plane_stride, src_pad, src_len,
+      fir, taps, dec);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
 }
 
 }  // namespace nnab
