@@ -61,7 +61,9 @@ WORKLOAD_BOUND = {"cfg2": "tensor", "stft2048": "tensor", "cfg3": "tensor", "cfg
 # the other configurations BASELINE.json's metric names, reported inside the same JSON line
 SECONDARY = ["stft2048", "cfg3", "cfg4", "cfg5"]
 
-GATHER_DESC = {"symm": "copy-engine pushes into symmetric memory over NVLink, no SMs, no NCCL kernels",
+GATHER_DESC = {"peer": "kernels write into symmetric memory, copy-engine pushes over NVLink, stream-memop "
+                       "handshakes: no SMs, no kernels, no NCCL on the data path",
+               "symm": "copy-engine pushes into symmetric memory over NVLink, torch barrier kernels",
                "nccl": "ncclAllGather on reserved SMs", "none": "-", "auto": "-"}
 
 # SMs left to the NCCL gather while the persistent kernels run, and the matching NCCL CTA cap
@@ -367,11 +369,12 @@ def _run():
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's cuDNN leg")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--e2e-copy-streams", type=int, default=1)
-    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "symm"],
-                    help="symm = copy-engine pushes into symmetric memory (no SMs reserved); nccl = "
-                         "all_gather_into_tensor with an SM reserve; auto = symm when it works on this box")
-    ap.add_argument("--gather-to", default="all", choices=["all", "root"],
-                    help="every rank receives the whole batch's spectrograms, or rank 0 only")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "symm", "peer"],
+                    help="peer = kernels write into symmetric memory, copy-engine pushes, stream-memop "
+                         "handshakes (no SMs, no kernels); symm = same pushes with torch's barrier kernels; "
+                         "nccl = all_gather_into_tensor with an SM reserve; auto = peer when it works here")
+    ap.add_argument("--gather-to", default="root", choices=["all", "root"],
+                    help="rank 0 receives the whole batch's spectrograms (the north star's gather), or every rank")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs kept free for the concurrent NCCL gather (default: by world size)")
     ap.add_argument("--nccl-max-ctas", type=int, default=-1,
@@ -439,32 +442,41 @@ def _run():
         # leave SMs free for it, nnaudio_b200.parallel) and 99 MB per step does not need more
         reserve_plan = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
         max_ctas = args.nccl_max_ctas if args.nccl_max_ctas >= 0 else reserve_plan
-        if max_ctas > 0 and args.gather != "symm":
+        if max_ctas > 0 and args.gather not in ("symm", "peer"):
             os.environ["NCCL_MAX_CTAS"] = str(max_ctas)
         dist.init_process_group("nccl", device_id=dev)
         gather_impl = args.gather
-        if args.gather in ("auto", "symm"):
-            # does the copy-engine gather work here?  (symmetric memory needs P2P / fabric handles);
-            # every rank must agree, so reduce the outcome
+        if args.gather in ("auto", "symm", "peer"):
+            # does the copy-engine gather work here?  (symmetric memory needs P2P / fabric handles,
+            # the handshakes need stream memory operations); every rank must agree: reduce the outcome
+            want_impl = "symm" if args.gather == "symm" else "peer"
             ok = 1
             try:
-                probe = BatchShardedTransform(lambda t: t, gather=True, reserve_sms=0)
-                xp = torch.full((2, 8), float(rank), device=dev)
-                wk, got = probe.forward_async_symm(xp, slot=0, gather_to="all")
-                wk.wait()
-                torch.cuda.synchronize(dev)
+                probe = BatchShardedTransform(lambda t: t * 1.0, gather=True, reserve_sms=0)
                 want = torch.arange(world, device=dev, dtype=torch.float32).repeat_interleave(2)[:, None].expand(-1, 8)
-                ok = int(torch.equal(got, want))
-                probe.release(0)
+                for it in range(3):  # slot reuse included
+                    xp = torch.full((2, 8), float(rank), device=dev)
+                    if want_impl == "peer":
+                        wk, got = probe.forward_async_peer(xp, slot=it & 1, gather_to="all")
+                    else:
+                        wk, got = probe.forward_async_symm(xp, slot=it & 1, gather_to="all")
+                    wk.wait()
+                    torch.cuda.synchronize(dev)
+                    ok &= int(torch.equal(got, want))
+                    if want_impl == "peer":
+                        probe.release_peer(it & 1)
+                    else:
+                        probe.release(it & 1)
+                torch.cuda.synchronize(dev)
             except Exception as e:  # noqa: BLE001
-                sys.stderr.write(f"[bench] rank {rank}: symmetric-memory gather unavailable: {type(e).__name__}: {e}\n")
+                sys.stderr.write(f"[bench] rank {rank}: {want_impl} gather unavailable: {type(e).__name__}: {e}\n")
                 ok = 0
             flag = torch.tensor([ok], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 1:
-                gather_impl = "symm"
-            elif args.gather == "symm":
-                raise RuntimeError("--gather symm requested but the symmetric-memory gather failed its probe")
+                gather_impl = want_impl
+            elif args.gather != "auto":
+                raise RuntimeError(f"--gather {args.gather} requested but it failed its probe")
             else:
                 gather_impl = "nccl"
 
@@ -491,7 +503,7 @@ def _run():
         return [float(v) for v in t.tolist()]
 
     reserve = args.reserve_sms if args.reserve_sms is not None else DEFAULT_RESERVE.get(world, 16)
-    if gather_impl == "symm" and args.reserve_sms is None:
+    if gather_impl in ("symm", "peer") and args.reserve_sms is None:
         reserve = 0  # the copy engines do the gather: the kernels keep every SM
 
     def measure(name, steps, warmup, gather):
@@ -516,14 +528,19 @@ def _run():
             every gather completes inside the timed region."""
             prev, y = None, None
             for i in range(n):
-                if gather_impl == "symm" and gather and world > 1:
+                if gather_impl == "peer" and gather and world > 1:
+                    work, y = sharded.forward_async_peer(xs[i % n_rot], slot=i & 1, gather_to=args.gather_to)
+                elif gather_impl == "symm" and gather and world > 1:
                     work, y = sharded.forward_async_symm(xs[i % n_rot], slot=i & 1, gather_to=args.gather_to)
                 else:
                     work, y = sharded.forward_async(xs[i % n_rot], slot=i & 1)
                 if prev is not None:
                     prev.wait()
-                    if gather_impl == "symm" and gather and world > 1:
-                        sharded.release((i - 1) & 1)
+                    if gather and world > 1:
+                        if gather_impl == "peer":
+                            sharded.release_peer((i - 1) & 1, None if args.gather_to == "all" else [0])
+                        elif gather_impl == "symm":
+                            sharded.release((i - 1) & 1)
                 prev = work
             if prev is not None:
                 prev.wait()

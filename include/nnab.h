@@ -117,6 +117,12 @@ int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int l
  * nnab_packed_block_bytes(n_fft, hop) bytes; the forward entry points recognise the layout.
  * nnab_block_layout_ok() is host-only: 1 when (n_fft, hop) is eligible. */
 int nnab_block_layout_ok(int n_fft, int hop);
+
+/* Stream-ordered 32-bit store / cyclic >= wait on a device address (may be peer-mapped): front-end
+ * memory operations (cuStreamWriteValue32 / cuStreamWaitValue32), no kernel, no SM.  The multi-GPU
+ * gather uses them for its slot handshakes (nnaudio_b200/parallel.py). */
+int nnab_stream_write_value32(void* stream, void* addr, uint32_t value);
+int nnab_stream_wait_value32_geq(void* stream, void* addr, uint32_t value);
 size_t nnab_packed_block_bytes(int n_fft, int hop);
 int nnab_pack_basis_block(int n_fft, int hop, void* packed, void* stream);
 

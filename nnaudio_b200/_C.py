@@ -91,6 +91,8 @@ SIGNATURES = {
     ),
     "nnab_pack_basis_ex": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "nnab_block_layout_ok": (c_int, [c_int, c_int]),
+    "nnab_stream_write_value32": (c_int, [_P, _P, ctypes.c_uint32]),
+    "nnab_stream_wait_value32_geq": (c_int, [_P, _P, ctypes.c_uint32]),
     "nnab_packed_block_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_basis_block": (c_int, [c_int, c_int, _P, _P]),
     "nnab_debug_varn_plan": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
@@ -212,6 +214,41 @@ def _workspace(nbytes: int, device):
 MAX_BATCH = 65535  # clips per C call (the pre-pass kernels put the clip index in gridDim.y)
 
 
+# --------------------------------------------------------------------------- #
+# caller-provided output buffers (multi-GPU gather: the kernels write straight into the slice of a
+# symmetric-memory buffer; see nnaudio_b200.parallel)
+# --------------------------------------------------------------------------- #
+import threading as _threading
+
+_OUT = _threading.local()
+
+
+class output_into:
+    """``with _C.output_into(buf): y = module(x)`` -- the forward call that runs inside writes its
+    result into ``buf`` (a contiguous fp32 CUDA tensor of exactly the result's shape) instead of
+    allocating one, and returns ``buf``.  Used once: the first matching allocation takes it."""
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf
+
+    def __enter__(self):
+        _OUT.buf = self.buf
+        return self
+
+    def __exit__(self, *exc):
+        _OUT.buf = None
+        return False
+
+
+def _new_out(shape, device) -> torch.Tensor:
+    buf = getattr(_OUT, "buf", None)
+    if buf is not None and tuple(buf.shape) == tuple(shape) and buf.device == device \
+            and buf.dtype == torch.float32 and buf.is_contiguous():
+        _OUT.buf = None
+        return buf
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
 def _batch_chunked(fn):
     """Forward wrappers take any batch size: more than ``MAX_BATCH`` clips are run as several C
     calls on the same stream and concatenated (every op of the path is per-clip, including the
@@ -264,6 +301,19 @@ def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor, layout: int = LAYOUT_DENS
                                       _stream(w_re.device))
         _check(rc, "nnab_pack_basis")
     return packed
+
+
+def stream_write_value32(stream: torch.cuda.Stream, addr: int, value: int):
+    """Stream-ordered 32-bit store to a (possibly peer-mapped) device address: a front-end memory
+    operation, no kernel and no SM (cuStreamWriteValue32)."""
+    _check(lib().nnab_stream_write_value32(ctypes.c_void_p(stream.cuda_stream), ctypes.c_void_p(addr),
+                                           int(value) & 0xFFFFFFFF), "nnab_stream_write_value32")
+
+
+def stream_wait_value32_geq(stream: torch.cuda.Stream, addr: int, value: int):
+    """Work queued on ``stream`` after this waits until (int32)(*addr - value) >= 0 (cuStreamWaitValue32)."""
+    _check(lib().nnab_stream_wait_value32_geq(ctypes.c_void_p(stream.cuda_stream), ctypes.c_void_p(addr),
+                                              int(value) & 0xFFFFFFFF), "nnab_stream_wait_value32_geq")
 
 
 def block_layout_ok(n_fft: int, hop: int) -> bool:
@@ -319,7 +369,7 @@ def stft_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, out_format
     pad = n_fft // 2 if center else 0
     T = (Ln + 2 * pad - n_fft) // hop + 1
     shape = (B, F, T, 2) if out_format == FMT_COMPLEX else (B, F, T)
-    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    out = _new_out(shape, x.device)
     path = resolve_path(path)
     with torch.cuda.device(x.device):
         ws, wsb = _workspace(L.nnab_stft_workspace_bytes(B, Ln, n_fft, F, hop, int(center), path),
@@ -340,7 +390,7 @@ def stft_filterbank_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode,
     n_fb = fb.shape[0]
     pad = n_fft // 2 if center else 0
     T = (Ln + 2 * pad - n_fft) // hop + 1
-    out = torch.empty((B, n_fb, T), dtype=torch.float32, device=x.device)
+    out = _new_out((B, n_fb, T), x.device)
     path = resolve_path(path)
     with torch.cuda.device(x.device):
         ws, wsb = _workspace(
@@ -365,7 +415,7 @@ def mfcc_forward(x, wcos, wsin, packed, n_fft, hop, center, pad_mode, sqrt_eps, 
     n_mfcc = dct.shape[0]
     pad = n_fft // 2 if center else 0
     T = (Ln + 2 * pad - n_fft) // hop + 1
-    out = torch.empty((B, n_mfcc, T), dtype=torch.float32, device=x.device)
+    out = _new_out((B, n_mfcc, T), x.device)
     path = resolve_path(path)
     with torch.cuda.device(x.device):
         ws, wsb = _workspace(
@@ -390,7 +440,7 @@ def cqt1992v2_forward(x, k_real, k_imag, packed, k_begin, k_end, hop, center, pa
     pad = width // 2 if center else 0
     T = (Ln + 2 * pad - width) // hop + 1
     shape = (B, n_bins, T) if out_format == FMT_MAGNITUDE else (B, n_bins, T, 2)
-    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    out = _new_out(shape, x.device)
     path = resolve_path(path)
     kb = k_begin.ctypes.data_as(c_void_p) if k_begin is not None else None
     ke = k_end.ctypes.data_as(c_void_p) if k_end is not None else None
@@ -422,7 +472,7 @@ def cqt_pyramid_forward(x, banks_real, banks_imag, packed, lowpass, lowpass_pack
     widths = (c_int32 * n_oct)(*[int(t.shape[1]) for t in banks_real])
     max_width = max(int(t.shape[1]) for t in banks_real)
     shape = (B, n_bins, T) if out_format == FMT_MAGNITUDE else (B, n_bins, T, 2)
-    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    out = _new_out(shape, x.device)
     path = resolve_path(path)
     with torch.cuda.device(x.device):
         ws, wsb = _workspace(

@@ -1,5 +1,6 @@
 // extern "C" entry points of libnnab.so — see include/nnab.h for the contract
 // and the reference file:line each call replaces.
+#include <cuda.h>
 #include <atomic>
 #include <mutex>
 #include <stdlib.h>
@@ -198,6 +199,32 @@ int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int l
   if (w_re == nullptr || w_im == nullptr || packed == nullptr || F <= 0 || K <= 0)
     return NNAB_EINVAL;
   return tc_pack_basis_layout(w_re, w_im, F, K, layout, packed, (cudaStream_t)stream);
+}
+
+// Stream memory operations (multi-GPU gather handshakes without kernels): thin wrappers over the driver
+// entry points, resolved at run time like cuTensorMapEncodeTiled.
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamValue32Fn memop_fn(const char* name) {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<StreamValue32Fn>(ptr);
+}
+int nnab_stream_write_value32(void* stream, void* addr, uint32_t value) {
+  static StreamValue32Fn fn = memop_fn("cuStreamWriteValue32");
+  if (fn == nullptr || addr == nullptr) return NNAB_EUNSUPPORTED;
+  const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)addr, value, 0 /* default */);
+  if (r != CUDA_SUCCESS) { set_error_text("cuStreamWriteValue32 failed"); return NNAB_ECUDA; }
+  return NNAB_OK;
+}
+int nnab_stream_wait_value32_geq(void* stream, void* addr, uint32_t value) {
+  static StreamValue32Fn fn = memop_fn("cuStreamWaitValue32");
+  if (fn == nullptr || addr == nullptr) return NNAB_EUNSUPPORTED;
+  const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)addr, value, 0 /* GEQ */);
+  if (r != CUDA_SUCCESS) { set_error_text("cuStreamWaitValue32 failed"); return NNAB_ECUDA; }
+  return NNAB_OK;
 }
 
 int nnab_block_layout_ok(int n_fft, int hop) { return tc_block_shape_ok(n_fft, hop) ? 1 : 0; }
@@ -649,9 +676,10 @@ size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int
       Lvl2 lv2[32];
       size_t full2 = 0;
       if (early_factor <= 1 &&
-          plan_pyramid2(B, L, n_octaves, hop, nullptr, max_width, NNAB_PAD_REFLECT, lv2, &full2) &&
-          full2 + 1024 > n)
-        n = full2 + 1024;
+          plan_pyramid2(B, L, n_octaves, hop, nullptr, max_width, NNAB_PAD_REFLECT, lv2, &full2)) {
+        full2 += 2048 + (size_t)n_octaves * align_up((size_t)768 * ((max_width + 63) / 64 * 64), 256);
+        if (full2 > n) n = full2;
+      }
     }
   }
   return n;
@@ -679,8 +707,23 @@ static int pyramid_fused2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
       break;
     }
   char* scratch = ws + scratch_off;
-  const size_t scratch_bytes = ws_bytes - 256 - scratch_off;
   int rc;
+  // packed octave banks in the 8-bin-group layout of the tall kernel, behind everything else
+  int max_w = 0;
+  for (int i = 0; i < n_octaves; ++i) max_w = lv[i].width > max_w ? lv[i].width : max_w;
+  const size_t vpack_stride = align_up((size_t)768 * ((max_w + 63) / 64 * 64), 256);
+  const bool use_tall = n_filters <= 96 && need + 512 + vpack_stride * n_octaves <= ws_bytes &&
+                        !(getenv("NNAB_TALL") != nullptr && atoi(getenv("NNAB_TALL")) == 0);
+  char* vpack_base = ws + align_up(need, 256);
+  bool vpack_done0 = false;
+  const size_t scratch_bytes = (use_tall ? (size_t)(vpack_base - ws) : ws_bytes - 256) - scratch_off;
+  auto prof_run_tall = [&](const FramedProblem& fp, const void* vp, cudaStream_t st) -> int {
+    std::pair<cudaEvent_t, cudaEvent_t> pr;
+    const bool timed = prof_begin(st, &pr);
+    const int r = launch_framed_tc_tall(fp, vp, nullptr, 0, st);
+    if (timed) prof_end(st, pr);
+    return r;
+  };
 
   // level 0: the caller's fp32 waveform -> planes (one pass; writes the whole clip slot)
   if (lv[0].planes) {
@@ -702,7 +745,32 @@ static int pyramid_fused2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
       p.presplit = ws + l.pc;
       p.presplit_t_slots = l.t_slots;
       p.presplit_plane_stride = l.plane;
-      if ((rc = run_framed(p, h_packed[i], nullptr, 0, NNAB_PATH_TCGEN05, s))) return rc;
+      // frames that overlap (hop < width): tall-A kernel on the same planes -- every sample is
+      // fetched once per tile instead of once per frame; hop < 64 runs as 64 / hop frame phases
+      bool done = false;
+      if (use_tall && l.hop < l.width && (l.hop % 64 == 0 || (l.hop >= 8 && 64 % l.hop == 0))) {
+        const int kpad = (l.width + 63) / 64 * 64;
+        const size_t vbytes = (size_t)768 * kpad;
+        char* vp = vpack_base + (size_t)i * vpack_stride;
+        if (vpack_stride >= vbytes) {
+          bool packed_now = true;
+          // CQT2010v2 shares one bank between the octaves: pack once
+          if (i > 0 && h_k_real[i] == h_k_real[0] && h_k_imag[i] == h_k_imag[0] && lv[i].width == lv[0].width &&
+              vpack_done0) {
+            vp = vpack_base;
+            packed_now = false;
+          }
+          if (packed_now) {
+            rc = tc_pack_basis_varn(h_k_real[i], h_k_imag[i], n_filters, l.width, vp, s);
+            if (rc) return rc;
+            if (i == 0) vpack_done0 = true;
+          }
+          rc = prof_run_tall(p, vp, s);
+          if (rc == NNAB_OK) done = true;
+          else if (rc != NNAB_EUNSUPPORTED) return rc;
+        }
+      }
+      if (!done && (rc = run_framed(p, h_packed[i], nullptr, 0, NNAB_PATH_TCGEN05, s))) return rc;
     } else {
       const float* src = (i == 0) ? x : (const float*)(ws + l.y32);
       p.x = src; p.x_pitch = (i == 0) ? x_pitch : l.y32_pitch;

@@ -27,6 +27,12 @@ int num_phases(int hop);
 int encode_3d(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
               uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int bk);
 
+int encode_4d(CUtensorMap* map, void* base, const uint64_t dims[4], const uint64_t strides[3],
+              const uint32_t box[3]);
+size_t tc_packed_bytes(int F, int K);
+int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void* packed,
+                       cudaStream_t stream);
+
 // layout of a packed basis, keyed by its device pointer
 enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2, PACK_RADIX4 = 3, PACK_BLOCK = 4 };
 int packed_kind(const void* packed);

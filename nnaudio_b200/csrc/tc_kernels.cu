@@ -1958,6 +1958,35 @@ int encode_3d(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1, uint64_t d
   return NNAB_OK;
 }
 
+// 4-D bf16 map, SWIZZLE_128B, box {box0, box1, box2, 1}; strides in bytes for dims 1..3 (any order of
+// magnitude: a dimension may step by less than the extent of the one below it -- overlapping views)
+int encode_4d(CUtensorMap* map, void* base, const uint64_t dims[4], const uint64_t strides[3],
+              const uint32_t box[3]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error_text("cuTensorMapEncodeTiled entry point not available");
+    return NNAB_ECUDA;
+  }
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides[0], strides[1], strides[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, bx, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[240];
+    snprintf(msg, sizeof(msg),
+             "cuTensorMapEncodeTiled(4d) failed (%d): dims {%llu,%llu,%llu,%llu} strides {%llu,%llu,%llu}",
+             (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+             (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+             (unsigned long long)strides[2]);
+    set_error_text(msg);
+    return NNAB_ECUDA;
+  }
+  return NNAB_OK;
+}
+
 template <int BK, int STAGES, int FMT>
 static int launch_tc_kernel_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
                                 int grid, cudaStream_t stream) {

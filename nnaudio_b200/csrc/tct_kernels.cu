@@ -49,13 +49,15 @@ struct TallPlan {
   int r_cnt[TCT_MAX_COLS];        // number of active shifts (contiguous)
   int r_first[TCT_MAX_COLS];      // shift visited first: the column's widest block
   int g_max[TCT_MAX_COLS];        // its width in 8-bin groups = columns the chunk initialises
-  int hb;                         // hop / 64
+  int hb;                         // hop_eff / 64
+  int a_rows;                     // rows of a tall A block (128 + widest shift span, multiple of 8)
   uint8_t groups[TCT_MAX_KB];     // 8-bin groups K block kb reaches (0 = inactive)
 };
 
 struct TctParams {
-  int num_m_tiles;                // 256-frame pair tiles
-  int64_t nv, t_slots, T;
+  int num_m_tiles;                // 256-frame pair tiles (per frame phase)
+  int n_phases;                   // frames t = s * n_phases + p: phase p reads the planes shifted by p * hop
+  int64_t nv, t_slots, T;         // per phase: virtual frames, frames per clip slot; T = frames of the output
   EpiParams epi;
 };
 
@@ -140,16 +142,18 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (elect_one()) {
       int stage = 0, abuf = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+      const int total_tiles = p.num_m_tiles * p.n_phases;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int ph = tile / p.num_m_tiles, m_tile = tile - ph * p.num_m_tiles;
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
         for (int ci = 0; ci < plan.n_cols; ++ci) {
           const int c = plan.col[ci], r_min = plan.r_min[ci], r_cnt = plan.r_cnt[ci];
-          // ---- the column's tall A block: rows m0 + r_min .. + 192, columns [64 c, 64 c + 64)
+          // ---- the column's tall A block: rows m0 + r_min .. + a_rows, columns [64 c, 64 c + 64)
           mbar_wait(a_empty(abuf), aphase ^ 1u);
           const uint32_t ab = base + (uint32_t)abuf * S::A_BUF;
-          mbar_expect_tx_remote(a_full(abuf), 0, S::A_BUF);
-          tma_load_3d_2sm(ab, &tm_a, a_full(abuf), c * BK, m0 + r_min, 0);
-          tma_load_3d_2sm(ab + S::A_PLANE, &tm_a, a_full(abuf), c * BK, m0 + r_min, 1);
+          mbar_expect_tx_remote(a_full(abuf), 0, 2u * (uint32_t)plan.a_rows * BK * 2u);
+          tma_load_4d_2sm(ab, &tm_a, a_full(abuf), c * BK, ph, m0 + r_min, 0);
+          tma_load_4d_2sm(ab + S::A_PLANE, &tm_a, a_full(abuf), c * BK, ph, m0 + r_min, 1);
           if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
           // ---- the basis rows of every K block of this column
           for (int i = 0; i < r_cnt; ++i) {
@@ -180,7 +184,8 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
       int stage = 0, abuf = 0, acc = 0;
       uint32_t phase = 0, aphase = 0, acc_phase = 0;
-      for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+      const int total_tiles = p.num_m_tiles * p.n_phases;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
         for (int ci = 0; ci < plan.n_cols; ++ci) {
           const int c = plan.col[ci], r_min = plan.r_min[ci], r_cnt = plan.r_cnt[ci];
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -226,7 +231,9 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     float sre[TCT_GROUPS_PER_PART][8], sim[TCT_GROUPS_PER_PART][8];
-    for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
+    const int total_tiles = p.num_m_tiles * p.n_phases;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int ph = tile / p.num_m_tiles, m_tile = tile - ph * p.num_m_tiles;
 #pragma unroll
       for (int gi = 0; gi < TCT_GROUPS_PER_PART; ++gi)
 #pragma unroll
@@ -259,7 +266,7 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       // ---- final format, once per tile
       const int64_t g_row = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
       const int64_t b = g_row / p.t_slots;
-      const int64_t t = g_row - b * p.t_slots;
+      const int64_t t = (g_row - b * p.t_slots) * p.n_phases + ph;  // frame index in the output
       if (g_row < p.nv && t < p.T) {
         constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
         float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
@@ -287,26 +294,39 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// frame phases: hop < 64 runs as P = 64 / hop interleaved problems with 64-sample rows, phase p
+// reading the planes p * hop samples further on (16-byte aligned for hop >= 8)
+static int tall_phases(int hop) { return hop >= 64 ? 1 : 64 / hop; }
+
 bool tc_tall_problem_ok(const FramedProblem& q) {
-  if (q.hop % 64 != 0 || q.hop / 64 > TCT_MAX_COLS) return false;
+  if (q.hop >= 64) {
+    if (q.hop % 64 != 0 || q.hop / 64 > TCT_MAX_COLS) return false;
+  } else if (q.hop < 8 || 64 % q.hop != 0) {
+    return false;
+  }
   if (q.F > 8 * 2 * TCT_GROUPS_PER_PART || q.K > 64 * TCT_MAX_KB) return false;
-  if (q.presplit != nullptr || q.bin_offset != 0 || q.out_bins != q.F) return false;
-  if (q.h_k_begin == nullptr || q.h_k_end == nullptr) return false;
+  if (q.presplit != nullptr && q.presplit_t_slots <= 0) return false;  // needs the explicit geometry
+  if (q.presplit == nullptr && q.hop < 64) return false;               // phases only on shared planes
   return q.fmt == NNAB_FMT_MAGNITUDE || q.fmt == NNAB_FMT_COMPLEX || q.fmt == NNAB_FMT_PHASE_UNIT;
 }
 
 // Returns NNAB_EUNSUPPORTED when the bank does not fit the tall layout (caller falls back).
 static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
-  const int hb = q.hop / 64;
+  const int hop_eff = q.hop >= 64 ? q.hop : 64;
+  const int hb = hop_eff / 64;
   const int nkb = (q.K + 63) / 64;
   memset(plan, 0, sizeof(*plan));
   plan->hb = hb;
   int kb_lo = nkb, kb_hi = -1;
   for (int kb = 0; kb < nkb; ++kb) {
     int gmax = 0;
-    for (int f = 0; f < q.F; ++f) {
-      const int lo = q.h_k_begin[f], hi = q.h_k_end[f];
-      if (hi > lo && hi > kb * 64 && lo < kb * 64 + 64) gmax = gmax > f / 8 + 1 ? gmax : f / 8 + 1;
+    if (q.h_k_begin == nullptr || q.h_k_end == nullptr) {
+      gmax = (q.F + 7) / 8;  // no support information: every block reaches every bin
+    } else {
+      for (int f = 0; f < q.F; ++f) {
+        const int lo = q.h_k_begin[f], hi = q.h_k_end[f];
+        if (hi > lo && hi > kb * 64 && lo < kb * 64 + 64) gmax = gmax > f / 8 + 1 ? gmax : f / 8 + 1;
+      }
     }
     plan->groups[kb] = (uint8_t)gmax;
     if (gmax > 0) { kb_lo = kb < kb_lo ? kb : kb_lo; kb_hi = kb; }
@@ -315,12 +335,13 @@ static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
   // inactive blocks inside the active interval (a gap in every wavelet) still get the narrowest MMA
   for (int kb = kb_lo; kb <= kb_hi; ++kb)
     if (plan->groups[kb] == 0) plan->groups[kb] = 1;
-  int n = 0;
+  int n = 0, span = 1;
   for (int c = 0; c < hb; ++c) {
     const int r_lo = (kb_lo - c + hb - 1) / hb > 0 ? (kb_lo - c + hb - 1) / hb : 0;
     const int r_hi = (kb_hi - c) >= 0 ? (kb_hi - c) / hb : -1;
     if (r_hi < r_lo) continue;
     if (r_hi - r_lo + 1 > 64) return NNAB_EUNSUPPORTED;  // A block rows: 128 + 63
+    span = r_hi - r_lo + 1 > span ? r_hi - r_lo + 1 : span;
     int best = r_lo;
     for (int r = r_lo; r <= r_hi; ++r)
       if (plan->groups[r * hb + c] > plan->groups[best * hb + c]) best = r;
@@ -332,6 +353,7 @@ static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
     ++n;
   }
   plan->n_cols = n;
+  plan->a_rows = round_up_i(128 + span - 1, 8);
   return n > 0 ? NNAB_OK : NNAB_EUNSUPPORTED;
 }
 
@@ -376,17 +398,32 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
   TallPlan plan;
   int rc = build_tall_plan(q, &plan);
   if (rc) return rc;
-  const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
-  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
   if (q.B > 65535) return NNAB_EUNSUPPORTED;
-  const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+  const int P = tall_phases(q.hop);
+  const int hop_eff = q.hop >= 64 ? q.hop : 64;
   const int kpad = round_up_i(q.K, 64);
   const int rows_w = 16 * ((q.F + 7) / 8);
-  __nv_bfloat16* planes =
-      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  rc = tc_pad_split(q.x, q.B, q.L, q.x_pitch, q.K, q.hop, q.pad, q.pad_mode, planes, stream);
-  if (rc) return rc;
-
+  __nv_bfloat16* planes;
+  int64_t t_slots, nv, plane_stride;
+  if (q.presplit != nullptr) {
+    // caller-managed planes (pyramid levels): clip slot = presplit_t_slots frames of `hop` samples
+    planes = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(q.presplit));
+    const int64_t pitch = q.presplit_t_slots * q.hop;
+    if (pitch % hop_eff != 0) return NNAB_EUNSUPPORTED;
+    t_slots = pitch / hop_eff;  // frames of ONE phase per clip slot
+    plane_stride = q.presplit_plane_stride;
+  } else {
+    const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
+    if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+    const SplitGeom g = split_geom(q.B, q.L, q.K, q.hop, q.pad);
+    planes = reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    rc = tc_pad_split(q.x, q.B, q.L, q.x_pitch, q.K, q.hop, q.pad, q.pad_mode, planes, stream);
+    if (rc) return rc;
+    t_slots = g.t_slots;
+    plane_stride = g.plane_stride;
+  }
+  nv = q.B * t_slots;
+  // frames of a phase that exist: ceil((T - p) / P) <= t_slots by construction of the planes
   int dev = 0, sms = 148;
   NNAB_CUDA_TRY(cudaGetDevice(&dev));
   NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -394,10 +431,16 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
   if (sms < 2) sms = 2;
 
   CUtensorMap ma, mb8, mb32;
-  // A: (rows x hop) view of a plane; one box = 192 rows x 64 columns (rows past the end: zero fill)
-  rc = encode_3d(&ma, planes, (uint64_t)q.hop, (uint64_t)g.rows, 2, (uint64_t)q.hop * 2,
-                 (uint64_t)g.plane_stride * 2, 64, TCT_A_ROWS, 64);
-  if (rc) return rc;
+  {
+    // A: {column within a row, frame phase, row, plane}; rows past the end: zero fill
+    const int64_t rows = (plane_stride - (int64_t)(P - 1) * q.hop) / hop_eff;
+    const uint64_t dims[4] = {(uint64_t)hop_eff, (uint64_t)P, (uint64_t)rows, 2};
+    const uint64_t strides[3] = {(uint64_t)(P > 1 ? q.hop : hop_eff) * 2, (uint64_t)hop_eff * 2,
+                                 (uint64_t)plane_stride * 2};
+    const uint32_t box[3] = {64, 1, (uint32_t)plan.a_rows};
+    rc = encode_4d(&ma, planes, dims, strides, box);
+    if (rc) return NNAB_EUNSUPPORTED;  // (e.g. a driver that rejects the overlapping phase stride)
+  }
   if ((rc = encode_3d(&mb8, const_cast<void*>(packed), (uint64_t)kpad, (uint64_t)rows_w, 2,
                       (uint64_t)kpad * 2, (uint64_t)rows_w * kpad * 2, 64, 8, 64)))
     return rc;
@@ -406,18 +449,20 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
     return rc;
 
   TctParams prm{};
-  prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
-  prm.nv = g.nv;
-  prm.t_slots = g.t_slots;
+  prm.num_m_tiles = (int)ceil_div64(nv, 2 * TC_BM);
+  prm.n_phases = P;
+  prm.nv = nv;
+  prm.t_slots = t_slots;
   prm.T = q.T;
   prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
   prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
   prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
-  const int n_pairs = prm.num_m_tiles < sms / 2 ? prm.num_m_tiles : sms / 2;
+  const int64_t tiles = (int64_t)prm.num_m_tiles * P;
+  const int n_pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
   {
     double cols = 0.0;
     for (int kb = 0; kb < TCT_MAX_KB; ++kb) cols += 16.0 * plan.groups[kb] * 64.0;
-    add_exec_flops(3.0 * 2.0 * (double)prm.num_m_tiles * (2 * TC_BM) * cols);
+    add_exec_flops(3.0 * 2.0 * (double)tiles * (2 * TC_BM) * cols);
   }
   switch (q.fmt) {
     case NNAB_FMT_MAGNITUDE: return launch_tc2t_fmt<0>(ma, mb8, mb32, prm, plan, n_pairs, stream);
@@ -426,7 +471,6 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
     default: return NNAB_EINVAL;
   }
 }
-
 
 // ===========================================================================
 // FIR decimator stage of the CQT pyramid (utils.py:73-124: conv1d(x, lowpass(256), stride=2,
@@ -618,18 +662,23 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 __global__ void __launch_bounds__(128) fir_edge_fix_kernel(
     const __nv_bfloat16* __restrict__ src, int64_t src_pitch, int64_t src_plane, int src_off,
     int64_t len_src, const float* __restrict__ fir, int taps, DecimParams d) {
-  const int64_t b = blockIdx.x;
-  const int i = threadIdx.x;  // 0..63: head outputs, 64..127: tail outputs
-  int64_t n = (i < 64) ? i : d.len_out - 128 + i;
+  // one warp per output (taps strided over the lanes, shuffle reduction): grid (32, B), 4 warps each
+  const int64_t b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);  // 0..63: head outputs, 64..127: tail outputs
+  const int64_t n = (i < 64) ? i : d.len_out - 128 + i;
   if (i >= 64 && n < 64) return;  // short clip: the head half already covers it
   if (n < 0 || n >= d.len_out) return;
   const __nv_bfloat16* sb = src + b * src_pitch + src_off;
   float acc = 0.f;
-  for (int m = 0; m < taps; ++m) {
+  for (int m = lane; m < taps; m += 32) {
     const int64_t j = 2 * n + m - (taps - 1) / 2;
     if (j >= 0 && j < len_src)
       acc = fmaf(__ldg(fir + m), __bfloat162float(sb[j]) + __bfloat162float(sb[src_plane + j]), acc);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane != 0) return;
   __nv_bfloat16 hi, lo;
   split_bf16(acc, hi, lo);
   if (d.pc != nullptr) {
@@ -705,7 +754,7 @@ int launch_fir_stage_tc(const void* src_planes, int64_t B, int64_t src_len, int6
   count_launch();
   add_exec_flops(3.0 * 2.0 * (double)prm.num_m_tiles * (2 * TC_BM) * 128.0 * 512.0);
   // clip edges
-  fir_edge_fix_kernel<<<(unsigned)B, 128, 0, stream>>>(
+  fir_edge_fix_kernel<<<dim3(32, (unsigned)B), 128, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(src_planes), src_pitch, src_plane_stride, src_pad, src_len,
       fir, taps, dec);
   NNAB_LAUNCH_CHECK();
