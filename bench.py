@@ -368,6 +368,7 @@ def _run():
     ap.add_argument("--workload-steps", type=int, default=10)
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's cuDNN leg")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=900, help="seconds after which a stuck run is aborted")
     ap.add_argument("--e2e-copy-streams", type=int, default=1)
     ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "symm", "peer"],
                     help="peer = kernels write into symmetric memory, copy-engine pushes, stream-memop "
@@ -383,6 +384,11 @@ def _run():
     if args.warmup < 3:
         args.warmup = 3
 
+    if args.impl == "ours":
+        # a wedged device-side handshake must end the run, not sit on the box until the driver's limit
+        import faulthandler
+
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -544,6 +550,12 @@ def _run():
                 prev = work
             if prev is not None:
                 prev.wait()
+                # the last step's slot must be handed back too: the next run_steps() reuses it
+                if gather and world > 1:
+                    if gather_impl == "peer":
+                        sharded.release_peer((n - 1) & 1, None if args.gather_to == "all" else [0])
+                    elif gather_impl == "symm":
+                        sharded.release((n - 1) & 1)
             return y
 
         with torch.no_grad():

@@ -712,8 +712,11 @@ static int pyramid_fused2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
   int max_w = 0;
   for (int i = 0; i < n_octaves; ++i) max_w = lv[i].width > max_w ? lv[i].width : max_w;
   const size_t vpack_stride = align_up((size_t)768 * ((max_w + 63) / 64 * 64), 256);
+  // Measured at cfg4 (B200): octaves on the tall kernel 1.84 ms/step vs 1.70 ms with the dense kernel --
+  // with N = 32 the octave MMAs are bound by their own A reads either way and the frame-phase tiles
+  // add launches' worth of ramp; kept as an experiment (NNAB_PYR_TALL=1).
   const bool use_tall = n_filters <= 96 && need + 512 + vpack_stride * n_octaves <= ws_bytes &&
-                        !(getenv("NNAB_TALL") != nullptr && atoi(getenv("NNAB_TALL")) == 0);
+                        getenv("NNAB_PYR_TALL") != nullptr && atoi(getenv("NNAB_PYR_TALL")) == 1;
   char* vpack_base = ws + align_up(need, 256);
   bool vpack_done0 = false;
   const size_t scratch_bytes = (use_tall ? (size_t)(vpack_base - ws) : ws_bytes - 256) - scratch_off;

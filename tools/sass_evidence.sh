@@ -17,5 +17,5 @@ cuobjdump -sass "$LIB" | awk '
   }' | sort
 echo
 echo "# registers / stack per tensor-core kernel (cuobjdump -res-usage; dynamic smem is set at launch: 197.9 KB)"
-cuobjdump -res-usage "$LIB" 2>/dev/null | grep -A1 "Function _ZN4nnab1[67]framed_tc" | grep -v "^--" | paste - - \
-  | sed -E 's/.*Function (_ZN4nnab1[67]framed_tc2?_kernelILi[0-9]+ELi[0-9]+ELi[0-9]+E)[^:]*:\s*/\1  /; s/ SHARED.*//' | sort
+cuobjdump -res-usage "$LIB" 2>/dev/null | grep -A1 -E "Function _ZN4nnab(1[6-9]framed_tc|13fir_tc_kernel)" | grep -v "^--" | paste - - \
+  | sed -E 's/.*Function (_ZN4nnab[0-9]+[a-z_0-9]+(ILi[0-9]+E?(Li[0-9]+E?)*E)?)[^:]*:\s*/\1  /; s/ SHARED.*//' | sort
