@@ -466,7 +466,7 @@ class _DecimateFn(torch.autograd.Function):
         gp = torch.nn.functional.pad(g.contiguous(), (Q - 1, max(M - T, 0)))[:, : M + Q - 1]
         # hop 1: CUDA-core kernel by default; NNAUDIO_B200_DECIM_BWD=tc runs the 8 frame phases
         # of the tensor-core kernel instead
-        use_tc = packed is not None and os.environ.get("NNAUDIO_B200_DECIM_BWD", "simt") == "tc"
+        use_tc = packed is not None and os.environ.get("NNAUDIO_B200_DECIM_BWD", "fir") == "tc"
         c = _C.cqt1992v2_forward(gp.contiguous(), poly, poly_zero, packed if use_tc else None, None,
                                  None, 1, False, _C.PAD_CONSTANT, None, 1.0, _C.FMT_COMPLEX, 0.0,
                                  path="tcgen05" if use_tc else "simt")
@@ -475,7 +475,7 @@ class _DecimateFn(torch.autograd.Function):
 
 
 class _FirDecimateFn(torch.autograd.Function):
-    """``nnab_fir_decimate`` / ``nnab_fir_decimate_adjoint`` (EXPERIMENTAL, branch radix2-wip)."""
+    """``nnab_fir_decimate`` / ``nnab_fir_decimate_adjoint``: one launch each way (GPU-verified round 2)."""
 
     @staticmethod
     def forward(ctx, sig, fir, n):
@@ -490,17 +490,17 @@ class _FirDecimateFn(torch.autograd.Function):
 def _decimate_autograd(mod, tag, sig, fir, n):
     """Differentiable ``downsampling_by_n`` / ``_by_2`` stage of the training path.
 
-    ``NNAUDIO_B200_DECIM_BWD`` picks the adjoint (round-1 measurements, CQT2010v2 32 x 30 s forward +
-    backward, worst dX error of the pyramid cases vs the reference's autograd):
-    ``simt`` (default) polyphase FIRs on the CUDA-core kernel — 42.0 ms, 6.1e-5 (2.2e-5 on the
-    Magnitude case); ``tc`` the same on the tensor-core kernel (8 frame phases) — 30.1 ms, 6.1e-5;
-    ``ola`` a K=1 adjoint GEMM + overlap-add atomics (256 atomics per input sample) — 24.4 ms but
-    1.04e-4 on the Magnitude case, i.e. over the parity bar.  A dedicated FIR-adjoint kernel is
-    the open item."""
-    if os.environ.get("NNAUDIO_B200_DECIM_BWD", "simt") == "fir":
-        # EXPERIMENTAL (radix2-wip): dedicated CUDA-core FIR stage and adjoint, one launch each
+    ``NNAUDIO_B200_DECIM_BWD`` picks the adjoint (CQT2010v2 32 x 30 s forward + backward, worst dX error
+    of the pyramid cases vs the reference's autograd):
+    ``fir`` (default since round 2) the dedicated CUDA-core FIR stage + adjoint kernel
+    (``nnab_fir_decimate`` / ``nnab_fir_decimate_adjoint``: every input sample written once, no
+    atomics) -- 2.96 ms, within the 1e-4 bar on every pyramid gradient case;
+    ``simt`` polyphase FIRs on the framed CUDA-core kernel -- 42.0 ms, 6.1e-5; ``tc`` the same on the
+    tensor-core kernel (8 frame phases) -- 30.1 ms, 6.1e-5; ``ola`` a K=1 adjoint GEMM + overlap-add
+    atomics (256 atomics per input sample) -- 24.4 ms but 1.04e-4 on the Magnitude case, over the bar."""
+    if os.environ.get("NNAUDIO_B200_DECIM_BWD", "fir") == "fir":
         return _FirDecimateFn.apply(sig, fir.detach().reshape(-1).contiguous(), int(n))
-    if os.environ.get("NNAUDIO_B200_DECIM_BWD", "simt") == "ola":
+    if os.environ.get("NNAUDIO_B200_DECIM_BWD", "fir") == "ola":
         taps = fir.numel()
         w_re = fir.detach().reshape(1, taps)
         zeros = mod.__dict__.setdefault("_fir_zeros", {})
