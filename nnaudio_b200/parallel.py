@@ -210,7 +210,7 @@ class BatchShardedTransform:
                 buf=buf, flags=flags,
                 bufs=[hdl.get_buffer(r, shape, dtype) for r in range(world)],
                 flag_ptr=[fh.get_buffer(r, (2, 2, world), torch.int32).data_ptr() for r in range(world)],
-                streams=[torch.cuda.Stream(device) for _ in range(2)],
+                streams=[torch.cuda.Stream(device) for _ in range(4)],
                 use=[0, 0], pushed=[None, None], handles=(hdl, fh))
             self._peer_key = key
         return self._peer
@@ -281,26 +281,40 @@ class BatchShardedTransform:
         ev_y.record(cur)
         targets = [d for d in dests if d != me]
         if targets:
-            s0, s1 = st["streams"]
-            evs = []
-            for i, d in enumerate(targets):
-                s = s0 if (i & 1) == 0 else s1   # two copy engines drive the NVLink ports together
+            streams = st["streams"]
+            # several copy engines per push: a shard goes out as row chunks on different streams
+            # (one destination: 4 chunks; many destinations: the destinations themselves spread over
+            # the streams)
+            n_chunks = max(1, min(len(streams) // len(targets), n))
+            jobs = []
+            for d in targets:
+                for c in range(n_chunks):
+                    r0, r1 = lo + (n * c) // n_chunks, lo + (n * (c + 1)) // n_chunks
+                    jobs.append((d, r0, r1, c == n_chunks - 1))
+            used = set()
+            pending = {d: [] for d in targets}
+            for i, (d, r0, r1, last) in enumerate(jobs):
+                s = streams[i % len(streams)]
                 with torch.cuda.stream(s):
-                    if i < 2:
+                    if id(s) not in used:
                         s.wait_event(ev_y)
+                        used.add(id(s))
                     # destination d has consumed the previous use of this slot
                     _C.stream_wait_value32_geq(
                         s, st["flag_ptr"][me] + 4 * ((slot * 2 + 1) * world + d), use - 1)
-                    st["bufs"][d][slot, lo:lo + n].copy_(mine, non_blocking=True)
-                    _C.stream_write_value32(
-                        s, st["flag_ptr"][d] + 4 * ((slot * 2 + 0) * world + me), use)
-            for s in (s0, s1):
-                ev = torch.cuda.Event()
-                ev.record(s)
-                evs.append(ev)
-            done = torch.cuda.Event()
+                    st["bufs"][d][slot, r0:r1].copy_(st["buf"][slot, r0:r1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+                    pending[d].append(ev)
+            # "landed" flag of destination d: after ALL of its chunks (any stream)
+            s0 = streams[0]
             with torch.cuda.stream(s0):
-                s0.wait_event(evs[1])
+                for d in targets:
+                    for ev in pending[d]:
+                        s0.wait_event(ev)
+                    _C.stream_write_value32(
+                        s0, st["flag_ptr"][d] + 4 * ((slot * 2 + 0) * world + me), use)
+                done = torch.cuda.Event()
                 done.record(s0)
             st["pushed"][slot] = done
         sources = list(range(world)) if me in dests else []
