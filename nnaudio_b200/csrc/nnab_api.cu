@@ -584,14 +584,14 @@ static bool plan_pyramid2(int64_t B, int64_t L, int n_octaves, int hop, const in
     l.planes = l.presplit || fir_src;
     l.pc = l.y32 = SIZE_MAX;
     l.pitch = l.plane = l.t_slots = l.y32_pitch = 0;
-    if (fir_src && (l.pad < 128 || (l.pad - 128) % 64 != 0 || (l.pad - 128) / 64 > 24)) return false;
+    if (fir_src && l.pad != 128) return false;  // FIR frame origin = CQT padding origin (256-tap banks)
     if (l.planes) {
       const int he = l.presplit ? cur_hop : 8;  // planes of multi-phase levels only feed the FIR
       const int kpad = (l.width + 63) / 64 * 64;
       int64_t need = len + 2 * (int64_t)l.pad + kpad;
       if (fir_src) {
         const int64_t FT = (decimated_len(len, 2) + 127) / 128;
-        const int64_t rows = FT + 1 + (7 + (l.pad - 128) / 64) / 4;
+        const int64_t rows = FT + 2;
         if (256 * rows > need) need = 256 * rows;
       }
       const int64_t gran = (int64_t)he / gcd64(he, 256) * 256;  // lcm(he, 256)

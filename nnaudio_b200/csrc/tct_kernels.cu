@@ -484,29 +484,34 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
 //     the first / last 64 outputs of a clip see the margins, and fir_edge_fix_kernel recomputes
 //     those (plus their mirror copies) afterwards.  One write + one read of 4 B per sample and level
 //     instead of two differently padded copies.
-//   * the 128 x 512 tap matrix (128 KB as hi / lo halves per CTA of the pair) stays in shared memory
-//     for the whole persistent kernel; per tile only the signal moves.
 //   * the signal is read through tall A blocks (see framed_tc2t_kernel): with 256-sample rows, K block
-//     kb' = kb + off64 is column kb' % 4 of row t + kb' / 4, so 4 blocks of (128 + r_max) rows x 64
-//     columns feed all 8 K blocks.  off64 = (pad - 128) / 64 aligns the CQT's padding origin.
+//     kb is column kb % 4 of row t + kb / 4, so 4 blocks of 129 rows x 64 columns feed all 8 K blocks
+//     (pad = 128, i.e. 256-tap octave banks: the CQT's padding origin is the FIR frame origin).
+//   * a 3-stage ring of (column block + its two tap blocks); the taps (256 KB) stream from L2.
 // ===========================================================================
 constexpr int FIR_KBLOCKS = 8;
-constexpr int FIR_A_ROWS = 136;   // 128 frames + up to 8 row shifts
+constexpr int FIR_A_ROWS = 136;   // 128 frames + row shifts 0 / 1 (multiple of 8)
 constexpr int FIR_THREADS = 128 + 32 * 8;
+constexpr int FIR_STAGES = 3;
 
+// One pipeline stage = one column block c of the 256-sample rows: the tall A block (136 rows x 64,
+// hi + lo) plus this CTA's 64 tap rows of the two K blocks the column feeds (kb = c at shift 0 and
+// kb = c + 4 at shift 1), hi + lo.  66 KB; three stages keep two column loads in flight while the
+// MMAs of a third run -- the first version kept the whole tap matrix resident (128 KB) and had room
+// for only two A buffers: one load in flight, tensor pipe 50 % active on HBM-sourced levels
+// (profiles/r02_ncu_cfg4_fir.txt).  The taps come from L2 (256 KB in total).
 struct FirSmem {
-  static constexpr uint32_t B_KB = 64 * TCT_BK * 2;            // one K block, one plane, this CTA's 64 rows
-  static constexpr uint32_t B_RES = 2 * FIR_KBLOCKS * B_KB;    // hi + lo, 8 K blocks = 128 KB
-  static constexpr uint32_t A_PLANE = FIR_A_ROWS * TCT_BK * 2; // 17 KB
-  static constexpr uint32_t A_BUF = 2 * A_PLANE;
-  static constexpr uint32_t A_OFFSET = B_RES;
-  static constexpr uint32_t BAR_OFFSET = A_OFFSET + 2 * A_BUF;
+  static constexpr uint32_t A_PLANE = FIR_A_ROWS * TCT_BK * 2;   // 17 KB
+  static constexpr uint32_t B_KB = 64 * TCT_BK * 2;              // one K block, one plane: 8 KB
+  static constexpr uint32_t A_OFF = 0;
+  static constexpr uint32_t B_OFF = 2 * A_PLANE;                 // [kb slot 0 hi][slot 0 lo][slot 1 hi][slot 1 lo]
+  static constexpr uint32_t STAGE = 2 * A_PLANE + 4 * B_KB;      // 66 KB
+  static constexpr uint32_t BAR_OFFSET = FIR_STAGES * STAGE;
   static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
 struct FirParams {
   int num_m_tiles;       // 256-frame pair tiles over the virtual frames b * t_slots + t
-  int off64;             // (source pad - 128) / 64
   int64_t nv, t_slots, FT;  // frames: virtual total, per clip slot, valid per clip
   DecimParams dec;
 };
@@ -514,17 +519,16 @@ struct FirParams {
 __global__ void __launch_bounds__(FIR_THREADS, 1)
 fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
               const FirParams p) {
-  constexpr int BK = TCT_BK;
+  constexpr int BK = TCT_BK, ST = FIR_STAGES;
   using S = FirSmem;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + S::BAR_OFFSET;
-  const uint32_t b_full = bar_base;                                       // leader
-  auto a_full = [&](int a) { return bar_base + 8u * (1 + a); };            // leader
-  auto a_empty = [&](int a) { return bar_base + 8u * (3 + a); };           // per CTA
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (5 + a); };         // per CTA
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (7 + a); };        // leader
-  const uint32_t tmem_slot = bar_base + 8u * 9;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                // leader
+  auto empty_bar = [&](int s) { return bar_base + 8u * (ST + s); };         // per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * ST + a); };     // per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * ST + 2 + a); };  // leader
+  const uint32_t tmem_slot = bar_base + 8u * (2 * ST + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -539,10 +543,11 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     prefetch_tmap(&tm_b);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(b_full, 2);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(a_full(a), 2);
-      mbar_init(a_empty(a), 1);
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 2 * 8);
     }
@@ -558,29 +563,27 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // K block kb reads column (kb + off64) % 4 at row shift (kb + off64) / 4
-  const int r_max = (FIR_KBLOCKS - 1 + p.off64) / 4;
-
   if (warp == 0) {
     if (elect_one()) {
-      // resident taps: this CTA's 64 rows of every K block, hi then lo
-      mbar_expect_tx_remote(b_full, 0, S::B_RES);
-      for (int kb = 0; kb < FIR_KBLOCKS; ++kb) {
-        tma_load_3d_2sm(base + (uint32_t)kb * S::B_KB, &tm_b, b_full, kb * BK, (int)cta * 64, 0);
-        tma_load_3d_2sm(base + (uint32_t)(FIR_KBLOCKS + kb) * S::B_KB, &tm_b, b_full, kb * BK,
-                        (int)cta * 64, 1);
-      }
-      int abuf = 0;
-      uint32_t aphase = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
         for (int c = 0; c < 4; ++c) {
-          mbar_wait(a_empty(abuf), aphase ^ 1u);
-          const uint32_t ab = base + S::A_OFFSET + (uint32_t)abuf * S::A_BUF;
-          mbar_expect_tx_remote(a_full(abuf), 0, S::A_BUF);
-          tma_load_3d_2sm(ab, &tm_a, a_full(abuf), c * BK, m0, 0);
-          tma_load_3d_2sm(ab + S::A_PLANE, &tm_a, a_full(abuf), c * BK, m0, 1);
-          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sb = base + (uint32_t)stage * S::STAGE;
+          mbar_expect_tx_remote(full_bar(stage), 0, S::STAGE);
+          tma_load_3d_2sm(sb + S::A_OFF, &tm_a, full_bar(stage), c * BK, m0, 0);
+          tma_load_3d_2sm(sb + S::A_OFF + S::A_PLANE, &tm_a, full_bar(stage), c * BK, m0, 1);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {  // this CTA's 64 tap rows of K blocks c and c + 4
+            const int kb = 4 * r + c;
+            tma_load_3d_2sm(sb + S::B_OFF + (uint32_t)(2 * r) * S::B_KB, &tm_b, full_bar(stage), kb * BK,
+                            (int)cta * 64, 0);
+            tma_load_3d_2sm(sb + S::B_OFF + (uint32_t)(2 * r + 1) * S::B_KB, &tm_b, full_bar(stage), kb * BK,
+                            (int)cta * 64, 1);
+          }
+          if (++stage == ST) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -588,28 +591,26 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     if (cta == 0 && elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) |
                              ((uint32_t)((2 * TC_BM) >> 4) << 24);
-      mbar_wait(b_full, 0);
-      int abuf = 0, acc = 0;
-      uint32_t aphase = 0, acc_phase = 0;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
       for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
         uint32_t accumulate = 0;
         for (int c = 0; c < 4; ++c) {
-          mbar_wait(a_full(abuf), aphase);
+          mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t ab = base + S::A_OFFSET + (uint32_t)abuf * S::A_BUF;
-          for (int r = 0; r <= r_max; ++r) {
-            const int kb = 4 * r + c - p.off64;
-            if (kb < 0 || kb >= FIR_KBLOCKS) continue;
-            const uint32_t a_row = (uint32_t)r * (BK * 2);
-            const uint32_t bh = base + (uint32_t)kb * S::B_KB, bl = base + (uint32_t)(FIR_KBLOCKS + kb) * S::B_KB;
+          const uint32_t sb = base + (uint32_t)stage * S::STAGE;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t a_row = (uint32_t)r * (BK * 2);  // frame t reads row t + r
+            const uint32_t bh = sb + S::B_OFF + (uint32_t)(2 * r) * S::B_KB, bl = bh + S::B_KB;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint32_t koff = (uint32_t)k * 32u;
-              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
-              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
+              const uint64_t a_hi = make_smem_desc<BK>(sb + S::A_OFF + a_row + koff);
+              const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_OFF + S::A_PLANE + a_row + koff);
               const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
               const uint64_t b_lo = make_smem_desc<BK>(bl + koff);
               umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
@@ -618,8 +619,8 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
               accumulate = 1u;
             }
           }
-          umma_commit_2sm(a_empty(abuf));
-          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == ST) { stage = 0; phase ^= 1u; }
         }
         umma_commit_2sm(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -700,13 +701,11 @@ __global__ void __launch_bounds__(128) fir_edge_fix_kernel(
 int launch_fir_stage_tc(const void* src_planes, int64_t B, int64_t src_len, int64_t src_pitch,
                         int64_t src_plane_stride, int src_pad, const void* fir_packed,
                         const float* fir, int taps, const DecimParams& dec, cudaStream_t stream) {
-  if (taps != 256 || src_pad < 128 || (src_pad - 128) % 64 != 0 || (src_pad - 128) / 64 > 24)
-    return NNAB_EUNSUPPORTED;
+  if (taps != 256 || src_pad != 128) return NNAB_EUNSUPPORTED;  // frame origin = row origin
   if (src_pitch % 256 != 0 || B > 65535 || dec.pf != nullptr) return NNAB_EUNSUPPORTED;
-  const int off64 = (src_pad - 128) / 64;
   const int64_t FT = (dec.len_out + 127) / 128;
   const int64_t t_slots = src_pitch / 256;
-  if (256 * (FT + 1 + (7 + off64) / 4) > src_pitch + 256) return NNAB_EUNSUPPORTED;  // last frame's rows
+  if (256 * (FT + 2) > src_pitch + 256) return NNAB_EUNSUPPORTED;  // last frame's rows
   int dev = 0, sms = 148;
   NNAB_CUDA_TRY(cudaGetDevice(&dev));
   NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -726,7 +725,6 @@ int launch_fir_stage_tc(const void* src_planes, int64_t B, int64_t src_len, int6
   prm.nv = B * t_slots;
   prm.t_slots = t_slots;
   prm.FT = FT;
-  prm.off64 = off64;
   prm.num_m_tiles = (int)ceil_div64(prm.nv, 2 * TC_BM);
   prm.dec = dec;
   const int n_pairs = prm.num_m_tiles < sms / 2 ? prm.num_m_tiles : sms / 2;
