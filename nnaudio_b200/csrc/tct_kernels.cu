@@ -494,19 +494,29 @@ constexpr int FIR_A_ROWS = 136;   // 128 frames + row shifts 0 / 1 (multiple of 
 constexpr int FIR_THREADS = 128 + 32 * 8;
 constexpr int FIR_STAGES = 3;
 
-// One pipeline stage = one column block c of the 256-sample rows: the tall A block (136 rows x 64,
-// hi + lo) plus this CTA's 64 tap rows of the two K blocks the column feeds (kb = c at shift 0 and
-// kb = c + 4 at shift 1), hi + lo.  66 KB; three stages keep two column loads in flight while the
-// MMAs of a third run -- the first version kept the whole tap matrix resident (128 KB) and had room
-// for only two A buffers: one load in flight, tensor pipe 50 % active on HBM-sourced levels
-// (profiles/r02_ncu_cfg4_fir.txt).  The taps come from L2 (256 KB in total).
+// The tap matrix H[j][k] = fir[k - 1 - 2 j] is banded: K block kb (64 samples) meets only the outputs
+// j in [32 kb - 128, 32 kb + 32), i.e. the column ranges below (multiples of 32, 640 of 1024 column
+// blocks).  Each K block issues MMAs of exactly that width into TMEM columns [lo, lo + n): 37.5 % fewer
+// MMA flops, and each CTA of the pair keeps only its half of every range resident: 320 rows = 80 KB.
+__device__ __host__ __forceinline__ int fir_col_lo(int kb) { return kb <= 4 ? 0 : 32 * (kb - 4); }
+__device__ __host__ __forceinline__ int fir_col_n(int kb) { return kb < 4 ? 32 * (kb + 1) : 32 * (8 - kb); }
+// first row (of this CTA's 320) of K block kb: prefix sums of n / 2 = {16,32,48,64,64,48,32,16}
+__device__ __host__ __forceinline__ int fir_row0(int kb) {
+  const int pre[9] = {0, 16, 48, 96, 160, 224, 272, 304, 320};
+  return pre[kb];
+}
+
+// Shared memory: resident banded taps (hi 40 KB + lo 40 KB) + a 3-deep ring of tall A blocks (one
+// column block of the 256-sample rows: 136 rows x 64, hi + lo = 34 KB).  Two column loads stay in
+// flight while the MMAs of a third run; the first version kept the full tap matrix (128 KB), had room
+// for two A buffers only -- one load in flight -- and sat at 50 % tensor / 46 % DRAM
+// (profiles/r02_ncu_cfg4_fir.txt); streaming the taps per stage instead doubled the L2->SM bytes.
 struct FirSmem {
+  static constexpr uint32_t B_PLANE = 320 * TCT_BK * 2;          // 40 KB
   static constexpr uint32_t A_PLANE = FIR_A_ROWS * TCT_BK * 2;   // 17 KB
-  static constexpr uint32_t B_KB = 64 * TCT_BK * 2;              // one K block, one plane: 8 KB
-  static constexpr uint32_t A_OFF = 0;
-  static constexpr uint32_t B_OFF = 2 * A_PLANE;                 // [kb slot 0 hi][slot 0 lo][slot 1 hi][slot 1 lo]
-  static constexpr uint32_t STAGE = 2 * A_PLANE + 4 * B_KB;      // 66 KB
-  static constexpr uint32_t BAR_OFFSET = FIR_STAGES * STAGE;
+  static constexpr uint32_t A_BUF = 2 * A_PLANE;
+  static constexpr uint32_t A_OFFSET = 2 * B_PLANE;
+  static constexpr uint32_t BAR_OFFSET = A_OFFSET + FIR_STAGES * A_BUF;
   static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
@@ -524,11 +534,12 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + S::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };                // leader
-  auto empty_bar = [&](int s) { return bar_base + 8u * (ST + s); };         // per CTA
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * ST + a); };     // per CTA
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * ST + 2 + a); };  // leader
-  const uint32_t tmem_slot = bar_base + 8u * (2 * ST + 4);
+  const uint32_t b_full = bar_base;                                           // leader
+  auto full_bar = [&](int s) { return bar_base + 8u * (1 + s); };              // leader
+  auto empty_bar = [&](int s) { return bar_base + 8u * (1 + ST + s); };        // per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (1 + 2 * ST + a); };    // per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 + 2 * ST + a); };   // leader
+  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * ST);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -543,6 +554,7 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     prefetch_tmap(&tm_b);
   }
   if (warp == 1 && lane == 0) {
+    mbar_init(b_full, 2);
     for (int s = 0; s < ST; ++s) {
       mbar_init(full_bar(s), 2);
       mbar_init(empty_bar(s), 1);
@@ -565,54 +577,62 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 
   if (warp == 0) {
     if (elect_one()) {
+      // resident taps: for every K block this CTA's half of the block's column range, 16-row boxes
+      mbar_expect_tx_remote(b_full, 0, 2 * S::B_PLANE);
+      for (int kb = 0; kb < FIR_KBLOCKS; ++kb) {
+        const int half = fir_col_n(kb) / 2;
+        const int j0 = fir_col_lo(kb) + (int)cta * half;  // first tap row (= output j) this CTA stages
+        for (int q = 0; q < half; q += 16) {
+          const uint32_t dst = base + (uint32_t)(fir_row0(kb) + q) * (BK * 2);
+          tma_load_3d_2sm(dst, &tm_b, b_full, kb * BK, j0 + q, 0);
+          tma_load_3d_2sm(dst + S::B_PLANE, &tm_b, b_full, kb * BK, j0 + q, 1);
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
-        for (int c = 0; c < 4; ++c) {
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = (ci + 3) & 3;  // 3, 0, 1, 2: the tile's first MMA (kb = 3) is full width
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sb = base + (uint32_t)stage * S::STAGE;
-          mbar_expect_tx_remote(full_bar(stage), 0, S::STAGE);
-          tma_load_3d_2sm(sb + S::A_OFF, &tm_a, full_bar(stage), c * BK, m0, 0);
-          tma_load_3d_2sm(sb + S::A_OFF + S::A_PLANE, &tm_a, full_bar(stage), c * BK, m0, 1);
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {  // this CTA's 64 tap rows of K blocks c and c + 4
-            const int kb = 4 * r + c;
-            tma_load_3d_2sm(sb + S::B_OFF + (uint32_t)(2 * r) * S::B_KB, &tm_b, full_bar(stage), kb * BK,
-                            (int)cta * 64, 0);
-            tma_load_3d_2sm(sb + S::B_OFF + (uint32_t)(2 * r + 1) * S::B_KB, &tm_b, full_bar(stage), kb * BK,
-                            (int)cta * 64, 1);
-          }
+          const uint32_t ab = base + S::A_OFFSET + (uint32_t)stage * S::A_BUF;
+          mbar_expect_tx_remote(full_bar(stage), 0, S::A_BUF);
+          tma_load_3d_2sm(ab, &tm_a, full_bar(stage), c * BK, m0, 0);
+          tma_load_3d_2sm(ab + S::A_PLANE, &tm_a, full_bar(stage), c * BK, m0, 1);
           if (++stage == ST) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     if (cta == 0 && elect_one()) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) |
-                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      mbar_wait(b_full, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int m_tile = pair; m_tile < p.num_m_tiles; m_tile += num_pairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
         uint32_t accumulate = 0;
-        for (int c = 0; c < 4; ++c) {
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = (ci + 3) & 3;
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t sb = base + (uint32_t)stage * S::STAGE;
+          const uint32_t ab = base + S::A_OFFSET + (uint32_t)stage * S::A_BUF;
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
-            const uint32_t a_row = (uint32_t)r * (BK * 2);  // frame t reads row t + r
-            const uint32_t bh = sb + S::B_OFF + (uint32_t)(2 * r) * S::B_KB, bl = bh + S::B_KB;
+            const int kb = 4 * r + c;  // frame t reads row t + r, column block c
+            const uint32_t idesc = idesc0 | ((uint32_t)(fir_col_n(kb) >> 3) << 17);
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u + (uint32_t)fir_col_lo(kb);
+            const uint32_t a_row = (uint32_t)r * (BK * 2);
+            const uint32_t bh = base + (uint32_t)fir_row0(kb) * (BK * 2), bl = bh + S::B_PLANE;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint32_t koff = (uint32_t)k * 32u;
-              const uint64_t a_hi = make_smem_desc<BK>(sb + S::A_OFF + a_row + koff);
-              const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_OFF + S::A_PLANE + a_row + koff);
+              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
+              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
               const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
               const uint64_t b_lo = make_smem_desc<BK>(bl + koff);
+              // kb = 3 (first of a tile) covers all 128 columns and starts the accumulation
               umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
               umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
               umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
@@ -719,7 +739,7 @@ int launch_fir_stage_tc(const void* src_planes, int64_t B, int64_t src_len, int6
   const int kf = tc_fir_k(taps, 2);  // 512
   if (kf != 64 * FIR_KBLOCKS) return NNAB_EUNSUPPORTED;
   rc = encode_3d(&mb, const_cast<void*>(fir_packed), (uint64_t)kf, 128, 2, (uint64_t)kf * 2,
-                 (uint64_t)128 * kf * 2, 64, 64, 64);
+                 (uint64_t)128 * kf * 2, 64, 16, 64);
   if (rc) return rc;
   FirParams prm{};
   prm.nv = B * t_slots;
@@ -750,7 +770,7 @@ int launch_fir_stage_tc(const void* src_planes, int64_t B, int64_t src_len, int6
   cfg.numAttrs = 1;
   NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, fir_tc_kernel, ma, mb, prm));
   count_launch();
-  add_exec_flops(3.0 * 2.0 * (double)prm.num_m_tiles * (2 * TC_BM) * 128.0 * 512.0);
+  add_exec_flops(3.0 * 2.0 * (double)prm.num_m_tiles * (2 * TC_BM) * 640.0 * 64.0);  // banded: 640 columns x 64
   // clip edges
   fir_edge_fix_kernel<<<dim3(32, (unsigned)B), 128, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(src_planes), src_pitch, src_plane_stride, src_pad, src_len,
