@@ -773,6 +773,15 @@ static int pyramid_fused2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
           else if (rc != NNAB_EUNSUPPORTED) return rc;
         }
       }
+      if (!done) {
+        // resident bank + tall A blocks + frame phases: one fetch per sample and tile
+        std::pair<cudaEvent_t, cudaEvent_t> pr;
+        const bool timed = prof_begin(s, &pr);
+        rc = launch_octave_tc(p, h_packed[i], s);
+        if (timed) prof_end(s, pr);
+        if (rc == NNAB_OK) done = true;
+        else if (rc != NNAB_EUNSUPPORTED) return rc;
+      }
       if (!done && (rc = run_framed(p, h_packed[i], nullptr, 0, NNAB_PATH_TCGEN05, s))) return rc;
     } else {
       const float* src = (i == 0) ? x : (const float*)(ws + l.y32);

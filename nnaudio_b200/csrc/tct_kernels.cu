@@ -779,4 +779,291 @@ int launch_fir_stage_tc(const void* src_planes, int64_t B, int64_t src_len, int6
   return NNAB_OK;
 }
 
+
+// ===========================================================================
+// Octave CQT of the pyramid (utils.py:498-521 get_cqt_complex: conv1d(x, bank(<=16 bins, 256 taps), hop))
+// on the level planes it shares with fir_tc_kernel.  With N = 32 columns the contraction is not an MMA
+// problem but an operand-delivery problem: the dense kernel fetched 1 KB of A per frame from L2 (338 MB
+// per octave whatever the level, ~80 us each) and re-fetched the bank per tile.  Here
+//   * the bank (this CTA's 16 rows of every K block, hi + lo: <= 32 KB) is resident,
+//   * the signal comes through tall A blocks (framed_tc2t_kernel): rows of hop_eff = max(hop, 64)
+//     samples, K block kb = column kb % HB at row shift kb / HB, so a sample is fetched once per tile
+//     however much the frames overlap (HB = hop_eff / 64),
+//   * hop < 64 runs as P = 64 / hop interleaved frame phases through a 4-D tensor map (phase p reads
+//     the planes p * hop samples further on),
+//   * a 5-deep ring of column blocks keeps four loads in flight.
+// Packed bank = the DENSE layout of tc_kernels.cu with bn = 32: rows [0,16) re, [16,32) negated im.
+// ===========================================================================
+constexpr int OCT_STAGES = 5;
+constexpr int OCT_A_ROWS = 136;
+constexpr int OCT_MAX_KB = 8;
+constexpr int OCT_THREADS = 256;
+
+struct OctSmem {
+  static constexpr uint32_t B_KB = 16 * TCT_BK * 2;               // one K block, one plane, 16 rows: 2 KB
+  static constexpr uint32_t B_PLANE = OCT_MAX_KB * B_KB;          // 16 KB
+  static constexpr uint32_t A_PLANE = OCT_A_ROWS * TCT_BK * 2;    // 17 KB
+  static constexpr uint32_t A_BUF = 2 * A_PLANE;
+  static constexpr uint32_t A_OFFSET = 2 * B_PLANE;
+  static constexpr uint32_t BAR_OFFSET = A_OFFSET + OCT_STAGES * A_BUF;
+  static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+struct OctParams {
+  int num_m_tiles;        // 256-frame pair tiles per frame phase
+  int n_phases, hb, n_kb; // frame phases, column blocks per row, K blocks (K / 64)
+  int64_t nv, t_slots, T; // per phase: virtual frames, frames per clip slot; T = frames of the output
+  EpiParams epi;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(OCT_THREADS, 1)
+octave_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const OctParams p) {
+  constexpr int BK = TCT_BK, ST = OCT_STAGES;
+  using S = OctSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + S::BAR_OFFSET;
+  const uint32_t b_full = bar_base;
+  auto full_bar = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (1 + ST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (1 + 2 * ST + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 + 2 * ST + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * ST);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int total_tiles = p.num_m_tiles * p.n_phases;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(b_full, 2);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * 4);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 64);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx_remote(b_full, 0, 2u * (uint32_t)p.n_kb * S::B_KB);
+      for (int kb = 0; kb < p.n_kb; ++kb) {  // resident bank: rows [16 cta, +16) of every K block
+        tma_load_3d_2sm(base + (uint32_t)kb * S::B_KB, &tm_b, b_full, kb * BK, (int)cta * 16, 0);
+        tma_load_3d_2sm(base + S::B_PLANE + (uint32_t)kb * S::B_KB, &tm_b, b_full, kb * BK, (int)cta * 16, 1);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int ph = tile / p.num_m_tiles, m_tile = tile - ph * p.num_m_tiles;
+        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
+        for (int c = 0; c < p.hb && c < p.n_kb; ++c) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t ab = base + S::A_OFFSET + (uint32_t)stage * S::A_BUF;
+          mbar_expect_tx_remote(full_bar(stage), 0, S::A_BUF);
+          tma_load_4d_2sm(ab, &tm_a, full_bar(stage), c * BK, ph, m0, 0);
+          tma_load_4d_2sm(ab + S::A_PLANE, &tm_a, full_bar(stage), c * BK, ph, m0, 1);
+          if (++stage == ST) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 0 && elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) |
+                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      mbar_wait(b_full, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 32u;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.hb && c < p.n_kb; ++c) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t ab = base + S::A_OFFSET + (uint32_t)stage * S::A_BUF;
+          for (int kb = c; kb < p.n_kb; kb += p.hb) {  // K blocks of this column: row shift kb / hb
+            const uint32_t a_row = (uint32_t)(kb / p.hb) * (BK * 2);
+            const uint32_t bh = base + (uint32_t)kb * S::B_KB, bl = bh + S::B_PLANE;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t koff = (uint32_t)k * 32u;
+              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
+              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
+              const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
+              const uint64_t b_lo = make_smem_desc<BK>(bl + koff);
+              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
+              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+              accumulate = 1u;
+            }
+          }
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == ST) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int ph = tile / p.num_m_tiles, m_tile = tile - ph * p.num_m_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
+      const int64_t b = g / p.t_slots;
+      const int64_t t = (g - b * p.t_slots) * p.n_phases + ph;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 32u;
+      uint32_t re[16], im[16];
+      tmem_ld8(trow, *reinterpret_cast<uint32_t(*)[8]>(&re[0]));
+      tmem_ld8(trow + 8u, *reinterpret_cast<uint32_t(*)[8]>(&re[8]));
+      tmem_ld8(trow + 16u, *reinterpret_cast<uint32_t(*)[8]>(&im[0]));
+      tmem_ld8(trow + 24u, *reinterpret_cast<uint32_t(*)[8]>(&im[8]));
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);  // the accumulator is in registers now
+      if (g < p.nv && t < p.T) {
+        float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+#pragma unroll
+        for (int f = 0; f < 16; ++f)
+          if (f < p.epi.F) epi_store_fmt<FMT>(p.epi, dst, f, __uint_as_float(re[f]), __uint_as_float(im[f]));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 64);
+  }
+}
+
+template <int FMT>
+static int launch_octave_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const OctParams& prm, int n_pairs,
+                             cudaStream_t stream) {
+  static std::atomic<uint64_t> configured_devs{0};
+  int cfg_dev = 0;
+  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
+  if (!((configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u)) {
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(octave_tc_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)OctSmem::TOTAL));
+    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+  cfg.blockDim = dim3(OCT_THREADS);
+  cfg.dynamicSmemBytes = OctSmem::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, octave_tc_kernel<FMT>, ma, mb, prm));
+  count_launch();
+  return NNAB_OK;
+}
+
+// q: an octave problem on caller-managed planes (presplit + presplit_t_slots); packed: the DENSE
+// packed bank (tc_pack_basis) with bn = 32.  NNAB_EUNSUPPORTED = not applicable, nothing enqueued.
+int launch_octave_tc(const FramedProblem& q, const void* packed, cudaStream_t stream) {
+  if (const char* e = getenv("NNAB_OCTAVE_TC")) {
+    if (atoi(e) == 0) return NNAB_EUNSUPPORTED;
+  }
+  if (q.presplit == nullptr || q.presplit_t_slots <= 0 || packed == nullptr) return NNAB_EUNSUPPORTED;
+  if (q.F > 16 || tc_tile_n(q.F) != 32 || q.K % 64 != 0 || q.K / 64 > OCT_MAX_KB || q.B > 65535)
+    return NNAB_EUNSUPPORTED;
+  if (q.h_k_begin != nullptr) return NNAB_EUNSUPPORTED;
+  if (q.fmt != NNAB_FMT_MAGNITUDE && q.fmt != NNAB_FMT_COMPLEX && q.fmt != NNAB_FMT_PHASE_UNIT)
+    return NNAB_EUNSUPPORTED;
+  int P = 1, hop_eff = q.hop;
+  if (q.hop >= 64) {
+    if (q.hop % 64 != 0) return NNAB_EUNSUPPORTED;
+  } else {
+    if (q.hop < 8 || 64 % q.hop != 0) return NNAB_EUNSUPPORTED;
+    P = 64 / q.hop;
+    hop_eff = 64;
+  }
+  const int hb = hop_eff / 64;
+  const int n_kb = q.K / 64;
+  if ((n_kb - 1) / hb > 8) return NNAB_EUNSUPPORTED;  // row shifts must fit the 136-row block
+  const int64_t pitch = q.presplit_t_slots * q.hop;
+  if (pitch % hop_eff != 0) return NNAB_EUNSUPPORTED;
+  const int64_t t_slots = pitch / hop_eff;
+  const int64_t plane_stride = q.presplit_plane_stride;
+  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(q.presplit));
+
+  int dev = 0, sms = 148;
+  NNAB_CUDA_TRY(cudaGetDevice(&dev));
+  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sm_reserve();
+  if (sms < 2) sms = 2;
+  CUtensorMap ma, mb;
+  {
+    const int64_t rows = (plane_stride - (int64_t)(P - 1) * q.hop) / hop_eff;
+    const uint64_t dims[4] = {(uint64_t)hop_eff, (uint64_t)P, (uint64_t)rows, 2};
+    const uint64_t strides[3] = {(uint64_t)(P > 1 ? q.hop : hop_eff) * 2, (uint64_t)hop_eff * 2,
+                                 (uint64_t)plane_stride * 2};
+    const uint32_t box[3] = {64, 1, OCT_A_ROWS};
+    if (encode_4d(&ma, planes, dims, strides, box)) return NNAB_EUNSUPPORTED;
+  }
+  const int kpad = round_up_i(q.K, 64);
+  int rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)kpad, 32, 2, (uint64_t)kpad * 2,
+                     (uint64_t)32 * kpad * 2, 64, 16, 64);
+  if (rc) return rc;
+  OctParams prm{};
+  prm.n_phases = P;
+  prm.hb = hb;
+  prm.n_kb = n_kb;
+  prm.nv = q.B * t_slots;
+  prm.t_slots = t_slots;
+  prm.T = q.T;
+  prm.num_m_tiles = (int)ceil_div64(prm.nv, 2 * TC_BM);
+  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
+  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
+  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
+  const int64_t tiles = (int64_t)prm.num_m_tiles * P;
+  const int n_pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
+  add_exec_flops(3.0 * 2.0 * (double)tiles * (2 * TC_BM) * 32.0 * q.K);
+  switch (q.fmt) {
+    case NNAB_FMT_MAGNITUDE: return launch_octave_fmt<0>(ma, mb, prm, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_octave_fmt<1>(ma, mb, prm, n_pairs, stream);
+    case NNAB_FMT_PHASE_UNIT: return launch_octave_fmt<3>(ma, mb, prm, n_pairs, stream);
+    default: return NNAB_EINVAL;
+  }
+}
+
 }  // namespace nnab
