@@ -692,10 +692,13 @@ __global__ void __launch_bounds__(128) fir_edge_fix_kernel(
   if (n < 0 || n >= d.len_out) return;
   const __nv_bfloat16* sb = src + b * src_pitch + src_off;
   float acc = 0.f;
-  for (int m = lane; m < taps; m += 32) {
+#pragma unroll 8
+  for (int m = lane; m < taps; m += 32) {  // taps / 32 independent loads in flight per lane
     const int64_t j = 2 * n + m - (taps - 1) / 2;
-    if (j >= 0 && j < len_src)
-      acc = fmaf(__ldg(fir + m), __bfloat162float(sb[j]) + __bfloat162float(sb[src_plane + j]), acc);
+    const bool in = j >= 0 && j < len_src;
+    const float hi = in ? __bfloat162float(sb[j]) : 0.f;
+    const float lo = in ? __bfloat162float(sb[src_plane + j]) : 0.f;
+    acc = fmaf(__ldg(fir + m), hi + lo, acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
