@@ -184,6 +184,52 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
         "r"(c2)
       : "memory");
 }
+// Cheap descriptor arithmetic for MMA issue loops whose MMAs are short (N <= 64: 8-32 clocks each, so
+// the single issuing thread must not spend ~25 instructions per K16 step on descriptor construction).
+// The high word of a K-major swizzled descriptor is a constant; the low word is (addr >> 4) | 1 << 16
+// and moving along K (+32 B per K16 slice) or down rows (+128 B per row) is an add of the low word
+// (no carry leaves the 14-bit address field for shared-memory addresses < 256 KB).
+template <int BK>
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) {
+  return ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+template <int BK>
+__device__ __forceinline__ uint32_t smem_desc_hi() {
+  constexpr uint32_t SBO = (8u * BK * 2u) >> 4;
+  constexpr uint32_t LAYOUT = (BK == 64) ? 2u : 4u;
+  return SBO | (1u << 14) | (LAYOUT << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// D (+)= A * B with the accumulate flag as an immediate (no per-call setp on a register)
+template <bool ACC>
+__device__ __forceinline__ void umma_bf16_2sm_i(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, %4, 1;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+// one K block (BK = 64: four K16 slices) of the 3-term bf16 split: A (hi, lo planes) x B (hi, lo planes)
+__device__ __forceinline__ void umma_kblock_split3(uint32_t d_tmem, uint32_t a_hi_lo, uint32_t a_lo_lo,
+                                                   uint32_t b_hi_lo, uint32_t b_lo_lo, uint32_t hi,
+                                                   uint32_t idesc, bool first_accumulates) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t a_hi = desc64(a_hi_lo + 2u * k, hi), a_lo = desc64(a_lo_lo + 2u * k, hi);
+    const uint64_t b_hi = desc64(b_hi_lo + 2u * k, hi), b_lo = desc64(b_lo_lo + 2u * k, hi);
+    if (k == 0 && !first_accumulates) umma_bf16_2sm_i<false>(d_tmem, a_lo, b_hi, idesc);
+    else umma_bf16_2sm_i<true>(d_tmem, a_lo, b_hi, idesc);
+    umma_bf16_2sm_i<true>(d_tmem, a_hi, b_lo, idesc);
+    umma_bf16_2sm_i<true>(d_tmem, a_hi, b_hi, idesc);
+  }
+}
+
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                                 int c0, int c1, int c2, int c3) {
   asm volatile(

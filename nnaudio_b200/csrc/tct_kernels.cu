@@ -51,6 +51,8 @@ struct TallPlan {
   int g_max[TCT_MAX_COLS];        // its width in 8-bin groups = columns the chunk initialises
   int hb;                         // hop_eff / 64
   int a_rows;                     // rows of a tall A block (128 + widest shift span, multiple of 8)
+  int col_off[TCT_MAX_COLS];      // first entry of the column in `order`
+  uint16_t order[TCT_MAX_KB];     // K blocks in visiting order, column after column (widest block first)
   uint8_t groups[TCT_MAX_KB];     // 8-bin groups K block kb reaches (0 = inactive)
 };
 
@@ -157,8 +159,7 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
           // ---- the basis rows of every K block of this column
           for (int i = 0; i < r_cnt; ++i) {
-            const int r = tct_visit(i, r_min, r_cnt, plan.r_first[ci]);
-            const int kb = r * plan.hb + c;
+            const int kb = plan.order[plan.col_off[ci] + i];
             const int rows = 8 * (int)plan.groups[kb];  // basis rows this CTA stages
             mbar_wait(b_empty(stage), phase ^ 1u);
             const uint32_t bh = base + S::B_OFFSET + (uint32_t)stage * S::B_STAGE, bl = bh + S::B_PLANE;
@@ -195,25 +196,17 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           const uint32_t ab = base + (uint32_t)abuf * S::A_BUF;
           uint32_t accumulate = 0;
           for (int i = 0; i < r_cnt; ++i) {
-            const int r = tct_visit(i, r_min, r_cnt, plan.r_first[ci]);
-            const int kb = r * plan.hb + c;
+            const int kb = plan.order[plan.col_off[ci] + i];
+            const int r = (kb - c) / plan.hb;
             const uint32_t idesc = idesc0 | ((uint32_t)(2 * (int)plan.groups[kb]) << 17);  // N = 16 G
             mbar_wait(b_full(stage), phase);
             tcgen05_fence_after();
             const uint32_t bh = base + S::B_OFFSET + (uint32_t)stage * S::B_STAGE;
             const uint32_t a_row = (uint32_t)(r - r_min) * (BK * 2);  // descriptor start: r rows down
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t koff = (uint32_t)k * 32u;
-              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
-              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
-              const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
-              const uint64_t b_lo = make_smem_desc<BK>(bh + S::B_PLANE + koff);
-              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
-              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
-              accumulate = 1u;
-            }
+            umma_kblock_split3(d_tmem, smem_desc_lo<BK>(ab + a_row), smem_desc_lo<BK>(ab + S::A_PLANE + a_row),
+                               smem_desc_lo<BK>(bh), smem_desc_lo<BK>(bh + S::B_PLANE), smem_desc_hi<BK>(),
+                               idesc, accumulate != 0);
+            accumulate = 1u;
             umma_commit_2sm(b_empty(stage));
             if (++stage == BS) { stage = 0; phase ^= 1u; }
           }
@@ -335,7 +328,7 @@ static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
   // inactive blocks inside the active interval (a gap in every wavelet) still get the narrowest MMA
   for (int kb = kb_lo; kb <= kb_hi; ++kb)
     if (plan->groups[kb] == 0) plan->groups[kb] = 1;
-  int n = 0, span = 1;
+  int n = 0, span = 1, n_order = 0;
   for (int c = 0; c < hb; ++c) {
     const int r_lo = (kb_lo - c + hb - 1) / hb > 0 ? (kb_lo - c + hb - 1) / hb : 0;
     const int r_hi = (kb_hi - c) >= 0 ? (kb_hi - c) / hb : -1;
@@ -350,6 +343,20 @@ static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
     plan->r_cnt[n] = r_hi - r_lo + 1;
     plan->r_first[n] = best;
     plan->g_max[n] = plan->groups[best * hb + c];
+    plan->col_off[n] = n_order;
+    {
+      // visiting order: the widest block first (it initialises every TMEM column the chunk touches),
+      // then alternately above / below it
+      const int cnt = r_hi - r_lo + 1, below = best - r_lo, above = r_hi - best;
+      const int pairs = below < above ? below : above;
+      for (int i = 0; i < cnt; ++i) {
+        int r;
+        if (i == 0) r = best;
+        else if (i <= 2 * pairs) r = (i & 1) ? best + (i + 1) / 2 : best - i / 2;
+        else r = above > below ? best + pairs + (i - 2 * pairs) : best - pairs - (i - 2 * pairs);
+        plan->order[n_order++] = (uint16_t)(r * hb + c);
+      }
+    }
     ++n;
   }
   plan->n_cols = n;
@@ -625,19 +632,11 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u + (uint32_t)fir_col_lo(kb);
             const uint32_t a_row = (uint32_t)r * (BK * 2);
             const uint32_t bh = base + (uint32_t)fir_row0(kb) * (BK * 2), bl = bh + S::B_PLANE;
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t koff = (uint32_t)k * 32u;
-              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
-              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
-              const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
-              const uint64_t b_lo = make_smem_desc<BK>(bl + koff);
-              // kb = 3 (first of a tile) covers all 128 columns and starts the accumulation
-              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
-              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
-              accumulate = 1u;
-            }
+            // kb = 3 (first of a tile) covers all 128 columns and starts the accumulation
+            umma_kblock_split3(d_tmem, smem_desc_lo<BK>(ab + a_row), smem_desc_lo<BK>(ab + S::A_PLANE + a_row),
+                               smem_desc_lo<BK>(bh), smem_desc_lo<BK>(bl), smem_desc_hi<BK>(), idesc,
+                               accumulate != 0);
+            accumulate = 1u;
           }
           umma_commit_2sm(empty_bar(stage));
           if (++stage == ST) { stage = 0; phase ^= 1u; }
@@ -814,7 +813,8 @@ struct OctSmem {
 
 struct OctParams {
   int num_m_tiles;        // 256-frame pair tiles per frame phase
-  int n_phases, hb, n_kb; // frame phases, column blocks per row, K blocks (K / 64)
+  int n_phases, hb, n_kb; // frame phases, column blocks per row (power of two), K blocks (K / 64)
+  int hb_log2;
   int64_t nv, t_slots, T; // per phase: virtual frames, frames per clip slot; T = frames of the output
   EpiParams epi;
 };
@@ -909,20 +909,12 @@ octave_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tcgen05_fence_after();
           const uint32_t ab = base + S::A_OFFSET + (uint32_t)stage * S::A_BUF;
           for (int kb = c; kb < p.n_kb; kb += p.hb) {  // K blocks of this column: row shift kb / hb
-            const uint32_t a_row = (uint32_t)(kb / p.hb) * (BK * 2);
+            const uint32_t a_row = (uint32_t)(kb >> p.hb_log2) * (BK * 2);  // row shift kb / hb
             const uint32_t bh = base + (uint32_t)kb * S::B_KB, bl = bh + S::B_PLANE;
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t koff = (uint32_t)k * 32u;
-              const uint64_t a_hi = make_smem_desc<BK>(ab + a_row + koff);
-              const uint64_t a_lo = make_smem_desc<BK>(ab + S::A_PLANE + a_row + koff);
-              const uint64_t b_hi = make_smem_desc<BK>(bh + koff);
-              const uint64_t b_lo = make_smem_desc<BK>(bl + koff);
-              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
-              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
-              accumulate = 1u;
-            }
+            umma_kblock_split3(d_tmem, smem_desc_lo<BK>(ab + a_row), smem_desc_lo<BK>(ab + S::A_PLANE + a_row),
+                               smem_desc_lo<BK>(bh), smem_desc_lo<BK>(bl), smem_desc_hi<BK>(), idesc,
+                               accumulate != 0);
+            accumulate = 1u;
           }
           umma_commit_2sm(empty_bar(stage));
           if (++stage == ST) { stage = 0; phase ^= 1u; }
@@ -1050,6 +1042,9 @@ int launch_octave_tc(const FramedProblem& q, const void* packed, cudaStream_t st
   OctParams prm{};
   prm.n_phases = P;
   prm.hb = hb;
+  prm.hb_log2 = 0;
+  while ((1 << prm.hb_log2) < hb) ++prm.hb_log2;
+  if ((1 << prm.hb_log2) != hb) return NNAB_EUNSUPPORTED;
   prm.n_kb = n_kb;
   prm.nv = q.B * t_slots;
   prm.t_slots = t_slots;
