@@ -291,11 +291,11 @@ __global__ void fb_steps_kernel(const FbEntry* __restrict__ table, int n_fb, int
       const FbEntry e = table[k];
       const int js[2] = {e.j0, e.j1};
       const float ws[2] = {e.w0, e.w1};
-      bool used_a = false, used_b = false;
+      bool used_a = false;
       for (int i = 0; i < 2; ++i) {  // filters already held keep their slot
         if (js[i] < 0) continue;
         if (js[i] == cur_a) { st.wa = ws[i]; used_a = true; }
-        else if (js[i] == cur_b) { st.wb = ws[i]; used_b = true; }
+        else if (js[i] == cur_b) { st.wb = ws[i]; }
       }
       for (int i = 0; i < 2; ++i) {  // new filters take a free slot (its old sum is flushed first)
         if (js[i] < 0 || js[i] == cur_a || js[i] == cur_b) continue;
@@ -304,7 +304,7 @@ __global__ void fb_steps_kernel(const FbEntry* __restrict__ table, int n_fb, int
           cur_a = js[i]; st.wa = ws[i]; used_a = true;
         } else {
           if (cur_b >= 0) st.flush_b = (short)cur_b;
-          cur_b = js[i]; st.wb = ws[i]; used_b = true;
+          cur_b = js[i]; st.wb = ws[i];
         }
       }
     }

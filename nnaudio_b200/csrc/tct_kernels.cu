@@ -53,6 +53,7 @@ struct TallPlan {
   int a_rows;                     // rows of a tall A block (128 + widest shift span, multiple of 8)
   int col_off[TCT_MAX_COLS];      // first entry of the column in `order`
   uint16_t order[TCT_MAX_KB];     // K blocks in visiting order, column after column (widest block first)
+  uint8_t shift[TCT_MAX_KB];      // row shift (kb - c) / hb of the same entries, relative to r_min
   uint8_t groups[TCT_MAX_KB];     // 8-bin groups K block kb reaches (0 = inactive)
 };
 
@@ -72,18 +73,6 @@ struct TctSmem {
   static constexpr uint32_t BAR_OFFSET = B_OFFSET + TCT_B_STAGES * B_STAGE;
   static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
 };
-
-// i-th shift of a column in visiting order: r_first, then alternately above / below, clipped to the
-// active range.  Every shift of [r_min, r_min + r_cnt) appears exactly once.
-__device__ __forceinline__ int tct_visit(int i, int r_min, int r_cnt, int r_first) {
-  const int below = r_first - r_min;              // shifts below r_first
-  const int above = r_min + r_cnt - 1 - r_first;  // shifts above
-  if (i == 0) return r_first;
-  const int pairs = below < above ? below : above;
-  if (i <= 2 * pairs) return (i & 1) ? r_first + (i + 1) / 2 : r_first - i / 2;
-  const int rest = i - 2 * pairs;                 // one side is exhausted
-  return above > below ? r_first + pairs + rest : r_first - pairs - rest;
-}
 
 template <int FMT>
 __global__ void __launch_bounds__(TCT_THREADS, 1)
@@ -188,7 +177,7 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const int total_tiles = p.num_m_tiles * p.n_phases;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
         for (int ci = 0; ci < plan.n_cols; ++ci) {
-          const int c = plan.col[ci], r_min = plan.r_min[ci], r_cnt = plan.r_cnt[ci];
+          const int r_cnt = plan.r_cnt[ci];
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           mbar_wait(a_full(abuf), aphase);
           tcgen05_fence_after();
@@ -197,12 +186,11 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           uint32_t accumulate = 0;
           for (int i = 0; i < r_cnt; ++i) {
             const int kb = plan.order[plan.col_off[ci] + i];
-            const int r = (kb - c) / plan.hb;
             const uint32_t idesc = idesc0 | ((uint32_t)(2 * (int)plan.groups[kb]) << 17);  // N = 16 G
             mbar_wait(b_full(stage), phase);
             tcgen05_fence_after();
             const uint32_t bh = base + S::B_OFFSET + (uint32_t)stage * S::B_STAGE;
-            const uint32_t a_row = (uint32_t)(r - r_min) * (BK * 2);  // descriptor start: r rows down
+            const uint32_t a_row = (uint32_t)plan.shift[plan.col_off[ci] + i] * (BK * 2);  // r rows down
             umma_kblock_split3(d_tmem, smem_desc_lo<BK>(ab + a_row), smem_desc_lo<BK>(ab + S::A_PLANE + a_row),
                                smem_desc_lo<BK>(bh), smem_desc_lo<BK>(bh + S::B_PLANE), smem_desc_hi<BK>(),
                                idesc, accumulate != 0);
@@ -354,6 +342,7 @@ static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
         if (i == 0) r = best;
         else if (i <= 2 * pairs) r = (i & 1) ? best + (i + 1) / 2 : best - i / 2;
         else r = above > below ? best + pairs + (i - 2 * pairs) : best - pairs - (i - 2 * pairs);
+        plan->shift[n_order] = (uint8_t)(r - r_lo);
         plan->order[n_order++] = (uint16_t)(r * hb + c);
       }
     }
