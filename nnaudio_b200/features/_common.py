@@ -160,16 +160,18 @@ def is_hann_dft(w_re: torch.Tensor, w_im: torch.Tensor, atol: float = 1e-6) -> b
     F, K = w_re.shape
     if F != K // 2 + 1 or K % 2 != 0 or w_im.shape != w_re.shape:
         return False
-    n = torch.arange(K, device=w_re.device, dtype=torch.float64)
-    k = torch.arange(F, device=w_re.device, dtype=torch.float64)
-    # exact phase reduction in integers before the trig call
-    m = (torch.arange(F, device=w_re.device)[:, None] * torch.arange(K, device=w_re.device)[None, :]) % K
-    ang = (2.0 * torch.pi / K) * m.to(torch.float64)
-    hann = 0.5 - 0.5 * torch.cos(2.0 * torch.pi * n / K)
-    del k
-    ok_re = bool(((torch.cos(ang) * hann) - w_re.double()).abs().max() <= atol)
-    ok_im = bool(((torch.sin(ang) * hann) - w_im.double()).abs().max() <= atol)
-    return ok_re and ok_im
+    n = torch.arange(K, device=w_re.device)
+    hann = 0.5 - 0.5 * torch.cos(2.0 * torch.pi * n.to(torch.float64) / K)
+    rows = max(1, (1 << 22) // K)          # <= 32 MB of float64 scratch per block of bins
+    for k0 in range(0, F, rows):
+        k = torch.arange(k0, min(F, k0 + rows), device=w_re.device)
+        m = (k[:, None] * n[None, :]) % K  # exact phase reduction in integers before the trig call
+        ang = (2.0 * torch.pi / K) * m.to(torch.float64)
+        if ((torch.cos(ang) * hann) - w_re[k0:k0 + rows].double()).abs().max() > atol:
+            return False
+        if ((torch.sin(ang) * hann) - w_im[k0:k0 + rows].double()).abs().max() > atol:
+            return False
+    return True
 
 
 class PackedBasis:
