@@ -89,20 +89,13 @@ int nnab_pack_tile_n(int F);
 size_t nnab_packed_basis_bytes(int F, int K);
 int nnab_pack_basis(const float* w_re, const float* w_im, int F, int K,
                     void* packed, void* stream);
-/* EXPERIMENTAL (branch radix2-wip): same buffer size, explicit layout request.
+/* Same buffer size, explicit layout request:
  *   NNAB_LAYOUT_DENSE (0)   the layout above
- *   NNAB_LAYOUT_RADIX2 (2)  decimation-in-time layout for a DFT-STRUCTURED basis with F = K/2 + 1,
- *                           K % 256 == 0: the caller vouches that rows k and F-1-k mirror each other
- *                           (w[F-1-k][n] = (-1)^n w[k][n] for cos rows, -(-1)^n for sin rows), which
- *                           holds for create_fourier_kernels(freq_scale='no') times any window
- *                           (utils.py:241-393) and for nothing trained;
- *   NNAB_LAYOUT_GROUPS (3)  8-bin (re | im) row groups for the per-K-block-width kernel (F <= 128).
+ *   NNAB_LAYOUT_GROUPS (3)  8-bin (re | im) row groups for long nested banks (F <= 128, CQT1992v2): the
+ *                           per-K-block-width and tall-A kernels skip the zeros of the shorter wavelets.
  * The forward entry points recognise the layout of the buffer they are given. */
 #define NNAB_LAYOUT_DENSE 0
-#define NNAB_LAYOUT_RADIX2 2
 #define NNAB_LAYOUT_GROUPS 3
-#define NNAB_LAYOUT_RADIX4 4 /* as RADIX2 with four sample phases; additionally needs rows k and k + K/4
-                                related by (-i)^n (true for the same bases) and hop % 256 == 0 */
 int nnab_pack_basis_ex(const float* w_re, const float* w_im, int F, int K, int layout,
                        void* packed, void* stream);
 
@@ -225,14 +218,14 @@ int nnab_cqt1992v2_forward(const float* x, int64_t B, int64_t L, int64_t x_pitch
 size_t nnab_packed_fir_bytes(int taps, int dec);
 int nnab_pack_fir(const float* fir, int taps, int dec, void* packed, void* stream);
 
-/* EXPERIMENTAL (branch radix2-wip), host only: the K-block plan of the per-block-width kernel
+/* Host only (tests / tooling): the K-block plan of the per-block-width kernel
  * (order[i] = 64-sample K block, groups[i] = 8-bin groups it reaches, widest first;
  * chunk_begin[0..n_chunks] = split-K chunks of equal modelled cost).  Arrays: 512 / 512 / 17 ints. */
 int nnab_debug_varn_plan(const int32_t* h_k_begin, const int32_t* h_k_end, int n_bins, int width,
                          int want_chunks, int32_t* order, int32_t* groups, int32_t* chunk_begin,
                          int32_t* n_blocks, int32_t* n_chunks);
 
-/* EXPERIMENTAL (branch radix2-wip): one decimating-FIR stage and its adjoint, for the training path
+/* One decimating-FIR stage and its adjoint, for the training path
  * of the pyramid.  Replace `downsampling_by_n` / `downsampling_by_2` (utils.py:73-124) and what
  * autograd derives from them.
  *   y  (B, Ly) = conv1d(x (B, L), fir (taps), stride=factor, padding=(taps-1)/2),

@@ -279,14 +279,13 @@ def _rows(x: torch.Tensor):
 # --------------------------------------------------------------------------- #
 # basis packing (tcgen05 path)
 # --------------------------------------------------------------------------- #
-LAYOUT_DENSE, LAYOUT_RADIX2, LAYOUT_GROUPS, LAYOUT_RADIX4 = 0, 2, 3, 4
+LAYOUT_DENSE, LAYOUT_GROUPS = 0, 3
 
 
 def pack_basis(w_re: torch.Tensor, w_im: torch.Tensor, layout: int = LAYOUT_DENSE):
     """bf16 hi/lo split of an (F, K) fp32 basis pair in the TMA/UMMA layout, or
-    ``None`` when the library has no tcgen05 kernel for it.  ``layout`` (EXPERIMENTAL):
-    LAYOUT_RADIX2 for a basis the caller has checked with ``is_dft_structured``,
-    LAYOUT_GROUPS for long CQT banks."""
+    ``None`` when the library has no tcgen05 kernel for it.  ``layout``: LAYOUT_GROUPS for long
+    nested CQT banks (per-K-block-width / tall-A kernels)."""
     L = lib()
     F, K = w_re.shape
     nbytes = L.nnab_packed_basis_bytes(F, K)

@@ -677,7 +677,7 @@ size_t nnab_cqt_pyramid_workspace_bytes(int64_t B, int64_t L, int n_octaves, int
       size_t full2 = 0;
       if (early_factor <= 1 &&
           plan_pyramid2(B, L, n_octaves, hop, nullptr, max_width, NNAB_PAD_REFLECT, lv2, &full2)) {
-        full2 += 2048 + (size_t)n_octaves * align_up((size_t)768 * ((max_width + 63) / 64 * 64), 256);
+        full2 += 2048;
         if (full2 > n) n = full2;
       }
     }
@@ -708,25 +708,7 @@ static int pyramid_fused2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
     }
   char* scratch = ws + scratch_off;
   int rc;
-  // packed octave banks in the 8-bin-group layout of the tall kernel, behind everything else
-  int max_w = 0;
-  for (int i = 0; i < n_octaves; ++i) max_w = lv[i].width > max_w ? lv[i].width : max_w;
-  const size_t vpack_stride = align_up((size_t)768 * ((max_w + 63) / 64 * 64), 256);
-  // Measured at cfg4 (B200): octaves on the tall kernel 1.84 ms/step vs 1.70 ms with the dense kernel --
-  // with N = 32 the octave MMAs are bound by their own A reads either way and the frame-phase tiles
-  // add launches' worth of ramp; kept as an experiment (NNAB_PYR_TALL=1).
-  const bool use_tall = n_filters <= 96 && need + 512 + vpack_stride * n_octaves <= ws_bytes &&
-                        getenv("NNAB_PYR_TALL") != nullptr && atoi(getenv("NNAB_PYR_TALL")) == 1;
-  char* vpack_base = ws + align_up(need, 256);
-  bool vpack_done0 = false;
-  const size_t scratch_bytes = (use_tall ? (size_t)(vpack_base - ws) : ws_bytes - 256) - scratch_off;
-  auto prof_run_tall = [&](const FramedProblem& fp, const void* vp, cudaStream_t st) -> int {
-    std::pair<cudaEvent_t, cudaEvent_t> pr;
-    const bool timed = prof_begin(st, &pr);
-    const int r = launch_framed_tc_tall(fp, vp, nullptr, 0, st);
-    if (timed) prof_end(st, pr);
-    return r;
-  };
+  const size_t scratch_bytes = ws_bytes - 256 - scratch_off;
 
   // level 0: the caller's fp32 waveform -> planes (one pass; writes the whole clip slot)
   if (lv[0].planes) {
@@ -748,31 +730,7 @@ static int pyramid_fused2(const float* x, int64_t B, int64_t L, int64_t x_pitch,
       p.presplit = ws + l.pc;
       p.presplit_t_slots = l.t_slots;
       p.presplit_plane_stride = l.plane;
-      // frames that overlap (hop < width): tall-A kernel on the same planes -- every sample is
-      // fetched once per tile instead of once per frame; hop < 64 runs as 64 / hop frame phases
       bool done = false;
-      if (use_tall && l.hop < l.width && (l.hop % 64 == 0 || (l.hop >= 8 && 64 % l.hop == 0))) {
-        const int kpad = (l.width + 63) / 64 * 64;
-        const size_t vbytes = (size_t)768 * kpad;
-        char* vp = vpack_base + (size_t)i * vpack_stride;
-        if (vpack_stride >= vbytes) {
-          bool packed_now = true;
-          // CQT2010v2 shares one bank between the octaves: pack once
-          if (i > 0 && h_k_real[i] == h_k_real[0] && h_k_imag[i] == h_k_imag[0] && lv[i].width == lv[0].width &&
-              vpack_done0) {
-            vp = vpack_base;
-            packed_now = false;
-          }
-          if (packed_now) {
-            rc = tc_pack_basis_varn(h_k_real[i], h_k_imag[i], n_filters, l.width, vp, s);
-            if (rc) return rc;
-            if (i == 0) vpack_done0 = true;
-          }
-          rc = prof_run_tall(p, vp, s);
-          if (rc == NNAB_OK) done = true;
-          else if (rc != NNAB_EUNSUPPORTED) return rc;
-        }
-      }
       if (!done) {
         // resident bank + tall A blocks + frame phases: one fetch per sample and tile
         std::pair<cudaEvent_t, cudaEvent_t> pr;

@@ -542,7 +542,7 @@ int launch_fir_decimate(const float* x, int64_t B, int64_t L, int64_t x_pitch, c
 }
 
 // --------------------------------------------------------------------------
-// EXPERIMENTAL (branch radix2-wip, not GPU-verified): adjoint of the decimating FIR,
+// Adjoint of the decimating FIR (GPU-verified round 2, default of the pyramid training path),
 //   dx[i] = sum_j g[j] * fir[i + half - factor*j],   half = (taps-1)/2,  0 <= i < L
 // (the gradient of y = conv1d(x, fir, stride=factor, padding=half), utils.py:73-100).
 // One CTA = 1024 consecutive inputs of one clip; the g samples and the filter they touch are

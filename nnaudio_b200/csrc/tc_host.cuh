@@ -34,7 +34,7 @@ int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void*
                        cudaStream_t stream);
 
 // layout of a packed basis, keyed by its device pointer
-enum { PACK_DENSE = 0, PACK_RADIX2 = 1, PACK_VARN = 2, PACK_RADIX4 = 3, PACK_BLOCK = 4 };
+enum { PACK_DENSE = 0, PACK_VARN = 2, PACK_BLOCK = 4 };
 int packed_kind(const void* packed);
 void mark_packed(const void* packed, int kind);
 

@@ -82,17 +82,9 @@ SplitGeom split_geom(int64_t B, int64_t L, int K, int hop, int pad) {
   return g;
 }
 
-size_t tc_radix2_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad);
-bool tc_radix2_enabled();
-
 size_t tc_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
   const SplitGeom g = split_geom(B, L, K, hop, pad);
-  size_t n = (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
-  if (hop % 2 == 0 && K % 256 == 0) {  // either layout may be chosen at pack time
-    const size_t r2 = tc_radix2_workspace_bytes(B, L, K, hop, pad);
-    if (r2 > n) n = r2;
-  }
-  return n;
+  return (size_t)(2 * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
 }
 
 bool tc_supported(const FramedProblem& p) {
@@ -204,39 +196,26 @@ __global__ void __launch_bounds__(256) pack_basis_kernel(
   *reinterpret_cast<uint4*>(packed + (int64_t)rows * kpad + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
-int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
-                         cudaStream_t stream);
-bool tc_radix2_basis_ok(int F, int K);
 void tc_forget_packed(const void* packed);
 bool tc_varn_enabled();
 bool tc_varn_basis_ok(int F, int K);
 int tc_pack_basis_varn(const float* w_re, const float* w_im, int F, int K, void* packed,
                        cudaStream_t stream);
 
-// layout: 0 = dense (always valid); 2 = two-segment decimation-in-time layout — the CALLER vouches
-// that the basis is DFT-structured (rows k and F-1-k mirror each other, see
-// nnaudio_b200/features/_common.py:is_dft_structured); 3 = 8-bin-group layout for the
-// per-K-block-width kernel (any basis with F <= 128).  NNAB_RADIX=0 / NNAB_VARN=0 force dense.
+// layout: 0 = dense (always valid); 3 = 8-bin-group layout for the per-K-block-width / tall-A kernels
+// (any basis with F <= 128).  NNAB_VARN=0 forces dense.
 int tc_pack_basis_layout(const float* w_re, const float* w_im, int F, int K, int layout, void* packed,
                          cudaStream_t stream) {
-  const char* er = getenv("NNAB_RADIX");
   const char* ev = getenv("NNAB_VARN");
-  if ((layout == 2 || layout == 4) && !(er != nullptr && atoi(er) == 0)) {
-    int tc_pack_basis_radix(const float*, const float*, int, int, int, void*, cudaStream_t);
-    const int rc = tc_pack_basis_radix(w_re, w_im, F, K, layout, packed, stream);
-    if (rc != NNAB_EINVAL) return rc;  // shape not eligible: fall through to dense
-  }
   if (layout == 3 && !(ev != nullptr && atoi(ev) == 0) && tc_varn_basis_ok(F, K))
     return tc_pack_basis_varn(w_re, w_im, F, K, packed, stream);
-  if (layout != 0 && layout != 2 && layout != 3 && layout != 4) return NNAB_EINVAL;
+  if (layout != 0 && layout != 3) return NNAB_EINVAL;
   return tc_pack_basis(w_re, w_im, F, K, packed, stream);
 }
 
 int tc_pack_basis(const float* w_re, const float* w_im, int F, int K, void* packed,
                   cudaStream_t stream) {
-  // legacy entry: experimental layouts only when the environment asks for them
-  if (tc_radix2_enabled() && tc_radix2_basis_ok(F, K))
-    return tc_pack_basis_radix2(w_re, w_im, F, K, packed, stream);
+  // (NNAB_VARN=1: debugging switch -- the 8-bin-group layout for every long bank)
   if (tc_varn_enabled() && tc_varn_basis_ok(F, K) && K >= 4096)
     return tc_pack_basis_varn(w_re, w_im, F, K, packed, stream);
   tc_forget_packed(packed);
@@ -718,8 +697,6 @@ struct TcParams {
   int t_mul, t_add;  // output frame index = t * t_mul + t_add (frame phases)
   int k_splits;      // >1: every (m, n) tile is cut into k_splits K-chunks (FMT_RAW epilogue)
   int split4;        // EXPERIMENTAL (NNAB_SPLIT4=1): add the x_lo * w_lo term (4 MMAs per K16 step)
-  int* sk_flags;     // split-K: one arrival counter per (m, n) tile, zeroed per launch (or nullptr)
-  int sk_warps;      // epilogue warps per unit (4, or 8 for a CTA pair)
   int64_t nv, t_slots, T;  // T = valid frames of this phase
   int kb_begin[TC_MAX_N_TILES];
   int kb_end[TC_MAX_N_TILES];
@@ -728,41 +705,13 @@ struct TcParams {
 
 // Work order of a persistent worker: its u-th unit (unit = tile * ks + K-chunk), or -1 when done.
 // Split-K partial sums are combined by ORDERED read-modify-writes (run-to-run identical; no atomics,
-// no zero-fill of the scratch): chunk c of a tile adds after chunk c-1 has stored.
-//   flags != nullptr: units are dealt round-robin (balanced); the epilogue of chunk c waits until
-//     the tile's flag counts c * (epilogue warps per unit) arrivals.  Unit u-1 sits on worker
-//     (u-1) % W at a queue position <= that of unit u, so the wait cannot deadlock a persistent grid.
-//   flags == nullptr: all chunks of a tile go to the same worker, consecutively (program order).
-__device__ __forceinline__ int sched_tile(int u, int worker, int n_workers, int num_mn, int ks,
-                                          const int* flags) {
-  if (flags != nullptr) {
-    const int64_t unit = (int64_t)worker + (int64_t)u * n_workers;
-    return unit < (int64_t)num_mn * ks ? (int)unit : -1;
-  }
+// no zero-fill of the scratch): all chunks of a tile go to the same worker, consecutively, so chunk c
+// of a tile adds after chunk c-1 has stored, in program order of one thread.  (A balanced round-robin
+// of the units with flag-ordered adds measured 2.04 ms vs 1.27 ms at cfg3: the chunks of a tile
+// finish their MMAs together and their epilogues then serialise while holding TMEM buffers.)
+__device__ __forceinline__ int sched_tile(int u, int worker, int n_workers, int num_mn, int ks) {
   const int mn = worker + (u / ks) * n_workers;
   return mn < num_mn ? mn * ks + (u % ks) : -1;
-}
-__device__ __forceinline__ void sk_wait(const int* flag, int need, int lane) {
-  if (lane == 0) {
-    int v;
-    unsigned long long t0 = 0;
-    uint32_t spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-      if (v < need && (++spins & 0x3FFFu) == 0) {  // bounded: a scheduling bug must trap, not hang
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000ull) { printf("nnab: split-K order wait timeout\n"); __trap(); }
-      }
-    } while (v < need);
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void sk_arrive(int* flag, int lane) {
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
 }
 
 // tile index -> (m tile, n tile, k-block range); K-chunks of one (m, n) tile are adjacent
@@ -811,8 +760,6 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
         // ---- split-K partial sums: ordered read-modify-write of the raw planes (this thread owns
         // the element for every chunk of the tile; chunk 0 stores, later chunks add) ----
         float* rre = p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t;
-        if (p.sk_flags != nullptr && k_chunk > 0)
-          sk_wait(p.sk_flags + mn_tile, k_chunk * p.sk_warps, threadIdx.x & 31);
 #pragma unroll 1
         for (int c0 = 0; c0 < half; c0 += 8) {
           uint32_t re[8], im[8];
@@ -832,7 +779,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t trow, 
               }
           }
         }
-        if (p.sk_flags != nullptr) sk_arrive(p.sk_flags + mn_tile, threadIdx.x & 31);
+
       } else if constexpr (FMT == 6) {
         // ---- FIR decimator stage: this thread holds outputs n0 .. n0 + 2*half - 1 of clip b ----
         epilogue_decim(p.epi.dec, trow, b, tl, valid, half);
@@ -982,7 +929,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * TC_BM;
@@ -1015,7 +962,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         (void)m_tile;
@@ -1052,7 +999,7 @@ framed_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int half = p.bn >> 1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
+    for (int u = 0, tile; (tile = sched_tile(u, blockIdx.x, gridDim.x, num_mn, p.k_splits)) >= 0; ++u) {
       int m_tile, n_tile, kb0, kb1;
       decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
       (void)kb0; (void)kb1;
@@ -1151,7 +1098,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
@@ -1183,7 +1130,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
         int m_tile, n_tile, kb0, kb1;
         decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
         (void)m_tile;
@@ -1223,7 +1170,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits, p.sk_flags)) >= 0; ++u) {
+    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, num_mn, p.k_splits)) >= 0; ++u) {
       int m_tile, n_tile, kb0, kb1;
       decode_tile(p, tile, m_tile, n_tile, kb0, kb1);
       (void)kb0; (void)kb1;
@@ -1251,386 +1198,7 @@ framed_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
 
 // ===========================================================================
-// EXPERIMENTAL (branch radix2-wip, not GPU-verified yet): decimation-in-time
-// variant of the STFT-family contraction, R = 2.
-//
-// For a DFT-structured basis (w_re[f][n] = win[n] cos(2 pi f n / N), w_im = ... sin, F = N/2+1)
-// the frame splits into its even / odd samples:
-//   S0[k] = sum_m xe[m] (w_re - i w_im)[k][2m]         (sub-DFT of the even samples)
-//   U [k] = sum_m xo[m] (w_re - i w_im)[k][2m+1]       (sub-DFT of the odd samples, twiddle included)
-//   X[k] = S0[k] + U[k],   X[N/2 - k] = conj(S0[k] - U[k]),   k = 0 .. N/4
-// i.e. two contractions with K = N/2 over N/4 bins: half the MACs of the dense form, and the
-// epilogue is add / subtract only.  The real Nyquist bins S0[N/4], Im U[N/4] ride in the
-// always-zero imaginary slots of k = 0, so N/4 (re, im) column pairs cover everything
-// (tools/radix_dft_prototype.py is the executable spec).
-//
-// Data: 4 signal planes [r][hi|lo], plane_r[i] = xpad[2 i + r] (hop/2, K/2 Toeplitz view each);
-// packed basis [hi|lo][seg r][tile][re half | negated im half][K/2]; TMEM: segment r of a tile
-// accumulates into columns [r*bn, (r+1)*bn) of the 256-column buffer (bn = 128).
-// ===========================================================================
-
-// One thread = 8 consecutive elements of ALL R sample-phase planes (8 R padded samples).
-// planes: [r][hi|lo], plane_r[i] = xpad[R i + r].
-template <int R>
-__global__ void __launch_bounds__(256) pad_split_radix_kernel(
-    const float* __restrict__ x, int64_t L, int64_t x_pitch, int pad, int pad_mode,
-    int64_t clip_pitch, int64_t plane_stride, __nv_bfloat16* __restrict__ planes) {
-  const int64_t b = blockIdx.y;
-  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;  // plane element
-  if (i0 >= clip_pitch) return;
-  const float* __restrict__ xb = x + b * x_pitch;
-  const int64_t padded_len = L + 2 * (int64_t)pad;
-  __align__(16) __nv_bfloat16 hi[R][8];
-  __align__(16) __nv_bfloat16 lo[R][8];
-#pragma unroll
-  for (int e = 0; e < 8 * R; ++e) {
-    const int64_t i = R * i0 + e;  // index into the centre-padded clip
-    float v = 0.f;
-    if (i < padded_len) {
-      int64_t j = i - pad;
-      if (j < 0) j = (pad_mode == NNAB_PAD_REFLECT) ? -j : -1;
-      else if (j >= L) j = (pad_mode == NNAB_PAD_REFLECT) ? 2 * (L - 1) - j : -1;
-      if (j >= 0 && j < L) v = __ldg(xb + j);
-    }
-    split_bf16(v, hi[e % R][e / R], lo[e % R][e / R]);
-  }
-  const int64_t o = b * clip_pitch + i0;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    *reinterpret_cast<uint4*>(planes + (2 * r) * plane_stride + o) = *reinterpret_cast<const uint4*>(hi[r]);
-    *reinterpret_cast<uint4*>(planes + (2 * r + 1) * plane_stride + o) = *reinterpret_cast<const uint4*>(lo[r]);
-  }
-}
-
-// packed[plane][seg][tile*bn + part*half + j][kk]: bin k = tile*half + j, sample n = R*kk + seg.
-// part 0 = w_re rows, part 1 = negated w_im rows.  The (k = 0, part 1) slot (always zero) carries
-// the real number that determines the sub-DFT's Nyquist bin U_seg[K/(2R)]:
-//   R = 2: seg 0 -> re, seg 1 -> im        R = 4: seg 0, 1, 3 -> re, seg 2 -> im
-// (tools/radix2_emulation.py, tools/radix4_emulation.py).
-__global__ void __launch_bounds__(256) pack_basis_radix_kernel(
-    const float* __restrict__ w_re, const float* __restrict__ w_im, int K, int R, int rows_seg,
-    int kpadr, int bn, __nv_bfloat16* __restrict__ packed) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int k8 = kpadr / 8;
-  if (idx >= (int64_t)R * rows_seg * k8) return;
-  const int row = (int)(idx / k8);  // 0 .. R*rows_seg-1
-  const int k0 = (int)(idx % k8) * 8;
-  const int seg = row / rows_seg, r = row % rows_seg;
-  const int half = bn / 2;
-  const int tile = r / bn, within = r % bn;
-  const int part = within / half, j = within % half;
-  const int k = tile * half + j;
-  const int nyq = K / (2 * R);
-  const bool slot_is_im = (R == 2) ? (seg == 1) : (seg == 2);
-  __align__(16) __nv_bfloat16 hi[8];
-  __align__(16) __nv_bfloat16 lo[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int kk = k0 + e;
-    const int n = R * kk + seg;
-    float v = 0.f;
-    if (k < nyq && n < K) {
-      if (part == 0) v = __ldg(w_re + (int64_t)k * K + n);
-      else if (k != 0) v = -__ldg(w_im + (int64_t)k * K + n);
-      else v = slot_is_im ? -__ldg(w_im + (int64_t)nyq * K + n) : __ldg(w_re + (int64_t)nyq * K + n);
-    }
-    split_bf16(v, hi[e], lo[e]);
-  }
-  const int64_t o = (int64_t)row * kpadr + k0;
-  *reinterpret_cast<uint4*>(packed + o) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(packed + (int64_t)R * rows_seg * kpadr + o) = *reinterpret_cast<const uint4*>(lo);
-}
-
-// Butterfly epilogue: TMEM columns [S0 re | S0 im | U re | U im], `half` bins each.
-// FMT: 0 Magnitude, 1 Complex, 4 POWER, 5 fused banded filterbank.
-template <int FMT>
-__device__ __forceinline__ void epilogue_tile_radix2(const TcParams& p, uint32_t trow, int64_t g,
-                                                     int n_tile, int half) {
-  const int64_t b = g / p.t_slots;
-  const int64_t tl = g - b * p.t_slots;
-  const bool valid = (g < p.nv) && (tl < p.T);
-  const int64_t t = tl * p.t_mul + p.t_add;
-  const int k_base = n_tile * half;
-  const int NH = p.epi.F - 1;  // N/2: bin k pairs with bin NH - k
-  constexpr int CH = (FMT == NNAB_FMT_COMPLEX) ? 2 : 1;
-  float* dst = nullptr;
-  float* mel = nullptr;
-  if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
-  else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
-  MelRun up, down;
-  auto emit = [&](MelRun& run, int bin, float re, float im) {
-    if constexpr (FMT == 5) {
-      run.add(p.epi, mel, valid, bin, epi_power(p.epi, re, im));
-    } else {
-      if (valid) epi_store_fmt<FMT>(p.epi, dst, bin, re, im);
-    }
-  };
-#pragma unroll 1
-  for (int c0 = 0; c0 < half; c0 += 8) {
-    uint32_t s0r[8], s0i[8], ur[8], ui[8];
-    tmem_ld8(trow + (uint32_t)c0, s0r);
-    tmem_ld8(trow + (uint32_t)(half + c0), s0i);
-    tmem_ld8(trow + (uint32_t)(2 * half + c0), ur);
-    tmem_ld8(trow + (uint32_t)(3 * half + c0), ui);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = k_base + c0 + j;
-      const float ar = __uint_as_float(s0r[j]), ai = __uint_as_float(s0i[j]);
-      const float br = __uint_as_float(ur[j]), bi = __uint_as_float(ui[j]);
-      if (k == 0) {
-        // DC, the mirror of DC (bin N/2) and the packed Nyquist pair (bin N/4)
-        MelRun one;
-        emit(one, 0, ar + br, 0.f);
-        emit(one, NH, ar - br, 0.f);
-        emit(one, NH / 2, ai, bi);
-        if constexpr (FMT == 5) one.flush(p.epi, mel, valid);
-      } else {
-        emit(up, k, ar + br, ai + bi);
-        emit(down, NH - k, ar - br, bi - ai);
-      }
-    }
-  }
-  if constexpr (FMT == 5) {
-    up.flush(p.epi, mel, valid);
-    down.flush(p.epi, mel, valid);
-  }
-}
-
-// CTA-pair kernel with two K segments per tile (see framed_tc2_kernel for the pipeline roles).
-// Radix-4 butterfly epilogue: TMEM columns of segment s at [s*bns, (s+1)*bns) = [re | im], `half`
-// bins each.  With the module's own basis rows the twiddles are inside the accumulators, so
-//   X[k]       =      U0 +   U1 + U2 +   U3        X[N/4 + k] = U0 - i U1 - U2 + i U3
-//   X[N/4 - k] = conj(U0) - i conj(U1) - conj(U2) + i conj(U3)
-//   X[N/2 - k] = conj(U0 - U1 + U2 - U3)
-// are additions, sign flips and re/im swaps (tools/radix4_emulation.py is the executable spec,
-// including the k = 0 column that also carries the sub-DFT Nyquist bins).
-template <int FMT>
-__device__ __forceinline__ void epilogue_tile_radix4(const TcParams& p, uint32_t trow, int64_t g,
-                                                     int n_tile, int half) {
-  const int64_t b = g / p.t_slots;
-  const int64_t tl = g - b * p.t_slots;
-  const bool valid = (g < p.nv) && (tl < p.T);
-  const int64_t t = tl * p.t_mul + p.t_add;
-  const int k_base = n_tile * half;
-  const int NH = p.epi.F - 1;  // N/2
-  const int NQ = NH / 2;       // N/4
-  const int NE = NH / 4;       // N/8: Nyquist bin of the sub-DFTs
-  const int bns = 2 * half;
-  constexpr int CH = (FMT == NNAB_FMT_COMPLEX) ? 2 : 1;
-  float* dst = nullptr;
-  float* mel = nullptr;
-  if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
-  else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
-  MelRun up0, up1, dn0, dn1;
-  auto emit = [&](MelRun& run, int bin, float re, float im) {
-    if constexpr (FMT == 5) {
-      run.add(p.epi, mel, valid, bin, epi_power(p.epi, re, im));
-    } else {
-      if (valid) epi_store_fmt<FMT>(p.epi, dst, bin, re, im);
-    }
-  };
-#pragma unroll 1
-  for (int c0 = 0; c0 < half; c0 += 8) {
-    uint32_t r0[8], i0[8], r1[8], i1[8], r2[8], i2[8], r3[8], i3[8];
-    tmem_ld8(trow + (uint32_t)(0 * bns + c0), r0);
-    tmem_ld8(trow + (uint32_t)(0 * bns + half + c0), i0);
-    tmem_ld8(trow + (uint32_t)(1 * bns + c0), r1);
-    tmem_ld8(trow + (uint32_t)(1 * bns + half + c0), i1);
-    tmem_ld8(trow + (uint32_t)(2 * bns + c0), r2);
-    tmem_ld8(trow + (uint32_t)(2 * bns + half + c0), i2);
-    tmem_ld8(trow + (uint32_t)(3 * bns + c0), r3);
-    tmem_ld8(trow + (uint32_t)(3 * bns + half + c0), i3);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = k_base + c0 + j;
-      const float a0 = __uint_as_float(r0[j]), b0 = __uint_as_float(i0[j]);
-      const float a1 = __uint_as_float(r1[j]), b1 = __uint_as_float(i1[j]);
-      const float a2 = __uint_as_float(r2[j]), b2 = __uint_as_float(i2[j]);
-      const float a3 = __uint_as_float(r3[j]), b3 = __uint_as_float(i3[j]);
-      if (k == 0) {
-        // U_s[0] = a_s (real); the im slots b_s hold the packed Nyquist numbers:
-        //   v0 = (b0, 0)  v1 = (b1, -b1)  v2 = (0, b2)  v3 = (b3, b3)
-        MelRun one;
-        emit(one, 0, a0 + a1 + a2 + a3, 0.f);
-        emit(one, NQ, a0 - a2, a3 - a1);
-        emit(one, NH, a0 - a1 + a2 - a3, 0.f);
-        emit(one, NE, b0 + b1 + b3, -b1 + b2 + b3);
-        emit(one, NQ + NE, b0 - b1 - b3, -b1 - b2 + b3);
-        if constexpr (FMT == 5) one.flush(p.epi, mel, valid);
-      } else {
-        emit(up0, k, a0 + a1 + a2 + a3, b0 + b1 + b2 + b3);
-        emit(up1, NQ + k, a0 + b1 - a2 - b3, b0 - a1 - b2 + a3);
-        emit(dn0, NQ - k, a0 - b1 - a2 + b3, -b0 - a1 + b2 + a3);
-        emit(dn1, NH - k, a0 - a1 + a2 - a3, -(b0 - b1 + b2 - b3));
-      }
-    }
-  }
-  if constexpr (FMT == 5) {
-    up0.flush(p.epi, mel, valid);
-    up1.flush(p.epi, mel, valid);
-    dn0.flush(p.epi, mel, valid);
-    dn1.flush(p.epi, mel, valid);
-  }
-}
-
-// BNS = columns per segment: 128 (64 bins; 2 x 128 columns per tile, TMEM double-buffered) or
-// 256 (128 bins; the two segments fill all 512 columns, so the epilogue of a tile is not overlapped
-// with the next tile's MMAs, but every MMA runs at the full N = 256).
-// RAD = segments (sample phases) per tile: RAD * BNS <= 256 leaves room for two accumulator buffers.
-template <int FMT, int BNS, int RAD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-framed_tc2r_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                   const TcParams p, const int seg_rows) {
-  constexpr int BK = 64, STAGES = 3;
-  constexpr int NACC = (RAD * BNS <= 256) ? 2 : 1;
-  static_assert(RAD * BNS <= 512, "segments of one tile must fit the 512 TMEM columns");
-  using S = Tc2Smem<BK, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + S::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t cta = cluster_ctarank();
-  const int pair = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm_a);
-    prefetch_tmap(&tm_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 2);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
-    }
-    fence_barrier_init();
-  }
-  cluster_sync_all();
-  if (warp == 2) {
-    tmem_alloc_2sm(tmem_slot, 512);
-    tmem_relinquish_2sm();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  constexpr int halfn = BNS / 2;
-  constexpr uint32_t b_half_bytes = (uint32_t)halfn * BK * 2;
-  const int kb_n = p.kb_end[0];  // K/2 in 64-sample blocks, same for every tile and segment
-
-  if (warp == 0) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
-        const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
-        for (int seg = 0; seg < RAD; ++seg) {
-          const int n0 = seg * seg_rows + n_tile * BNS + (int)cta * halfn;
-          for (int kb = 0; kb < kb_n; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sb = base + stage * S::STAGE_BYTES;
-            mbar_expect_tx_remote(full_bar(stage), 0, 2 * S::A_BYTES + 2 * b_half_bytes);
-            const int k0 = kb * BK;
-            const int c1 = m0 + k0 / p.hop;          // rows mode: (rows x hop) view of a plane
-            const int c0 = k0 - (k0 / p.hop) * p.hop;
-            tma_load_3d_2sm(sb, &tm_a, full_bar(stage), c0, c1, 2 * seg);
-            tma_load_3d_2sm(sb + S::A_BYTES, &tm_a, full_bar(stage), c0, c1, 2 * seg + 1);
-            tma_load_3d_2sm(sb + 2 * S::A_BYTES, &tm_b, full_bar(stage), k0, n0, 0);
-            tma_load_3d_2sm(sb + 2 * S::A_BYTES + S::B_BYTES, &tm_b, full_bar(stage), k0, n0, 1);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (cta == 0 && elect_one()) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNS >> 3) << 17) |
-                             ((uint32_t)((2 * TC_BM) >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tcgen05_fence_after();
-        for (int seg = 0; seg < RAD; ++seg) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE + (uint32_t)(seg * BNS);
-          uint32_t accumulate = 0;
-          for (int kb = 0; kb < kb_n; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tcgen05_fence_after();
-            const uint32_t sb = base + stage * S::STAGE_BYTES;
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t koff = (uint32_t)k * 32u;
-              const uint64_t a_hi = make_smem_desc<BK>(sb + koff);
-              const uint64_t a_lo = make_smem_desc<BK>(sb + S::A_BYTES + koff);
-              const uint64_t b_hi = make_smem_desc<BK>(sb + 2 * S::A_BYTES + koff);
-              const uint64_t b_lo = make_smem_desc<BK>(sb + 2 * S::A_BYTES + S::B_BYTES + koff);
-              umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, accumulate);
-              umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
-              accumulate = 1u;
-            }
-            umma_commit_2sm(empty_bar(stage));
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          }
-        }
-        umma_commit_2sm(tfull_bar(acc));
-        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else if (warp >= 4) {
-    const int quarter = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      const int64_t g = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
-      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                            (uint32_t)acc * TC_ACC_STRIDE;
-      if constexpr (RAD == 2) epilogue_tile_radix2<FMT>(p, trow, g, n_tile, halfn);
-      else epilogue_tile_radix4<FMT>(p, trow, g, n_tile, halfn);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
-      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 2) {
-    tcgen05_fence_after();
-    tmem_dealloc_2sm(tmem_base, 512);
-  }
-}
-
-
-// ===========================================================================
-// EXPERIMENTAL (branch radix2-wip, not GPU-verified yet): per-K-block MMA width for banks
+// Per-K-block MMA width for banks
 // whose rows have nested, centred supports (CQT1992v2).
 //
 // Packed rows are ordered in 8-bin groups, [re bins 8g..8g+7 | negated im of the same bins], so
@@ -1686,10 +1254,6 @@ __device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t t
   constexpr int CH = (FMT == NNAB_FMT_COMPLEX || FMT == NNAB_FMT_PHASE_UNIT) ? 2 : 1;
   float* dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
   float* rre = (FMT == 7) ? p.epi.raw + ((int64_t)b * p.epi.F) * p.epi.T + t : nullptr;
-  if constexpr (FMT == 7) {
-    if (p.sk_flags != nullptr && k_chunk > 0)
-      sk_wait(p.sk_flags + mn_tile, k_chunk * p.sk_warps, threadIdx.x & 31);
-  }
 #pragma unroll 1
   for (int gi = 0; gi < n_groups; ++gi) {
     uint32_t re[8], im[8];
@@ -1713,9 +1277,6 @@ __device__ __forceinline__ void epilogue_tile_varn(const TcParams& p, uint32_t t
         }
       }
     }
-  }
-  if constexpr (FMT == 7) {
-    if (p.sk_flags != nullptr) sk_arrive(p.sk_flags + mn_tile, threadIdx.x & 31);
   }
 }
 
@@ -1774,7 +1335,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks, p.sk_flags)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
         const int chunk = tile % plan.n_chunks;
         const int m_tile = tile / plan.n_chunks;
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
@@ -1813,7 +1374,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks, p.sk_flags)) >= 0; ++u) {
+      for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
         const int chunk = tile % plan.n_chunks;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
@@ -1847,7 +1408,7 @@ framed_tc2v_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks, p.sk_flags)) >= 0; ++u) {
+    for (int u = 0, tile; (tile = sched_tile(u, pair, num_pairs, p.num_m_tiles, plan.n_chunks)) >= 0; ++u) {
       const int chunk = tile % plan.n_chunks;
       const int m_tile = tile / plan.n_chunks;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -1886,27 +1447,9 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const EpiParams e,
 
 // Long kernels only: the scratch exists to bound the tensor-core accumulation length
 // (its error grows with the number of accumulated MMAs) and to even out the tile count.
-constexpr size_t SK_FLAG_BYTES = 1u << 20;  // arrival counters of the ordered split-K combine
 size_t tc_splitk_scratch_bytes(int64_t B, int F, int64_t T, int K) {
   if (K < 8192) return 0;
-  return (size_t)2 * B * F * T * sizeof(float) + 512 + SK_FLAG_BYTES;
-}
-
-// flags behind the two raw planes; nullptr (-> same-worker chunk order) when there are too many tiles
-static int* sk_flags_of(float* raw, int64_t plane, int64_t num_mn, cudaStream_t stream, int* rc) {
-  *rc = NNAB_OK;
-  // Measured on cfg3 (B200): 2.04 ms with the flag-ordered round-robin vs 1.27 ms with all chunks of
-  // a tile on one worker -- the chunks of a tile finish their MMAs together and their epilogues then
-  // run one after the other while holding TMEM buffers.  Kept for experiments (NNAB_SK_FLAGS=1).
-  static const bool use_flags = [] { const char* e = getenv("NNAB_SK_FLAGS"); return e != nullptr && atoi(e) == 1; }();
-  if (!use_flags) return nullptr;
-  if (num_mn * (int64_t)sizeof(int) > (int64_t)SK_FLAG_BYTES) return nullptr;
-  int* flags = reinterpret_cast<int*>(((uintptr_t)(raw + 2 * plane) + 255) & ~(uintptr_t)255);
-  if (cudaMemsetAsync(flags, 0, (size_t)num_mn * sizeof(int), stream) != cudaSuccess) {
-    *rc = NNAB_ECUDA;
-    return nullptr;
-  }
-  return flags;
+  return (size_t)2 * B * F * T * sizeof(float) + 256;
 }
 
 // ---------------------------------------------------------------------------
@@ -2073,225 +1616,30 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
 
 
 // ---------------------------------------------------------------------------
-// EXPERIMENTAL decimation-in-time host side: radix R = 2 or 4 (NNAB_RADIX=2|4, or an explicit
-// layout request through nnab_pack_basis_ex)
+// layout of a packed basis, keyed by its device pointer.  Every function that produces a buffer for the
+// `packed` argument of launch_framed_tc sets (or clears) the tag, so a recycled address cannot carry a
+// stale layout.
 // ---------------------------------------------------------------------------
-static int radix_env() {
-  const char* e = getenv("NNAB_RADIX");
-  const int r = e != nullptr ? atoi(e) : -1;
-  return r;  // -1 unset, 0 = force dense, 2 / 4
-}
-bool tc_radix2_enabled() { const int r = radix_env(); return r == 2 || r == 4; }
-
-// columns per segment: R = 2: 128 (default) or 256 (NNAB_RADIX_BN=256); R = 4: 64 (default) or 128.
-// Read at pack and at launch time, so it must not change while a packed basis is alive.
-static int radix_bn(int R) {
-  const char* e = getenv("NNAB_RADIX_BN");
-  const int v = e != nullptr ? atoi(e) : 0;
-  if (R == 2) return v == 256 ? 256 : 128;
-  return v == 128 ? 128 : 64;
-}
-
-// basis shapes the radix packing accepts (the caller vouches that the basis is DFT-structured);
-// K < 8192: longer kernels take the split-K path of the dense kernel (accumulation-length bound)
-static bool radix_basis_ok(int F, int K, int R) {
-  if (R != 2 && R != 4) return false;
-  return K >= 512 && K < 8192 && K % (R * radix_bn(R)) == 0 && F == K / 2 + 1;
-}
-bool tc_radix2_basis_ok(int F, int K) {
-  const int r = radix_env();
-  return radix_basis_ok(F, K, r == 4 ? 4 : 2);
-}
-
-// layout of an experimental packed basis, keyed by its device pointer (WIP: a header inside the
-// packed buffer should replace this registry)
-static std::mutex g_r2_mu;
+static std::mutex g_pack_mu;
 static std::unordered_map<const void*, int> g_pack_kind;
 
 int packed_kind(const void* packed) {
-  std::lock_guard<std::mutex> lk(g_r2_mu);
+  std::lock_guard<std::mutex> lk(g_pack_mu);
   auto it = g_pack_kind.find(packed);
   return it == g_pack_kind.end() ? PACK_DENSE : it->second;
 }
 
 void mark_packed(const void* packed, int kind) {
-  std::lock_guard<std::mutex> lk(g_r2_mu);
+  std::lock_guard<std::mutex> lk(g_pack_mu);
   if (kind == PACK_DENSE) g_pack_kind.erase(packed);
   else g_pack_kind[packed] = kind;
 }
 
-static bool is_radix2_packed(const void* packed) {
-  const int k = packed_kind(packed);
-  return k == PACK_RADIX2 || k == PACK_RADIX4;
-}
-
 void tc_forget_packed(const void* packed) { mark_packed(packed, PACK_DENSE); }
-
-static SplitGeom radix_geom(int64_t B, int64_t L, int K, int hop, int pad, int R) {
-  const int64_t lp = L + 2 * (int64_t)pad;
-  return split_geom(B, (lp + R - 1) / R, K / R, hop / R, 0);
-}
-
-size_t tc_radix2_workspace_bytes(int64_t B, int64_t L, int K, int hop, int pad) {
-  size_t n = 0;
-  for (int R = 2; R <= 4; R += 2) {
-    if (hop % R != 0 || K % R != 0) continue;
-    const SplitGeom g = radix_geom(B, L, K, hop, pad, R);
-    const size_t v = (size_t)(2 * R * g.plane_stride) * sizeof(__nv_bfloat16) + 256;
-    if (v > n) n = v;
-  }
-  return n;
-}
-
-int tc_pack_basis_radix(const float* w_re, const float* w_im, int F, int K, int R, void* packed,
-                        cudaStream_t stream) {
-  if (!radix_basis_ok(F, K, R)) return NNAB_EINVAL;
-  const int rows_seg = K / R;  // (K / (2R) bins) x (re, im)
-  const int kpadr = K / R;     // already a multiple of 64
-  const int64_t threads = (int64_t)R * rows_seg * (kpadr / 8);
-  pack_basis_radix_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
-      w_re, w_im, K, R, rows_seg, kpadr, radix_bn(R), (__nv_bfloat16*)packed);
-  NNAB_LAUNCH_CHECK();
-  mark_packed(packed, R == 4 ? PACK_RADIX4 : PACK_RADIX2);
-  return NNAB_OK;
-}
-int tc_pack_basis_radix2(const float* w_re, const float* w_im, int F, int K, void* packed,
-                         cudaStream_t stream) {
-  return tc_pack_basis_radix(w_re, w_im, F, K, radix_env() == 4 ? 4 : 2, packed, stream);
-}
-
-static bool radix_problem_ok(const FramedProblem& q, int R) {
-  if (!radix_basis_ok(q.F, q.K, R)) return false;
-  if (q.hop % R != 0 || num_phases(q.hop / R) != 1 || (q.hop / R) % 64 != 0) return false;
-  if (q.presplit != nullptr || q.h_k_begin != nullptr || q.raw != nullptr) return false;
-  switch (q.fmt) {
-    case NNAB_FMT_MAGNITUDE: case NNAB_FMT_COMPLEX: case FMT_POWER:
-      return q.bin_offset == 0 && q.out_bins >= q.F;
-    case FMT_FBANK: return q.fb_table != nullptr && q.n_fb > 0;  // out_bins = n_fb there
-    default: return false;
-  }
-}
-
-template <int FMT, int BNS, int RAD>
-static int launch_tc2r_fmt(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
-                           int seg_rows, int n_pairs, cudaStream_t stream) {
-  using S = Tc2Smem<64, 3>;
-  // the attribute is per device: one process may drive several GPUs (torch.nn.DataParallel)
-  static std::atomic<uint64_t> configured_devs{0};
-  int cfg_dev = 0;
-  NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
-  const bool configured = (configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u;
-  if (!configured) {
-    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2r_kernel<FMT, BNS, RAD>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * n_pairs));
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = S::TOTAL;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2r_kernel<FMT, BNS, RAD>, ma, mb, prm, seg_rows));
-  count_launch();
-  return NNAB_OK;
-}
-
-template <int BNS, int RAD>
-static int launch_tc2r(int fmt, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& prm,
-                       int seg_rows, int n_pairs, cudaStream_t stream) {
-  switch (fmt) {
-    case NNAB_FMT_MAGNITUDE: return launch_tc2r_fmt<0, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case NNAB_FMT_COMPLEX: return launch_tc2r_fmt<1, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case FMT_POWER: return launch_tc2r_fmt<4, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
-    case FMT_FBANK: return launch_tc2r_fmt<5, BNS, RAD>(ma, mb, prm, seg_rows, n_pairs, stream);
-    default: return NNAB_EINVAL;
-  }
-}
-
-static int launch_framed_tc_radix2(const FramedProblem& q, const void* packed, void* workspace,
-                                   size_t ws_bytes, cudaStream_t stream) {
-  const int R = packed_kind(packed) == PACK_RADIX4 ? 4 : 2;
-  if (!radix_problem_ok(q, R)) return NNAB_EINVAL;  // the basis was packed for the radix kernel only
-  const size_t need = tc_radix2_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
-  if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
-  if (q.B > 65535) return NNAB_EUNSUPPORTED;
-  const int hopr = q.hop / R, kr = q.K / R;
-  const SplitGeom g = radix_geom(q.B, q.L, q.K, q.hop, q.pad, R);
-  __nv_bfloat16* planes =
-      reinterpret_cast<__nv_bfloat16*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  const int64_t clip_pitch = g.t_slots * hopr;
-  // K overhang past the last clip: finite zeros in all 2R planes
-  const int64_t tail = g.plane_stride - g.nv * hopr;
-  for (int pl = 0; pl < 2 * R; ++pl)
-    NNAB_CUDA_TRY(cudaMemsetAsync(planes + pl * g.plane_stride + g.nv * hopr, 0,
-                                  (size_t)tail * sizeof(__nv_bfloat16), stream));
-  dim3 pgrid((unsigned)ceil_div64(clip_pitch, 256 * 8), (unsigned)q.B);
-  if (R == 2)
-    pad_split_radix_kernel<2><<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
-                                                          clip_pitch, g.plane_stride, planes);
-  else
-    pad_split_radix_kernel<4><<<pgrid, 256, 0, stream>>>(q.x, q.L, q.x_pitch, q.pad, q.pad_mode,
-                                                          clip_pitch, g.plane_stride, planes);
-  NNAB_LAUNCH_CHECK();
-
-  int dev = 0, sms = 148;
-  NNAB_CUDA_TRY(cudaGetDevice(&dev));
-  NNAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  sms -= sm_reserve();
-  if (sms < 2) sms = 2;
-
-  const int seg_rows = kr;            // rows of one segment in the packed basis
-  const int bns = radix_bn(R);
-  const int n_tiles = seg_rows / bns;
-  CUtensorMap ma, mb;
-  int rc = encode_3d(&ma, planes, (uint64_t)hopr, (uint64_t)g.rows, (uint64_t)(2 * R), (uint64_t)hopr * 2,
-                     (uint64_t)g.plane_stride * 2, 64, TC_BM, 64);
-  if (rc) return rc;
-  rc = encode_3d(&mb, const_cast<void*>(packed), (uint64_t)kr, (uint64_t)(R * seg_rows), 2,
-                 (uint64_t)kr * 2, (uint64_t)(R * seg_rows) * kr * 2, 64, bns / 2, 64);
-  if (rc) return rc;
-
-  TcParams prm{};
-  prm.num_n_tiles = n_tiles;
-  prm.bn = bns;
-  prm.rows_mode = 1;
-  prm.hop = hopr;
-  prm.nv = g.nv;
-  prm.t_slots = g.t_slots;
-  prm.t_mul = 1;
-  prm.t_add = 0;
-  prm.T = q.T;
-  prm.k_splits = 1;
-  for (int tl = 0; tl < n_tiles; ++tl) { prm.kb_begin[tl] = 0; prm.kb_end[tl] = kr / 64; }
-  prm.epi.scale = q.scale; prm.epi.scale_all = q.scale_all; prm.epi.fmt = q.fmt;
-  prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
-  prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
-  prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb;
-  prm.epi.dec = q.dec;
-  prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
-  prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
-  prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
-  const int64_t ptiles = (int64_t)prm.num_m_tiles * n_tiles;
-  const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
-  add_exec_flops(3.0 * 2.0 * (double)ptiles * (2 * TC_BM) * (double)bns * R * kr);
-  if (R == 2) {
-    return bns == 256 ? launch_tc2r<256, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream)
-                      : launch_tc2r<128, 2>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream);
-  }
-  return bns == 128 ? launch_tc2r<128, 4>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream)
-                    : launch_tc2r<64, 4>(q.fmt, ma, mb, prm, seg_rows, n_pairs, stream);
-}
 
 
 // ---------------------------------------------------------------------------
-// EXPERIMENTAL per-K-block MMA width, host side (NNAB_VARN=1)
+// per-K-block MMA width, host side (layout NNAB_LAYOUT_GROUPS; NNAB_VARN=0 forces dense)
 // ---------------------------------------------------------------------------
 bool tc_varn_enabled() {
   const char* e = getenv("NNAB_VARN");
@@ -2498,12 +1846,6 @@ static int launch_framed_tc_varn(const FramedProblem& q, const void* packed, voi
     final_epi.raw_plane = plane;
   }
   prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);
-  prm.sk_flags = nullptr;
-  prm.sk_warps = 8;
-  if (split) {
-    prm.sk_flags = sk_flags_of(prm.epi.raw, prm.epi.raw_plane, prm.num_m_tiles, stream, &rc);
-    if (rc) return rc;
-  }
   const int64_t ptiles = (int64_t)prm.num_m_tiles * plan.n_chunks;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
   {
@@ -2535,8 +1877,6 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
     return launch_framed_tc_block(q, packed, workspace, ws_bytes, stream);
   if (packed_kind(packed) == PACK_VARN)
     return launch_framed_tc_varn(q, packed, workspace, ws_bytes, stream);
-  if (is_radix2_packed(packed))
-    return launch_framed_tc_radix2(q, packed, workspace, ws_bytes, stream);
   if (q.presplit == nullptr) {
     const size_t need = tc_workspace_bytes(q.B, q.L, q.K, q.hop, q.pad);
     if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
@@ -2707,13 +2047,6 @@ int launch_framed_tc(const FramedProblem& q, const void* packed, void* workspace
       for (int tl = 0; tl < n_tiles; ++tl) kcols += (double)(prm.kb_end[tl] - prm.kb_begin[tl]) * bk * bn;
       add_exec_flops((prm.split4 && cta_group == 2 ? 4.0 : 3.0) * 2.0 *
                      (double)ceil_div64(g.nv, mrows) * mrows * kcols);
-    }
-    prm.sk_flags = nullptr;
-    prm.sk_warps = cta_group == 2 ? 8 : 4;
-    if (split) {  // arrival counters are per launch: every frame phase starts from zero
-      const int64_t num_mn = ceil_div64(g.nv, (cta_group == 2 ? 2 : 1) * TC_BM) * prm.num_n_tiles;
-      prm.sk_flags = sk_flags_of(prm.epi.raw, prm.epi.raw_plane, num_mn, stream, &rc);
-      if (rc) return rc;
     }
     if (cta_group == 2) {
       prm.num_m_tiles = (int)ceil_div64(g.nv, 2 * TC_BM);  // 256-frame pair tiles

@@ -119,36 +119,6 @@ class AdjointBasis:
                                   keep=(w_re, w_im))
 
 
-def is_dft_structured(w_re: torch.Tensor, w_im: torch.Tensor, rtol: float = 1e-6, radix: int = 2) -> bool:
-    """True when an (F, K) basis pair has the structure of a one-sided windowed DFT with F = K/2 + 1
-    that the decimation-in-time kernels rely on, checked on the buffers themselves (a loaded or
-    trained basis that lost it simply takes the dense kernel).  With W = w_re - i w_im:
-      radix 2:  W[F-1-k][n] = (-1)^n conj(W[k][n])            (mirror about N/4)
-      radix 4:  additionally W[k + K/4][n] = (-i)^n W[k][n]   (quarter-period shift)
-    Any window is fine: it multiplies columns.  EXPERIMENTAL (branch radix2-wip)."""
-    F, K = w_re.shape
-    if F != K // 2 + 1 or K % 256 != 0 or K < 512 or K >= 8192 or radix not in (2, 4):
-        return False
-    scale = float(torch.maximum(w_re.abs().max(), w_im.abs().max()))
-    if scale == 0.0:
-        return False
-    tol = rtol * scale
-    n = torch.arange(K, device=w_re.device)
-    sign = (1.0 - 2.0 * (n % 2)).to(w_re.dtype)
-    if (w_re.flip(0) - w_re * sign).abs().max() > tol or (w_im.flip(0) + w_im * sign).abs().max() > tol:
-        return False
-    if radix == 4:
-        q = K // 4
-        # (-i)^n = 1, -i, -1, i: (re - i im) * (-i)^n for n mod 4 = 0..3 -> (re, im), (-im, re), (-re, -im), (im, -re)
-        r, m = w_re[: q + 1], w_im[: q + 1]
-        ph = n % 4
-        want_re = torch.where(ph == 0, r, torch.where(ph == 1, -m, torch.where(ph == 2, -r, m)))
-        want_im = torch.where(ph == 0, m, torch.where(ph == 1, r, torch.where(ph == 2, -m, -r)))
-        if (w_re[q: 2 * q + 1] - want_re).abs().max() > tol or (w_im[q: 2 * q + 1] - want_im).abs().max() > tol:
-            return False
-    return True
-
-
 def is_hann_dft(w_re: torch.Tensor, w_im: torch.Tensor, atol: float = 1e-6) -> bool:
     """True when an (F, K) basis pair IS the one-sided DFT with a periodic Hann window of length K:
     ``w_re[k][n] = hann[n] cos(2 pi k n / K)``, ``w_im[k][n] = hann[n] sin(2 pi k n / K)``, F = K/2 + 1
@@ -182,15 +152,10 @@ class PackedBasis:
     def __init__(self):
         self._cache = PerDeviceCache()
 
-    def get(self, w_re: torch.Tensor, w_im: torch.Tensor, allow_radix=False,
-            groups: bool = False, block_hop: int = 0):
-        """``allow_radix`` (False, 2 or 4 = the largest radix the module's hop allows): the module
-        computes a plain one-sided STFT with this basis, so the decimation-in-time layout may be
-        used when the buffers pass ``is_dft_structured``;
-        ``groups``: long CQT bank for the per-K-block-width kernel (default);
-        ``block_hop``: STFT-family module -> block-partial layout when the buffers are the Hann DFT.
-        The radix layouts stay EXPERIMENTAL (NNAUDIO_B200_EXPERIMENTAL=1): the block-partial kernel
-        supersedes them."""
+    def get(self, w_re: torch.Tensor, w_im: torch.Tensor, groups: bool = False, block_hop: int = 0):
+        """``groups``: long nested CQT bank -> 8-bin-group layout (per-K-block-width / tall-A kernels);
+        ``block_hop``: STFT-family module -> block-partial layout when the buffers ARE the periodic-Hann
+        DFT (checked here on the tensors)."""
         import os
 
         def build():
@@ -201,22 +166,14 @@ class PackedBasis:
                     and _C.block_layout_ok(int(w_re.shape[1]), int(block_hop)) \
                     and is_hann_dft(w_re, w_im):
                 return _C.pack_basis_block(w_re, int(block_hop))
-            layout = _C.LAYOUT_DENSE
-            if os.environ.get("NNAUDIO_B200_EXPERIMENTAL", "0") == "1":
-                radix = 4 if os.environ.get("NNAUDIO_B200_RADIX", "2") == "4" else 2
-                if allow_radix == 4 and radix == 4 and is_dft_structured(w_re, w_im, radix=4):
-                    layout = _C.LAYOUT_RADIX4
-                elif allow_radix and is_dft_structured(w_re, w_im):
-                    layout = _C.LAYOUT_RADIX2
             # long CQT banks (CQT1992v2): per-K-block MMA width, the default since round 2
             # (GPU-verified: reference chirp goldens + cfg3 full size; NNAUDIO_B200_VARN=0: dense)
-            if layout == _C.LAYOUT_DENSE and groups and w_re.shape[0] <= 128 and w_re.shape[1] >= 4096 \
+            if groups and w_re.shape[0] <= 128 and w_re.shape[1] >= 4096 \
                     and os.environ.get("NNAUDIO_B200_VARN", "1") != "0":
-                layout = _C.LAYOUT_GROUPS
-            return _C.pack_basis(w_re, w_im, layout) if layout else _C.pack_basis(w_re, w_im)
+                return _C.pack_basis(w_re, w_im, _C.LAYOUT_GROUPS)
+            return _C.pack_basis(w_re, w_im)
 
-        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, allow_radix, groups,
-               int(block_hop))
+        key = (w_re.data_ptr(), w_re._version, w_im.data_ptr(), w_im._version, groups, int(block_hop))
         return self._cache.lookup(w_re.device, key, build, keep=(w_re, w_im))
 
 

@@ -77,7 +77,7 @@ class Gammatonegram(nn.Module):
         x = self.stft._checked_input(x)
         if wants_grad(self, x):
             return torch.matmul(self.gammatone_basis, self.stft._magnitude_diff(x) ** self.power)
-        wcos, wsin, packed = self.stft._bases(radix_ok=True, block_ok=True)
+        wcos, wsin, packed = self.stft._bases(block_ok=True)
         fb = self.gammatone_basis.detach()
         _C._dev_f32(fb, "gammatone_basis")
         fb = fb if fb.is_contiguous() else fb.contiguous()

@@ -82,7 +82,7 @@ class MelSpectrogram(nn.Module):
         x = self.stft._checked_input(x)
         if wants_grad(self, x):  # mel.py:186-188 on top of the differentiable STFT magnitude
             return torch.matmul(self._filterbank(), self.stft._magnitude_diff(x) ** self.power)
-        wcos, wsin, packed = self.stft._bases(radix_ok=True, block_ok=True)
+        wcos, wsin, packed = self.stft._bases(block_ok=True)
         fb = self._filterbank().detach()
         _C._dev_f32(fb, "filterbank")
         fb = fb if fb.is_contiguous() else fb.contiguous()
@@ -142,7 +142,7 @@ class MFCC(nn.Module):
                 peak = log_spec.flatten(1).max(1)[0][:, None, None]
                 log_spec = torch.max(log_spec, peak - self.top_db)
             return torch.matmul(self._dct_rows, log_spec)
-        wcos, wsin, packed = mel.stft._bases(radix_ok=True, block_ok=True)
+        wcos, wsin, packed = mel.stft._bases(block_ok=True)
         fb = mel.mel_basis.detach()
         _C._dev_f32(fb, "mel_basis")
         fb = fb if fb.is_contiguous() else fb.contiguous()

@@ -234,23 +234,19 @@ class STFT(nn.Module):
             raise RuntimeError("Kernel size can't be greater than actual input size")
         return x
 
-    def _bases(self, radix_ok=False, block_ok=False):
-        """``radix_ok``: the caller's output format has a decimation-in-time epilogue (Magnitude,
-        Complex, power / fused filterbank); the layout is still only used when the buffers pass
-        ``is_dft_structured`` and the hop allows the half-rate planes (EXPERIMENTAL)."""
+    def _bases(self, block_ok=False):
+        """``block_ok``: the caller's output format has a block-partial epilogue (all STFT formats,
+        power / fused filterbank); the layout is still only used when the module is forward-only, the
+        hop fits and the buffers pass ``is_hann_dft``."""
         wcos, wsin = as_matrix(self.wcos), as_matrix(self.wsin)
         if self.freq_bins is not None and self.freq_bins < wcos.shape[0]:
             wcos, wsin = wcos[: self.freq_bins], wsin[: self.freq_bins]
-        allow = False
-        if radix_ok and not self.trainable and self.stride % 128 == 0:
-            allow = 4 if self.stride % 256 == 0 else 2
         # block-partial kernel: forward-only modules whose buffers are the periodic-Hann DFT
         block_hop = self.stride if (block_ok and not self.trainable) else 0
-        return wcos, wsin, self._packed.get(wcos, wsin, allow_radix=allow, block_hop=block_hop)
+        return wcos, wsin, self._packed.get(wcos, wsin, block_hop=block_hop)
 
     def _run(self, x, output_format):
-        wcos, wsin, packed = self._bases(radix_ok=output_format in ("Magnitude", "Complex"),
-                                         block_ok=True)
+        wcos, wsin, packed = self._bases(block_ok=True)
         eps = 1e-8 if (self.trainable and output_format == "Magnitude") else 0.0
         return _C.stft_forward(
             x, wcos, wsin, packed, self.n_fft, self.stride, self.center,
