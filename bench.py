@@ -647,28 +647,57 @@ def _run():
     e2e, pcie = None, None
     if not args.no_e2e:
         with torch.no_grad():
-            # raw link rate of this box, pinned memory, one big copy per direction
+            # raw link rate of this box, pinned memory, per direction: one big copy, and the same bytes as
+            # 8 MB chunks on the copy streams the pipeline uses (on some of this pool's boxes one 256 MB
+            # copy reads the host at 35 GB/s while the pipeline's chunk copies reach 52); the better one is
+            # the link rate `frac_of_link` is quoted against
             probe_n = 64 << 20  # floats = 256 MB
-            hp, place = alloc_pinned((probe_n,), device_index=local_rank)
+            hp, place = alloc_pinned((probe_n,), device_index=local_rank, fill="zeros")
             dp = torch.empty(probe_n, dtype=torch.float32, device=dev)
-            rates = {}
+            n_str = max(1, int(args.e2e_copy_streams))
+            streams = [torch.cuda.Stream(device=dev) for _ in range(n_str)]
+            pieces = 32  # 8 MB each, the size of the pipeline's chunk copies
+            step_n = probe_n // pieces
+
+            def one_copy(dst, src):
+                dst.copy_(src, non_blocking=True)
+
+            def striped_copy(dst, src):
+                cur = torch.cuda.current_stream(dev)
+                fork = torch.cuda.Event()
+                fork.record(cur)
+                for i in range(pieces):
+                    st = streams[i % n_str]
+                    if i < n_str:
+                        st.wait_event(fork)
+                    with torch.cuda.stream(st):
+                        dst[i * step_n:(i + 1) * step_n].copy_(src[i * step_n:(i + 1) * step_n], non_blocking=True)
+                for st in streams:
+                    join = torch.cuda.Event()
+                    join.record(st)
+                    cur.wait_event(join)
+
+            rates, how = {}, {}
             for key, (dst, src) in (("h2d", (dp, hp)), ("d2h", (hp, dp))):
-                for _ in range(2):  # warm the link (power state) and the page tables
-                    dst.copy_(src, non_blocking=True)
-                torch.cuda.synchronize(dev)
-                best = 0.0
-                for _ in range(5):  # best single copy of 5: the link rate, not its jitter
-                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    dst.copy_(src, non_blocking=True)
-                    b_.record()
+                best, best_how = 0.0, ""
+                for name, fn in (("one copy", one_copy), (f"{pieces} chunks on {n_str} streams", striped_copy)):
+                    for _ in range(2):  # warm the link (power state) and the page tables
+                        fn(dst, src)
                     torch.cuda.synchronize(dev)
-                    best = max(best, probe_n * 4 / (a.elapsed_time(b_) * 1e-3) / 1e9)
-                rates[key] = best
-            del hp, dp
-            pcie = {"h2d_gbs": rates["h2d"], "d2h_gbs": rates["d2h"], "pinned": place,
-                    "what": "cudaMemcpyAsync of a 256 MB pinned buffer, best of 5 copies per direction after 2 warm-up "
-                            "copies, CUDA events"}
+                    for _ in range(5):  # best of 5: the link rate, not its jitter
+                        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        fn(dst, src)
+                        b_.record()
+                        torch.cuda.synchronize(dev)
+                        r = probe_n * 4 / (a.elapsed_time(b_) * 1e-3) / 1e9
+                        if r > best:
+                            best, best_how = r, name
+                rates[key], how[key] = best, best_how
+            del hp, dp, streams
+            pcie = {"h2d_gbs": rates["h2d"], "d2h_gbs": rates["d2h"], "pinned": place, "best": how,
+                    "what": "cudaMemcpyAsync of a 256 MB pinned buffer per direction, as one copy and as chunks striped "
+                            "over the pipeline's copy streams; best of 5 after 2 warm-up copies each, CUDA events"}
 
             x_hosts = [alloc_pinned((B, w["L"]), device_index=local_rank, fill="randn")[0] for _ in range(2)]
             y_host, _ = alloc_pinned(out_shape, device_index=local_rank)
@@ -688,7 +717,13 @@ def _run():
             h2d_b, d2h_b = x_hosts[0].numel() * 4, y_host.numel() * 4
             T_ = frames_per_clip(w)
             ms_step = e2e_ms / n_e2e
-            link_ms = max(h2d_b / (rates["h2d"] * 1e9), d2h_b / (rates["d2h"] * 1e9)) * 1e3
+            # The host side of a pool box is shared (other tenants' copies cross the same root complex), so a
+            # probe taken seconds earlier can read BELOW what the pipeline then sustains (35-39 vs 52 GB/s seen).
+            # The link rate is therefore the better of the probe and the pipeline's own sustained rate.
+            h2d_link = max(rates["h2d"], h2d_b / (ms_step * 1e-3) / 1e9)
+            pcie["h2d_gbs_link"] = h2d_link
+            pcie["probe_below_pipeline"] = bool(h2d_link > rates["h2d"])
+            link_ms = max(h2d_b / (h2d_link * 1e9), d2h_b / (rates["d2h"] * 1e9)) * 1e3
             e2e = {"value": world * B * T_ * n_e2e / (e2e_ms * 1e-3), "unit": "frames/s",
                    "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "ms_per_step": ms_step,
                    "steps": n_e2e, "h2d_gbs_achieved": h2d_b / (ms_step * 1e-3) / 1e9,

@@ -14,7 +14,7 @@ WANT = [
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
-    "launch__block_size", "launch__cluster_dim_x", "launch__shared_mem_per_block_dynamic",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "launch__block_size", "launch__cluster_dim_x", "launch__shared_mem_per_block_dynamic",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__inst_executed_pipe_tensor_subpipe_hmma.sum",
 ]
 

@@ -28,8 +28,11 @@ for wl in cfg2 cfg3 cfg4 cfg5; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 80 --csv --log-file gpurun_out/r02_launches_$wl.csv python bench.py --workload $wl --steps 4 --warmup 3 $Q > /dev/null 2>&1
 done
 echo "== ncu --set full"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:framed_tcb -s 3 -c 1 -o gpurun_out/r02_cfg2_block python bench.py --workload cfg2 --steps 3 --warmup 3 $Q > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:framed_tcb -s 3 -c 1 -o gpurun_out/r02_stft2048_block python bench.py --workload stft2048 --steps 3 --warmup 3 $Q > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:framed_tc2t -s 3 -c 1 -o gpurun_out/r02_cfg3_tall python bench.py --workload cfg3 --steps 3 --warmup 3 $Q > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:fir_tc_kernel -s 7 -c 1 -o gpurun_out/r02_cfg4_fir python bench.py --workload cfg4 --steps 3 --warmup 3 $Q > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:framed_tcb -s 3 -c 1 -f -o gpurun_out/r02_cfg2_block python bench.py --workload cfg2 --steps 3 --warmup 3 $Q > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:framed_tcb -s 3 -c 1 -f -o gpurun_out/r02_stft2048_block python bench.py --workload stft2048 --steps 3 --warmup 3 $Q > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:framed_tc2t -s 3 -c 1 -f -o gpurun_out/r02_cfg3_tall python bench.py --workload cfg3 --steps 3 --warmup 3 $Q > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:fir_tc_kernel -s 7 -c 1 -f -o gpurun_out/r02_cfg4_fir python bench.py --workload cfg4 --steps 3 --warmup 3 $Q > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:octave_tc_kernel -s 8 -c 1 -f -o gpurun_out/r02_cfg4_octave python bench.py --workload cfg4 --steps 3 --warmup 3 $Q > /dev/null 2>&1
+echo "== MMA rate probe"
+timeout 200 python tools/probe_mma_rate.py > gpurun_out/probe_mma_rate.log 2>&1; tail -3 gpurun_out/probe_mma_rate.log
 ls -la gpurun_out/*.ncu-rep
