@@ -416,3 +416,77 @@ def dct2_ortho_matrix(n_out: int, n_in: int) -> np.ndarray:
     mat[0] *= 1.0 / math.sqrt(n_in)
     mat[1:] *= math.sqrt(2.0 / n_in)
     return mat.astype(np.float32)
+
+
+# --------------------------------------------------------------------------- #
+# Combined frequency / periodicity representation (cfp.py)
+# --------------------------------------------------------------------------- #
+def blackmanharris_window(window_size: int) -> np.ndarray:
+    """cfp.py:89 — ``scipy.signal.blackmanharris(window_size)`` (symmetric, 4-term), float64.
+    (SciPy >= 1.13 only keeps the function under ``scipy.signal.windows``.)"""
+    return _sps.windows.blackmanharris(int(window_size))
+
+
+def cfp_axes(fr, fs, fc, tc):
+    """cfp.py:83-106 — the transform size and the crops of a CFP module:
+    ``N = int(fs / fr)``, the frequency axis ``f`` (first ``HighFreqIdx`` points of
+    ``fs * linspace(0, 0.5, N // 2)``), the quefrency axis ``q = arange(HighQuefIdx) / fs``, and
+    the two cut-off indices of the non-linearities."""
+    N = int(fs / float(fr))
+    f_full = fs * np.linspace(0, 0.5, np.round(N // 2), endpoint=True)
+    tc_idx = round(fs * tc)
+    fc_idx = round(fc / fr)
+    high_freq = int(round((1 / tc) / fr) + 1)
+    high_quef = int(round(fs / fc) + 1)
+    return dict(N=N, f=f_full[:high_freq], q=np.arange(high_quef) / float(fs), tc_idx=tc_idx,
+                fc_idx=fc_idx, HighFreqIdx=high_freq, HighQuefIdx=high_quef)
+
+
+def _triangle_rows(axis_hz: np.ndarray, lo: int, hi: int, left: float, centre: float, right: float,
+                   row: np.ndarray) -> None:
+    """One band of a log-frequency matrix: points of ``axis_hz[lo:hi]`` strictly inside
+    (left, centre) get the rising edge, strictly inside (centre, right) the falling edge
+    (cfp.py:219-227 / 233-244; points equal to a centre stay 0, as in the reference)."""
+    if hi > axis_hz.shape[0]:  # the reference indexes point by point and fails on the first one past the end
+        raise IndexError(f"index {axis_hz.shape[0]} is out of bounds for axis 0 with size {axis_hz.shape[0]}")
+    seg = axis_hz[lo:hi]
+    rising = (seg > left) & (seg < centre)
+    falling = (seg > centre) & (seg < right)
+    vals = np.zeros(seg.shape[0], dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        vals[rising] = (seg[rising] - left) / (centre - left)
+        vals[falling] = (right - seg[falling]) / (right - centre)
+    row[lo:hi] = vals
+
+
+def cfp_logfreq_matrices(f: np.ndarray, q: np.ndarray, fr, fc, tc, NumPerOct, fs):
+    """cfp.py:195-246 ``create_logfreq_matrix`` — triangular maps from the linear frequency axis
+    ``f`` and from the quefrency axis ``q`` (as pitch ``1 / q``) onto ``NumPerOct`` bands per
+    octave between ``fc`` and ``1 / tc``; float64 ``(Nest - 1, len(f))`` and ``(Nest - 1, len(q))``.
+    Rows 0 and Nest - 2 stay empty, as in the reference (its loops run over the interior bands)."""
+    start, stop = fc, 1 / tc
+    n_est = int(np.ceil(np.log2(stop / start)) * NumPerOct)
+    centres = []
+    for i in range(0, n_est):
+        c = start * pow(2, float(i) / NumPerOct)
+        if c < stop:
+            centres.append(c)
+        else:
+            break
+    n_est = len(centres)
+    freq_map = np.zeros((n_est - 1, len(f)), dtype=np.double)
+    for i in range(1, n_est - 1):
+        lo = int(round(centres[i - 1] / fr))
+        hi = int(round(centres[i + 1] / fr) + 1)
+        if lo >= hi - 1:
+            freq_map[i, lo] = 1  # the band is narrower than one bin
+        else:
+            _triangle_rows(f, lo, hi, centres[i - 1], centres[i], centres[i + 1], freq_map[i])
+    with np.errstate(divide="ignore"):
+        pitch = 1 / q  # q[0] = 0 -> inf, never inside a band
+    quef_map = np.zeros((n_est - 1, len(pitch)), dtype=np.double)
+    for i in range(1, n_est - 1):
+        lo = int(round(fs / centres[i + 1]))
+        hi = int(round(fs / centres[i - 1]) + 1)
+        _triangle_rows(pitch, lo, hi, centres[i - 1], centres[i], centres[i + 1], quef_map[i])
+    return freq_map, quef_map

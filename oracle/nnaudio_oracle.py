@@ -12,8 +12,8 @@ against (i) the reference's own golden vectors
 ``tests/golden/ref_ground_truths.npz``) and (ii) outputs of the unmodified
 reference imported in the build container (``tests/golden/make_golden.py`` ->
 ``tests/golden/ref_outputs.npz``) — this covers STFT, the inverse STFT, Mel,
-MFCC, Gammatone, CQT1992v2, CQT2010v2, VQT and the first-generation
-``cqt1992`` / ``cqt2010``.  ONE EXCEPTION, PARITY UNPINNED: ``griffin_lim`` — the
+MFCC, Gammatone, CQT1992v2, CQT2010v2, VQT, the first-generation
+``cqt1992`` / ``cqt2010`` and ``cfp`` (fixtures: ``tests/golden/make_golden_cfp.py``).  ONE EXCEPTION, PARITY UNPINNED: ``griffin_lim`` — the
 reference module does not execute under torch >= 2.0 (its ``torch.istft`` /
 ``torch.stft`` calls are rejected), so that function follows the source and the
 documented semantics of the two torch calls without reference outputs to check.
@@ -51,6 +51,7 @@ __all__ = [
     "griffin_lim",
     "torch_stft_restated",
     "torch_istft_restated",
+    "cfp",
 ]
 
 
@@ -534,3 +535,67 @@ def griffin_lim(S, rand_phase, n_fft, n_iter=32, hop=None, win_length=None, wind
         angles = rebuilt - (momentum / (1 + momentum)) * tprev
         angles = angles / (np.abs(angles) + 1e-16)
     return torch_istft_restated(S * angles, n_fft, hop, w, center)
+
+
+# --------------------------------------------------------------------------- #
+# Combined frequency / periodicity (features/cfp.py)
+# --------------------------------------------------------------------------- #
+def cfp(x, h, freq2logfreq, quef2logfreq, N, hop, g, tc_idx, fc_idx, high_freq, high_quef,
+        drop_edge_frames=False, dtype=np.float64):
+    """``Combined_Frequency_Periodicity.forward`` (cfp.py:137-180, ``drop_edge_frames=True``) and
+    ``CFP.forward`` (cfp.py:375-418): returns ``(Z, tfrL0, tfrLF, tfrLQ)``, each (B, bands, T).
+
+    Follows the source step by step with full length-N FFTs: ``torch.stft(n_fft=N, win_length=len(h),
+    center=True, pad_mode="constant", onesided=False)`` = N//2 zeros either side, the window zero-padded
+    to N with ``(N - len(h)) // 2`` zeros in front, frames every ``hop``; magnitude / ``|h|``;
+    ``_CFP`` (cfp.py:119-135) with ``nonlinear_func`` (cfp.py:182-193, including ``X[..., -0:] = 0``
+    zeroing everything when the cut-off index is 0); the crops and the two matmuls."""
+    x = np.asarray(x, dtype=dtype)
+    if x.ndim != 2:
+        raise IndexError("cfp: the reference's transpose(1, 2) needs a (batch, len) input")
+    h = np.asarray(h, dtype=dtype)
+    W = h.shape[0]
+    B, L = x.shape
+    xp = np.pad(x, ((0, 0), (N // 2, N // 2)))
+    win = np.zeros(N, dtype=dtype)
+    left = (N - W) // 2
+    win[left:left + W] = h
+    T = 1 + L // hop
+    idx = np.arange(T)[:, None] * hop + np.arange(N)[None, :]
+    spec_c = np.fft.fft(xp[:, idx] * win, axis=-1)                   # (B, T, N)
+    tfr0 = (np.abs(spec_c) / np.linalg.norm(h)).astype(dtype)
+    if drop_edge_frames:
+        tfr0 = tfr0[:, 1:-1]
+
+    def nonlinear(X, gg, cutoff):
+        cutoff = int(cutoff)
+        X = np.maximum(X, 0)
+        if gg != 0:
+            X = X.copy()
+            X[:, :, :cutoff] = 0
+            X[:, :, X.shape[2] - cutoff if cutoff else 0:] = 0
+            return X ** gg
+        X = np.log(X + 1e-8)
+        X[:, :, :cutoff] = 0
+        X[:, :, X.shape[2] - cutoff if cutoff else 0:] = 0
+        return X
+
+    spec = np.maximum(tfr0, 0) ** g[0]
+    ceps = None
+    for gc in range(1, int(np.size(g))):
+        if gc % 2 == 1:
+            ceps = nonlinear(np.fft.fft(spec, axis=-1).real.astype(dtype) / np.sqrt(N), g[gc], tc_idx)
+        else:
+            spec = nonlinear(np.fft.fft(ceps, axis=-1).real.astype(dtype) / np.sqrt(N), g[gc], fc_idx)
+    if ceps is None:
+        raise UnboundLocalError("cfp: fewer than two layers leave `ceps` unassigned (cfp.py:135)")
+    half = int(round(N / 2))
+    tfr0 = tfr0[:, :, :half][:, :, :high_freq]
+    tfr = spec[:, :, :half][:, :, :high_freq]
+    ceps = ceps[:, :, :half][:, :, :high_quef]
+    f2l = np.asarray(freq2logfreq, dtype=dtype)
+    q2l = np.asarray(quef2logfreq, dtype=dtype)
+    tfrL0 = f2l @ tfr0.transpose(0, 2, 1)
+    tfrLF = f2l @ tfr.transpose(0, 2, 1)
+    tfrLQ = q2l @ ceps.transpose(0, 2, 1)
+    return tfrLF * tfrLQ, tfrL0, tfrLF, tfrLQ

@@ -314,3 +314,31 @@ def loss_weights(case_id: str, shape) -> np.ndarray:
 def out_key(case_id: str, fwd_kwargs: dict) -> str:
     tag = "_".join(f"{k[:3]}-{v}" for k, v in sorted(fwd_kwargs.items()))
     return f"{case_id}|{tag}" if tag else case_id
+
+
+# --------------------------------------------------------------------------- #
+# Combined_Frequency_Periodicity / CFP (features/cfp.py) — fixtures from make_golden_cfp.py
+# --------------------------------------------------------------------------- #
+# id, class name, ctor kwargs, input spec
+CFP_CASES = [
+    ("cfp_default", "CFP", dict(), ("randn", 40, (2, 16000))),
+    ("cfp_combined_default", "Combined_Frequency_Periodicity", dict(), ("randn", 41, (2, 8000))),
+    ("cfp_fr4_four_layers", "CFP",
+     dict(fr=4, hop_length=160, window_size=1025, g=[0.2, 0.5, 0.8, 1.0], NumPerOct=24), ("randn", 42, (3, 6000))),
+    ("cfp_odd_n_log_layer", "Combined_Frequency_Periodicity", dict(fr=3, g=[0.3, 0], window_size=1500),
+     ("randn", 43, (1, 7000))),
+    ("cfp_fs22050_36_per_octave", "CFP",
+     dict(fs=22050, fr=2, fc=55, tc=1 / 2000, NumPerOct=36, hop_length=256), ("randn", 44, (1, 5000))),
+]
+# constructor-only configurations (buffers + attributes)
+CFP_DESIGN_CASES = [
+    ("cfp_design_fr1", "CFP", dict(fr=1, fc=27.5, tc=1 / 4000, NumPerOct=60)),
+    ("cfp_design_short_window", "Combined_Frequency_Periodicity", dict(window_size=513, hop_length=80, fc=110)),
+]
+# id, class, ctor, input shape: the exception type the reference raises
+CFP_ERROR_CASES = [
+    ("cfp_1d_input", "CFP", dict(), (4000,)),
+    ("cfp_3d_input", "CFP", dict(), (1, 1, 4000)),
+    ("cfp_single_layer", "CFP", dict(g=[0.5]), (1, 4000)),
+    ("cfp_window_longer_than_n", "CFP", dict(fr=8, window_size=2049), (1, 4000)),
+]

@@ -53,7 +53,7 @@ def split_forward(x, k_real, k_imag, packed, kb, ke, hop, center, pad_mode, scal
 
 
 class _Patch:
-    def setattr(self, obj, name, value):
+    def setattr(self, obj, name, value, raising=True):
         setattr(obj, name, value)
 
 
