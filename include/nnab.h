@@ -325,6 +325,9 @@ int nnab_profile_read(double* framed_ms, uint64_t* framed_launches);
 /* MMA flops the tensor-core launches EXECUTED since the last read (all bf16 split terms, tile
  * padding and structural zeros included) -> bench.py's roofline.tensor_pipe. */
 int nnab_profile_read_exec_flops(double* exec_flops);
+/* Launches of the tall-A CQT kernel that ran the balanced schedule (tiles shared between two CTA
+ * pairs, framed_tc2t_kernel<., true>) since load -- lets a test tell which schedule it exercised. */
+uint64_t nnab_balanced_launch_count(void);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -33,6 +33,7 @@ SIGNATURES = {
     "nnab_profile_enable": (None, [c_int]),
     "nnab_profile_read": (c_int, [_P, _P]),
     "nnab_profile_read_exec_flops": (c_int, [_P]),
+    "nnab_balanced_launch_count": (c_uint64, []),
     "nnab_pack_tile_n": (c_int, [c_int]),
     "nnab_packed_basis_bytes": (c_size_t, [c_int, c_int]),
     "nnab_pack_basis": (c_int, [_P, _P, c_int, c_int, _P, _P]),
@@ -149,6 +150,11 @@ def resolve_path(path) -> int:
 
 def launch_count() -> int:
     return int(lib().nnab_launch_count())
+
+
+def balanced_launch_count() -> int:
+    """Tall-A CQT launches that ran the balanced (shared-tile) schedule since load."""
+    return int(lib().nnab_balanced_launch_count())
 
 
 def set_sm_reserve(n_sms: int) -> int:

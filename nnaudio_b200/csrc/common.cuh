@@ -13,6 +13,7 @@ namespace nnab {
 void set_cuda_error(const char* where, cudaError_t e);
 void set_error_text(const char* text);
 void count_launch();
+void count_balanced_launch();
 int sm_reserve();
 // tensor-pipe accounting for bench.py: MMA flops a tensor-core launch EXECUTES (all split terms,
 // tile padding and structural zeros included); summed while nnab_profile_enable(1)

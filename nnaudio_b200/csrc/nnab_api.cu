@@ -16,12 +16,14 @@ namespace nnab {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_balanced_launches{0};
 
 void set_cuda_error(const char* where, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 void set_error_text(const char* text) { snprintf(g_err, sizeof(g_err), "%s", text); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_balanced_launch() { g_balanced_launches.fetch_add(1, std::memory_order_relaxed); }
 static std::atomic<int> g_sm_reserve{0};
 int sm_reserve() { return g_sm_reserve.load(std::memory_order_relaxed); }
 
@@ -151,6 +153,8 @@ const char* nnab_strerror(int status) {
 const char* nnab_last_cuda_error(void) { return g_err; }
 
 uint64_t nnab_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+uint64_t nnab_balanced_launch_count(void) { return g_balanced_launches.load(std::memory_order_relaxed); }
 
 int nnab_set_sm_reserve(int n_sms) {
   if (n_sms < 0) n_sms = 0;

@@ -62,7 +62,77 @@ struct TctParams {
   int n_phases;                   // frames t = s * n_phases + p: phase p reads the planes shifted by p * hop
   int64_t nv, t_slots, T;         // per phase: virtual frames, frames per clip slot; T = frames of the output
   EpiParams epi;
+  float* sk_scratch;              // balanced schedule only: partial sums of the tiles two pairs share
+  uint32_t* sk_flags;             //   one word per (slot, CTA, epilogue warp), zeroed before the launch
 };
+
+// Work of one CTA pair.  Static schedule (SK = false): tiles pair, pair + num_pairs, ... -- whole tiles,
+// so a launch lasts ceil(tiles / pairs) tiles (cfg3: 463 tiles on 74 pairs = 7 rounds for 6.26 of work).
+// Balanced schedule (SK = true): the (tile, column chunk) units are cut into num_pairs equal contiguous
+// ranges.  A range is at least one tile long (pairs <= tiles), so a tile is shared by at most two pairs:
+// the pair that owns its LAST chunks meets it first, parks its register sums in `sk_scratch` and raises
+// the flags; the pair that owns its FIRST chunks meets it at the end of its range, adds the parked sums in
+// a fixed order (own + other: bit-repeatable) and writes the output.
+constexpr int TCT_SK_WARP_VALUES = 2 * 8 * TCT_GROUPS_PER_PART;                      // (re, im) x 8 x 6
+constexpr size_t TCT_SK_SLOT_BYTES = (size_t)2 * TCT_EPI_WARPS * TCT_SK_WARP_VALUES * 32 * sizeof(float);
+constexpr size_t TCT_SK_FLAG_BYTES_PER_SLOT = (size_t)2 * TCT_EPI_WARPS * sizeof(uint32_t);
+
+template <bool SK>
+struct TallSched {
+  int tile, ci_lo, ci_hi;  // the current piece: column chunks [ci_lo, ci_hi) of `tile`
+  int64_t u, u_end;
+  int n_cols, stride;
+  __device__ TallSched(int pair, int num_pairs, int total_tiles, int n_cols_) : n_cols(n_cols_) {
+    if (SK) {
+      const int64_t U = (int64_t)total_tiles * n_cols;
+      u = U * pair / num_pairs;
+      u_end = U * (pair + 1) / num_pairs;
+      stride = 0;
+    } else {
+      u = pair;
+      u_end = total_tiles;
+      stride = num_pairs;
+    }
+  }
+  __device__ bool next() {
+    if (u >= u_end) return false;
+    if (SK) {
+      tile = (int)(u / n_cols);
+      ci_lo = (int)(u - (int64_t)tile * n_cols);
+      const int64_t rem = u_end - (int64_t)tile * n_cols;
+      ci_hi = rem < n_cols ? (int)rem : n_cols;
+      u = (int64_t)tile * n_cols + ci_hi;
+    } else {
+      tile = (int)u;
+      ci_lo = 0;
+      ci_hi = n_cols;
+      u += stride;
+    }
+    return true;
+  }
+};
+
+// Bounded spin on a flag word another CTA pair raises (release / acquire at GPU scope).
+__device__ __forceinline__ void sk_wait_flag(const uint32_t* flag) {
+  unsigned long long t0 = 0;
+  uint32_t spins = 0, v;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v != 0u) return;
+    if ((++spins & 0x3FFu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {  // 4 s
+        printf("nnab: stream-K flag wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void sk_raise_flag(uint32_t* flag) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+}
 
 struct TctSmem {
   static constexpr uint32_t A_PLANE = TCT_A_ROWS * TCT_BK * 2;   // 24 KB
@@ -74,7 +144,7 @@ struct TctSmem {
   static constexpr uint32_t TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <int FMT>
+template <int FMT, bool SK>
 __global__ void __launch_bounds__(TCT_THREADS, 1)
 framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b8,
                    const __grid_constant__ CUtensorMap tm_b32, const TctParams p,
@@ -133,11 +203,11 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (elect_one()) {
       int stage = 0, abuf = 0;
       uint32_t phase = 0, aphase = 0;
-      const int total_tiles = p.num_m_tiles * p.n_phases;
-      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        const int ph = tile / p.num_m_tiles, m_tile = tile - ph * p.num_m_tiles;
+      TallSched<SK> it(pair, num_pairs, p.num_m_tiles * p.n_phases, plan.n_cols);
+      while (it.next()) {
+        const int ph = it.tile / p.num_m_tiles, m_tile = it.tile - ph * p.num_m_tiles;
         const int m0 = m_tile * (2 * TC_BM) + (int)cta * TC_BM;
-        for (int ci = 0; ci < plan.n_cols; ++ci) {
+        for (int ci = it.ci_lo; ci < it.ci_hi; ++ci) {
           const int c = plan.col[ci], r_min = plan.r_min[ci], r_cnt = plan.r_cnt[ci];
           // ---- the column's tall A block: rows m0 + r_min .. + a_rows, columns [64 c, 64 c + 64)
           mbar_wait(a_empty(abuf), aphase ^ 1u);
@@ -174,9 +244,9 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
       int stage = 0, abuf = 0, acc = 0;
       uint32_t phase = 0, aphase = 0, acc_phase = 0;
-      const int total_tiles = p.num_m_tiles * p.n_phases;
-      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        for (int ci = 0; ci < plan.n_cols; ++ci) {
+      TallSched<SK> it(pair, num_pairs, p.num_m_tiles * p.n_phases, plan.n_cols);
+      while (it.next()) {
+        for (int ci = it.ci_lo; ci < it.ci_hi; ++ci) {
           const int r_cnt = plan.r_cnt[ci];
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           mbar_wait(a_full(abuf), aphase);
@@ -212,14 +282,14 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     float sre[TCT_GROUPS_PER_PART][8], sim[TCT_GROUPS_PER_PART][8];
-    const int total_tiles = p.num_m_tiles * p.n_phases;
-    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-      const int ph = tile / p.num_m_tiles, m_tile = tile - ph * p.num_m_tiles;
+    TallSched<SK> it(pair, num_pairs, p.num_m_tiles * p.n_phases, plan.n_cols);
+    while (it.next()) {
+      const int ph = it.tile / p.num_m_tiles, m_tile = it.tile - ph * p.num_m_tiles;
 #pragma unroll
       for (int gi = 0; gi < TCT_GROUPS_PER_PART; ++gi)
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sre[gi][j] = 0.f; sim[gi][j] = 0.f; }
-      for (int ci = 0; ci < plan.n_cols; ++ci) {
+      for (int ci = it.ci_lo; ci < it.ci_hi; ++ci) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
@@ -243,6 +313,41 @@ framed_tc2t_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (SK) {
+        // a tile shared with a neighbour pair: its last chunks (met first, by pair + 1) are parked in
+        // scratch slot `pair`, its first chunks (met last, by this pair) pick them up
+        const int ew = warp - 4;
+        if (it.ci_lo > 0) {
+          float* dst = p.sk_scratch +
+                       (((size_t)pair * 2 + cta) * TCT_EPI_WARPS + ew) * (TCT_SK_WARP_VALUES * 32) + lane;
+#pragma unroll
+          for (int gi = 0; gi < TCT_GROUPS_PER_PART; ++gi)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __stcg(dst + (size_t)((gi * 8 + j) * 2) * 32, sre[gi][j]);
+              __stcg(dst + (size_t)((gi * 8 + j) * 2 + 1) * 32, sim[gi][j]);
+            }
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) sk_raise_flag(p.sk_flags + ((size_t)pair * 2 + cta) * TCT_EPI_WARPS + ew);
+          continue;  // the neighbour writes this tile's output
+        }
+        if (it.ci_hi < plan.n_cols) {
+          const int other = pair + 1;
+          if (lane == 0) sk_wait_flag(p.sk_flags + ((size_t)other * 2 + cta) * TCT_EPI_WARPS + ew);
+          __syncwarp();
+          __threadfence();
+          const float* src = p.sk_scratch +
+                             (((size_t)other * 2 + cta) * TCT_EPI_WARPS + ew) * (TCT_SK_WARP_VALUES * 32) + lane;
+#pragma unroll
+          for (int gi = 0; gi < TCT_GROUPS_PER_PART; ++gi)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sre[gi][j] += __ldcg(src + (size_t)((gi * 8 + j) * 2) * 32);
+              sim[gi][j] += __ldcg(src + (size_t)((gi * 8 + j) * 2 + 1) * 32);
+            }
+        }
       }
       // ---- final format, once per tile
       const int64_t g_row = (int64_t)m_tile * (2 * TC_BM) + (int64_t)cta * TC_BM + quarter * 32 + lane;
@@ -289,6 +394,12 @@ bool tc_tall_problem_ok(const FramedProblem& q) {
   if (q.presplit != nullptr && q.presplit_t_slots <= 0) return false;  // needs the explicit geometry
   if (q.presplit == nullptr && q.hop < 64) return false;               // phases only on shared planes
   return q.fmt == NNAB_FMT_MAGNITUDE || q.fmt == NNAB_FMT_COMPLEX || q.fmt == NNAB_FMT_PHASE_UNIT;
+}
+
+// NNAB_TALL_BALANCE=1|0: balanced (shared-tile) schedule of framed_tc2t_kernel on / off.
+static bool tall_balance_enabled() {
+  if (const char* e = getenv("NNAB_TALL_BALANCE")) return atoi(e) != 0;
+  return false;  // default until the GPU run of this round confirms it (parity, repeatability, speed)
 }
 
 // Returns NNAB_EUNSUPPORTED when the bank does not fit the tall layout (caller falls back).
@@ -353,7 +464,7 @@ static int build_tall_plan(const FramedProblem& q, TallPlan* plan) {
   return n > 0 ? NNAB_OK : NNAB_EUNSUPPORTED;
 }
 
-template <int FMT>
+template <int FMT, bool SK>
 static int launch_tc2t_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const CUtensorMap& mb32,
                            const TctParams& prm, const TallPlan& plan, int n_pairs,
                            cudaStream_t stream) {
@@ -362,7 +473,7 @@ static int launch_tc2t_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const 
   int cfg_dev = 0;
   NNAB_CUDA_TRY(cudaGetDevice(&cfg_dev));
   if (!((configured_devs.load(std::memory_order_relaxed) >> (cfg_dev & 63)) & 1u)) {
-    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2t_kernel<FMT>,
+    NNAB_CUDA_TRY(cudaFuncSetAttribute(framed_tc2t_kernel<FMT, SK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
     configured_devs.fetch_or(1ull << (cfg_dev & 63), std::memory_order_relaxed);
   }
@@ -378,7 +489,7 @@ static int launch_tc2t_fmt(const CUtensorMap& ma, const CUtensorMap& mb8, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2t_kernel<FMT>, ma, mb8, mb32, prm, plan));
+  NNAB_CUDA_TRY(cudaLaunchKernelEx(&cfg, framed_tc2t_kernel<FMT, SK>, ma, mb8, mb32, prm, plan));
   count_launch();
   return NNAB_OK;
 }
@@ -445,6 +556,8 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
     return rc;
 
   TctParams prm{};
+  prm.sk_scratch = nullptr;
+  prm.sk_flags = nullptr;
   prm.num_m_tiles = (int)ceil_div64(nv, 2 * TC_BM);
   prm.n_phases = P;
   prm.nv = nv;
@@ -454,16 +567,44 @@ int launch_framed_tc_tall(const FramedProblem& q, const void* packed, void* work
   prm.epi.eps = q.eps; prm.epi.power = q.power; prm.epi.out = q.out; prm.epi.T = q.T;
   prm.epi.out_bins = q.out_bins; prm.epi.bin_offset = q.bin_offset; prm.epi.F = q.F;
   const int64_t tiles = (int64_t)prm.num_m_tiles * P;
-  const int n_pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
+  int n_pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
+  if (const char* e = getenv("NNAB_TALL_PAIRS")) {  // tests: force shared tiles on small problems
+    const int v = atoi(e);
+    if (v >= 1 && v < n_pairs) n_pairs = v;
+  }
   {
     double cols = 0.0;
     for (int kb = 0; kb < TCT_MAX_KB; ++kb) cols += 16.0 * plan.groups[kb] * 64.0;
     add_exec_flops(3.0 * 2.0 * (double)tiles * (2 * TC_BM) * cols);
   }
+  // Balanced schedule (TallSched<true>): only when the static one leaves a ragged last round, and the
+  // split-K scratch of this problem (long kernels: attach_splitk_scratch) can hold one slot per pair.
+  // The pairs of a launch wait on each other, so the whole grid must be resident: n_pairs <= SMs / 2.
+  bool balanced = false;
+  if (tall_balance_enabled() && q.raw != nullptr && tiles > n_pairs && tiles % n_pairs != 0) {
+    const size_t flag_bytes = ((size_t)n_pairs * TCT_SK_FLAG_BYTES_PER_SLOT + 255) / 256 * 256;
+    const size_t have = tc_splitk_scratch_bytes(q.B, q.F, q.T, q.K);
+    if (have >= flag_bytes + (size_t)n_pairs * TCT_SK_SLOT_BYTES + 256) {
+      char* base = reinterpret_cast<char*>(((uintptr_t)q.raw + 255) & ~(uintptr_t)255);
+      prm.sk_flags = reinterpret_cast<uint32_t*>(base);
+      prm.sk_scratch = reinterpret_cast<float*>(base + flag_bytes);
+      NNAB_CUDA_TRY(cudaMemsetAsync(prm.sk_flags, 0, flag_bytes, stream));
+      balanced = true;
+    }
+  }
+  if (balanced) {
+    count_balanced_launch();
+    switch (q.fmt) {
+      case NNAB_FMT_MAGNITUDE: return launch_tc2t_fmt<0, true>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+      case NNAB_FMT_COMPLEX: return launch_tc2t_fmt<1, true>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+      case NNAB_FMT_PHASE_UNIT: return launch_tc2t_fmt<3, true>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+      default: return NNAB_EINVAL;
+    }
+  }
   switch (q.fmt) {
-    case NNAB_FMT_MAGNITUDE: return launch_tc2t_fmt<0>(ma, mb8, mb32, prm, plan, n_pairs, stream);
-    case NNAB_FMT_COMPLEX: return launch_tc2t_fmt<1>(ma, mb8, mb32, prm, plan, n_pairs, stream);
-    case NNAB_FMT_PHASE_UNIT: return launch_tc2t_fmt<3>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+    case NNAB_FMT_MAGNITUDE: return launch_tc2t_fmt<0, false>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+    case NNAB_FMT_COMPLEX: return launch_tc2t_fmt<1, false>(ma, mb8, mb32, prm, plan, n_pairs, stream);
+    case NNAB_FMT_PHASE_UNIT: return launch_tc2t_fmt<3, false>(ma, mb8, mb32, prm, plan, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
 }
