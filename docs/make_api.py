@@ -14,23 +14,26 @@ import nnaudio_b200 as nb  # noqa: E402
 REF = {"STFT": "stft.py:66-362", "iSTFT": "stft.py:364-546", "MelSpectrogram": "mel.py:9-194",
        "MFCC": "mel.py:197-329", "Gammatonegram": "gammatone.py:9-194", "CQT1992v2": "cqt.py:561-803",
        "CQT": "cqt.py:1142-1145", "CQT2010v2": "cqt.py:805-1139", "VQT": "vqt.py:9-215",
-       "CQT1992": "cqt.py:9-256", "CQT2010": "cqt.py:259-558", "Griffin_Lim": "griffin_lim.py:9-148"}
+       "CQT1992": "cqt.py:9-256", "CQT2010": "cqt.py:259-558", "Griffin_Lim": "griffin_lim.py:9-148",
+       "Combined_Frequency_Periodicity": "cfp.py:9-246", "CFP": "cfp.py:249-484"}
 
 HEADER = """# API — `nnaudio_b200.features` (generated from the signatures by `python docs/make_api.py`)
 
 Same class names, constructor arguments (names, order, defaults), `forward` signatures, buffer names and public
 attributes as `nnAudio.features` v0.3.3 — checked against the unmodified reference by the fixtures in `tests/golden/`
-(signatures, buffers bit-identical for 49 configurations, attribute surface, exception types, outputs ≤1e-4). What differs:
+(signatures, buffers bit-identical for 49 + 7 configurations, attribute surface, exception types, outputs ≤1e-4). What differs:
 
 * inputs must be **CUDA float32** tensors on a B200 (sm_100a); anything else raises — there is no CPU fallback;
-* one process per GPU (`nnaudio_b200.parallel.BatchShardedTransform`) instead of `nn.DataParallel` (INTEGRATION.md);
-* `Griffin_Lim.forward(S, rand_phase=None)` takes an optional initial phase (reproducible runs); its `device`
-  argument is accepted and ignored (buffers follow `.to()` / `.cuda()`);
+* multi-GPU: one process per GPU (`nnaudio_b200.parallel.BatchShardedTransform`, INTEGRATION.md) is the fast path;
+  `torch.nn.DataParallel`, the reference's own mode, also works (per-device launch attributes and caches);
+* `Griffin_Lim.forward(S, rand_phase=None)` takes an optional initial phase (reproducible runs); `device` moves the
+  module's buffers at construction, as the reference creates its window there;
 * trainable inverse kernels / window of `iSTFT` raise `NotImplementedError` under autograd (no dW path yet);
-* `CFP` / `Combined_Frequency_Periodicity` are not provided (DESIGN.md §7).
+* `CFP` / `Combined_Frequency_Periodicity` are forward-only (the reference has no parameters there; a waveform that
+  requires grad raises `NotImplementedError`); their FFT stages run as dense contractions (DESIGN.md §3.9).
 
-Environment switches: `NNAUDIO_B200_PATH=auto|simt|tcgen05` (kernel family), `NNAUDIO_B200_DECIM_BWD=simt|tc|ola`
-(adjoint of the pyramid's FIR stages in training).
+Environment switches: `NNAUDIO_B200_PATH=auto|simt|tcgen05` (kernel family), `NNAUDIO_B200_DECIM_BWD=fir|simt|tc|ola`
+(adjoint of the pyramid's FIR stages in training), `NNAB_TALL_BALANCE=0|1` (balanced tile schedule of the CQT1992v2 kernel).
 
 """
 
