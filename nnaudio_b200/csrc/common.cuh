@@ -49,6 +49,10 @@ constexpr int FMT_FBANK = 101;  // internal (tcgen05 only): power -> banded filt
 constexpr int FMT_DECIM = 102;  // internal (tcgen05 only): FIR decimator stage of the CQT pyramid
 constexpr int FMT_RAW = 103;    // internal (tcgen05 only): split-K partial sums -> raw (re, im) scratch
 constexpr int FMT_OLA = 104;    // internal (tcgen05 only): inverse STFT frames -> overlap-add buffer
+constexpr int FMT_PLANES = 105;   // internal (block-partial kernel only): power spectrum -> bf16 hi/lo operand
+                                  //   planes of the dense-filterbank GEMM (`out` = plane base, see planes_*)
+constexpr int FMT_REALPAIR = 106; // internal (dense tcgen05 kernel only): two real outputs per complex column
+                                  //   pair: re -> row f, im -> row f + F of a real (B, out_bins, T) tensor
 
 // FMT_DECIM epilogue target: the NEXT pyramid level, written as bf16 hi/lo planes in
 // the layout the tensor-core kernels read (sample m of clip b at b*pitch + off + m).
@@ -117,6 +121,8 @@ struct FramedProblem {
   int64_t ola_pitch;         // FMT_OLA: out = overlap-add buffer (B, ola_pitch); scale = window/n_fft
   int ola_hop;
   int k_splits_hint;         // FMT_OLA only (its atomics already accumulate): cut K into chunks
+  int64_t planes_stride;     // FMT_PLANES: elements between the hi and the lo plane
+  int planes_pitch;          // FMT_PLANES: elements per frame row (multiple of 64)
 };
 
 int launch_framed_simt(const FramedProblem& p, cudaStream_t stream);
@@ -167,6 +173,10 @@ int tc_istft_finalize(const float* ola, int64_t ola_pitch, int64_t B, const floa
                       int n_fft, int hop, int64_t T, int64_t offset, float* out, int64_t out_len,
                       cudaStream_t stream);
 size_t tc_splitk_scratch_bytes(int64_t B, int F, int64_t T, int K);
+// block-partial kernel (tcb_kernels.cu): default N-tile geometry for F bins (nb packed columns per tile,
+// nb - 2 new bins each) -- the column layout of the FMT_PLANES operand planes
+void tc_block_tile_geometry(int F, int* nb, int* n_tiles);
+bool tc_block_shape_ok(int n_fft, int hop);
 size_t tc_packed_fir_bytes(int taps, int dec);
 int tc_fir_k(int taps, int dec);
 int tc_pack_fir(const float* fir, int taps, int dec, void* packed, cudaStream_t stream);
@@ -180,6 +190,8 @@ int launch_fb_steps(const FbEntry* table, int n_fb, int F, FbStep* steps, int* d
 // filterbank / MFCC tail / FIR decimation (simt_kernels.cu)
 int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t T, int n_fb,
                       float* out, cudaStream_t stream);
+int launch_fb_tile_bank(const float* fb, int n_fb, int F, int nb, int n_tiles, int kp, int fh, float* w_re,
+                        float* w_im, cudaStream_t stream);
 int launch_mfcc_tail(const float* mel, int64_t B, int n_mels, int64_t T, float amin, float ref,
                      float top_db, const float* dct, int n_mfcc, float* out,
                      unsigned int* scratch /* B words */, cudaStream_t stream);

@@ -27,6 +27,8 @@ struct EpiParams {
   int64_t raw_plane;
   int64_t ola_pitch;        // FMT_OLA
   int ola_hop;
+  int64_t planes_stride;    // FMT_PLANES (block-partial kernel): hi -> lo plane distance, elements
+  int planes_pitch;         //   and elements per frame row; `out` is the plane base
 };
 
 __device__ __forceinline__ float epi_power(const EpiParams& e, float re, float im) {
@@ -83,7 +85,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int64_t b, int f, 
 
 // Compile-time-format variant for the tcgen05 kernel: keeps the 32x unrolled
 // TMEM read-out loop small enough to stay in the instruction cache.
-//   FMT: 0..3 = NNAB_FMT_*, 4 = FMT_POWER.  `dst` already points at element
+//   FMT: 0..3 = NNAB_FMT_*, 4 = FMT_POWER, 9 = FMT_REALPAIR.  `dst` already points at element
 //   (b, bin_offset, t) of the output (float2 elements for the 2-channel formats).
 template <int FMT>
 __device__ __forceinline__ void epi_store_fmt(const EpiParams& e, float* dst, int f, float re,
@@ -108,6 +110,10 @@ __device__ __forceinline__ void epi_store_fmt(const EpiParams& e, float* dst, in
     float sn, cs;
     sincosf(ang, &sn, &cs);
     reinterpret_cast<float2*>(dst)[off] = make_float2(cs, sn);
+  } else if constexpr (FMT == 9) {
+    // two real rows per complex column pair (real GEMMs on the complex kernel: dense filterbanks)
+    dst[off] = re;
+    if (row + e.F < e.out_bins) dst[off + (int64_t)e.F * e.T] = im;
   } else {
     float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
     if (e.eps != 0.f) p = __fadd_rn(p, e.eps);

@@ -1,6 +1,7 @@
 // extern "C" entry points of libnnab.so — see include/nnab.h for the contract
 // and the reference file:line each call replaces.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <atomic>
 #include <mutex>
 #include <stdlib.h>
@@ -317,6 +318,38 @@ int nnab_build_filterbank_table(const float* fb, int n_fb, int F, void* table, i
   return NNAB_OK;
 }
 
+// ---- dense filterbank (Gammatonegram, dense mel banks) on the tensor cores -------------------------
+// The block-partial STFT kernel writes |X| ** power straight into bf16 hi/lo operand planes (FMT_PLANES: one
+// row per frame, 4 B per value, no fp32 (B, F, T) intermediate), a second tcgen05 launch contracts the rows
+// with the re-indexed bank (real GEMM on the complex kernel, FMT_REALPAIR) and writes (B, n_fb, T).
+// Workspace: [signal planes of the STFT][operand planes][bank fp32 re | im][packed bank].
+static bool fb_planes_enabled() {
+  if (const char* e = getenv("NNAB_FB_PLANES")) return atoi(e) != 0;
+  return false;  // default until the GPU run confirms it
+}
+
+struct FbPlanes {
+  int nb, n_tiles, kp, fh;
+  int64_t rows;  // B * T frame rows
+  size_t off_planes, off_w, off_packed, total;
+};
+
+static bool fb_planes_layout(int64_t B, int64_t L, int n_fft, int F, int hop, int pad, int64_t T, int n_fb,
+                             FbPlanes* o) {
+  if (!tc_block_shape_ok(n_fft, hop) || F != n_fft / 2 + 1 || n_fb < 1 || T <= 0 || B <= 0) return false;
+  tc_block_tile_geometry(F, &o->nb, &o->n_tiles);
+  o->kp = (o->nb * o->n_tiles + 63) / 64 * 64;
+  o->fh = (n_fb + 1) / 2;
+  o->rows = B * T;
+  if (o->rows >= (1ll << 31) || o->kp > 32768) return false;
+  size_t off = align_up(tc_workspace_bytes(B, L, n_fft, hop, pad), 256);
+  o->off_planes = off; off += align_up((size_t)2 * o->rows * o->kp * 2, 256);
+  o->off_w = off;      off += 2 * align_up((size_t)o->fh * o->kp * sizeof(float), 256);
+  o->off_packed = off; off += align_up(tc_packed_bytes(o->fh, o->kp), 256);
+  o->total = off + 256;
+  return true;
+}
+
 static bool fused_fbank(int path, const void* packed, const void* fb_table, int n_fft, int hop) {
   return fb_table != nullptr && packed != nullptr && path != NNAB_PATH_SIMT &&
          wants_tc(path, n_fft, hop);
@@ -324,13 +357,16 @@ static bool fused_fbank(int path, const void* packed, const void* fb_table, int 
 
 size_t nnab_filterbank_workspace_bytes(int64_t B, int64_t L, int n_fft, int F, int hop,
                                        int center, int n_fb, int path, int has_table) {
-  (void)n_fb;
   const int pad = center ? n_fft / 2 : 0;
   const int64_t T = frames_of(L, n_fft, hop, pad);
   const bool tc = wants_tc(path, n_fft, hop);
   size_t n = 0;
   if (!(has_table && tc)) n += power_bytes(B, F, T);  // un-fused: (B,F,T) power spectrogram
   if (tc) n += tc_workspace_bytes(B, L, n_fft, hop, pad);
+  if (!has_table && tc) {  // dense bank on the tensor cores: operand planes instead of the fp32 spectrogram
+    FbPlanes fp;
+    if (fb_planes_layout(B, L, n_fft, F, hop, pad, T, n_fb, &fp) && fp.total > n) n = fp.total;
+  }
   return n;
 }
 
@@ -383,6 +419,44 @@ int nnab_stft_filterbank_forward(const float* x, int64_t B, int64_t L, int64_t x
   }
   const size_t need = nnab_filterbank_workspace_bytes(B, L, n_fft, F, hop, center, n_fb, path, 0);
   if (workspace == nullptr || ws_bytes < need) return NNAB_EWORKSPACE;
+  {
+    FbPlanes fp;
+    if (fb_planes_enabled() && path != NNAB_PATH_SIMT && packed != nullptr && packed_kind(packed) == PACK_BLOCK &&
+        wants_tc(path, n_fft, hop) && B <= 65535 &&
+        fb_planes_layout(B, L, n_fft, F, hop, pad, T, n_fb, &fp) && ws_bytes >= fp.total) {
+      char* ws = reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+      __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(ws + fp.off_planes);
+      float* w_re = reinterpret_cast<float*>(ws + fp.off_w);
+      float* w_im = reinterpret_cast<float*>(ws + fp.off_w + align_up((size_t)fp.fh * fp.kp * sizeof(float), 256));
+      void* bank = ws + fp.off_packed;
+      const int64_t plane_stride = fp.rows * fp.kp;
+      // the re-indexed bank (tiny: fh x kp) and its bf16 hi/lo packing
+      if ((rc = launch_fb_tile_bank(fb, n_fb, F, fp.nb, fp.n_tiles, fp.kp, fp.fh, w_re, w_im, s))) return rc;
+      if ((rc = tc_pack_basis(w_re, w_im, fp.fh, fp.kp, bank, s))) return rc;
+      // columns no tile writes (kp is the 64-multiple above n_tiles * nb): finite zeros in both planes
+      if (fp.kp > fp.nb * fp.n_tiles)
+        NNAB_CUDA_TRY(cudaMemset2DAsync(planes + fp.nb * fp.n_tiles, (size_t)fp.kp * 2, 0,
+                                        (size_t)(fp.kp - fp.nb * fp.n_tiles) * 2, (size_t)(2 * fp.rows), s));
+      // 1. STFT -> |X| ** power as operand planes (block-partial kernel, FMT_PLANES)
+      FramedProblem p{};
+      p.x = x; p.B = B; p.L = L; p.x_pitch = x_pitch;
+      p.w_re = wcos; p.w_im = wsin; p.F = F; p.K = n_fft; p.hop = hop;
+      p.pad = pad; p.pad_mode = pad_mode; p.scale = nullptr; p.scale_all = 1.f;
+      p.fmt = FMT_PLANES; p.eps = sqrt_eps; p.power = power; p.out = reinterpret_cast<float*>(planes); p.T = T;
+      p.out_bins = F; p.bin_offset = 0;
+      p.planes_stride = plane_stride; p.planes_pitch = fp.kp;
+      if ((rc = run_framed(p, packed, ws, fp.off_planes, NNAB_PATH_TCGEN05, s))) return rc;
+      // 2. rows x bank on the dense kernel: every frame is one "hop" of kp samples
+      FramedProblem g{};
+      g.x = nullptr; g.B = B; g.L = T * fp.kp; g.x_pitch = T * fp.kp;
+      g.w_re = w_re; g.w_im = w_im; g.F = fp.fh; g.K = fp.kp; g.hop = fp.kp;
+      g.pad = 0; g.pad_mode = NNAB_PAD_CONSTANT; g.scale = nullptr; g.scale_all = 1.f;
+      g.fmt = FMT_REALPAIR; g.eps = 0.f; g.power = 1.f; g.out = out; g.T = T;
+      g.out_bins = n_fb; g.bin_offset = 0;
+      g.presplit = planes; g.presplit_t_slots = T; g.presplit_plane_stride = plane_stride;
+      return run_framed(g, bank, nullptr, 0, NNAB_PATH_TCGEN05, s);
+    }
+  }
   float* P = (float*)workspace;
   const size_t pb = power_bytes(B, F, T);
   rc = power_spectrogram(x, B, L, x_pitch, wcos, wsin, packed, n_fft, F, hop, pad, pad_mode,

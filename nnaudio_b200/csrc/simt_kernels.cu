@@ -359,6 +359,39 @@ int launch_filterbank(const float* P, const float* fb, int64_t B, int F, int64_t
   return NNAB_OK;
 }
 
+// Dense filterbank as the B operand of a real GEMM on the complex tcgen05 kernel: the (n_fb, F) weights
+// re-indexed to the column layout of the block-partial kernel's FMT_PLANES output (tile n, packed column
+// i  <->  FFT bin n (nb - 2) + i - 2; columns 0, 1 of a tile and bins >= F carry zeros), filters
+// [0, fh) in the real bank and filters [fh, 2 fh) NEGATED in the imaginary bank (the contraction returns
+// -sum x w_im, FMT_REALPAIR then writes re -> row f, im -> row f + fh).
+__global__ void __launch_bounds__(256) fb_tile_bank_kernel(const float* __restrict__ fb, int n_fb, int F,
+                                                           int nb, int n_tiles, int kp, int fh,
+                                                           float* __restrict__ w_re, float* __restrict__ w_im) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)fh * kp) return;
+  const int j = (int)(idx / kp), col = (int)(idx % kp);
+  const int n = col / nb, i = col - n * nb;
+  float a = 0.f, b = 0.f;
+  if (n < n_tiles && i >= 2) {
+    const int k = n * (nb - 2) + i - 2;
+    if (k < F) {
+      a = __ldg(fb + (int64_t)j * F + k);
+      if (j + fh < n_fb) b = -__ldg(fb + (int64_t)(j + fh) * F + k);
+    }
+  }
+  w_re[idx] = a;
+  w_im[idx] = b;
+}
+
+int launch_fb_tile_bank(const float* fb, int n_fb, int F, int nb, int n_tiles, int kp, int fh, float* w_re,
+                        float* w_im, cudaStream_t stream) {
+  const int64_t n = (int64_t)fh * kp;
+  fb_tile_bank_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(fb, n_fb, F, nb, n_tiles, kp, fh,
+                                                                        w_re, w_im);
+  NNAB_LAUNCH_CHECK();
+  return NNAB_OK;
+}
+
 // --------------------------------------------------------------------------
 // MFCC tail
 //   pass 1: per-clip max of max(S, amin)  (float bits are monotone for > 0)

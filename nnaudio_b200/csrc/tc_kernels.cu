@@ -1593,6 +1593,7 @@ static int launch_tc2_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const
     case FMT_DECIM: return launch_tc2_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, n_pairs, stream);
     case FMT_RAW: return launch_tc2_kernel_fmt<BK, STAGES, 7>(ma, mb, prm, n_pairs, stream);
     case FMT_OLA: return launch_tc2_kernel_fmt<BK, STAGES, 8>(ma, mb, prm, n_pairs, stream);
+    case FMT_REALPAIR: return launch_tc2_kernel_fmt<BK, STAGES, 9>(ma, mb, prm, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -1610,6 +1611,7 @@ static int launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, const 
     case FMT_DECIM: return launch_tc_kernel_fmt<BK, STAGES, 6>(ma, mb, prm, grid, stream);
     case FMT_RAW: return launch_tc_kernel_fmt<BK, STAGES, 7>(ma, mb, prm, grid, stream);
     case FMT_OLA: return launch_tc_kernel_fmt<BK, STAGES, 8>(ma, mb, prm, grid, stream);
+    case FMT_REALPAIR: return launch_tc_kernel_fmt<BK, STAGES, 9>(ma, mb, prm, grid, stream);
     default: return NNAB_EINVAL;
   }
 }

@@ -37,6 +37,7 @@
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 #include "tc_host.cuh"
+#include "tc_decim.cuh"
 
 namespace nnab {
 
@@ -72,6 +73,10 @@ static int block_choose_nb(int F) {
   return best;
 }
 static int block_n_tiles(int F, int nb) { return (F + nb - 3) / (nb - 2); }
+void tc_block_tile_geometry(int F, int* nb, int* n_tiles) {
+  *nb = block_choose_nb(F);
+  *n_tiles = block_n_tiles(F, *nb);
+}
 // rows of one (plane, part) slab: bins -1 .. F plus zero rows so that the last tile of ANY nb <= 128
 // stays inside the slab (the launch picks nb, e.g. wider tiles for the fused filterbank)
 static int block_p_rows(int F) { return round_up_i(F + 2 + 128, 8); }
@@ -177,7 +182,7 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
   float* dst = nullptr;
   float* mel = nullptr;
   if constexpr (FMT == 5) mel = p.epi.out + ((int64_t)b * p.epi.n_fb) * p.epi.T + t;
-  else dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
+  else if constexpr (FMT != 9) dst = p.epi.out + (((int64_t)b * p.epi.out_bins + p.epi.bin_offset) * p.epi.T + t) * CH;
   MelRun run;
   // FMT 5 fast path: static action list and the default power 2 without eps; anything else (other
   // powers, trainable eps, no action list) takes the rolled MelRun path below
@@ -282,6 +287,28 @@ __device__ __forceinline__ void epilogue_tile_block(const TcbParams& p, uint32_t
           if (ok) *q = v;
         }
         q += step;
+      }
+    } else if constexpr (FMT == 9) {
+      // operand planes of the dense-filterbank GEMM (FMT_PLANES): frame (b, t) is row b * T + t, the 8
+      // packed columns of chunk c of tile n sit at nb * n + 8 c (16-byte aligned: nb is a multiple of 8),
+      // |X| ** power as bf16 hi / lo.  The two columns a tile repeats from its left neighbour and the bins
+      // past F are written as zeros (the re-indexed bank has zero rows there).
+      __align__(16) __nv_bfloat16 hi[8];
+      __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float pw = __fadd_rn(__fmul_rn(xr[e], xr[e]), __fmul_rn(xi[e], xi[e]));
+        if (p.epi.eps != 0.f) pw = __fadd_rn(pw, p.epi.eps);
+        float v = (p.epi.power == 2.0f) ? pw
+                  : ((p.epi.power == 1.0f) ? sqrt_approx(pw) : powf(sqrt_approx(pw), p.epi.power));
+        if (e < e_lo || (k0 + e) >= p.epi.F) v = 0.f;
+        split_bf16(v, hi[e], lo[e]);
+      }
+      if (valid) {
+        __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.epi.out) +
+                           (b * p.epi.T + t) * (int64_t)p.epi.planes_pitch + (int64_t)nb * n_tile + 8 * c;
+        *reinterpret_cast<uint4*>(q) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(q + p.epi.planes_stride) = *reinterpret_cast<const uint4*>(lo);
       }
     } else if constexpr (FMT == 5) {
       if (fast_fb) {
@@ -542,6 +569,7 @@ static int launch_tcb(int fmt, const CUtensorMap& ma, const CUtensorMap& mb, con
     case NNAB_FMT_PHASE_ANGLE: return launch_tcb_fmt<2, R>(ma, mb, prm, n_pairs, stream);
     case FMT_POWER: return launch_tcb_fmt<4, R>(ma, mb, prm, n_pairs, stream);
     case FMT_FBANK: return launch_tcb_fmt<5, R>(ma, mb, prm, n_pairs, stream);
+    case FMT_PLANES: return launch_tcb_fmt<9, R>(ma, mb, prm, n_pairs, stream);
     default: return NNAB_EINVAL;
   }
 }
@@ -565,6 +593,11 @@ int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* wor
       break;
     case FMT_FBANK:
       if (q.fb_table == nullptr || q.n_fb <= 0) return NNAB_EINVAL;
+      break;
+    case FMT_PLANES:
+      if (q.out == nullptr || q.planes_pitch <= 0 || q.planes_pitch % 8 != 0 || q.planes_stride <= 0 ||
+          q.planes_stride % 8 != 0 || ((uintptr_t)q.out & 15u) != 0)
+        return NNAB_EINVAL;
       break;
     default: return NNAB_EINVAL;
   }
@@ -625,6 +658,8 @@ int launch_framed_tc_block(const FramedProblem& q, const void* packed, void* wor
   prm.epi.fb_table = q.fb_table; prm.epi.n_fb = q.n_fb; prm.epi.fb_steps = q.fb_steps;
   prm.epi.raw = nullptr; prm.epi.raw_plane = 0;
   prm.epi.ola_pitch = 0; prm.epi.ola_hop = 0;
+  prm.epi.planes_stride = q.planes_stride; prm.epi.planes_pitch = q.planes_pitch;
+  if (q.fmt == FMT_PLANES && (int64_t)n_tiles * nb > q.planes_pitch) return NNAB_EINVAL;
   const int64_t ptiles = (int64_t)prm.num_m_pairs * n_tiles;
   const int n_pairs = (int)(ptiles < sms / 2 ? ptiles : sms / 2);
   add_exec_flops(3.0 * 2.0 * (double)ptiles * (2 * TC_BM) * (2 * nb) * q.hop);
