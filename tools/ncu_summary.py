@@ -38,7 +38,12 @@ def main(rep):
     if len(src) > 2:
         h = src[1]
         ix = {k: i for i, k in enumerate(h)}
-        data = [r for r in src[2:] if len(r) == len(h)]
+        data = []
+        for r in src[2:]:  # a report with several launches repeats the two header rows: keep the first
+            if r and r[0] == "Kernel Name":
+                break
+            if len(r) == len(h):
+                data.append(r)
         stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
         tot = sum(int(r[ix["# Samples"]] or 0) for r in data) or 1
         agg = sorted(((sum(int(r[ix[k]] or 0) for r in data), k) for k in stalls), reverse=True)[:8]
