@@ -17,7 +17,7 @@ try:
     r = d["roofline"]
     print("cfg2 value %.4e ms %.4f frac %.3f | e2e %.4f ms | launches %s" % (d["value"], d["ms_per_step"], r["frac"], d["e2e"]["ms_per_step"], d.get("gpu_launches")))
     for k, v in d["workloads"].items():
-        print(k, "ms %.4f value %.3e frac %.3f" % (v["ms_per_step"], v["value"], v["roofline"]["frac"]))
+        print(k, v.get("error") or "ms %.4f value %.3e frac %.3f" % (v["ms_per_step"], v["value"], v["roofline"]["frac"]))
     print("clocks", d["clocks"])
 except Exception as e:
     print("default bench unreadable:", e)
