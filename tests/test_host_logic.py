@@ -118,6 +118,7 @@ def test_nnaudio_import_shim():
         # the reference's per-file import paths (`from nnAudio.features.stft import STFT`, ...)
         for sub, names in (("stft", ["STFT", "iSTFT"]), ("mel", ["MelSpectrogram", "MFCC"]),
                            ("gammatone", ["Gammatonegram"]), ("vqt", ["VQT"]), ("griffin_lim", ["Griffin_Lim"]),
+                           ("cfp", ["CFP", "Combined_Frequency_Periodicity"]),
                            ("cqt", ["CQT1992v2", "CQT2010v2", "CQT", "CQT1992", "CQT2010"])):
             m = importlib.import_module("nnAudio.features." + sub)
             for n in names:
