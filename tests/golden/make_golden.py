@@ -9,6 +9,9 @@ outputs are committed:
                          Installation/tests/ground-truths/*.npy (test fixtures,
                          not source code) — pinned by tests/test_cqt.py:94-262
 
+(The Combined_Frequency_Periodicity / CFP fixtures have their own generator, make_golden_cfp.py ->
+ref_cfp.npz / ref_cfp.json.)
+
 Run:  PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 """
 from __future__ import annotations
